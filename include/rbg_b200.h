@@ -1,0 +1,208 @@
+/*
+ * rbg_b200.h -- C-ABI of the B200-native routing-board engine (librbg_b200.so).
+ *
+ * The drop-in boundary for the ONE hot path of mwolinska/Routing-Board-Generation:
+ * ParallelRandomWalk / SeedExtension / Uniform board generation behind the
+ * generator plugin `__call__(key) -> State`, and the Jumanji Connector
+ * reset / step / action-mask / observation.  The reference is pure Python
+ * (JAX); there is no FFI in it today.  Each entry point below names the
+ * reference function (file:line under /root/reference) whose jit(vmap(...))
+ * it replaces; the leading axis B of every array is that vmap axis.
+ * INTEGRATION.md shows the reference-side binding (ctypes + DLPack).
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch / CUDA types in any signature.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - unless a function name ends in `_host`, every array pointer is a DEVICE
+ *     pointer on the current CUDA device (what a DLPack capsule of a torch or
+ *     JAX GPU array carries); `_host` variants take host pointers and do the
+ *     H2D / D2H copies themselves.
+ *   - dtypes as the reference with x64 disabled: int32 grids / coordinates /
+ *     actions, uint32[2] raw threefry keys, float32 rewards, bool masks as
+ *     uint8, step_type int8.
+ *   - all arrays are C-contiguous, and int32 arrays of the bulk outputs
+ *     (grid, obs_grid, solved) must be 16-byte aligned (torch / XLA
+ *     allocations are).
+ *   - return value: 0 on success, negative RBG_E* otherwise (never throws,
+ *     never falls back to a CPU path); rbg_last_error() has the message.
+ *   - kernels are launched asynchronously on `stream`; nothing synchronises
+ *     except the `_host` variants.
+ *   - square grids only (the reference's _adjacent_cells strides by rows but
+ *     divmods by cols, parallel_random_walk.py:276,284): 2 <= G <= 40,
+ *     1 <= N <= 32, N <= G*G (2N for the uniform generator).
+ *
+ * Abbreviations for citations:
+ *   PRW  routing_board_generation/board_generation_methods/jax_implementation/board_generation/parallel_random_walk.py
+ *   SE   .../jax_implementation/board_generation/seed_extension.py
+ *   PRWG routing_board_generation/rl_training/online_generators/parallel_random_walk_generator.py
+ *   UG   routing_board_generation/rl_training/online_generators/uniform_generator.py
+ *   RSG  routing_board_generation/rl_training/online_generators/random_seed_generator.py
+ *   ST   routing_board_generation/rl_training/setup_train.py
+ *   JUM  jumanji==0.2.2 jumanji/environments/routing/connector/ (UPSTREAM, requirements.txt:5)
+ */
+#ifndef RBG_B200_H
+#define RBG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RBG_VERSION 100
+
+#define RBG_OK 0
+#define RBG_EINVAL (-1)   /* bad size / null pointer / unsupported config */
+#define RBG_EALIGN (-2)   /* bulk pointer not 16-byte aligned */
+#define RBG_ECUDA (-3)    /* CUDA runtime error (see rbg_last_error) */
+#define RBG_ENOMEM (-4)
+
+#define RBG_MAX_G 40
+#define RBG_MAX_N 32
+
+/* generator kinds: which `Generator.__call__` a State comes from */
+#define RBG_GEN_PRW 0     /* ParallelRandomWalkGenerator  PRWG:46-77 */
+#define RBG_GEN_UNIFORM 1 /* UniformRandomGenerator       UG:70-109  */
+#define RBG_GEN_SEEDEXT 2 /* SeedExtensionGenerator       RSG:28-57  */
+
+/* jumanji Connector `State` pytree (JUM types.py; field order as printed in
+ * package_evaluation/profiling_generators.ipynb cell 4), struct-of-arrays with
+ * the vmap axis leading. */
+typedef struct rbg_state {
+  int32_t *grid;       /* [B,G,G] */
+  int32_t *step_count; /* [B]     */
+  int32_t *agent_id;   /* [B,N]   */
+  int32_t *start;      /* [B,N,2] */
+  int32_t *target;     /* [B,N,2] */
+  int32_t *position;   /* [B,N,2] */
+  uint32_t *key;       /* [B,2]   */
+} rbg_state;
+
+/* jumanji `TimeStep[Observation]` + extras (JUM env.py step/reset). */
+typedef struct rbg_timestep {
+  int32_t *obs_grid;          /* [B,N,G,G] observation.grid        */
+  uint8_t *action_mask;       /* [B,N,5]   observation.action_mask */
+  int32_t *obs_step_count;    /* [B]       observation.step_count  */
+  float *reward;              /* [B,N] */
+  float *discount;            /* [B,N] */
+  int8_t *step_type;          /* [B]  0 FIRST, 1 MID, 2 LAST */
+  int32_t *num_connections;   /* [B]  extras */
+  float *ratio_connections;   /* [B]  extras */
+  int32_t *total_path_length; /* [B]  extras */
+} rbg_timestep;
+
+/* Connector constructor arguments (JUM env.py __init__; ST:158). */
+typedef struct rbg_env_params {
+  int32_t time_limit;     /* 50   */
+  float timestep_reward;  /* -0.03 (DenseRewardFn) */
+  float connected_reward; /* 0.1  */
+  int32_t autoreset_kind; /* <0: plain Connector.step; else VmapAutoResetWrapper
+                             (ST:166) resetting with that RBG_GEN_* generator */
+} rbg_env_params;
+
+int rbg_version(void);
+const char *rbg_last_error(void);
+/* sm major*10+minor of the current device, SM count; returns RBG_ECUDA if no device */
+int rbg_device_info(int *sm_arch, int *sm_count);
+
+/* rows [offset, offset+count) of jax.random.split(key, B)  (the reference's key
+ * convention: dataset_generator_jax.py:76, ST:397-399; each GPU derives its own
+ * slice).  key is a HOST uint32[2]; out is a device uint32[count,2]. */
+int rbg_split_keys(const uint32_t key[2], int64_t B, int64_t offset,
+                   int64_t count, uint32_t *out, void *stream);
+
+/* ParallelRandomWalkBoard(G,G,N).generate_board(key)   PRW:60-90
+ * keys[B,2] -> heads[B,2,N], targets[B,2,N], solved[B,G,G].
+ * stats (may be NULL): int32[B,2] = (while-loop trips, collided moves). */
+int rbg_prw_generate(const uint32_t *keys, int64_t B, int G, int N,
+                     int32_t *heads, int32_t *targets, int32_t *solved,
+                     int32_t *stats, void *stream);
+
+/* Generator.__call__(key) -> State for kind in RBG_GEN_*  (PRWG:46-77,
+ * UG:70-109, RSG:28-57).  keys[B,2] -> *out. */
+int rbg_generator_state(int kind, const uint32_t *keys, int64_t B, int G, int N,
+                        const rbg_state *out, void *stream);
+
+/* SeedExtensionBoard(G,G,N).return_solved_board(key, randomness, two_sided,
+ * extension_iterations, extension_steps)   SE:149-227.
+ * extension_steps < 0 means unlimited (the reference default 1e23). */
+int rbg_seedext_solved(const uint32_t *keys, int64_t B, int G, int N,
+                       float randomness, int two_sided, int iterations,
+                       int64_t extension_steps, int32_t *solved, void *stream);
+/* SeedExtensionBoard.generate_starts_ends   SE:257-304 -> starts[B,2,N], ends[B,2,N] */
+int rbg_seedext_starts_ends(const uint32_t *keys, int64_t B, int G, int N,
+                            float randomness, int two_sided, int iterations,
+                            int64_t extension_steps, int32_t *starts,
+                            int32_t *ends, void *stream);
+
+/* The observation half of Connector.reset on an existing State (the recipe
+ * at demos/board_generator_demo.py:83-96): action mask, per-agent
+ * observation, extras, restart() reward 0 / discount 1 / step_type FIRST. */
+int rbg_connector_observe(const rbg_state *state, int64_t B, int G, int N,
+                          const rbg_timestep *ts, void *stream);
+
+/* Connector(generator).reset(key)  (JUM env.py reset; ST:400) = generator + observe */
+int rbg_connector_reset(int kind, const uint32_t *keys, int64_t B, int G, int N,
+                        const rbg_state *state, const rbg_timestep *ts,
+                        void *stream);
+
+/* bytes of device scratch rbg_connector_step needs when autoreset is on */
+int64_t rbg_step_workspace_bytes(int64_t B, int G, int N);
+
+/* Connector.step(state, action) (JUM env.py step), or with
+ * params->autoreset_kind >= 0 VmapAutoResetWrapper(Connector).step (ST:166).
+ * in and out may alias (in-place update).  action int32[B,N].
+ * workspace: device scratch of rbg_step_workspace_bytes (may be NULL when
+ * autoreset is off). */
+int rbg_connector_step(const rbg_state *in, const rbg_state *out,
+                       const int32_t *action, int64_t B, int G, int N,
+                       const rbg_env_params *params, const rbg_timestep *ts,
+                       void *workspace, void *stream);
+
+/* Random policy over the legal actions, NOOP included (distribution-equal to
+ * jumanji's make_random_policy_connector, ST:246; NOT a bit-parity surface:
+ * upstream draws a float32 Gumbel).  bits = threefry2x32(state.key;
+ * step_count, agent).o0; pick = (bits * m) >> 32 among the m legal actions. */
+int rbg_random_actions(const rbg_state *state, int64_t B, int G, int N,
+                       int32_t *action, void *stream);
+
+/* rbg_random_actions + rbg_connector_step in one launch sequence
+ * (the agent=random benchmark loop, benchmark_on_random_agent.py:59-102).
+ * action_out may be NULL. */
+int rbg_connector_step_random(const rbg_state *in, const rbg_state *out,
+                              int32_t *action_out, int64_t B, int G, int N,
+                              const rbg_env_params *params,
+                              const rbg_timestep *ts, void *workspace,
+                              void *stream);
+
+/* Board validity (numpy_implementation/utils/post_processor_utils_numpy.py:34-155,
+ * board_processor.py:111-162).  flags int32[B]: 0 valid; bit0 encoding out of
+ * range, bit1 head/target count, bit2 neighbour-count rule, bit3 head and
+ * target not connected, bit4 zero-length wire (lone TARGET, a PRW quirk). */
+int rbg_validate(const int32_t *boards, int64_t B, int G, int N, int32_t *flags,
+                 void *stream);
+
+/* ---- host-buffer variants: same semantics, HOST pointers, copies inside,
+ * synchronous.  device < 0 = current device. ------------------------------ */
+int rbg_prw_generate_host(const uint32_t *keys, int64_t B, int G, int N,
+                          int32_t *heads, int32_t *targets, int32_t *solved,
+                          int device);
+int rbg_connector_reset_host(int kind, const uint32_t *keys, int64_t B, int G,
+                             int N, const rbg_state *state,
+                             const rbg_timestep *ts, int device);
+int rbg_connector_step_host(const rbg_state *in, const rbg_state *out,
+                            const int32_t *action, int64_t B, int G, int N,
+                            const rbg_env_params *params,
+                            const rbg_timestep *ts, int device);
+/* pinned host allocation helpers for the _host variants (optional) */
+void *rbg_host_alloc(int64_t bytes);
+void rbg_host_free(void *p);
+
+/* counters for bench.py's gpu_launches claim: number of kernels this library
+ * launched since the last reset */
+int64_t rbg_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RBG_B200_H */

@@ -1,0 +1,625 @@
+// c_api.cu -- the extern "C" surface declared in include/rbg_b200.h:
+// argument validation, error reporting, launch sequencing, and the
+// host-buffer variants (pipelined H2D -> kernels -> D2H over env slices).
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+
+#include "rbg_host.h"
+
+namespace rbg {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+int set_error(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int set_cuda_error(cudaError_t e, const char *what) {
+  return set_error(RBG_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+int check_launch(const char *what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, what);
+  return RBG_OK;
+}
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static int check_dims(int64_t B, int G, int N, int need_cells_per_agent) {
+  if (B < 0) return set_error(RBG_EINVAL, "B=%lld must be >= 0", (long long)B);
+  if (B > 0x3fffffffLL) return set_error(RBG_EINVAL, "B=%lld too large (max 2^30-1 per call)", (long long)B);
+  if (G < 2 || G > RBG_MAX_G) return set_error(RBG_EINVAL, "grid size G=%d outside [2,%d]", G, RBG_MAX_G);
+  if (N < 1 || N > RBG_MAX_N) return set_error(RBG_EINVAL, "num_agents N=%d outside [1,%d]", N, RBG_MAX_N);
+  if ((int64_t)need_cells_per_agent * N > (int64_t)G * G)
+    return set_error(RBG_EINVAL, "N=%d agents need %d cells on a %dx%d grid (choice(replace=False) would raise)",
+                     N, need_cells_per_agent * N, G, G);
+  return RBG_OK;
+}
+
+static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static bool aligned8(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }
+
+static int check_state(const rbg_state *s, const char *name) {
+  if (!s) return set_error(RBG_EINVAL, "%s is NULL", name);
+  if (!s->grid || !s->step_count || !s->agent_id || !s->start || !s->target || !s->position || !s->key)
+    return set_error(RBG_EINVAL, "%s has a NULL field", name);
+  if (!aligned16(s->grid)) return set_error(RBG_EALIGN, "%s.grid not 16-byte aligned", name);
+  if (!aligned8(s->start) || !aligned8(s->target) || !aligned8(s->position))
+    return set_error(RBG_EALIGN, "%s.start/target/position not 8-byte aligned", name);
+  return RBG_OK;
+}
+
+static int check_timestep(const rbg_timestep *t) {
+  if (!t) return set_error(RBG_EINVAL, "timestep is NULL");
+  if (!t->obs_grid || !t->action_mask || !t->obs_step_count || !t->reward || !t->discount || !t->step_type ||
+      !t->num_connections || !t->ratio_connections || !t->total_path_length)
+    return set_error(RBG_EINVAL, "timestep has a NULL field");
+  if (!aligned16(t->obs_grid)) return set_error(RBG_EALIGN, "timestep.obs_grid not 16-byte aligned");
+  return RBG_OK;
+}
+
+static int debug_flags() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("RBG_DEBUG_FLAGS");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+static int env_int(const char *name) {
+  const char *e = getenv(name);
+  return e ? atoi(e) : 0;
+}
+
+static int generator_state_impl(int kind, const uint32_t *keys, int64_t B, int G, int N, const rbg_state *out,
+                                const rbg_timestep *ts, int extra_split, const int32_t *list,
+                                const int32_t *list_count, cudaStream_t stream) {
+  if (kind == RBG_GEN_PRW || kind == RBG_GEN_UNIFORM) {
+    PrwParams p;
+    memset(&p, 0, sizeof(p));
+    p.keys = keys;
+    p.B = B;
+    p.G = G;
+    p.N = N;
+    p.mode = kind == RBG_GEN_PRW ? PRW_MODE_STATE : PRW_MODE_UNIFORM;
+    // PRWG:52 key, pos_key = split(key): the board uses split(key)[0].
+    // UG:76 the uniform generator consumes the split itself (both halves).
+    p.extra_split = (kind == RBG_GEN_PRW ? 1 : 0) + extra_split;
+    p.debug = debug_flags();
+    p.st = *out;
+    if (ts) {
+      p.ts = *ts;
+      p.observe = 1;
+    }
+    p.list = list;
+    p.list_count = list_count;
+    return launch_prw(p, B, env_int("RBG_PRW_M"), env_int("RBG_PRW_THREADS"), stream);
+  }
+  if (kind == RBG_GEN_SEEDEXT) {
+    SeedExtParams p;
+    memset(&p, 0, sizeof(p));
+    p.keys = keys;
+    p.B = B;
+    p.G = G;
+    p.N = N;
+    p.randomness = 0.0f;  // RSG:30 jit(generate_starts_ends) with the defaults
+    p.two_sided = 1;
+    p.iterations = 1;
+    p.ext_steps = -1;
+    p.extra_split = 1 + extra_split;  // RSG:34 key, pos_key = split(key)
+    p.mode = 2;
+    p.st = *out;
+    if (ts) {
+      p.ts = *ts;
+      p.observe = 1;
+    }
+    p.list = list;
+    p.list_count = list_count;
+    return launch_seedext(p, B, stream);
+  }
+  return set_error(RBG_EINVAL, "unknown generator kind %d", kind);
+}
+
+static int connector_step_impl(const rbg_state *in, const rbg_state *out, const int32_t *action, int32_t *action_out,
+                               int random_policy, int64_t B, int G, int N, const rbg_env_params *params,
+                               const rbg_timestep *ts, void *workspace, cudaStream_t stream) {
+  int rc;
+  if ((rc = check_dims(B, G, N, 1))) return rc;
+  if ((rc = check_state(in, "state_in"))) return rc;
+  if ((rc = check_state(out, "state_out"))) return rc;
+  if ((rc = check_timestep(ts))) return rc;
+  if (!params) return set_error(RBG_EINVAL, "params is NULL");
+  if (!random_policy && !action) return set_error(RBG_EINVAL, "action is NULL");
+  const bool autoreset = params->autoreset_kind >= 0;
+  if (autoreset && !workspace) return set_error(RBG_EINVAL, "auto-reset needs a workspace (rbg_step_workspace_bytes)");
+  if (autoreset && params->autoreset_kind > RBG_GEN_SEEDEXT)
+    return set_error(RBG_EINVAL, "unknown autoreset generator kind %d", params->autoreset_kind);
+  if (B == 0) return RBG_OK;
+  EnvParams p;
+  memset(&p, 0, sizeof(p));
+  p.in = *in;
+  p.out = *out;
+  p.ts = *ts;
+  p.action = action;
+  p.action_out = action_out;
+  p.random_policy = random_policy;
+  p.B = B;
+  p.G = G;
+  p.N = N;
+  p.mode = ENV_MODE_STEP;
+  p.env = *params;
+  int32_t *count = nullptr, *list = nullptr;
+  if (autoreset) {
+    count = reinterpret_cast<int32_t *>(workspace);
+    list = count + 4;
+    cudaError_t e = cudaMemsetAsync(count, 0, 16, stream);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(reset count)");
+    p.list = list;
+    p.list_count = count;
+  }
+  if ((rc = launch_env(p, env_int("RBG_ENV_E"), stream))) return rc;
+  if (autoreset) {
+    // VmapAutoResetWrapper._auto_reset: key, _ = split(state.key); reset(key):
+    // one more leading split()[0] than a plain generator call.
+    rc = generator_state_impl(params->autoreset_kind, out->key, B, G, N, out, ts, 1, list, count, stream);
+  }
+  return rc;
+}
+
+// ---- device scratch for the _host variants --------------------------------
+struct Scratch {
+  void *ptr = nullptr;
+  size_t bytes = 0;
+  int device = -1;
+};
+static std::mutex g_scratch_mu;
+static Scratch g_scratch;
+static cudaStream_t g_streams[3] = {nullptr, nullptr, nullptr};
+
+static int scratch_get(size_t bytes, int device, void **out) {
+  if (g_scratch.ptr && (g_scratch.bytes < bytes || g_scratch.device != device)) {
+    cudaFree(g_scratch.ptr);
+    g_scratch = Scratch();
+  }
+  if (!g_scratch.ptr) {
+    cudaError_t e = cudaMalloc(&g_scratch.ptr, bytes);
+    if (e != cudaSuccess) {
+      g_scratch = Scratch();
+      return set_cuda_error(e, "cudaMalloc(host-variant scratch)");
+    }
+    g_scratch.bytes = bytes;
+    g_scratch.device = device;
+  }
+  for (int i = 0; i < 3; ++i)
+    if (!g_streams[i]) {
+      cudaError_t e = cudaStreamCreateWithFlags(&g_streams[i], cudaStreamNonBlocking);
+      if (e != cudaSuccess) return set_cuda_error(e, "cudaStreamCreate");
+    }
+  *out = g_scratch.ptr;
+  return RBG_OK;
+}
+
+struct Carver {
+  uint8_t *base;
+  size_t off = 0;
+  template <typename T>
+  T *take(size_t n) {
+    off = (off + 255) & ~(size_t)255;
+    T *p = base ? reinterpret_cast<T *>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+static void carve_state(Carver &c, int64_t B, int G, int N, rbg_state *s) {
+  s->grid = c.take<int32_t>((size_t)B * G * G);
+  s->step_count = c.take<int32_t>((size_t)B);
+  s->agent_id = c.take<int32_t>((size_t)B * N);
+  s->start = c.take<int32_t>((size_t)B * N * 2);
+  s->target = c.take<int32_t>((size_t)B * N * 2);
+  s->position = c.take<int32_t>((size_t)B * N * 2);
+  s->key = c.take<uint32_t>((size_t)B * 2);
+}
+static void carve_timestep(Carver &c, int64_t B, int G, int N, rbg_timestep *t) {
+  t->obs_grid = c.take<int32_t>((size_t)B * N * G * G);
+  t->action_mask = c.take<uint8_t>((size_t)B * N * 5);
+  t->obs_step_count = c.take<int32_t>((size_t)B);
+  t->reward = c.take<float>((size_t)B * N);
+  t->discount = c.take<float>((size_t)B * N);
+  t->step_type = c.take<int8_t>((size_t)B);
+  t->num_connections = c.take<int32_t>((size_t)B);
+  t->ratio_connections = c.take<float>((size_t)B);
+  t->total_path_length = c.take<int32_t>((size_t)B);
+}
+
+#define RBG_CPY(dst, src, n, kind, st)                                                    \
+  do {                                                                                    \
+    cudaError_t e_ = cudaMemcpyAsync((dst), (src), (n), (kind), (st));                    \
+    if (e_ != cudaSuccess) return set_cuda_error(e_, "cudaMemcpyAsync " #dst);            \
+  } while (0)
+
+static int copy_state(const rbg_state *dst, const rbg_state *src, int64_t off, int64_t n, int G, int N,
+                      cudaMemcpyKind kind, int64_t dst_off, cudaStream_t st) {
+  const size_t c = (size_t)G * G;
+  RBG_CPY(dst->grid + dst_off * c, src->grid + off * c, n * c * 4, kind, st);
+  RBG_CPY(dst->step_count + dst_off, src->step_count + off, n * 4, kind, st);
+  RBG_CPY(dst->agent_id + dst_off * N, src->agent_id + off * N, n * N * 4, kind, st);
+  RBG_CPY(dst->start + dst_off * N * 2, src->start + off * N * 2, n * N * 8, kind, st);
+  RBG_CPY(dst->target + dst_off * N * 2, src->target + off * N * 2, n * N * 8, kind, st);
+  RBG_CPY(dst->position + dst_off * N * 2, src->position + off * N * 2, n * N * 8, kind, st);
+  RBG_CPY(dst->key + dst_off * 2, src->key + off * 2, n * 8, kind, st);
+  return RBG_OK;
+}
+static int copy_timestep(const rbg_timestep *dst, const rbg_timestep *src, int64_t off, int64_t n, int G, int N,
+                         cudaMemcpyKind kind, int64_t dst_off, cudaStream_t st) {
+  const size_t c = (size_t)G * G * N;
+  RBG_CPY(dst->obs_grid + dst_off * c, src->obs_grid + off * c, n * c * 4, kind, st);
+  RBG_CPY(dst->action_mask + dst_off * N * 5, src->action_mask + off * N * 5, n * N * 5, kind, st);
+  RBG_CPY(dst->obs_step_count + dst_off, src->obs_step_count + off, n * 4, kind, st);
+  RBG_CPY(dst->reward + dst_off * N, src->reward + off * N, n * N * 4, kind, st);
+  RBG_CPY(dst->discount + dst_off * N, src->discount + off * N, n * N * 4, kind, st);
+  RBG_CPY(dst->step_type + dst_off, src->step_type + off, n, kind, st);
+  RBG_CPY(dst->num_connections + dst_off, src->num_connections + off, n * 4, kind, st);
+  RBG_CPY(dst->ratio_connections + dst_off, src->ratio_connections + off, n * 4, kind, st);
+  RBG_CPY(dst->total_path_length + dst_off, src->total_path_length + off, n * 4, kind, st);
+  return RBG_OK;
+}
+
+static rbg_state state_at(const rbg_state &s, int64_t off, int G, int N) {
+  rbg_state r;
+  r.grid = s.grid + off * G * G;
+  r.step_count = s.step_count + off;
+  r.agent_id = s.agent_id + off * N;
+  r.start = s.start + off * N * 2;
+  r.target = s.target + off * N * 2;
+  r.position = s.position + off * N * 2;
+  r.key = s.key + off * 2;
+  return r;
+}
+static rbg_timestep timestep_at(const rbg_timestep &t, int64_t off, int G, int N) {
+  rbg_timestep r;
+  r.obs_grid = t.obs_grid + off * N * G * G;
+  r.action_mask = t.action_mask + off * N * 5;
+  r.obs_step_count = t.obs_step_count + off;
+  r.reward = t.reward + off * N;
+  r.discount = t.discount + off * N;
+  r.step_type = t.step_type + off;
+  r.num_connections = t.num_connections + off;
+  r.ratio_connections = t.ratio_connections + off;
+  r.total_path_length = t.total_path_length + off;
+  return r;
+}
+
+// slices are multiples of 64 envs so that every slice base keeps the 16-byte
+// alignment of the bulk arrays for any (G, N)
+static int64_t slice_size(int64_t B, int nslices) {
+  int64_t s = (B + nslices - 1) / nslices;
+  s = (s + 63) / 64 * 64;
+  return s < 64 ? 64 : s;
+}
+
+}  // namespace rbg
+
+using namespace rbg;
+
+extern "C" {
+
+int rbg_version(void) { return RBG_VERSION; }
+const char *rbg_last_error(void) { return g_err; }
+
+int rbg_device_info(int *sm_arch, int *sm_count) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return set_cuda_error(e, "cudaGetDevice");
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) return set_cuda_error(e, "cudaGetDeviceProperties");
+  if (sm_arch) *sm_arch = prop.major * 10 + prop.minor;
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  return RBG_OK;
+}
+
+int64_t rbg_launch_count(int reset) {
+  return reset ? g_launches.exchange(0) : g_launches.load();
+}
+
+int rbg_split_keys(const uint32_t key[2], int64_t B, int64_t offset, int64_t count, uint32_t *out, void *stream) {
+  if (!key || !out) return set_error(RBG_EINVAL, "rbg_split_keys: NULL pointer");
+  if (B < 1 || B > 0x7fffffffLL || offset < 0 || count < 0 || offset + count > B)
+    return set_error(RBG_EINVAL, "rbg_split_keys: bad slice [%lld,+%lld) of B=%lld", (long long)offset,
+                     (long long)count, (long long)B);
+  return launch_split_keys(key[0], key[1], B, offset, count, out, (cudaStream_t)stream);
+}
+
+int rbg_prw_generate(const uint32_t *keys, int64_t B, int G, int N, int32_t *heads, int32_t *targets,
+                     int32_t *solved, int32_t *stats, void *stream) {
+  int rc;
+  if ((rc = check_dims(B, G, N, 1))) return rc;
+  if (!keys || !heads || !targets || !solved) return set_error(RBG_EINVAL, "rbg_prw_generate: NULL pointer");
+  if (!aligned16(solved)) return set_error(RBG_EALIGN, "rbg_prw_generate: solved not 16-byte aligned");
+  if (B == 0) return RBG_OK;
+  PrwParams p;
+  memset(&p, 0, sizeof(p));
+  p.keys = keys;
+  p.B = B;
+  p.G = G;
+  p.N = N;
+  p.mode = PRW_MODE_BOARD;
+  p.debug = debug_flags();
+  p.heads = heads;
+  p.targets = targets;
+  p.solved = solved;
+  p.stats = stats;
+  return launch_prw(p, B, env_int("RBG_PRW_M"), env_int("RBG_PRW_THREADS"), (cudaStream_t)stream);
+}
+
+int rbg_generator_state(int kind, const uint32_t *keys, int64_t B, int G, int N, const rbg_state *out, void *stream) {
+  int rc;
+  if ((rc = check_dims(B, G, N, kind == RBG_GEN_UNIFORM ? 2 : 1))) return rc;
+  if (!keys) return set_error(RBG_EINVAL, "keys is NULL");
+  if ((rc = check_state(out, "state"))) return rc;
+  if (B == 0) return RBG_OK;
+  return generator_state_impl(kind, keys, B, G, N, out, nullptr, 0, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int rbg_seedext_solved(const uint32_t *keys, int64_t B, int G, int N, float randomness, int two_sided,
+                       int iterations, int64_t extension_steps, int32_t *solved, void *stream) {
+  int rc;
+  if ((rc = check_dims(B, G, N, 1))) return rc;
+  if (!keys || !solved) return set_error(RBG_EINVAL, "rbg_seedext_solved: NULL pointer");
+  if (!aligned16(solved)) return set_error(RBG_EALIGN, "rbg_seedext_solved: solved not 16-byte aligned");
+  if (B == 0) return RBG_OK;
+  SeedExtParams p;
+  memset(&p, 0, sizeof(p));
+  p.keys = keys;
+  p.B = B;
+  p.G = G;
+  p.N = N;
+  p.randomness = randomness;
+  p.two_sided = two_sided;
+  p.iterations = iterations;
+  p.ext_steps = extension_steps;
+  p.mode = 0;
+  p.solved = solved;
+  return launch_seedext(p, B, (cudaStream_t)stream);
+}
+
+int rbg_seedext_starts_ends(const uint32_t *keys, int64_t B, int G, int N, float randomness, int two_sided,
+                            int iterations, int64_t extension_steps, int32_t *starts, int32_t *ends, void *stream) {
+  int rc;
+  if ((rc = check_dims(B, G, N, 1))) return rc;
+  if (!keys || !starts || !ends) return set_error(RBG_EINVAL, "rbg_seedext_starts_ends: NULL pointer");
+  if (B == 0) return RBG_OK;
+  SeedExtParams p;
+  memset(&p, 0, sizeof(p));
+  p.keys = keys;
+  p.B = B;
+  p.G = G;
+  p.N = N;
+  p.randomness = randomness;
+  p.two_sided = two_sided;
+  p.iterations = iterations;
+  p.ext_steps = extension_steps;
+  p.mode = 1;
+  p.starts = starts;
+  p.ends = ends;
+  return launch_seedext(p, B, (cudaStream_t)stream);
+}
+
+int rbg_connector_observe(const rbg_state *state, int64_t B, int G, int N, const rbg_timestep *ts, void *stream) {
+  int rc;
+  if ((rc = check_dims(B, G, N, 1))) return rc;
+  if ((rc = check_state(state, "state"))) return rc;
+  if ((rc = check_timestep(ts))) return rc;
+  if (B == 0) return RBG_OK;
+  EnvParams p;
+  memset(&p, 0, sizeof(p));
+  p.in = *state;
+  p.out = *state;
+  p.ts = *ts;
+  p.B = B;
+  p.G = G;
+  p.N = N;
+  p.mode = ENV_MODE_OBSERVE;
+  p.env.autoreset_kind = -1;
+  return launch_env(p, env_int("RBG_ENV_E"), (cudaStream_t)stream);
+}
+
+int rbg_connector_reset(int kind, const uint32_t *keys, int64_t B, int G, int N, const rbg_state *state,
+                        const rbg_timestep *ts, void *stream) {
+  int rc = rbg_generator_state(kind, keys, B, G, N, state, stream);
+  if (rc) return rc;
+  return rbg_connector_observe(state, B, G, N, ts, stream);
+}
+
+int64_t rbg_step_workspace_bytes(int64_t B, int G, int N) {
+  (void)G;
+  (void)N;
+  return 16 + 4 * (B > 0 ? B : 0);
+}
+
+int rbg_connector_step(const rbg_state *in, const rbg_state *out, const int32_t *action, int64_t B, int G, int N,
+                       const rbg_env_params *params, const rbg_timestep *ts, void *workspace, void *stream) {
+  return connector_step_impl(in, out, action, nullptr, 0, B, G, N, params, ts, workspace, (cudaStream_t)stream);
+}
+
+int rbg_connector_step_random(const rbg_state *in, const rbg_state *out, int32_t *action_out, int64_t B, int G, int N,
+                              const rbg_env_params *params, const rbg_timestep *ts, void *workspace, void *stream) {
+  return connector_step_impl(in, out, nullptr, action_out, 1, B, G, N, params, ts, workspace, (cudaStream_t)stream);
+}
+
+int rbg_random_actions(const rbg_state *state, int64_t B, int G, int N, int32_t *action, void *stream) {
+  int rc;
+  if ((rc = check_dims(B, G, N, 1))) return rc;
+  if ((rc = check_state(state, "state"))) return rc;
+  if (!action) return set_error(RBG_EINVAL, "action is NULL");
+  return launch_random_actions(*state, B, G, N, action, (cudaStream_t)stream);
+}
+
+int rbg_validate(const int32_t *boards, int64_t B, int G, int N, int32_t *flags, void *stream) {
+  int rc;
+  if ((rc = check_dims(B, G, N, 0))) return rc;
+  if (!boards || !flags) return set_error(RBG_EINVAL, "rbg_validate: NULL pointer");
+  return launch_validate(boards, B, G, N, flags, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------- _host
+void *rbg_host_alloc(int64_t bytes) {
+  void *p = nullptr;
+  if (cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) {
+    set_error(RBG_ENOMEM, "cudaMallocHost(%lld) failed", (long long)bytes);
+    return nullptr;
+  }
+  return p;
+}
+void rbg_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
+static int use_device(int device, int *cur) {
+  cudaError_t e = cudaGetDevice(cur);
+  if (e != cudaSuccess) return set_cuda_error(e, "cudaGetDevice (no CUDA device: this library has no CPU path)");
+  if (device >= 0 && device != *cur) {
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaSetDevice");
+    *cur = device;
+  }
+  return RBG_OK;
+}
+
+int rbg_prw_generate_host(const uint32_t *keys, int64_t B, int G, int N, int32_t *heads, int32_t *targets,
+                          int32_t *solved, int device) {
+  int rc, dev;
+  if ((rc = check_dims(B, G, N, 1))) return rc;
+  if (!keys || !heads || !targets || !solved) return set_error(RBG_EINVAL, "rbg_prw_generate_host: NULL pointer");
+  if (B == 0) return RBG_OK;
+  if ((rc = use_device(device, &dev))) return rc;
+  std::lock_guard<std::mutex> lock(g_scratch_mu);
+  Carver size{nullptr};
+  size.take<uint32_t>((size_t)B * 2);
+  size.take<int32_t>((size_t)B * 2 * N);
+  size.take<int32_t>((size_t)B * 2 * N);
+  size.take<int32_t>((size_t)B * G * G);
+  void *base;
+  if ((rc = scratch_get(size.off + 256, dev, &base))) return rc;
+  Carver c{reinterpret_cast<uint8_t *>(base)};
+  uint32_t *dk = c.take<uint32_t>((size_t)B * 2);
+  int32_t *dh = c.take<int32_t>((size_t)B * 2 * N);
+  int32_t *dt = c.take<int32_t>((size_t)B * 2 * N);
+  int32_t *ds = c.take<int32_t>((size_t)B * G * G);
+  const int nsl = B >= 4096 ? 4 : 1;
+  const int64_t sl = slice_size(B, nsl);
+  int si = 0;
+  for (int64_t off = 0; off < B; off += sl, ++si) {
+    const int64_t n = (B - off) < sl ? (B - off) : sl;
+    cudaStream_t st = g_streams[si % 3];
+    RBG_CPY(dk + off * 2, keys + off * 2, n * 8, cudaMemcpyHostToDevice, st);
+    rc = rbg_prw_generate(dk + off * 2, n, G, N, dh + off * 2 * N, dt + off * 2 * N, ds + off * G * G, nullptr, st);
+    if (rc) return rc;
+    RBG_CPY(heads + off * 2 * N, dh + off * 2 * N, n * 2 * N * 4, cudaMemcpyDeviceToHost, st);
+    RBG_CPY(targets + off * 2 * N, dt + off * 2 * N, n * 2 * N * 4, cudaMemcpyDeviceToHost, st);
+    RBG_CPY(solved + off * G * G, ds + off * G * G, n * G * G * 4, cudaMemcpyDeviceToHost, st);
+  }
+  for (int i = 0; i < 3; ++i) {
+    cudaError_t e = cudaStreamSynchronize(g_streams[i]);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaStreamSynchronize");
+  }
+  return RBG_OK;
+}
+
+int rbg_connector_reset_host(int kind, const uint32_t *keys, int64_t B, int G, int N, const rbg_state *state,
+                             const rbg_timestep *ts, int device) {
+  int rc, dev;
+  if ((rc = check_dims(B, G, N, kind == RBG_GEN_UNIFORM ? 2 : 1))) return rc;
+  if (!keys || !state || !ts) return set_error(RBG_EINVAL, "rbg_connector_reset_host: NULL pointer");
+  if (B == 0) return RBG_OK;
+  if ((rc = use_device(device, &dev))) return rc;
+  std::lock_guard<std::mutex> lock(g_scratch_mu);
+  Carver size{nullptr};
+  rbg_state ds;
+  rbg_timestep dt;
+  size.take<uint32_t>((size_t)B * 2);
+  carve_state(size, B, G, N, &ds);
+  carve_timestep(size, B, G, N, &dt);
+  void *base;
+  if ((rc = scratch_get(size.off + 256, dev, &base))) return rc;
+  Carver c{reinterpret_cast<uint8_t *>(base)};
+  uint32_t *dk = c.take<uint32_t>((size_t)B * 2);
+  carve_state(c, B, G, N, &ds);
+  carve_timestep(c, B, G, N, &dt);
+  const int nsl = B >= 4096 ? 4 : 1;
+  const int64_t sl = slice_size(B, nsl);
+  int si = 0;
+  for (int64_t off = 0; off < B; off += sl, ++si) {
+    const int64_t n = (B - off) < sl ? (B - off) : sl;
+    cudaStream_t st = g_streams[si % 3];
+    RBG_CPY(dk + off * 2, keys + off * 2, n * 8, cudaMemcpyHostToDevice, st);
+    rbg_state dss = state_at(ds, off, G, N);
+    rbg_timestep dts = timestep_at(dt, off, G, N);
+    if ((rc = rbg_connector_reset(kind, dk + off * 2, n, G, N, &dss, &dts, st))) return rc;
+    if ((rc = copy_state(state, &ds, off, n, G, N, cudaMemcpyDeviceToHost, off, st))) return rc;
+    if ((rc = copy_timestep(ts, &dt, off, n, G, N, cudaMemcpyDeviceToHost, off, st))) return rc;
+  }
+  for (int i = 0; i < 3; ++i) {
+    cudaError_t e = cudaStreamSynchronize(g_streams[i]);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaStreamSynchronize");
+  }
+  return RBG_OK;
+}
+
+int rbg_connector_step_host(const rbg_state *in, const rbg_state *out, const int32_t *action, int64_t B, int G,
+                            int N, const rbg_env_params *params, const rbg_timestep *ts, int device) {
+  int rc, dev;
+  if ((rc = check_dims(B, G, N, 1))) return rc;
+  if (!in || !out || !action || !params || !ts) return set_error(RBG_EINVAL, "rbg_connector_step_host: NULL pointer");
+  if (B == 0) return RBG_OK;
+  if ((rc = use_device(device, &dev))) return rc;
+  std::lock_guard<std::mutex> lock(g_scratch_mu);
+  const int nsl = B >= 4096 ? 8 : 1;
+  const int64_t sl = slice_size(B, nsl);
+  const int64_t nslices = (B + sl - 1) / sl;
+  Carver size{nullptr};
+  rbg_state ds;
+  rbg_timestep dt;
+  carve_state(size, B, G, N, &ds);
+  carve_timestep(size, B, G, N, &dt);
+  size.take<int32_t>((size_t)B * N);
+  size.take<uint8_t>((size_t)(nslices * (16 + 4 * sl)));
+  void *base;
+  if ((rc = scratch_get(size.off + 256, dev, &base))) return rc;
+  Carver c{reinterpret_cast<uint8_t *>(base)};
+  carve_state(c, B, G, N, &ds);
+  carve_timestep(c, B, G, N, &dt);
+  int32_t *da = c.take<int32_t>((size_t)B * N);
+  uint8_t *ws = c.take<uint8_t>((size_t)(nslices * (16 + 4 * sl)));
+  int si = 0;
+  for (int64_t off = 0; off < B; off += sl, ++si) {
+    const int64_t n = (B - off) < sl ? (B - off) : sl;
+    cudaStream_t st = g_streams[si % 3];
+    if ((rc = copy_state(&ds, in, off, n, G, N, cudaMemcpyHostToDevice, off, st))) return rc;
+    RBG_CPY(da + off * N, action + off * N, n * N * 4, cudaMemcpyHostToDevice, st);
+    rbg_state dss = state_at(ds, off, G, N);
+    rbg_timestep dts = timestep_at(dt, off, G, N);
+    if ((rc = rbg_connector_step(&dss, &dss, da + off * N, n, G, N, params, &dts, ws + (size_t)si * (16 + 4 * sl), st)))
+      return rc;
+    if ((rc = copy_state(out, &ds, off, n, G, N, cudaMemcpyDeviceToHost, off, st))) return rc;
+    if ((rc = copy_timestep(ts, &dt, off, n, G, N, cudaMemcpyDeviceToHost, off, st))) return rc;
+  }
+  for (int i = 0; i < 3; ++i) {
+    cudaError_t e = cudaStreamSynchronize(g_streams[i]);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaStreamSynchronize");
+  }
+  return RBG_OK;
+}
+
+}  // extern "C"

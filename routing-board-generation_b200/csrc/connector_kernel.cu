@@ -1,0 +1,342 @@
+// connector_kernel.cu -- Jumanji Connector step / observe for sm_100a.
+//
+// Replaces jit(vmap(Connector.step)) and the observation half of
+// jit(vmap(Connector.reset)) (jumanji==0.2.2 environments/routing/connector/
+// env.py -- UPSTREAM; reference call sites rl_training/setup_train.py:158-166,400,
+// demos/board_generator_demo.py:83-96; the agent-stepping / collision rule is
+// mirrored in the reference at parallel_random_walk.py:101-145,376-429).
+//
+// One launch fuses: (optional) random-policy action sampling, _step_agents
+// with the collision rule, step_count, DenseRewardFn, action mask, done /
+// discount / step_type, extras, the per-agent observation and (with
+// auto-reset) the compaction of finished envs into a reset list.
+//
+// The kernel is HBM-write bound (DESIGN.md "K2"): per env-step it reads the
+// State once (int32 -> uint8 into shared memory) and writes State +
+// observation [N,G,G] int32 exactly once, all bulk traffic as 128-bit
+// coalesced accesses over the CTA's contiguous slab of E envs.
+#include "connector_device.cuh"
+#include "rbg_host.h"
+
+namespace rbg {
+
+struct EnvSmem {
+  uint8_t *grid;  // [E*cells] flat, same layout as the int32 input
+  int *pos;       // [E*N] (r<<8|c)
+  int *tgt;       // [E*N]
+  int *dest;      // [E*N] destination flat cell or unique negative
+  int *flag;      // [E*N] bit0 was_connected, bit1 win, bit2 done, bits 4..7 mask
+  float *rew;     // [E*N]
+  int *cnt;       // [E*4] path cells, #done, #connected, #moved
+  int *term;      // [E]   bit0 terminal, bit1 skip (auto-reset takes over)
+};
+
+__host__ __device__ inline size_t env_carve(int E, int N, int cells,
+                                            uint8_t *base, EnvSmem *s) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += (bytes + 15) / 16 * 16;
+    return o;
+  };
+  const size_t en = (size_t)E * N;
+  size_t o_grid = take((size_t)E * cells);
+  size_t o_pos = take(en * 4), o_tgt = take(en * 4), o_dest = take(en * 4);
+  size_t o_flag = take(en * 4), o_rew = take(en * 4);
+  size_t o_cnt = take((size_t)E * 16), o_term = take((size_t)E * 4);
+  if (s) {
+    s->grid = base + o_grid;
+    s->pos = reinterpret_cast<int *>(base + o_pos);
+    s->tgt = reinterpret_cast<int *>(base + o_tgt);
+    s->dest = reinterpret_cast<int *>(base + o_dest);
+    s->flag = reinterpret_cast<int *>(base + o_flag);
+    s->rew = reinterpret_cast<float *>(base + o_rew);
+    s->cnt = reinterpret_cast<int *>(base + o_cnt);
+    s->term = reinterpret_cast<int *>(base + o_term);
+  }
+  return off;
+}
+
+__device__ __forceinline__ int is_path_code(int v) {
+  return (v > 0 && (v - 1) % 3 == 0) ? 1 : 0;
+}
+
+// uniform pick over the legal actions, NOOP included (include/rbg_b200.h
+// rbg_random_actions): mk bit (a-1) <=> action a legal.
+__device__ __forceinline__ int random_action(uint32_t k0, uint32_t k1,
+                                             uint32_t step, uint32_t agent,
+                                             uint32_t mk) {
+  uint32_t o0, o1;
+  tf_block(k0, k1, step, agent, o0, o1);
+  const uint32_t n = 1u + __popc(mk);
+  int pick = (int)__umulhi(o0, n);
+  if (pick == 0) return NOOP;
+  int act = 0;
+#pragma unroll
+  for (int a = 1; a <= 4; ++a) {
+    if ((mk >> (a - 1)) & 1u) {
+      if (--pick == 0 && act == 0) act = a;
+    }
+  }
+  return act;
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(256) env_kernel(const EnvParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int G = p.G, N = p.N, cells = p.cells, E = p.E;
+  const long long env0 = (long long)blockIdx.x * E;
+  if (env0 >= p.B) return;
+  const int Ec = (int)((p.B - env0) < (long long)E ? (p.B - env0) : (long long)E);
+  const bool is_step = (p.mode == ENV_MODE_STEP);
+  const bool autoreset = is_step && p.env.autoreset_kind >= 0 && p.list != nullptr;
+  EnvSmem s;
+  env_carve(E, N, cells, smem_raw, &s);
+
+  for (int i = tid; i < E * 4; i += nt) s.cnt[i] = 0;
+  __syncthreads();
+
+  // ---- phase 1: State.grid int32 -> uint8 shared memory, count PATH cells
+  if (VEC) {
+    const int c4 = cells >> 2;
+    const int4 *src = reinterpret_cast<const int4 *>(p.in.grid) + env0 * c4;
+    uint32_t *g32 = reinterpret_cast<uint32_t *>(s.grid);
+    for (int q = tid; q < Ec * c4; q += nt) {
+      const int4 v = __ldg(src + q);
+      g32[q] = (uint32_t)(v.x & 0xff) | ((uint32_t)(v.y & 0xff) << 8) |
+               ((uint32_t)(v.z & 0xff) << 16) | ((uint32_t)(v.w & 0xff) << 24);
+      const int np = is_path_code(v.x) + is_path_code(v.y) + is_path_code(v.z) + is_path_code(v.w);
+      if (np) atomicAdd(&s.cnt[4 * p.divC4.div((uint32_t)q)], np);
+    }
+  } else {
+    const int32_t *src = p.in.grid + env0 * cells;
+    for (int i = tid; i < Ec * cells; i += nt) {
+      const int v = __ldg(src + i);
+      s.grid[i] = (uint8_t)v;
+      if (is_path_code(v)) atomicAdd(&s.cnt[4 * p.divCells.div((uint32_t)i)], 1);
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: per agent: (sample action,) move_position, is_valid_position
+  for (int t = tid; t < Ec * N; t += nt) {
+    const int m = (int)p.divN.div((uint32_t)t), a = t - m * N;
+    const int2 ps = reinterpret_cast<const int2 *>(p.in.position)[env0 * N + t];
+    const int2 tg = reinterpret_cast<const int2 *>(p.in.target)[env0 * N + t];
+    const int r = ps.x, c = ps.y;
+    const bool was = (r == tg.x && c == tg.y);
+    s.pos[t] = (r << 8) | c;
+    s.tgt[t] = (tg.x << 8) | tg.y;
+    int dest = -1 - t, fl = was ? 1 : 0;
+    if (is_step) {
+      SmemGrid sg{s.grid + (size_t)m * cells, G, 0, G};
+      int action;
+      if (p.random_policy) {
+        const uint32_t mk = move_mask(sg, r, c, a, was);
+        action = random_action(p.in.key[2 * (env0 + m)], p.in.key[2 * (env0 + m) + 1],
+                               (uint32_t)p.in.step_count[env0 + m], (uint32_t)a, mk);
+        if (p.action_out) p.action_out[env0 * N + t] = action;
+      } else {
+        action = p.action[env0 * N + t];
+      }
+      const int am = action < 0 ? 0 : (action > 4 ? 4 : action);  // lax.switch clamps
+      const int nr = r + (am == UP ? -1 : (am == DOWN ? 1 : 0));
+      const int nc = c + (am == RIGHT ? 1 : (am == LEFT ? -1 : 0));
+      const bool inb = (unsigned)nr < (unsigned)G && (unsigned)nc < (unsigned)G;
+      const uint32_t v = inb ? sg.at(nr, nc) : 0xFFu;
+      const bool valid = inb && (v == 0u || v == 3u * a + TARGET) && !was && action != NOOP;
+      if (valid) dest = nr * G + nc;
+    }
+    s.dest[t] = dest;
+    s.flag[t] = fl;
+  }
+  __syncthreads();
+  if (is_step) {
+    // collisions: same destination -> only the highest agent id moves
+    for (int t = tid; t < Ec * N; t += nt) {
+      const int m = (int)p.divN.div((uint32_t)t), a = t - m * N;
+      const int d = s.dest[t];
+      bool win = d >= 0;
+      for (int j = a + 1; j < N && win; ++j) win = (s.dest[m * N + j] != d);
+      if (win) s.flag[t] |= 2;
+    }
+    __syncthreads();
+    for (int t = tid; t < Ec * N; t += nt) {
+      if (s.flag[t] & 2) {  // move_agent: old head -> PATH, new cell -> POSITION
+        const int m = (int)p.divN.div((uint32_t)t), a = t - m * N;
+        const int pr = s.pos[t] >> 8, pcol = s.pos[t] & 255, d = s.dest[t];
+        uint8_t *g = s.grid + (size_t)m * cells;
+        g[pr * G + pcol] = (uint8_t)(3 * a + PATH);
+        g[d] = (uint8_t)(3 * a + POSITION);
+        uint32_t nr, nc;
+        p.divG.divmod((uint32_t)d, nr, nc);
+        s.pos[t] = (int)((nr << 8) | nc);
+        atomicAdd(&s.cnt[4 * m + 3], 1);
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- phase 3: action mask, connected / done, reward on the new grid
+  for (int t = tid; t < Ec * N; t += nt) {
+    const int m = (int)p.divN.div((uint32_t)t), a = t - m * N;
+    const int r = s.pos[t] >> 8, c = s.pos[t] & 255;
+    const bool now = (s.pos[t] == s.tgt[t]);
+    const bool was = s.flag[t] & 1;
+    SmemGrid sg{s.grid + (size_t)m * cells, G, 0, G};
+    const uint32_t mk = move_mask(sg, r, c, a, now);
+    const bool done = now || mk == 0u;  // connected_or_blocked
+    if (done) atomicAdd(&s.cnt[4 * m + 1], 1);
+    if (now) atomicAdd(&s.cnt[4 * m + 2], 1);
+    s.flag[t] |= (done ? 4 : 0) | (int)(mk << 4);
+    // DenseRewardFn: connected_reward*(~was & now) + timestep_reward*(~was)
+    s.rew[t] = __fadd_rn(__fmul_rn(p.env.connected_reward, (!was && now) ? 1.0f : 0.0f),
+                         __fmul_rn(p.env.timestep_reward, was ? 0.0f : 1.0f));
+  }
+  __syncthreads();
+  for (int m = tid; m < Ec; m += nt) {
+    const long long e = env0 + m;
+    const int sc = p.in.step_count[e] + (is_step ? 1 : 0);
+    const int nconn = s.cnt[4 * m + 2];
+    const bool terminal = is_step && (s.cnt[4 * m + 1] == N || sc >= p.env.time_limit);
+    const bool skip = terminal && autoreset;
+    s.term[m] = (terminal ? 1 : 0) | (skip ? 2 : 0);
+    p.ts.step_type[e] = (int8_t)(is_step ? (terminal ? 2 : 1) : 0);
+    p.ts.num_connections[e] = nconn;
+    p.ts.ratio_connections[e] = __fdiv_rn((float)nconn, (float)N);
+    p.ts.total_path_length[e] = s.cnt[4 * m] + s.cnt[4 * m + 3] + N;
+    if (!skip) p.ts.obs_step_count[e] = sc;
+    if (is_step) {
+      p.out.step_count[e] = sc;
+      if (p.out.key != p.in.key) {
+        p.out.key[2 * e] = p.in.key[2 * e];
+        p.out.key[2 * e + 1] = p.in.key[2 * e + 1];
+      }
+      if (skip) p.list[atomicAdd(p.list_count, 1)] = (int32_t)e;
+    }
+  }
+  __syncthreads();
+  for (int t = tid; t < Ec * N; t += nt) {
+    const int m = (int)p.divN.div((uint32_t)t);
+    const long long ga = env0 * N + t;
+    const int term = s.term[m];
+    const int fl = s.flag[t];
+    p.ts.reward[ga] = is_step ? s.rew[t] : 0.0f;
+    p.ts.discount[ga] = is_step ? (((term & 1) || (fl & 4)) ? 0.0f : 1.0f) : 1.0f;
+    if (!(term & 2)) store_mask5(p.ts.action_mask + ga * 5, (uint32_t)(fl >> 4) & 15u);
+    if (is_step) {
+      reinterpret_cast<int2 *>(p.out.position)[ga] = make_int2(s.pos[t] >> 8, s.pos[t] & 255);
+      if (p.out.target != p.in.target) {
+        reinterpret_cast<int2 *>(p.out.target)[ga] = make_int2(s.tgt[t] >> 8, s.tgt[t] & 255);
+        reinterpret_cast<int2 *>(p.out.start)[ga] = reinterpret_cast<const int2 *>(p.in.start)[ga];
+        p.out.agent_id[ga] = p.in.agent_id[ga];
+      }
+    }
+  }
+
+  // ---- phase 4: bulk outputs: State.grid and observation.grid
+  const int n3 = 3 * N;
+  if (VEC) {
+    const int c4 = cells >> 2;
+    const uint32_t *g32 = reinterpret_cast<const uint32_t *>(s.grid);
+    if (is_step) {
+      int4 *dst = reinterpret_cast<int4 *>(p.out.grid) + env0 * c4;
+      for (int q = tid; q < Ec * c4; q += nt) {
+        const int m = (int)p.divC4.div((uint32_t)q);
+        if (s.term[m] & 2) continue;
+        dst[q] = bytes_to_int4(g32[q]);
+      }
+    }
+    int4 *odst = reinterpret_cast<int4 *>(p.ts.obs_grid) + env0 * N * c4;
+    for (int idx = tid; idx < Ec * N * c4; idx += nt) {
+      const uint32_t slice = p.divC4.div((uint32_t)idx);
+      const int q = idx - (int)slice * c4;
+      const int m = (int)p.divN.div(slice), a = (int)slice - m * N;
+      if (s.term[m] & 2) continue;
+      const uint32_t w = g32[m * c4 + q];
+      const int a3 = 3 * a;
+      odst[idx] = make_int4(obs_value((int)(w & 0xffu), a3, n3), obs_value((int)((w >> 8) & 0xffu), a3, n3),
+                            obs_value((int)((w >> 16) & 0xffu), a3, n3), obs_value((int)(w >> 24), a3, n3));
+    }
+  } else {
+    if (is_step) {
+      int32_t *dst = p.out.grid + env0 * cells;
+      for (int i = tid; i < Ec * cells; i += nt) {
+        const int m = (int)p.divCells.div((uint32_t)i);
+        if (s.term[m] & 2) continue;
+        dst[i] = s.grid[i];
+      }
+    }
+    int32_t *odst = p.ts.obs_grid + env0 * N * cells;
+    for (int idx = tid; idx < Ec * N * cells; idx += nt) {
+      const uint32_t slice = p.divCells.div((uint32_t)idx);
+      const int cell = idx - (int)slice * cells;
+      const int m = (int)p.divN.div(slice), a = (int)slice - m * N;
+      if (s.term[m] & 2) continue;
+      odst[idx] = obs_value((int)s.grid[m * cells + cell], 3 * a, n3);
+    }
+  }
+}
+
+// standalone random policy: one thread per (env, agent), grid read from global
+__global__ void __launch_bounds__(256) random_actions_kernel(rbg_state st, long long B, int G, int N,
+                                                             FastDiv divN, int32_t *action) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * N) return;
+  const long long e = t / N;
+  const int a = (int)(t - e * N);
+  const int2 ps = reinterpret_cast<const int2 *>(st.position)[t];
+  const int2 tg = reinterpret_cast<const int2 *>(st.target)[t];
+  const bool connected = ps.x == tg.x && ps.y == tg.y;
+  const int32_t *g = st.grid + e * G * G;
+  const uint32_t tgt = 3u * a + TARGET;
+  auto ok = [&](int r, int c) {
+    if ((unsigned)r >= (unsigned)G || (unsigned)c >= (unsigned)G) return 0u;
+    const uint32_t v = (uint32_t)__ldg(g + r * G + c);
+    return (v == 0u || v == tgt) ? 1u : 0u;
+  };
+  uint32_t mk = ok(ps.x - 1, ps.y) | (ok(ps.x, ps.y + 1) << 1) | (ok(ps.x + 1, ps.y) << 2) | (ok(ps.x, ps.y - 1) << 3);
+  if (connected) mk = 0;
+  action[t] = random_action(st.key[2 * e], st.key[2 * e + 1], (uint32_t)st.step_count[e], (uint32_t)a, mk);
+}
+
+int launch_env(EnvParams p, int force_E, cudaStream_t stream) {
+  const int G = p.G, N = p.N;
+  p.cells = G * G;
+  const bool vec = (p.cells & 3) == 0;
+  // ~32 KB of observation per CTA keeps the slab contiguous and the grid large
+  int E = (int)(32768 / ((int64_t)N * p.cells * 4));
+  if (E < 1) E = 1;
+  if (E > 32) E = 32;
+  if (force_E > 0) E = force_E;
+  if (!vec) E = (E + 3) & ~3;  // scalar path: keep slabs 16-byte aligned anyway
+  p.E = E;
+  p.divN = FastDiv::make((uint32_t)N);
+  p.divG = FastDiv::make((uint32_t)G);
+  p.divC4 = FastDiv::make((uint32_t)(vec ? p.cells >> 2 : 1));
+  p.divCells = FastDiv::make((uint32_t)p.cells);
+  const size_t smem = env_carve(E, N, p.cells, nullptr, nullptr);
+  if (smem > 200 * 1024) return set_error(RBG_EINVAL, "connector: shared memory %zu too large", smem);
+  const int64_t ctas = (p.B + E - 1) / E;
+  if (ctas <= 0) return RBG_OK;
+  if (vec) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(env_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    env_kernel<true><<<(unsigned)ctas, 256, smem, stream>>>(p);
+  } else {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(env_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    env_kernel<false><<<(unsigned)ctas, 256, smem, stream>>>(p);
+  }
+  count_launch();
+  return check_launch("env_kernel");
+}
+
+int launch_random_actions(const rbg_state &st, int64_t B, int G, int N, int32_t *action, cudaStream_t stream) {
+  const int64_t n = B * N;
+  if (n <= 0) return RBG_OK;
+  random_actions_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(st, B, G, N, FastDiv::make((uint32_t)N), action);
+  count_launch();
+  return check_launch("random_actions_kernel");
+}
+
+}  // namespace rbg

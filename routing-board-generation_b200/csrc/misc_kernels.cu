@@ -1,0 +1,143 @@
+// misc_kernels.cu -- key derivation for sharded batches and the on-device
+// board validity check.
+#include "rbg_host.h"
+
+namespace rbg {
+
+// rows [offset, offset+count) of jax.random.split(key, B):
+// flat word f of the split output is o0(f, f+B) for f < B, o1(f-B, f) otherwise.
+// Reference convention: keys = split(PRNGKey(0), B) (dataset_generator_jax.py:76),
+// per-device contiguous slices (rl_training/setup_train.py:397-399).
+__global__ void __launch_bounds__(256) split_keys_kernel(uint32_t k0, uint32_t k1, long long B,
+                                                         long long offset, long long count,
+                                                         uint32_t *__restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * count) return;
+  const long long f = 2 * offset + i;
+  uint32_t o0, o1;
+  if (f < B) {
+    tf_block(k0, k1, (uint32_t)f, (uint32_t)(f + B), o0, o1);
+    out[i] = o0;
+  } else {
+    tf_block(k0, k1, (uint32_t)(f - B), (uint32_t)f, o0, o1);
+    out[i] = o1;
+  }
+}
+
+int launch_split_keys(uint32_t k0, uint32_t k1, int64_t B, int64_t offset, int64_t count,
+                      uint32_t *out, cudaStream_t stream) {
+  if (count <= 0) return RBG_OK;
+  const int64_t n = 2 * count;
+  split_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(k0, k1, B, offset, count, out);
+  count_launch();
+  return check_launch("split_keys_kernel");
+}
+
+// Board validity, one warp per board (rules: reference
+// numpy_implementation/utils/post_processor_utils_numpy.py:34-155 and the
+// head->target connectivity of board_processor.py:111-162).
+// flags: bit0 encoding range, bit1 head/target count, bit2 neighbour-count
+// rule, bit3 head and target not connected, bit4 zero-length wire.
+constexpr int VAL_WARPS = 4;
+
+__global__ void __launch_bounds__(VAL_WARPS * 32) validate_kernel(const int32_t *__restrict__ boards, long long B,
+                                                                  int G, int N, int32_t *__restrict__ flags) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cells = G * G;
+  const int cp = (cells + 15) & ~15;
+  uint8_t *grid = smem_raw + (size_t)warp * (2 * cp + 4 * 4 * RBG_MAX_N);
+  uint8_t *reached = grid + cp;
+  int *heads = reinterpret_cast<int *>(reached + cp);
+  int *targets = heads + RBG_MAX_N, *hpos = targets + RBG_MAX_N, *tpos = hpos + RBG_MAX_N;
+  for (long long b = (long long)blockIdx.x * VAL_WARPS + warp; b < B; b += (long long)gridDim.x * VAL_WARPS) {
+    const int32_t *src = boards + b * cells;
+    int fl = 0;
+    if (lane < N) heads[lane] = targets[lane] = 0;
+    __syncwarp();
+    for (int i = lane; i < cells; i += 32) {
+      const int v = __ldg(src + i);
+      if (v < 0 || v > 3 * N) fl |= 1;
+      grid[i] = (uint8_t)v;
+      reached[i] = 0;
+    }
+    fl = __reduce_or_sync(FULL, fl);
+    if (fl) {  // the oracle stops at the first rule, so do we
+      if (lane == 0) flags[b] = fl;
+      __syncwarp();
+      continue;
+    }
+    __syncwarp();
+    for (int i = lane; i < cells; i += 32) {
+      const int v = grid[i];
+      if (v == 0) continue;
+      const int w = (v - 1) / 3, t = (v - 1) % 3 + 1;
+      if (t == POSITION) {
+        atomicAdd(&heads[w], 1);
+        hpos[w] = i;
+      }
+      if (t == TARGET) {
+        atomicAdd(&targets[w], 1);
+        tpos[w] = i;
+      }
+    }
+    __syncwarp();
+    bool eligible = false;
+    if (lane < N) {
+      if (heads[lane] == 0 && targets[lane] == 1) fl |= 16;
+      else if (heads[lane] != 1 || targets[lane] != 1) fl |= 2;
+      else eligible = true;
+    }
+    auto same = [&](int i, int w) { const int v = grid[i]; return v > 0 && (v - 1) / 3 == w; };
+    for (int i = lane; i < cells; i += 32) {
+      const int v = grid[i];
+      if (v == 0) continue;
+      const int w = (v - 1) / 3, t = (v - 1) % 3 + 1;
+      if (heads[w] == 0) continue;
+      const int r = i / G, c = i - r * G;
+      int nb = 0;
+      nb += (r > 0 && same(i - G, w));
+      nb += (r < G - 1 && same(i + G, w));
+      nb += (c > 0 && same(i - 1, w));
+      nb += (c < G - 1 && same(i + 1, w));
+      if (t == PATH ? nb != 2 : nb != 1) fl |= 4;
+    }
+    // connectivity: flood from every eligible head through own-wire cells
+    if (eligible) reached[hpos[lane]] = 1;
+    __syncwarp();
+    for (int it = 0; it < cells; ++it) {
+      bool changed = false;
+      for (int i = lane; i < cells; i += 32) {
+        const int v = grid[i];
+        if (v == 0 || reached[i]) continue;
+        const int w = (v - 1) / 3;
+        const int r = i / G, c = i - r * G;
+        const bool hit = (r > 0 && reached[i - G] && same(i - G, w)) || (r < G - 1 && reached[i + G] && same(i + G, w)) ||
+                         (c > 0 && reached[i - 1] && same(i - 1, w)) || (c < G - 1 && reached[i + 1] && same(i + 1, w));
+        if (hit) {
+          reached[i] = 1;
+          changed = true;
+        }
+      }
+      __syncwarp();
+      if (!__any_sync(FULL, changed)) break;
+    }
+    if (eligible && !reached[tpos[lane]]) fl |= 8;
+    fl = __reduce_or_sync(FULL, fl);
+    if (lane == 0) flags[b] = fl;
+    __syncwarp();
+  }
+}
+
+int launch_validate(const int32_t *boards, int64_t B, int G, int N, int32_t *flags, cudaStream_t stream) {
+  if (B <= 0) return RBG_OK;
+  const int cells = G * G, cp = (cells + 15) & ~15;
+  const size_t smem = (size_t)VAL_WARPS * (2 * cp + 4 * 4 * RBG_MAX_N);
+  int64_t ctas = (B + VAL_WARPS - 1) / VAL_WARPS;
+  if (ctas > 148 * 64) ctas = 148 * 64;
+  validate_kernel<<<(unsigned)ctas, VAL_WARPS * 32, smem, stream>>>(boards, B, G, N, flags);
+  count_launch();
+  return check_launch("validate_kernel");
+}
+
+}  // namespace rbg

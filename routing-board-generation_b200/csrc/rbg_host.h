@@ -1,0 +1,93 @@
+// rbg_host.h -- host-side declarations shared by the kernel translation units
+// and the C-ABI (c_api.cu).  Internal; the public surface is include/rbg_b200.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rbg_b200.h"
+#include "rbg_device.cuh"
+
+namespace rbg {
+
+// error plumbing (c_api.cu)
+int set_error(int code, const char *fmt, ...);
+int set_cuda_error(cudaError_t e, const char *what);
+int check_launch(const char *what);
+void count_launch();
+
+// ---- generator kernel (prw_kernel.cu) -----------------------------------
+enum : int { PRW_MODE_BOARD = 0, PRW_MODE_STATE = 1, PRW_MODE_UNIFORM = 2 };
+
+struct PrwParams {
+  const uint32_t *keys;  // [B,2]; with `list`: state.key of all envs
+  long long B;
+  int G, N;
+  int mode;         // PRW_MODE_*
+  int extra_split;  // leading key = split(key)[0] applications
+  int debug;        // bit0: force the exact selection fallback
+  int observe;      // write observation + action mask of the fresh state
+  int32_t *heads, *targets, *solved, *stats;
+  rbg_state st;
+  rbg_timestep ts;
+  const int32_t *list;        // optional env list (auto-reset)
+  const int32_t *list_count;  // device count of list entries
+  // filled by launch_prw
+  int W, S, SBp, cells, M, cap, Np, nsel;
+  uint32_t thresh;
+  FastDiv divG;
+};
+
+int launch_prw(PrwParams p, int64_t max_boards, int force_M, int force_threads,
+               cudaStream_t stream);
+
+// ---- connector kernel (connector_kernel.cu) -----------------------------
+enum : int { ENV_MODE_STEP = 0, ENV_MODE_OBSERVE = 1 };
+
+struct EnvParams {
+  rbg_state in, out;
+  rbg_timestep ts;
+  const int32_t *action;  // [B,N] (STEP)
+  int32_t *action_out;    // optional (random policy)
+  long long B;
+  int G, N;
+  int mode;           // ENV_MODE_*
+  int random_policy;  // sample actions in-kernel
+  rbg_env_params env;
+  int32_t *list;        // auto-reset list (device), may be NULL
+  int32_t *list_count;  // device counter
+  // filled by launch_env
+  int cells, E;
+  FastDiv divN, divG, divC4, divCells;
+};
+
+int launch_env(EnvParams p, int force_E, cudaStream_t stream);
+int launch_random_actions(const rbg_state &st, int64_t B, int G, int N,
+                          int32_t *action, cudaStream_t stream);
+
+// ---- misc kernels (misc_kernels.cu) --------------------------------------
+int launch_split_keys(uint32_t k0, uint32_t k1, int64_t B, int64_t offset,
+                      int64_t count, uint32_t *out, cudaStream_t stream);
+int launch_validate(const int32_t *boards, int64_t B, int G, int N,
+                    int32_t *flags, cudaStream_t stream);
+
+// ---- seed extension (seedext_kernel.cu) ---------------------------------
+struct SeedExtParams {
+  const uint32_t *keys;
+  long long B;
+  int G, N;
+  float randomness;
+  int two_sided, iterations;
+  long long ext_steps;  // < 0 unlimited
+  int extra_split;
+  int mode;  // 0 solved board, 1 starts/ends, 2 State
+  int32_t *solved, *starts, *ends;
+  rbg_state st;
+  rbg_timestep ts;
+  int observe;
+  const int32_t *list;
+  const int32_t *list_count;
+};
+int launch_seedext(SeedExtParams p, int64_t max_boards, cudaStream_t stream);
+
+}  // namespace rbg

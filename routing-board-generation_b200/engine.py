@@ -1,0 +1,255 @@
+"""Batched functional layer over the C-ABI: torch CUDA tensors in / out.
+
+Every function takes a leading batch axis B (the reference's vmap axis) and
+launches on torch's current CUDA stream.  Arrays from other frameworks come in
+through DLPack (`as_tensor`), results can go back out the same way
+(`tensor.__dlpack__()` / `jax.dlpack.from_dlpack`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import GEN_PRW, GEN_SEEDEXT, GEN_UNIFORM, rbg_env_params, rbg_state, rbg_timestep
+from .types import Agent, Observation, State, TimeStep
+
+GENERATOR_KINDS = {"parallel_random_walk": GEN_PRW, "uniform": GEN_UNIFORM, "seed_extension": GEN_SEEDEXT}
+
+
+def _device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("routing-board-generation_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def as_tensor(x, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """torch tensor / DLPack producer (JAX, CuPy, ...) / NumPy / list -> contiguous CUDA tensor."""
+    dev = _device()
+    if isinstance(x, torch.Tensor):
+        t = x
+    elif hasattr(x, "__dlpack__"):
+        t = torch.from_dlpack(x)
+    else:
+        a = np.asarray(x)
+        if a.dtype == np.uint32:  # keep the bits, torch's uint32 host support is thin
+            t = torch.from_numpy(a.view(np.int32).copy()).view(torch.uint32)
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(a))
+    if t.device != dev:
+        t = t.to(dev, non_blocking=True)
+    if dtype is not None and t.dtype != dtype:
+        if dtype == torch.uint32 and t.dtype == torch.int32:
+            t = t.view(torch.uint32)
+        elif dtype == torch.int32 and t.dtype == torch.uint32:
+            t = t.view(torch.int32)
+        else:
+            t = t.to(dtype)
+    return t.contiguous()
+
+
+def as_keys(key) -> Tuple[torch.Tensor, bool]:
+    """Raw threefry keys uint32[2] or uint32[B,2] -> (uint32[B,2] on device, was_batched)."""
+    t = as_tensor(key)
+    if t.dtype == torch.int32:
+        t = t.view(torch.uint32)
+    elif t.dtype != torch.uint32:  # wider ints: keep the low 32 bits
+        t = t.to(torch.int64).to(torch.int32).view(torch.uint32)
+    if t.shape[-1] != 2 or t.dim() not in (1, 2):
+        raise ValueError(f"PRNG key must have shape (2,) or (B, 2), got {tuple(t.shape)}")
+    return t.reshape(-1, 2).contiguous(), t.dim() == 2
+
+
+def PRNGKey(seed: int) -> torch.Tensor:
+    """jax.random.PRNGKey(seed) for the threefry2x32 impl: (seed >> 32, seed & 0xffffffff)."""
+    a = np.array([(int(seed) >> 32) & 0xFFFFFFFF, int(seed) & 0xFFFFFFFF], dtype=np.uint32)
+    return as_tensor(a, torch.uint32)
+
+
+def key_to_host(key) -> np.ndarray:
+    t = key if isinstance(key, torch.Tensor) else as_tensor(key)
+    return t.view(torch.int32).cpu().numpy().view(np.uint32)
+
+
+def split(key, num: int = 2, offset: int = 0, count: Optional[int] = None) -> torch.Tensor:
+    """Rows [offset, offset+count) of jax.random.split(key, num) as uint32[count,2] on the device."""
+    k = key_to_host(key).reshape(-1)
+    if k.shape != (2,):
+        raise ValueError("split() takes a single key of shape (2,)")
+    count = num - offset if count is None else count
+    out = torch.empty((count, 2), dtype=torch.uint32, device=_device())
+    karr = (C.c_uint32 * 2)(int(k[0]), int(k[1]))
+    _lib.check(_lib.load().rbg_split_keys(karr, num, offset, count, out.data_ptr(), _stream()))
+    return out
+
+
+# ------------------------------------------------------------------ structs
+def _state_struct(st: State) -> rbg_state:
+    a = st.agents
+    return rbg_state(st.grid.data_ptr(), st.step_count.data_ptr(), a.id.data_ptr(), a.start.data_ptr(), a.target.data_ptr(), a.position.data_ptr(), st.key.data_ptr())
+
+
+def alloc_state(B: int, G: int, N: int) -> State:
+    dev = _device()
+    i32 = dict(dtype=torch.int32, device=dev)
+    return State(
+        key=torch.empty((B, 2), dtype=torch.uint32, device=dev),
+        grid=torch.empty((B, G, G), **i32),
+        step_count=torch.empty((B,), **i32),
+        agents=Agent(id=torch.empty((B, N), **i32), start=torch.empty((B, N, 2), **i32), target=torch.empty((B, N, 2), **i32), position=torch.empty((B, N, 2), **i32)),
+    )
+
+
+def alloc_timestep(B: int, G: int, N: int) -> TimeStep:
+    dev = _device()
+    return TimeStep(
+        step_type=torch.empty((B,), dtype=torch.int8, device=dev),
+        reward=torch.empty((B, N), dtype=torch.float32, device=dev),
+        discount=torch.empty((B, N), dtype=torch.float32, device=dev),
+        observation=Observation(
+            grid=torch.empty((B, N, G, G), dtype=torch.int32, device=dev),
+            action_mask=torch.empty((B, N, 5), dtype=torch.bool, device=dev),
+            step_count=torch.empty((B,), dtype=torch.int32, device=dev),
+        ),
+        extras={
+            "num_connections": torch.empty((B,), dtype=torch.int32, device=dev),
+            "ratio_connections": torch.empty((B,), dtype=torch.float32, device=dev),
+            "total_path_length": torch.empty((B,), dtype=torch.int32, device=dev),
+        },
+    )
+
+
+def _timestep_struct(ts: TimeStep) -> rbg_timestep:
+    o, x = ts.observation, ts.extras
+    return rbg_timestep(o.grid.data_ptr(), o.action_mask.data_ptr(), o.step_count.data_ptr(), ts.reward.data_ptr(), ts.discount.data_ptr(), ts.step_type.data_ptr(), x["num_connections"].data_ptr(), x["ratio_connections"].data_ptr(), x["total_path_length"].data_ptr())
+
+
+def _dims(st: State) -> Tuple[int, int, int]:
+    B, G, _ = st.grid.shape
+    return B, G, st.agents.id.shape[1]
+
+
+def _contig_state(st: State) -> State:
+    return st.map(lambda t: t if t.is_contiguous() else t.contiguous())
+
+
+# --------------------------------------------------------------- generators
+def prw_generate(keys: torch.Tensor, G: int, N: int, with_stats: bool = False):
+    """ParallelRandomWalkBoard.generate_board over keys[B,2] -> heads[B,2,N], targets[B,2,N], solved[B,G,G]."""
+    B = keys.shape[0]
+    dev = _device()
+    heads = torch.empty((B, 2, N), dtype=torch.int32, device=dev)
+    targets = torch.empty((B, 2, N), dtype=torch.int32, device=dev)
+    solved = torch.empty((B, G, G), dtype=torch.int32, device=dev)
+    stats = torch.empty((B, 2), dtype=torch.int32, device=dev) if with_stats else None
+    _lib.check(_lib.load().rbg_prw_generate(keys.data_ptr(), B, G, N, heads.data_ptr(), targets.data_ptr(), solved.data_ptr(), stats.data_ptr() if with_stats else None, _stream()))
+    return (heads, targets, solved, stats) if with_stats else (heads, targets, solved)
+
+
+def generator_state(kind, keys: torch.Tensor, G: int, N: int, out: Optional[State] = None) -> State:
+    kind = GENERATOR_KINDS[kind] if isinstance(kind, str) else kind
+    B = keys.shape[0]
+    st = alloc_state(B, G, N) if out is None else out
+    s = _state_struct(st)
+    _lib.check(_lib.load().rbg_generator_state(kind, keys.data_ptr(), B, G, N, C.byref(s), _stream()))
+    return st
+
+
+def seedext_solved(keys: torch.Tensor, G: int, N: int, randomness: float = 0.0, two_sided: bool = True, iterations: int = 1, extension_steps: float = 1e23) -> torch.Tensor:
+    B = keys.shape[0]
+    solved = torch.empty((B, G, G), dtype=torch.int32, device=_device())
+    steps = -1 if extension_steps >= 2**62 else int(extension_steps)
+    _lib.check(_lib.load().rbg_seedext_solved(keys.data_ptr(), B, G, N, float(randomness), int(bool(two_sided)), int(iterations), steps, solved.data_ptr(), _stream()))
+    return solved
+
+
+def seedext_starts_ends(keys: torch.Tensor, G: int, N: int, randomness: float = 0.0, two_sided: bool = True, iterations: int = 1, extension_steps: float = 1e23):
+    B = keys.shape[0]
+    dev = _device()
+    starts = torch.empty((B, 2, N), dtype=torch.int32, device=dev)
+    ends = torch.empty((B, 2, N), dtype=torch.int32, device=dev)
+    steps = -1 if extension_steps >= 2**62 else int(extension_steps)
+    _lib.check(_lib.load().rbg_seedext_starts_ends(keys.data_ptr(), B, G, N, float(randomness), int(bool(two_sided)), int(iterations), steps, starts.data_ptr(), ends.data_ptr(), _stream()))
+    return starts, ends
+
+
+def validate(boards: torch.Tensor, N: int) -> torch.Tensor:
+    boards = as_tensor(boards, torch.int32)
+    if boards.dim() == 2:
+        boards = boards[None]
+    B, G, _ = boards.shape
+    flags = torch.empty((B,), dtype=torch.int32, device=_device())
+    _lib.check(_lib.load().rbg_validate(boards.data_ptr(), B, G, N, flags.data_ptr(), _stream()))
+    return flags
+
+
+# ---------------------------------------------------------------- connector
+def connector_observe(st: State, out: Optional[TimeStep] = None) -> TimeStep:
+    st = _contig_state(st)
+    B, G, N = _dims(st)
+    ts = alloc_timestep(B, G, N) if out is None else out
+    s, t = _state_struct(st), _timestep_struct(ts)
+    _lib.check(_lib.load().rbg_connector_observe(C.byref(s), B, G, N, C.byref(t), _stream()))
+    return ts
+
+
+def connector_reset(kind, keys: torch.Tensor, G: int, N: int) -> Tuple[State, TimeStep]:
+    kind = GENERATOR_KINDS[kind] if isinstance(kind, str) else kind
+    B = keys.shape[0]
+    st, ts = alloc_state(B, G, N), alloc_timestep(B, G, N)
+    s, t = _state_struct(st), _timestep_struct(ts)
+    _lib.check(_lib.load().rbg_connector_reset(kind, keys.data_ptr(), B, G, N, C.byref(s), C.byref(t), _stream()))
+    return st, ts
+
+
+_workspaces: Dict[Tuple[int, int], torch.Tensor] = {}
+
+
+def _workspace(B: int, G: int, N: int) -> torch.Tensor:
+    dev = _device()
+    k = (dev.index, B)
+    if k not in _workspaces:
+        nbytes = int(_lib.load().rbg_step_workspace_bytes(B, G, N))
+        _workspaces[k] = torch.empty((nbytes + 15) // 16 * 16, dtype=torch.uint8, device=dev)
+    return _workspaces[k]
+
+
+def connector_step(st: State, action, time_limit: int = 50, timestep_reward: float = -0.03, connected_reward: float = 0.1, autoreset_kind=-1, inplace: bool = False, random_policy: bool = False, out: Optional[TimeStep] = None):
+    """Connector.step (autoreset_kind < 0) or VmapAutoResetWrapper(Connector).step over a batch.
+
+    random_policy=True ignores `action`, samples the uniform-over-legal-actions policy in the
+    same launch and returns the sampled actions as a third value.
+    """
+    if isinstance(autoreset_kind, str):
+        autoreset_kind = GENERATOR_KINDS[autoreset_kind]
+    st = _contig_state(st)
+    B, G, N = _dims(st)
+    new = st if inplace else alloc_state(B, G, N)
+    ts = alloc_timestep(B, G, N) if out is None else out
+    params = rbg_env_params(int(time_limit), float(timestep_reward), float(connected_reward), int(autoreset_kind))
+    ws = _workspace(B, G, N) if autoreset_kind >= 0 else None
+    s_in, s_out, t = _state_struct(st), _state_struct(new), _timestep_struct(ts)
+    lib = _lib.load()
+    if random_policy:
+        act = torch.empty((B, N), dtype=torch.int32, device=_device())
+        _lib.check(lib.rbg_connector_step_random(C.byref(s_in), C.byref(s_out), act.data_ptr(), B, G, N, C.byref(params), C.byref(t), ws.data_ptr() if ws is not None else None, _stream()))
+        return new, ts, act
+    act = as_tensor(action, torch.int32).reshape(B, N)
+    _lib.check(lib.rbg_connector_step(C.byref(s_in), C.byref(s_out), act.data_ptr(), B, G, N, C.byref(params), C.byref(t), ws.data_ptr() if ws is not None else None, _stream()))
+    return new, ts
+
+
+def random_actions(st: State) -> torch.Tensor:
+    st = _contig_state(st)
+    B, G, N = _dims(st)
+    act = torch.empty((B, N), dtype=torch.int32, device=_device())
+    s = _state_struct(st)
+    _lib.check(_lib.load().rbg_random_actions(C.byref(s), B, G, N, act.data_ptr(), _stream()))
+    return act
