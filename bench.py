@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path (BASELINE.json): Connector env-steps/s with the random agent at
+10x10 / 5 agents, 65 536 envs per GPU (configs[1]), plus solved ParallelRandomWalk boards/s
+as secondary lines.
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU arm (oracle, all host threads)
+
+A "step" is one VmapAutoResetWrapper(Connector).step over the whole batch with actions from the
+random policy: random-action sampling + Connector.step + observation + auto-reset (regeneration
+of finished envs with ParallelRandomWalkGenerator), i.e. one iteration of the reference's
+`agent=random` benchmark loop (benchmark_on_random_agent.py:59-102).  Prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+G, N = 10, 5
+ENVS_PER_GPU = 65536
+TIME_LIMIT = 50
+CELLS = G * G
+STATE_BYTES = 4 * CELLS + 4 + 28 * N + 8            # 552
+TS_BYTES = 4 * N * CELLS + 5 * N + 4 + 8 * N + 1 + 12  # obs + mask + step_count + reward/discount + step_type + extras = 2082
+STEP_BYTES = STATE_BYTES + 4 * N + STATE_BYTES + TS_BYTES  # 3206 B per env-step
+PRW_BOARD_BYTES = {(10, 5): 488, (20, 10): 1768, (32, 16): 4360}
+METRIC = "connector_env_steps_per_sec"
+UNIT = "env-steps/s"
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        with open(self.path) as f:
+            for line in f:
+                p = [x.strip() for x in line.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1]))
+                    mx.append(float(p[2]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, p[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------ our arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as ge
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank == 0:
+        ge.build_library()
+    if world > 1:
+        dist.barrier()
+    import routing_board_generation_b200 as rbg
+    from routing_board_generation_b200 import engine, sharding
+
+    lib = rbg._lib.load()
+    dev = torch.device("cuda", local)
+    B = args.envs
+    total = B * world  # weak scaling: 65 536 envs per GPU
+    keys = sharding.shard_keys(rbg.PRNGKey(0), total, rank, world)
+    env = rbg.VmapAutoResetWrapper(rbg.Connector(generator=rbg.ParallelRandomWalkGenerator(G, N), time_limit=TIME_LIMIT))
+    state, ts = env.reset(keys)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step():
+        nonlocal state, ts
+        state, ts, _ = engine.connector_step(state, None, TIME_LIMIT, -0.03, 0.1, autoreset_kind="parallel_random_walk", inplace=True, random_policy=True, out=ts)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync_all()
+
+    # ---- timed region: exactly K steps, device-timed, max over ranks
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    rbg.launch_count(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    sync_all()
+    launches = rbg.launch_count()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = total * args.steps / (ms_max / 1e3)
+
+    # ---- the dominant kernel alone (env_kernel), event pairs inside the library, same loop
+    rbg._lib.kernel_timing(True)
+    for k in ("env", "prw"):
+        rbg._lib.kernel_time(k)
+    for _ in range(args.steps):
+        step()
+    torch.cuda.synchronize()
+    n_env, ms_env = rbg._lib.kernel_time("env")
+    n_prw, ms_prw = rbg._lib.kernel_time("prw")
+    rbg._lib.kernel_timing(False)
+    peak, peak_src = _peaks()
+    env_ms = ms_env / max(n_env, 1)
+    achieved = STEP_BYTES * B / (env_ms / 1e3) / 1e9
+    roofline = {"kernel": "env_kernel", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": _traffic_from_profile("env_kernel"),
+                "algorithmic_bytes_per_launch": STEP_BYTES * B, "avg_launch_ms": round(env_ms, 5), "peak_source": peak_src,
+                "kernel_share_of_step": round(ms_env / max(ms_env + ms_prw, 1e-9), 4), "prw_reset_kernel_avg_ms": round(ms_prw / max(n_prw, 1), 5)}
+
+    # ---- e2e: the env-step call with HOST buffers through the C-ABI (rbg_connector_step_host):
+    # State + actions H2D from pinned memory, step, State + TimeStep D2H, every step.
+    e2e = None
+    secondary = []
+    cpu_baseline = None
+    if not args.skip_e2e:
+        e2e = _e2e_host(args, rbg, lib, state, B, world, rank, dev)
+    if rank == 0 and world == 1 and not args.skip_secondary:
+        secondary = _secondary_prw(args, rbg, peak)
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        cpu_baseline = _cpu_baseline(budget_s=args.cpu_seconds)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": round(ms_max / args.steps, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+            "data": "synthetic (keys = split(PRNGKey(0), B), random-policy actions)",
+            "config": {"workload": "connector_step_random_agent_autoreset_prw", "grid": G, "agents": N, "envs_per_gpu": B, "envs_total": total, "time_limit": TIME_LIMIT,
+                       "generator": "ParallelRandomWalkGenerator", "parallelism": f"env-sharded x{world}",
+                       "l2": f"no flush: per-step traffic {STEP_BYTES * B / 1e6:.0f} MB per GPU exceeds the 126 MB L2"},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "secondary": secondary,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def _traffic_from_profile(kernel: str):
+    """dram bytes per launch from the committed ncu --set full capture, if one exists (profiles/*.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
+
+
+def _e2e_host(args, rbg, lib, state, B, world, rank, dev):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    L = rbg._lib
+
+    def pinned(shape, dtype):
+        return torch.empty(shape, dtype=dtype).pin_memory()
+
+    hs = dict(grid=pinned((B, G, G), torch.int32), step_count=pinned((B,), torch.int32), agent_id=pinned((B, N), torch.int32), start=pinned((B, N, 2), torch.int32),
+              target=pinned((B, N, 2), torch.int32), position=pinned((B, N, 2), torch.int32), key=pinned((B, 2), torch.int32))
+    a = state.agents
+    for k, t in dict(grid=state.grid, step_count=state.step_count, agent_id=a.id, start=a.start, target=a.target, position=a.position, key=state.key.view(torch.int32)).items():
+        hs[k].copy_(t.cpu())
+    hts = dict(obs=pinned((B, N, G, G), torch.int32), mask=pinned((B, N, 5), torch.uint8), sc=pinned((B,), torch.int32), reward=pinned((B, N), torch.float32), discount=pinned((B, N), torch.float32),
+               step_type=pinned((B,), torch.int8), nc=pinned((B,), torch.int32), rc=pinned((B,), torch.float32), tpl=pinned((B,), torch.int32))
+    act = pinned((B, N), torch.int32)
+    rng = np.random.default_rng(rank)
+    act.copy_(torch.from_numpy(rng.integers(0, 5, size=(B, N)).astype(np.int32)))
+    s = L.rbg_state(*(hs[k].data_ptr() for k in ("grid", "step_count", "agent_id", "start", "target", "position", "key")))
+    t = L.rbg_timestep(*(hts[k].data_ptr() for k in ("obs", "mask", "sc", "reward", "discount", "step_type", "nc", "rc", "tpl")))
+    params = L.rbg_env_params(TIME_LIMIT, -0.03, 0.1, 0)
+    h2d = sum(v.numel() * v.element_size() for v in hs.values()) + act.numel() * 4
+    d2h = sum(v.numel() * v.element_size() for v in hs.values()) + sum(v.numel() * v.element_size() for v in hts.values())
+
+    def step():
+        L.check(lib.rbg_connector_step_host(C.byref(s), C.byref(s), act.data_ptr(), B, G, N, C.byref(params), C.byref(t), -1))
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    k = max(3, min(args.steps, 20))
+    t0 = time.perf_counter()
+    for _ in range(k):
+        step()  # synchronous: returns after the D2H copies have landed
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt = float(tt.item())
+    return {"value": round(B * world * k / dt, 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": k,
+            "api": "rbg_connector_step_host (pinned host State + actions in, State + TimeStep out, auto-reset on)", "timer": "host wall clock around synchronous calls, max over ranks"}
+
+
+def _secondary_prw(args, rbg, peak):
+    """Solved boards/s of ParallelRandomWalkBoard.generate_board (the other half of BASELINE's metric)."""
+    import torch
+
+    out = []
+    for (g, n, b) in ((10, 5, 65536), (20, 10, 131072), (32, 16, 32768)):
+        keys = rbg.split(rbg.PRNGKey(0), b)
+        board = rbg.ParallelRandomWalkBoard(g, g, n)
+        for _ in range(3):
+            board.generate_board(keys)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        e0.record()
+        for _ in range(reps):
+            board.generate_board(keys)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        bytes_ = PRW_BOARD_BYTES[(g, n)] * b
+        out.append({"metric": "prw_solved_boards_per_sec", "workload": f"ParallelRandomWalkBoard.generate_board {g}x{g}/{n} B={b}", "value": round(b / (ms / 1e3), 1), "unit": "boards/s", "ms_per_batch": round(ms, 4),
+                    "output_gbs": round(bytes_ / (ms / 1e3) / 1e9, 2), "hbm_frac": round(bytes_ / (ms / 1e3) / 1e9 / peak, 5), "bound": "integer issue (threefry2x32), see DESIGN.md"})
+    return out
+
+
+# ------------------------------------------------------------------ CPU arm
+def _cpu_workload(orc, B, nthreads):
+    """reset B envs with the oracle and return a stepping closure (random policy + auto-reset step)."""
+    kref = orc.split(orc.PRNGKey(0), B)
+    st, _ = orc.connector_reset_batch("parallel_random_walk", kref, G, N, nthreads=nthreads)
+    box = {"st": st}
+
+    def step():
+        act = orc.random_actions_batch(box["st"], nthreads=nthreads)
+        box["st"], ts = orc.connector_step_batch(box["st"], act, time_limit=TIME_LIMIT, autoreset_kind="parallel_random_walk", nthreads=nthreads, inplace=True)
+        return ts
+
+    return step
+
+
+def _cpu_baseline(budget_s: float = 15.0):
+    from oracle import oracle as orc
+
+    orc.build()
+    cores = orc.max_threads()
+    B = 16384
+    step = _cpu_workload(orc, B, cores)
+    for _ in range(2):
+        step()
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < budget_s:
+        step()
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": round(B * n / dt, 1), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} auto-reset random-agent steps over {B} envs 10x10/5 (same workload, smaller batch), OpenMP over envs, {dt:.1f} s"}
+
+
+def run_reference(args):
+    """The reference's CPU implementation of the path.  The reference is pure Python on JAX and
+    neither jax nor jumanji exist in this image, so this arm times the C oracle port
+    with every host thread."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+
+    orc.build()
+    cores = orc.max_threads()
+    B = args.envs
+    step = _cpu_workload(orc, B, cores)
+    for _ in range(max(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = B * args.steps / dt
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": round(dt / args.steps * 1e3, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic (keys = split(PRNGKey(0), B), random-policy actions)",
+        "config": {"workload": "connector_step_random_agent_autoreset_prw", "grid": G, "agents": N, "envs_per_gpu": B, "envs_total": B, "time_limit": TIME_LIMIT, "generator": "ParallelRandomWalkGenerator",
+                   "parallelism": f"OpenMP x{cores} host threads"},
+        "cpu_baseline": {"value": round(value, 1), "unit": UNIT, "cores": cores, "kind": "port", "sample": f"{args.steps} steps over {B} envs (rank 0 only; the CPU arm does not scale with --gpus)"},
+        "e2e": {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-secondary", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -202,6 +202,21 @@ void rbg_host_free(void *p);
  * launched since the last reset */
 int64_t rbg_launch_count(int reset);
 
+/* Per-kernel device timing for bench.py's roofline figures.  While enabled,
+ * every kernel launch is bracketed by a pair of CUDA events recorded on the
+ * launching stream.  rbg_kernel_time synchronises on the recorded events,
+ * returns the number of launches of `kernel` (RBG_K_*) and their summed device
+ * time since the last call, and clears that kernel's record. */
+#define RBG_K_PRW 0        /* prw_kernel: ParallelRandomWalk / Uniform generator */
+#define RBG_K_ENV 1        /* env_kernel: Connector step / observe */
+#define RBG_K_RANDACT 2    /* random_actions_kernel */
+#define RBG_K_SPLIT 3      /* split_keys_kernel */
+#define RBG_K_VALIDATE 4   /* validate_kernel */
+#define RBG_K_SEEDEXT 5    /* seedext_kernel */
+#define RBG_K_COUNT 6
+int rbg_kernel_timing(int enable);
+int rbg_kernel_time(int kernel, int64_t *launches, double *total_ms);
+
 #ifdef __cplusplus
 }
 #endif

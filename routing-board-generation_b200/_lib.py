@@ -60,6 +60,8 @@ SYMBOLS = {
     "rbg_host_alloc": (_vp, [_i64]),
     "rbg_host_free": (None, [_vp]),
     "rbg_launch_count": (_i64, [_int]),
+    "rbg_kernel_timing": (_int, [_int]),
+    "rbg_kernel_time": (_int, [_int, C.POINTER(_i64), C.POINTER(C.c_double)]),
 }
 
 _lib = None
@@ -90,3 +92,18 @@ def check(rc: int) -> None:
 
 def launch_count(reset: bool = False) -> int:
     return int(load().rbg_launch_count(1 if reset else 0))
+
+
+KERNELS = {"prw": 0, "env": 1, "random_actions": 2, "split": 3, "validate": 4, "seedext": 5}
+
+
+def kernel_timing(enable: bool) -> None:
+    check(load().rbg_kernel_timing(1 if enable else 0))
+
+
+def kernel_time(kernel) -> tuple:
+    """(launches, total device ms) of one kernel since the last call; synchronises on its events."""
+    kid = KERNELS[kernel] if isinstance(kernel, str) else int(kernel)
+    n, ms = _i64(0), C.c_double(0.0)
+    check(load().rbg_kernel_time(kid, C.byref(n), C.byref(ms)))
+    return int(n.value), float(ms.value)

@@ -7,6 +7,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <vector>
 
 #include "rbg_host.h"
 
@@ -33,7 +34,34 @@ int check_launch(const char *what) {
   return RBG_OK;
 }
 
-void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+// ---- per-kernel event timing (rbg_kernel_timing / rbg_kernel_time) --------
+struct EventPair {
+  cudaEvent_t a, b;
+};
+static std::atomic<int> g_timing{0};
+static std::mutex g_timing_mu;
+static std::vector<EventPair> g_events[RBG_K_COUNT];
+
+LaunchScope::LaunchScope(int kernel_id, cudaStream_t s) : id(kernel_id), stream(s), rec(nullptr) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (!g_timing.load(std::memory_order_relaxed) || id < 0 || id >= RBG_K_COUNT) return;
+  EventPair *ep = new EventPair;
+  if (cudaEventCreate(&ep->a) != cudaSuccess || cudaEventCreate(&ep->b) != cudaSuccess) {
+    delete ep;
+    return;
+  }
+  cudaEventRecord(ep->a, stream);
+  rec = ep;
+}
+
+LaunchScope::~LaunchScope() {
+  if (!rec) return;
+  EventPair *ep = static_cast<EventPair *>(rec);
+  cudaEventRecord(ep->b, stream);
+  std::lock_guard<std::mutex> lock(g_timing_mu);
+  g_events[id].push_back(*ep);
+  delete ep;
+}
 
 static int check_dims(int64_t B, int G, int N, int need_cells_per_agent) {
   if (B < 0) return set_error(RBG_EINVAL, "B=%lld must be >= 0", (long long)B);
@@ -333,6 +361,34 @@ int64_t rbg_launch_count(int reset) {
   return reset ? g_launches.exchange(0) : g_launches.load();
 }
 
+int rbg_kernel_timing(int enable) {
+  g_timing.store(enable ? 1 : 0);
+  return RBG_OK;
+}
+
+int rbg_kernel_time(int kernel, int64_t *launches, double *total_ms) {
+  if (kernel < 0 || kernel >= RBG_K_COUNT) return set_error(RBG_EINVAL, "rbg_kernel_time: unknown kernel id %d", kernel);
+  std::vector<EventPair> evs;
+  {
+    std::lock_guard<std::mutex> lock(g_timing_mu);
+    evs.swap(g_events[kernel]);
+  }
+  double ms = 0.0;
+  int rc = RBG_OK;
+  for (EventPair &ep : evs) {
+    float t = 0.0f;
+    cudaError_t e = cudaEventSynchronize(ep.b);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&t, ep.a, ep.b);
+    if (e != cudaSuccess) rc = set_cuda_error(e, "rbg_kernel_time");
+    ms += t;
+    cudaEventDestroy(ep.a);
+    cudaEventDestroy(ep.b);
+  }
+  if (launches) *launches = (int64_t)evs.size();
+  if (total_ms) *total_ms = ms;
+  return rc;
+}
+
 int rbg_split_keys(const uint32_t key[2], int64_t B, int64_t offset, int64_t count, uint32_t *out, void *stream) {
   if (!key || !out) return set_error(RBG_EINVAL, "rbg_split_keys: NULL pointer");
   if (B < 1 || B > 0x7fffffffLL || offset < 0 || count < 0 || offset + count > B)
@@ -345,9 +401,9 @@ int rbg_prw_generate(const uint32_t *keys, int64_t B, int G, int N, int32_t *hea
                      int32_t *solved, int32_t *stats, void *stream) {
   int rc;
   if ((rc = check_dims(B, G, N, 1))) return rc;
+  if (B == 0) return RBG_OK;  // an empty batch has no buffers to check
   if (!keys || !heads || !targets || !solved) return set_error(RBG_EINVAL, "rbg_prw_generate: NULL pointer");
   if (!aligned16(solved)) return set_error(RBG_EALIGN, "rbg_prw_generate: solved not 16-byte aligned");
-  if (B == 0) return RBG_OK;
   PrwParams p;
   memset(&p, 0, sizeof(p));
   p.keys = keys;

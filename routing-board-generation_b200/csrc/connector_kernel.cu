@@ -320,22 +320,26 @@ int launch_env(EnvParams p, int force_E, cudaStream_t stream) {
   if (smem > 200 * 1024) return set_error(RBG_EINVAL, "connector: shared memory %zu too large", smem);
   const int64_t ctas = (p.B + E - 1) / E;
   if (ctas <= 0) return RBG_OK;
-  if (vec) {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(env_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    env_kernel<true><<<(unsigned)ctas, 256, smem, stream>>>(p);
-  } else {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(env_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    env_kernel<false><<<(unsigned)ctas, 256, smem, stream>>>(p);
+  {
+    LaunchScope scope(RBG_K_ENV, stream);
+    if (vec) {
+      if (smem > 48 * 1024) cudaFuncSetAttribute(env_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      env_kernel<true><<<(unsigned)ctas, 256, smem, stream>>>(p);
+    } else {
+      if (smem > 48 * 1024) cudaFuncSetAttribute(env_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      env_kernel<false><<<(unsigned)ctas, 256, smem, stream>>>(p);
+    }
   }
-  count_launch();
   return check_launch("env_kernel");
 }
 
 int launch_random_actions(const rbg_state &st, int64_t B, int G, int N, int32_t *action, cudaStream_t stream) {
   const int64_t n = B * N;
   if (n <= 0) return RBG_OK;
-  random_actions_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(st, B, G, N, FastDiv::make((uint32_t)N), action);
-  count_launch();
+  {
+    LaunchScope scope(RBG_K_RANDACT, stream);
+    random_actions_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(st, B, G, N, FastDiv::make((uint32_t)N), action);
+  }
   return check_launch("random_actions_kernel");
 }
 

@@ -28,8 +28,10 @@ int launch_split_keys(uint32_t k0, uint32_t k1, int64_t B, int64_t offset, int64
                       uint32_t *out, cudaStream_t stream) {
   if (count <= 0) return RBG_OK;
   const int64_t n = 2 * count;
-  split_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(k0, k1, B, offset, count, out);
-  count_launch();
+  {
+    LaunchScope scope(RBG_K_SPLIT, stream);
+    split_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(k0, k1, B, offset, count, out);
+  }
   return check_launch("split_keys_kernel");
 }
 
@@ -135,8 +137,10 @@ int launch_validate(const int32_t *boards, int64_t B, int G, int N, int32_t *fla
   const size_t smem = (size_t)VAL_WARPS * (2 * cp + 4 * 4 * RBG_MAX_N);
   int64_t ctas = (B + VAL_WARPS - 1) / VAL_WARPS;
   if (ctas > 148 * 64) ctas = 148 * 64;
-  validate_kernel<<<(unsigned)ctas, VAL_WARPS * 32, smem, stream>>>(boards, B, G, N, flags);
-  count_launch();
+  {
+    LaunchScope scope(RBG_K_VALIDATE, stream);
+    validate_kernel<<<(unsigned)ctas, VAL_WARPS * 32, smem, stream>>>(boards, B, G, N, flags);
+  }
   return check_launch("validate_kernel");
 }
 

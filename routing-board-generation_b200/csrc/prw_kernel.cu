@@ -504,8 +504,10 @@ int launch_prw(PrwParams p, int64_t max_boards, int force_M, int force_threads,
   }
   const int64_t ctas = (max_boards + M - 1) / M;
   if (ctas <= 0) return RBG_OK;
-  prw_kernel<<<(unsigned)ctas, threads, smem, stream>>>(p);
-  count_launch();
+  {
+    LaunchScope scope(RBG_K_PRW, stream);
+    prw_kernel<<<(unsigned)ctas, threads, smem, stream>>>(p);
+  }
   return check_launch("prw_kernel");
 }
 

@@ -14,7 +14,15 @@ namespace rbg {
 int set_error(int code, const char *fmt, ...);
 int set_cuda_error(cudaError_t e, const char *what);
 int check_launch(const char *what);
-void count_launch();
+// Brackets one kernel launch: counts it (rbg_launch_count) and, while
+// rbg_kernel_timing is on, records a CUDA event pair on `stream` around it.
+struct LaunchScope {
+  int id;
+  cudaStream_t stream;
+  void *rec;
+  LaunchScope(int kernel_id, cudaStream_t s);
+  ~LaunchScope();
+};
 
 // ---- generator kernel (prw_kernel.cu) -----------------------------------
 enum : int { PRW_MODE_BOARD = 0, PRW_MODE_STATE = 1, PRW_MODE_UNIFORM = 2 };

@@ -1,0 +1,291 @@
+"""Parity of the CUDA path (through the C-ABI, librbg_b200.so) with the CPU oracle.
+
+Bit-exact everywhere: boards, coordinates, keys, masks, step types and extras are
+integers; rewards / discounts / ratio_connections are float32 values produced by
+the same two IEEE operations in both implementations (tolerance 0, compared by
+bits).  Runs only on a CUDA device (`-m gpu`).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+PRW_CONFIGS = [(2, 1), (3, 2), (5, 3), (7, 8), (9, 9), (10, 5), (14, 7), (16, 16), (17, 17), (20, 10), (32, 16), (40, 32)]
+
+
+def _np(t):
+    import torch
+
+    if t.dtype == torch.uint32:
+        return t.view(torch.int32).cpu().numpy().view(np.uint32)
+    if t.dtype == torch.bool:
+        return t.cpu().numpy().astype(np.uint8)
+    return t.cpu().numpy()
+
+
+def _keys(rbg, orc, seed, B):
+    """split(PRNGKey(seed), B) on the device (checked against the oracle)."""
+    k = rbg.split(rbg.PRNGKey(seed), B)
+    ref = orc.split(orc.PRNGKey(seed), B)
+    assert np.array_equal(_np(k), ref)
+    return k, ref
+
+
+def _state_np(st):
+    a = st.agents
+    return dict(grid=_np(st.grid), step_count=_np(st.step_count), agent_id=_np(a.id), start=_np(a.start), target=_np(a.target), position=_np(a.position), key=_np(st.key))
+
+
+def _assert_state(st, ref, where=""):
+    got = _state_np(st)
+    for k in ("grid", "step_count", "agent_id", "start", "target", "position", "key"):
+        assert np.array_equal(got[k], ref[k]), f"state.{k} differs {where}"
+
+
+def _assert_timestep(ts, ref, where=""):
+    o = ts.observation
+    assert np.array_equal(_np(o.grid), ref["obs"]), f"observation.grid differs {where}"
+    assert np.array_equal(_np(o.action_mask), ref["action_mask"]), f"action_mask differs {where}"
+    assert np.array_equal(_np(o.step_count), ref["obs_step_count"]), f"observation.step_count differs {where}"
+    assert np.array_equal(_np(ts.step_type), ref["step_type"]), f"step_type differs {where}"
+    # float32, tolerance 0: same bits
+    assert np.array_equal(_np(ts.reward).view(np.uint32), ref["reward"].view(np.uint32)), f"reward differs {where}"
+    assert np.array_equal(_np(ts.discount).view(np.uint32), ref["discount"].view(np.uint32)), f"discount differs {where}"
+    assert np.array_equal(_np(ts.extras["num_connections"]), ref["num_connections"]), where
+    assert np.array_equal(_np(ts.extras["ratio_connections"]).view(np.uint32), ref["ratio_connections"].view(np.uint32)), where
+    assert np.array_equal(_np(ts.extras["total_path_length"]), ref["total_path_length"]), where
+
+
+# ------------------------------------------------------------------- library
+def test_library_is_the_cuda_one(rbg):
+    lib = rbg._lib.load()
+    arch, sms = C.c_int(), C.c_int()
+    assert lib.rbg_device_info(C.byref(arch), C.byref(sms)) == 0
+    assert arch.value >= 100 and sms.value > 0
+    assert lib.rbg_version() == 100
+
+
+def test_split_keys(rbg, orc):
+    for seed, B in ((0, 1), (0, 2), (0, 5), (7, 1024), (3, 4097)):
+        _keys(rbg, orc, seed, B)
+    k = rbg.split(rbg.PRNGKey(5), 1000, offset=333, count=100)
+    assert np.array_equal(_np(k), orc.split(orc.PRNGKey(5), 1000)[333:433])
+
+
+# -------------------------------------------------------- ParallelRandomWalk
+def test_reference_goldens_on_gpu(rbg, goldens):
+    """test_parallel_random_walk_board.py:161-186 and notebook cells 4/13, on the CUDA path."""
+    g = goldens["prw_5x5_3"]
+    heads, targets, solved = rbg.ParallelRandomWalkBoard(5, 5, 3).generate_board(rbg.PRNGKey(0))
+    assert _np(heads).tolist() == g["heads"]
+    assert _np(targets).tolist() == g["targets"]
+    assert _np(solved).tolist() == g["valid_end_grid2"]
+    g = goldens["prw_generator_10x10_5_key0"]
+    st = rbg.ParallelRandomWalkGenerator(10, 5)(rbg.PRNGKey(0))
+    assert _np(st.agents.start).tolist() == g["start"]
+    assert _np(st.agents.target).tolist() == g["target"]
+    assert _np(st.agents.position).tolist() == g["start"]
+    assert _np(st.key).tolist() == g["key"]
+    assert int(st.step_count) == 0
+    g = goldens["uniform_generator_10x10_5_key0"]
+    st = rbg.UniformRandomGenerator(10, 5)(rbg.PRNGKey(0))
+    assert _np(st.agents.start).tolist() == g["start"]
+    assert _np(st.agents.target).tolist() == g["target"]
+    assert _np(st.key).tolist() == g["key"]
+
+
+@pytest.mark.parametrize("G,N", PRW_CONFIGS)
+def test_prw_generate_matches_oracle(rbg, orc, G, N):
+    B = 2048 if G <= 20 else 512
+    keys, kref = _keys(rbg, orc, 11 + G, B)
+    heads, targets, solved, stats = rbg.ParallelRandomWalkBoard(G, G, N).generate_board_with_stats(keys)
+    rh, rt, rs, rstats = orc.prw_generate_batch(kref, G, N)
+    assert np.array_equal(_np(solved), rs)
+    assert np.array_equal(_np(heads), rh)
+    assert np.array_equal(_np(targets), rt)
+    assert np.array_equal(_np(stats), rstats)  # while-loop trips and collided moves too
+    if G >= 10:
+        assert rstats[:, 1].sum() > 0  # the collision branch is exercised
+
+
+@pytest.mark.parametrize("B", [1, 2, 3, 31, 33, 63, 65, 257])
+def test_prw_ragged_batches(rbg, orc, B):
+    keys, kref = _keys(rbg, orc, 99, B)
+    _, _, solved = rbg.ParallelRandomWalkBoard(10, 10, 5).generate_board(keys)
+    assert np.array_equal(_np(solved), orc.prw_generate_batch(kref, 10, 5)[2])
+
+
+def test_prw_large_batch_10x10(rbg, orc):
+    """BASELINE config 1/2 size class: 65 536 boards at 10x10/5 vs the oracle."""
+    B = 65536
+    keys, kref = _keys(rbg, orc, 0, B)
+    heads, targets, solved = rbg.ParallelRandomWalkBoard(10, 10, 5).generate_board(keys)
+    rh, rt, rs, _ = orc.prw_generate_batch(kref, 10, 5)
+    assert np.array_equal(_np(solved), rs) and np.array_equal(_np(heads), rh) and np.array_equal(_np(targets), rt)
+
+
+def test_prw_empty_batch(rbg):
+    import torch
+
+    keys = torch.empty((0, 2), dtype=torch.uint32, device="cuda")
+    h, t, s = rbg.ParallelRandomWalkBoard(10, 10, 5).generate_board(keys)
+    assert h.shape == (0, 2, 5) and s.shape == (0, 10, 10)
+
+
+@pytest.mark.parametrize("G,N,B", [(20, 10, 131072), (32, 16, 16384)])
+def test_prw_full_size_invariants(rbg, G, N, B):
+    """BASELINE config 3 per-GPU slice (131 072 boards 20x20/10): every board passes the validity
+    rules on the device (wires connect their own start and target, no crossings, solvable)."""
+    keys = rbg.split(rbg.PRNGKey(0), 1048576 if G == 20 else B, 0, B)
+    heads, targets, solved = rbg.ParallelRandomWalkBoard(G, G, N).generate_board(keys)
+    flags = rbg.engine.validate(solved, N)
+    assert int((flags & ~16).abs().max()) == 0
+    # heads / targets agree with the codes on the board
+    import torch
+
+    b = torch.arange(B, device="cuda")[:, None]
+    i = torch.arange(N, device="cuda")[None, :]
+    tcode = solved[b, targets[:, 0].long(), targets[:, 1].long()]
+    assert bool((tcode == 3 * i + 3).all())
+    hcode = solved[b, heads[:, 0].long(), heads[:, 1].long()]
+    zero_len = (heads == targets).all(dim=1)
+    assert bool(((hcode == 3 * i + 2) | zero_len).all())
+
+
+# ----------------------------------------------------------- generator State
+@pytest.mark.parametrize("kind", ["parallel_random_walk", "uniform"])
+@pytest.mark.parametrize("G,N", [(5, 3), (10, 5), (14, 7), (20, 10), (32, 16)])
+def test_generator_state_matches_oracle(rbg, orc, kind, G, N):
+    B = 1024
+    keys, kref = _keys(rbg, orc, 5, B)
+    gen = {"parallel_random_walk": rbg.ParallelRandomWalkGenerator, "uniform": rbg.UniformRandomGenerator}[kind](G, N)
+    st = gen(keys)
+    _assert_state(st, orc.state_batch(kind, kref, G, N))
+
+
+# ------------------------------------------------------------------ Connector
+@pytest.mark.parametrize("kind", ["parallel_random_walk", "uniform"])
+@pytest.mark.parametrize("G,N", [(5, 3), (10, 5), (9, 4), (32, 16)])
+def test_connector_reset_matches_oracle(rbg, orc, kind, G, N):
+    B = 512
+    keys, kref = _keys(rbg, orc, 21, B)
+    gen = {"parallel_random_walk": rbg.ParallelRandomWalkGenerator, "uniform": rbg.UniformRandomGenerator}[kind](G, N)
+    st, ts = rbg.Connector(generator=gen).reset(keys)
+    rst, rts = orc.connector_reset_batch(kind, kref, G, N)
+    _assert_state(st, rst)
+    _assert_timestep(ts, rts)
+
+
+def _rollout(rbg, orc, kind, G, N, B, steps, autoreset, time_limit=50, seed=3):
+    import torch
+
+    keys, kref = _keys(rbg, orc, seed, B)
+    gen = {"parallel_random_walk": rbg.ParallelRandomWalkGenerator, "uniform": rbg.UniformRandomGenerator}[kind](G, N)
+    env = rbg.Connector(generator=gen, time_limit=time_limit)
+    st, ts = env.reset(keys)
+    rst, rts = orc.connector_reset_batch(kind, kref, G, N)
+    rng = np.random.default_rng(seed)
+    n_last = 0
+    for t in range(steps):
+        if t % 3 == 2:  # unconstrained actions: illegal moves, collisions, out-of-range codes
+            act = rng.integers(-1, 7, size=(B, N)).astype(np.int32)
+        else:  # the library's random policy (legal moves): long walks, connections
+            act = orc.random_actions_batch(rst)
+            got = _np(rbg.make_random_policy_connector()(st))
+            assert np.array_equal(got, act), f"random policy differs at step {t}"
+        if autoreset:
+            st, ts = rbg.VmapAutoResetWrapper(env).step(st, torch.from_numpy(act).cuda())
+        else:
+            st, ts = env.step(st, torch.from_numpy(act).cuda())
+        rst, rts = orc.connector_step_batch(rst, act, time_limit=time_limit, autoreset_kind=kind if autoreset else -1)
+        _assert_state(st, rst, f"at step {t}")
+        _assert_timestep(ts, rts, f"at step {t}")
+        n_last += int((rts["step_type"] == 2).sum())
+    return n_last
+
+
+@pytest.mark.parametrize("kind", ["parallel_random_walk", "uniform"])
+@pytest.mark.parametrize("G,N", [(5, 3), (10, 5), (7, 6)])
+def test_connector_step_matches_oracle(rbg, orc, kind, G, N):
+    n_last = _rollout(rbg, orc, kind, G, N, B=1024, steps=30, autoreset=False, time_limit=20)
+    assert n_last > 0
+
+
+@pytest.mark.parametrize("kind", ["parallel_random_walk", "uniform"])
+def test_connector_autoreset_matches_oracle(rbg, orc, kind):
+    n_last = _rollout(rbg, orc, kind, 10, 5, B=2048, steps=60, autoreset=True, time_limit=25)
+    assert n_last > 2048  # every env has been through at least one auto-reset
+
+
+def test_connector_autoreset_32x32(rbg, orc):
+    _rollout(rbg, orc, "parallel_random_walk", 32, 16, B=256, steps=24, autoreset=True, time_limit=10)
+
+
+def test_fused_random_step_matches_two_calls(rbg, orc):
+    """rbg_connector_step_random == rbg_random_actions + rbg_connector_step."""
+    keys, kref = _keys(rbg, orc, 8, 4096)
+    env = rbg.VmapAutoResetWrapper(rbg.Connector(generator=rbg.ParallelRandomWalkGenerator(10, 5)))
+    st, _ = env.reset(keys)
+    rst, _ = orc.connector_reset_batch("parallel_random_walk", kref, 10, 5)
+    for t in range(55):
+        act_ref = orc.random_actions_batch(rst)
+        st, ts, act = env.step_random(st)
+        assert np.array_equal(_np(act), act_ref)
+        rst, rts = orc.connector_step_batch(rst, act_ref, autoreset_kind="parallel_random_walk")
+        _assert_state(st, rst, f"at step {t}")
+        _assert_timestep(ts, rts, f"at step {t}")
+
+
+def test_multi_to_single_wrapper(rbg, orc):
+    keys, kref = _keys(rbg, orc, 8, 64)
+    env = rbg.MultiToSingleWrapper(rbg.Connector(generator=rbg.ParallelRandomWalkGenerator(10, 5)))
+    st, ts = env.reset(keys)
+    assert ts.reward.shape == (64,) and ts.discount.shape == (64,)
+    assert float(ts.discount.min()) == 1.0
+
+
+# -------------------------------------------------------------- board validity
+def test_validate_matches_oracle_on_corrupted_boards(rbg, orc):
+    import torch
+
+    G, N, B = 10, 5, 2048
+    keys = orc.split(orc.PRNGKey(4), B)
+    boards = orc.prw_generate_batch(keys, G, N)[2]
+    rng = np.random.default_rng(0)
+    for b in range(0, B, 2):  # corrupt every other board: overwrite 1-3 random cells
+        for _ in range(rng.integers(1, 4)):
+            boards[b, rng.integers(G), rng.integers(G)] = rng.integers(-1, 3 * N + 2)
+    ref = orc.validate_batch(boards, N)
+    got = _np(rbg.engine.validate(torch.from_numpy(boards).cuda(), N))
+    assert np.array_equal(got, ref)
+    assert (ref != 0).sum() > B // 8 and (ref == 0).sum() >= B // 2
+
+
+# --------------------------------------------------------------- host variants
+def test_host_variants(rbg, orc):
+    lib = rbg._lib.load()
+    G, N, B = 10, 5, 5000
+    kref = orc.split(orc.PRNGKey(6), B)
+    heads = np.empty((B, 2, N), np.int32)
+    targets = np.empty((B, 2, N), np.int32)
+    solved = np.empty((B, G, G), np.int32)
+    rc = lib.rbg_prw_generate_host(kref.ctypes.data, B, G, N, heads.ctypes.data, targets.ctypes.data, solved.ctypes.data, -1)
+    assert rc == 0, lib.rbg_last_error()
+    rh, rt, rs, _ = orc.prw_generate_batch(kref, G, N)
+    assert np.array_equal(solved, rs) and np.array_equal(heads, rh) and np.array_equal(targets, rt)
+
+
+def test_errors_are_reported_not_swallowed(rbg):
+    import torch
+
+    keys = rbg.split(rbg.PRNGKey(0), 4)
+    with pytest.raises(rbg.RbgError):
+        rbg.ParallelRandomWalkBoard(41, 41, 3).generate_board(keys)
+    with pytest.raises(rbg.RbgError):
+        rbg.ParallelRandomWalkBoard(3, 3, 10).generate_board(keys)  # N > G*G: choice(replace=False) would raise
+    with pytest.raises(ValueError):
+        rbg.ParallelRandomWalkBoard(4, 5, 2)
+    with pytest.raises(ValueError):
+        rbg.ParallelRandomWalkBoard(5, 5, 2).generate_board(torch.zeros(3, dtype=torch.int32, device="cuda"))

@@ -1,0 +1,90 @@
+"""Host-side logic that needs no GPU: shard bounds, the plugin surface (names,
+constructor arguments, properties) and the multi-rank statistics gather over
+gloo with world_size 2."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_bounds_cover_everything():
+    from routing_board_generation_b200 import sharding
+
+    for total in (0, 1, 7, 8, 1024, 1048576, 1000003):
+        for world in (1, 2, 3, 4, 8):
+            spans = [sharding.shard_bounds(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0
+            for (o0, c0), (o1, _) in zip(spans, spans[1:]):
+                assert o0 + c0 == o1
+            assert spans[-1][0] + spans[-1][1] == total
+            counts = [c for _, c in spans]
+            assert max(counts) - min(counts) <= 1
+
+
+def test_sharded_split_equals_global_split(orc):
+    """Each rank derives rows [offset, offset+count) of split(key, B) itself (setup_train.py:397-399)."""
+    from routing_board_generation_b200 import sharding
+
+    key = orc.PRNGKey(0)
+    B = 4099
+    full = orc.split(key, B)
+    for world in (2, 8):
+        parts = []
+        for r in range(world):
+            off, cnt = sharding.shard_bounds(B, r, world)
+            parts.append(orc.split_slice(key, B, off, cnt))
+        assert np.array_equal(np.concatenate(parts), full)
+
+
+def test_plugin_surface_names():
+    import routing_board_generation_b200 as pkg
+
+    gen = pkg.ParallelRandomWalkGenerator(grid_size=10, num_agents=5)
+    assert gen.grid_size == 10 and gen.num_agents == 5
+    assert isinstance(gen, pkg.Generator)
+    assert isinstance(gen.board_generator, pkg.ParallelRandomWalkBoard)
+    assert (gen.board_generator.rows, gen.board_generator.cols, gen.board_generator.num_agents) == (10, 10, 5)
+    assert isinstance(pkg.SeedExtensionGenerator(10, 5).board_generator, pkg.SeedExtensionBoard)
+    assert isinstance(pkg.UniformRandomGenerator(10, 5), pkg.Generator)
+    # interface/board_generator_interface.py:45-46,55,64
+    assert pkg.BoardGenerator.get_board_generator(pkg.BoardName("offline_parallel_rw")) is pkg.ParallelRandomWalkBoard
+    assert pkg.BoardGenerator.get_board_generator(pkg.BoardName.JAX_SEED_EXTENSION) is pkg.SeedExtensionBoard
+    env = pkg.Connector(generator=gen, time_limit=50)
+    assert env.num_agents == 5 and env.grid_size == 10 and env.time_limit == 50
+    for name in ("reset", "step", "_get_action_mask", "_obs_from_grid", "_get_extras"):
+        assert callable(getattr(env, name))
+    with pytest.raises(ValueError):
+        pkg.ParallelRandomWalkBoard(4, 5, 2)
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import torch, torch.distributed as dist
+from routing_board_generation_b200 import sharding
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+r, w = sharding.rank_world()
+off, cnt = sharding.shard_bounds(1001, r, w)
+out = sharding.gather_stats({{"boards": cnt, "ms": 10.0 + r, "first": off}})
+assert out["sum"]["boards"] == 1001, out
+assert out["max"]["ms"] == 11.0 and out["min"]["ms"] == 10.0
+assert out["max"]["first"] == 501
+dist.barrier()
+dist.destroy_process_group()
+print("ok", r)
+"""
+
+
+def test_gather_stats_gloo_world2(tmp_path):
+    port = 29500 + (os.getpid() % 2000)
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "ok" in o
