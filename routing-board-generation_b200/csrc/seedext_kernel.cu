@@ -1,9 +1,602 @@
-// seedext_kernel.cu -- SeedExtension generator (placeholder until the kernel lands).
+// seedext_kernel.cu -- SeedExtension board generation for sm_100a.
+//
+// Replaces jit(vmap(SeedExtensionBoard.return_solved_board / generate_starts_ends))
+// and jit(vmap(SeedExtensionGenerator.__call__)):
+//   reference seed_extension.py:93-304 (seeding, extension/optimise loop, starts/ends),
+//   post_processor_utils_jax.py:24-195,200-234,283-429 (extend_wires_jax),
+//   grid_utils.py:59-224,242-260,299-346,491-612 (optimise_wire BFS),
+//   random_seed_generator.py:28-57 (generator wrapper)
+//   (all under /root/reference/routing_board_generation/).
+//
+// The algorithm is a per-board sequential program whose cost is a threefry2x32
+// hash CHAIN: every cell of every sweep advances the key by `key = split(key)[0]`
+// (post_processor_utils_jax.py:156), G*G*sweeps dependent 2-block steps that no
+// amount of intra-board parallelism can shorten.  So the parallel axis is the
+// batch (DESIGN.md "K3"):
+//   se_seed_kernel      one warp per board: key derivation, lattice seeding
+//                       (the same warp-cooperative top-N selection as the
+//                       ParallelRandomWalk start cells), uint8 board -> scratch
+//   se_extend_kernel    one LANE per board, board + sweep snapshot in that lane's
+//                       slice of shared memory (odd word stride: conflict-free
+//                       when lanes touch the same cell); the two chain blocks of a
+//                       cell are independent instruction streams (ILP 2); flips
+//                       are coordinate transforms, never data movement
+//   se_optimise_kernel  one lane per board: per wire a FIFO breadth-first search
+//                       (the reference's argmin/max queue is a FIFO in disguise),
+//                       parents as 3-bit direction codes tagged with the wire id
+//   se_finish_kernel    one warp per board: uint8 -> int32 with 128-bit stores,
+//                       starts/ends extraction, State / observation / action mask
+// Boards travel between the kernels as uint8 in a stream-ordered scratch
+// allocation (1 byte per cell, L2-resident for any realistic batch).
+#include "connector_device.cuh"
 #include "rbg_host.h"
+#include "select.cuh"
 
 namespace rbg {
-int launch_seedext(SeedExtParams p, int64_t max_boards, cudaStream_t stream) {
-  (void)p; (void)max_boards; (void)stream;
-  return set_error(RBG_EINVAL, "SeedExtension kernel not built into this library yet");
+
+struct SeScratch {
+  uint8_t *board;   // [B, CB]  row-major G*G codes, CB = cells rounded up to 16
+  uint32_t *keys;   // [B, 4]   loop key (2), optkey of the current iteration (2)
+  uint32_t *gkey;   // [B, 2]   State.key (random_seed_generator.py:34,57)
+  int32_t *status;  // [B]      bit0 BFS ran dry / pop limit (never seen), bits 8.. sweeps
+  int CB;
+};
+
+struct SeDims {
+  int G, N, wires, cells;
+  int cnt, K;         // lattice side and size (seed_extension.py:104-117)
+  uint32_t thresh;    // selection filter
+  int cap;
+  int S2, SB2w;       // extend: padded stride (G+4), words per padded board
+  int lane_words_ext; // extend: words per lane (board + snapshot), odd
+  int S1, SB1;        // optimise: padded stride (G+2), bytes per padded board
+  int lane_bytes_opt; // optimise: bytes per lane (board, parents, fifo, pins), multiple of 4 with odd word count
+};
+
+__device__ __forceinline__ long long se_total(const SeedExtParams &p) {
+  return p.list ? (long long)(*p.list_count) : p.B;
 }
+
+// ---------------------------------------------------------------- seeding
+constexpr int SE_SEED_WARPS = 4;
+
+__global__ void __launch_bounds__(SE_SEED_WARPS * 32) se_seed_kernel(const SeedExtParams p, const SeDims d, const SeScratch sc) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long m = (long long)blockIdx.x * SE_SEED_WARPS + warp;
+  if (m >= se_total(p)) return;
+  const int nselp = (d.N + 1) & ~1;
+  uint64_t *cand = reinterpret_cast<uint64_t *>(smem_raw) + (size_t)warp * d.cap;
+  uint16_t *sel = reinterpret_cast<uint16_t *>(smem_raw + sizeof(uint64_t) * (size_t)SE_SEED_WARPS * d.cap) + warp * nselp;
+
+  const long long e = p.list ? (long long)p.list[m] : m;
+  uint32_t k0 = p.keys[2 * e], k1 = p.keys[2 * e + 1];
+  uint32_t a0, a1, b0, b1;
+  for (int sp = 0; sp < p.extra_split; ++sp) {  // generator / auto-reset: key = split(key)[0]
+    split2(k0, k1, a0, a1, b0, b1);
+    k0 = a0;
+    k1 = a1;
+  }
+  const uint32_t g0 = k0, g1 = k1;
+  split2(k0, k1, a0, a1, b0, b1);  // key, seedkey = split(key)            SE:171
+  k0 = a0;
+  k1 = a1;
+  // return_seeded_board(seedkey) SE:93-147: randint, choice(replace=False) and
+  // choice(offsets) all consume the SAME key; each starts with split(seedkey)
+  // and draws from its second half.
+  uint32_t s0, s1;
+  split2(b0, b1, a0, a1, s0, s1);
+  const int side = (int)(bits_scalar(s0, s1) & 1u);  // randint(key, (), 0, 2)
+  const int lo = side ? 1 : 0;
+  select_smallest(s0, s1, d.K, d.N, d.thresh, d.cap, cand, sel, lane, false);
+  // offsets: randint(key, (N,), 0, 2) = random_bits(k2, (N,)) & 1
+  const int h = (d.N + 1) >> 1;
+  uint32_t o0 = 0, o1 = 0;
+  if (lane < h) tf_block(s0, s1, (uint32_t)lane, (lane + h) < d.N ? (uint32_t)(lane + h) : 0u, o0, o1);
+  const int src = lane < h ? lane : lane - h;
+  const uint32_t t0 = __shfl_sync(FULL, o0, src & 31), t1 = __shfl_sync(FULL, o1, src & 31);
+  const int off = (int)((lane < h ? t0 : t1) & 1u);
+
+  uint8_t *board = sc.board + (size_t)m * sc.CB;
+  uint32_t *b32 = reinterpret_cast<uint32_t *>(board);
+  for (int q = lane; q < (sc.CB >> 2); q += 32) b32[q] = 0u;
+  __syncwarp();
+  int hr = 0, hc = 0, tr = 0, tc = 0;
+  if (lane < d.N) {
+    const int idx = sel[lane];
+    hr = lo + 2 * (idx / d.cnt);
+    hc = lo + 2 * (idx % d.cnt);
+    // side != 0: offsets [(-1,0),(0,-1)]; side == 0: [(0,1),(1,0)]   SE:106-112
+    const int dr = side ? (off ? 0 : -1) : (off ? 1 : 0);
+    const int dc = side ? (off ? -1 : 0) : (off ? 0 : 1);
+    tr = hr + dr;
+    tc = hc + dc;
+    board[hr * d.G + hc] = (uint8_t)(3 * lane + TARGET);  // heads carry TARGET codes  SE:145
+  }
+  __syncwarp();
+  if (lane < d.N) board[tr * d.G + tc] = (uint8_t)(3 * lane + POSITION);  // SE:146
+  if (lane == 0) {
+    sc.keys[4 * m] = k0;
+    sc.keys[4 * m + 1] = k1;
+    sc.gkey[2 * m] = g0;
+    sc.gkey[2 * m + 1] = g1;
+    sc.status[m] = 0;
+  }
+}
+
+// ------------------------------------------------------------ extension
+// split(key, 3): blocks (0,3), (1,4), (2,5); flat = [o0_0, o0_1, o0_2, o1_0, o1_1, o1_2]
+__device__ __forceinline__ void split3(uint32_t k0, uint32_t k1, uint32_t out[6]) {
+  tf_block(k0, k1, 0u, 3u, out[0], out[3]);
+  tf_block(k0, k1, 1u, 4u, out[1], out[4]);
+  tf_block(k0, k1, 2u, 5u, out[2], out[5]);
+}
+
+__global__ void __launch_bounds__(128) se_extend_kernel(const SeedExtParams p, const SeDims d, const SeScratch sc) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = m < se_total(p);
+  const int G = d.G, S = d.S2;
+  uint8_t *mine = smem_raw + ((size_t)warp * 32 + lane) * d.lane_words_ext * 4;
+  uint8_t *board = mine;
+  uint8_t *snap = mine + d.SB2w * 4;
+
+  // key, extkey, optkey = split(key, 3)   SE:189
+  uint32_t key0 = 0, key1 = 0;
+  if (live) {
+    uint32_t f[6];
+    split3(sc.keys[4 * m], sc.keys[4 * m + 1], f);
+    sc.keys[4 * m] = f[0];
+    sc.keys[4 * m + 1] = f[1];
+    sc.keys[4 * m + 2] = f[4];
+    sc.keys[4 * m + 3] = f[5];
+    key0 = f[2];
+    key1 = f[3];
+    // padded board: 0xFF outside the grid (never EMPTY, never anybody's wire)
+    uint32_t *w = reinterpret_cast<uint32_t *>(board);
+    for (int q = 0; q < d.SB2w; ++q) w[q] = 0xFFFFFFFFu;
+    const uint8_t *src = sc.board + (size_t)m * sc.CB;
+    for (int r = 0; r < G; ++r)
+      for (int c = 0; c < G; ++c) board[(r + 2) * S + (c + 2)] = src[r * G + c];
+  }
+  const bool two_sided = p.two_sided != 0;
+  const bool use_rand = p.randomness > 0.0f;
+  bool again = live;  // prev_layout differs from the board by construction  PPU:47
+  long long step_num = 0;
+  int sweeps = 0;
+  while (again && (p.ext_steps < 0 || step_num < p.ext_steps)) {
+    ++step_num;
+    ++sweeps;
+    // key, flipkey, flopkey = split(key, 3); choice over [True, False]  PPU:63-67
+    uint32_t f[6];
+    split3(key0, key1, f);
+    key0 = f[0];
+    key1 = f[1];
+    const bool flip = randint_pow2(f[2], f[3], 2u) == 0u;
+    const bool flop = randint_pow2(f[4], f[5], 2u) == 0u;
+    const bool mirrored = flip || flop;
+    if (mirrored) {  // the convergence test needs the pre-sweep board  PPU:70,186-189
+      const uint32_t *a = reinterpret_cast<const uint32_t *>(board);
+      uint32_t *b = reinterpret_cast<uint32_t *>(snap);
+      for (int q = 0; q < d.SB2w; ++q) b[q] = a[q];
+    }
+    bool modified = false;
+    // walking the FLIPPED board row-major == walking the board with mirrored
+    // coordinates and mirrored neighbour directions
+    const int sr = flip ? -S : S, scol = flop ? -1 : 1;
+    uint8_t *prow = board + ((flip ? G - 1 : 0) + 2) * S + ((flop ? G - 1 : 0) + 2);
+    for (int row = 0; row < G; ++row, prow += sr) {
+      uint8_t *pc = prow;
+      for (int col = 0; col < G; ++col, pc += scol) {
+        // key, random_key = split(key)   PPU:156 -- runs for EVERY cell
+        uint32_t n0, r0, n1, r1;
+        tf_block(key0, key1, 0u, 2u, n0, r0);
+        tf_block(key0, key1, 1u, 3u, n1, r1);
+        const uint32_t v = pc[0];
+        const uint32_t wv = v - 1u;           // v == 0 wraps: type test below fails
+        const uint32_t w3 = (wv / 3u) * 3u;   // 3 * wire
+        const uint32_t ctype = wv - w3 + 1u;  // PATH 1, POSITION 2, TARGET 3
+        const bool extendable = v != 0u && (two_sided ? ctype != PATH : ctype == TARGET);  // PPU:109-116
+        if (extendable) {
+          const uint32_t b3 = w3 + 1u;
+          // candidates in list order up, left, down, right (PPU:322-369); a
+          // candidate is dropped when it touches the wire anywhere but through
+          // the current cell (PPU:86-97)
+          const uint32_t u = pc[-sr], l = pc[-scol], dn = pc[sr], r = pc[scol];
+          const bool oul = own_wire(pc[-sr - scol], b3), our = own_wire(pc[-sr + scol], b3);
+          const bool odl = own_wire(pc[sr - scol], b3), odr = own_wire(pc[sr + scol], b3);
+          uint32_t ok = 0;
+          ok |= (u == 0u && !own_wire(pc[-2 * sr], b3) && !oul && !our) ? 1u : 0u;
+          ok |= (l == 0u && !own_wire(pc[-2 * scol], b3) && !oul && !odl) ? 2u : 0u;
+          ok |= (dn == 0u && !own_wire(pc[2 * sr], b3) && !odl && !odr) ? 4u : 0u;
+          ok |= (r == 0u && !own_wire(pc[2 * scol], b3) && !our && !odr) ? 8u : 0u;
+          if (ok) {
+            // previous neighbour: last match among up, down, left (PPU:200-234);
+            // the priority cell mirrors it through the current cell (PPU:99-103)
+            uint32_t pri = 0;
+            if (own_wire(u, b3)) pri = 4u;   // came from above -> continue down
+            if (own_wire(dn, b3)) pri = 1u;  // from below -> up
+            if (own_wire(l, b3)) pri = 8u;   // from the left -> right
+            bool take_pri = (ok & pri) != 0u;
+            if (take_pri && use_rand) {  // PPU:157-162
+              const float uni = bits_to_uniform(bits_scalar(r0, r1));
+              take_pri = !(p.randomness > uni);
+            }
+            uint32_t pick = pri;
+            if (!take_pri) {
+              // repeat `k, ck = split(k); pos = list[randint(ck, 0, 4)]` until valid,
+              // from the cell's key, which is NOT advanced by this loop  PPU:127-144
+              uint32_t lk0 = key0, lk1 = key1;
+              for (;;) {
+                uint32_t x0, x1, c0, c1;
+                split2(lk0, lk1, x0, x1, c0, c1);
+                lk0 = x0;
+                lk1 = x1;
+                pick = 1u << randint_pow2(c0, c1, 4u);
+                if (ok & pick) break;
+              }
+            }
+            const int delta = pick == 1u ? -sr : (pick == 2u ? -scol : (pick == 4u ? sr : scol));
+            pc[delta] = (uint8_t)v;   // the head / target moves      PPU:165-167
+            pc[0] = (uint8_t)b3;      // and leaves PATH behind       PPU:168-173
+            modified = true;
+          }
+        }
+        key0 = n0;
+        key1 = n1;
+      }
+    }
+    // PPU:186-189: un-flip the board (a no-op here) and loop while the FLIPPED
+    // pre-sweep layout differs from the un-flipped result
+    if (!mirrored) {
+      again = modified;
+    } else {
+      bool diff = false;
+      for (int r = 0; r < G; ++r) {
+        const uint8_t *a = board + (r + 2) * S + 2;
+        const uint8_t *b = snap + ((flip ? G - 1 - r : r) + 2) * S + 2 + (flop ? G - 1 : 0);
+        for (int c = 0; c < G; ++c, b += scol) diff |= (a[c] != b[0]);
+      }
+      again = diff;
+    }
+  }
+  if (live) {
+    uint8_t *dst = sc.board + (size_t)m * sc.CB;
+    for (int r = 0; r < G; ++r)
+      for (int c = 0; c < G; ++c) dst[r * G + c] = board[(r + 2) * S + (c + 2)];
+    sc.status[m] += sweeps << 8;
+  }
+}
+
+// ------------------------------------------------------- optimise_wire (BFS)
+__global__ void __launch_bounds__(128) se_optimise_kernel(const SeedExtParams p, const SeDims d, const SeScratch sc) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= se_total(p)) return;
+  const int G = d.G, S = d.S1, cells = d.cells;
+  uint8_t *mine = smem_raw + ((size_t)warp * 32 + lane) * d.lane_bytes_opt;
+  uint8_t *board = mine;                                      // [(G+2)^2] 0xFF border
+  uint8_t *par = mine + d.SB1;                                // parents: (wire << 3) | (dir + 1)
+  uint16_t *fifo = reinterpret_cast<uint16_t *>(mine + 2 * d.SB1);  // [cells + 2]
+  uint16_t *pins = fifo + ((cells + 3) & ~1);                 // [2N] first POSITION / TARGET per wire
+
+  for (int q = 0; q < (d.SB1 >> 2); ++q) {
+    reinterpret_cast<uint32_t *>(board)[q] = 0xFFFFFFFFu;
+    reinterpret_cast<uint32_t *>(par)[q] = 0u;
+  }
+  for (int i = 0; i < 2 * d.N; ++i) pins[i] = 0xFFFFu;
+  uint8_t *gb = sc.board + (size_t)m * sc.CB;
+  for (int r = 0; r < G; ++r)
+    for (int c = 0; c < G; ++c) {
+      const uint32_t v = gb[r * G + c];
+      const int idx = (r + 1) * S + (c + 1);
+      board[idx] = (uint8_t)v;
+      if (v) {  // argmax of (board == code): the first cell in row-major order  GU:512-517
+        const uint32_t w = (v - 1u) / 3u, t = v - 3u * w;
+        if (t == POSITION && pins[2 * w] == 0xFFFFu) pins[2 * w] = (uint16_t)idx;
+        if (t == TARGET && pins[2 * w + 1] == 0xFFFFu) pins[2 * w + 1] = (uint16_t)idx;
+      }
+    }
+  const uint32_t ok0 = sc.keys[4 * m + 2], ok1 = sc.keys[4 * m + 3];
+  const int origin = S + 1;  // cell (0,0): what argmax returns when the code is absent
+  int bad = 0;
+  for (int w = 0; w < d.wires; ++w) {
+    // optkeys = split(optkey, wires); this wire's key = flat[2w], flat[2w+1]   SE:194
+    uint32_t wk[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int f = 2 * w + t;
+      uint32_t x0, x1;
+      if (f < d.wires) {
+        tf_block(ok0, ok1, (uint32_t)f, (uint32_t)(f + d.wires), x0, x1);
+        wk[t] = x0;
+      } else {
+        tf_block(ok0, ok1, (uint32_t)(f - d.wires), (uint32_t)f, x0, x1);
+        wk[t] = x1;
+      }
+    }
+    // neighbour order: permutation(key, arange(4)) = one _shuffle round  GU:91
+    uint32_t a0, a1, s0, s1, bits[4];
+    split2(wk[0], wk[1], a0, a1, s0, s1);
+    tf_block(s0, s1, 0u, 2u, bits[0], bits[2]);
+    tf_block(s0, s1, 1u, 3u, bits[1], bits[3]);
+    int delta[4];
+    {
+      const int dlt[4] = {-S, 1, S, -1};  // rows [-1,0,1,0], cols [0,1,0,-1]  GU:87-88
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {  // stable rank of bits[i]
+        int rank = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rank += (bits[j] < bits[i] || (bits[j] == bits[i] && j < i)) ? 1 : 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (rank == q) delta[q] = dlt[i];
+      }
+    }
+    const uint32_t path_num = 3u * w + PATH, start_num = 3u * w + POSITION, end_num = 3u * w + TARGET;
+    const int start = pins[2 * w] == 0xFFFFu ? origin : (int)pins[2 * w];
+    const int end = pins[2 * w + 1] == 0xFFFFu ? origin : (int)pins[2 * w + 1];
+    board[start] = (uint8_t)path_num;  // GU:519-520
+    board[end] = (uint8_t)path_num;
+    const uint32_t tag = (uint32_t)w << 3;
+    int head = 0, tail = 0, pops = 0;
+    fifo[tail++] = (uint16_t)start;
+    auto seen = [&](int q) { const uint32_t b = par[q]; return (b & 7u) != 0u && (b & ~7u) == tag; };
+    bool dry = false;
+    while (pops < cells && !seen(end)) {  // GU:560-566
+      if (head == tail) {
+        dry = true;
+        break;
+      }
+      const int cur = fifo[head++];
+      ++pops;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int q = cur + delta[j];
+        const uint32_t bv = board[q];
+        if ((bv == path_num || bv == 0u) && !seen(q)) {  // GU:118-160
+          par[q] = (uint8_t)(tag | (uint32_t)(j + 1));
+          fifo[tail++] = (uint16_t)q;
+        }
+      }
+    }
+    if (dry || !seen(end)) {  // not reachable on boards this pipeline makes
+      board[start] = (uint8_t)start_num;
+      board[end] = (uint8_t)end_num;
+      bad = 1;
+      continue;
+    }
+    // remove_path + jax_fill_grid: the wire becomes the BFS path   GU:242-346
+    for (int r = 0; r < G; ++r) {
+      uint8_t *rowp = board + (r + 1) * S + 1;
+      for (int c = 0; c < G; ++c)
+        if (rowp[c] == path_num) rowp[c] = 0;
+    }
+    int cur = end, n = 0, last = end;
+    for (;;) {
+      board[cur] = (uint8_t)path_num;
+      last = cur;
+      ++n;
+      if (cur == start || n >= cells) break;
+      cur -= delta[(par[cur] & 7u) - 1u];
+    }
+    board[last] = (uint8_t)start_num;
+    board[end] = (uint8_t)end_num;
+  }
+  for (int r = 0; r < G; ++r)
+    for (int c = 0; c < G; ++c) gb[r * G + c] = board[(r + 1) * S + (c + 1)];
+  if (bad) sc.status[m] |= 1;
+}
+
+// ------------------------------------------------------------------ outputs
+constexpr int SE_FIN_WARPS = 8;
+
+__global__ void __launch_bounds__(SE_FIN_WARPS * 32) se_finish_kernel(const SeedExtParams p, const SeDims d, const SeScratch sc, const FastDiv divG) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long m = (long long)blockIdx.x * SE_FIN_WARPS + warp;
+  if (m >= se_total(p)) return;
+  const int G = d.G, N = d.N, cells = d.cells, CB = sc.CB;
+  uint8_t *mine = smem_raw + (size_t)warp * (2 * CB + 8 * RBG_MAX_N);
+  uint8_t *grid = mine;        // solved board
+  uint8_t *pinsg = mine + CB;  // pins-only board (training grid)
+  int *first = reinterpret_cast<int *>(mine + 2 * CB);  // [2N] first POSITION / TARGET cell per wire
+  const long long e = p.list ? (long long)p.list[m] : m;
+
+  const uint32_t *src = reinterpret_cast<const uint32_t *>(sc.board + (size_t)m * CB);
+  for (int q = lane; q < (CB >> 2); q += 32) {
+    reinterpret_cast<uint32_t *>(grid)[q] = src[q];
+    reinterpret_cast<uint32_t *>(pinsg)[q] = 0u;
+  }
+  if (lane < N) first[2 * lane] = first[2 * lane + 1] = cells;
+  __syncwarp();
+
+  if (p.mode == 0) {  // return_solved_board: int32[G,G]
+    int32_t *out = p.solved + e * cells;
+    if ((cells & 3) == 0) {
+      int4 *o = reinterpret_cast<int4 *>(out);
+      for (int q = lane; q < (cells >> 2); q += 32) o[q] = bytes_to_int4(reinterpret_cast<const uint32_t *>(grid)[q]);
+    } else {
+      for (int i = lane; i < cells; i += 32) out[i] = grid[i];
+    }
+    return;
+  }
+  // generate_starts_ends SE:282-293: first POSITION / TARGET cell per wire in
+  // row-major order, (0,0) when absent (argwhere(size=2) fill value)
+  for (int i = lane; i < cells; i += 32) {
+    const uint32_t v = grid[i];
+    if (v == 0u || v > 3u * N) continue;
+    const uint32_t w = (v - 1u) / 3u, t = v - 3u * w;
+    if (t == POSITION) atomicMin(&first[2 * w], i);
+    if (t == TARGET) atomicMin(&first[2 * w + 1], i);
+  }
+  __syncwarp();
+  int sr = 0, scol = 0, tr = 0, tc = 0;
+  if (lane < N) {
+    const int fs = first[2 * lane] == cells ? 0 : first[2 * lane];
+    const int ft = first[2 * lane + 1] == cells ? 0 : first[2 * lane + 1];
+    uint32_t q, r;
+    divG.divmod((uint32_t)fs, q, r);
+    sr = (int)q;
+    scol = (int)r;
+    divG.divmod((uint32_t)ft, q, r);
+    tr = (int)q;
+    tc = (int)r;
+  }
+  if (p.mode == 1) {
+    if (lane < N) {
+      p.starts[e * 2 * N + lane] = sr;
+      p.starts[e * 2 * N + N + lane] = scol;
+      p.ends[e * 2 * N + lane] = tr;
+      p.ends[e * 2 * N + N + lane] = tc;
+    }
+    return;
+  }
+  // SeedExtensionGenerator.__call__ RSG:34-57: pins-only grid (heads, then targets), Agent pytree
+  if (lane < N) pinsg[sr * G + scol] = (uint8_t)(3 * lane + POSITION);
+  __syncwarp();
+  if (lane < N) pinsg[tr * G + tc] = (uint8_t)(3 * lane + TARGET);
+  __syncwarp();
+  int32_t *gout = p.st.grid + e * cells;
+  if ((cells & 3) == 0) {
+    int4 *o = reinterpret_cast<int4 *>(gout);
+    for (int q = lane; q < (cells >> 2); q += 32) o[q] = bytes_to_int4(reinterpret_cast<const uint32_t *>(pinsg)[q]);
+  } else {
+    for (int i = lane; i < cells; i += 32) gout[i] = pinsg[i];
+  }
+  if (lane < N) {
+    p.st.agent_id[e * N + lane] = lane;
+    reinterpret_cast<int2 *>(p.st.start)[e * N + lane] = make_int2(sr, scol);
+    reinterpret_cast<int2 *>(p.st.target)[e * N + lane] = make_int2(tr, tc);
+    reinterpret_cast<int2 *>(p.st.position)[e * N + lane] = make_int2(sr, scol);
+    if (p.observe) {
+      SmemGrid sg{pinsg, G, 0, G};
+      store_mask5(p.ts.action_mask + (e * N + lane) * 5, move_mask(sg, sr, scol, lane, sr == tr && scol == tc));
+    }
+  }
+  if (lane == 0) {
+    p.st.step_count[e] = 0;
+    p.st.key[2 * e] = sc.gkey[2 * m];
+    p.st.key[2 * e + 1] = sc.gkey[2 * m + 1];
+    if (p.observe) p.ts.obs_step_count[e] = 0;
+  }
+  if (p.observe) {
+    SmemGrid sg{pinsg, G, 0, G};
+    warp_write_obs(sg, N, divG, p.ts.obs_grid + (size_t)e * N * cells, lane);
+  }
+}
+
+// ---------------------------------------------------------------- host side
+static size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static int set_smem(const void *fn, size_t bytes, const char *name) {
+  if (bytes > 227 * 1024) return set_error(RBG_EINVAL, "%s needs %zu bytes of shared memory per CTA", name, bytes);
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return set_cuda_error(e, name);
+  }
+  return RBG_OK;
+}
+
+int launch_seedext(SeedExtParams p, int64_t max_boards, cudaStream_t stream) {
+  const int G = p.G, N = p.N;
+  SeDims d;
+  d.G = G;
+  d.N = N;
+  d.cells = G * G;
+  d.wires = N < d.cells / 3 ? N : d.cells / 3;  // SE:60-63
+  d.cnt = G / 2;
+  d.K = d.cnt * d.cnt;
+  if (N > d.K)
+    return set_error(RBG_EINVAL, "SeedExtension: %d agents need %d seed cells but the %dx%d lattice has %d (choice(replace=False) would raise)", N, N, G, G, d.K);
+  if (p.iterations < 0) return set_error(RBG_EINVAL, "SeedExtension: extension_iterations=%d", p.iterations);
+  d.cap = 4 * N + 32;
+  {
+    const double frac = (2.0 * N + 16.0) / (double)d.K;
+    d.thresh = frac >= 1.0 ? 0xffffffffu : (uint32_t)(frac * 4294967296.0);
+  }
+  d.S2 = G + 4;
+  d.SB2w = (int)(round_up((size_t)d.S2 * d.S2, 4) / 4);
+  d.lane_words_ext = 2 * d.SB2w + 1;  // odd: lanes on the same cell hit 32 different banks
+  d.S1 = G + 2;
+  d.SB1 = (int)round_up((size_t)d.S1 * d.S1, 4);
+  {
+    size_t b = 2 * (size_t)d.SB1 + 2 * (size_t)((d.cells + 3) & ~1) + 2 * (size_t)(2 * N);
+    b = round_up(b, 4);
+    if (((b / 4) & 1) == 0) b += 4;
+    d.lane_bytes_opt = (int)b;
+  }
+  SeScratch sc;
+  sc.CB = (int)round_up((size_t)d.cells, 16);
+  const size_t n = (size_t)max_boards;
+  const size_t o_keys = round_up(n * sc.CB, 256), o_gkey = o_keys + round_up(n * 16, 256), o_status = o_gkey + round_up(n * 8, 256);
+  const size_t total = o_status + round_up(n * 4, 256);
+  uint8_t *base = nullptr;
+  {  // keep the stream-ordered pool's memory cached between calls (default: released at every sync)
+    static bool pool_ready = false;
+    if (!pool_ready) {
+      int dev = 0;
+      cudaMemPool_t pool;
+      if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+      }
+      pool_ready = true;
+    }
+  }
+  cudaError_t ce = cudaMallocAsync(reinterpret_cast<void **>(&base), total, stream);
+  if (ce != cudaSuccess) return set_cuda_error(ce, "cudaMallocAsync(SeedExtension scratch)");
+  sc.board = base;
+  sc.keys = reinterpret_cast<uint32_t *>(base + o_keys);
+  sc.gkey = reinterpret_cast<uint32_t *>(base + o_gkey);
+  sc.status = reinterpret_cast<int32_t *>(base + o_status);
+
+  int rc = RBG_OK;
+  do {
+    {  // seeding: one warp per board
+      const size_t smem = sizeof(uint64_t) * SE_SEED_WARPS * d.cap + sizeof(uint16_t) * SE_SEED_WARPS * ((N + 1) & ~1);
+      const unsigned ctas = (unsigned)((max_boards + SE_SEED_WARPS - 1) / SE_SEED_WARPS);
+      LaunchScope scope(RBG_K_SEEDEXT, stream);
+      se_seed_kernel<<<ctas, SE_SEED_WARPS * 32, smem, stream>>>(p, d, sc);
+    }
+    if ((rc = check_launch("se_seed_kernel"))) break;
+    // lane-per-board kernels: as many warps per CTA as ~100 KB of shared memory allow
+    auto warps_for = [](size_t per_warp) {
+      int w = 4;
+      while (w > 1 && per_warp * w > 100 * 1024) w >>= 1;
+      return w;
+    };
+    const size_t ext_warp = (size_t)32 * d.lane_words_ext * 4, opt_warp = (size_t)32 * d.lane_bytes_opt;
+    const int ext_w = warps_for(ext_warp), opt_w = warps_for(opt_warp);
+    if ((rc = set_smem(reinterpret_cast<const void *>(se_extend_kernel), ext_warp * ext_w, "se_extend_kernel"))) break;
+    if ((rc = set_smem(reinterpret_cast<const void *>(se_optimise_kernel), opt_warp * opt_w, "se_optimise_kernel"))) break;
+    for (int it = 0; it < p.iterations && rc == RBG_OK; ++it) {  // SE:180-200 while_loop over extension_iterations
+      {
+        const unsigned ctas = (unsigned)((max_boards + ext_w * 32 - 1) / (ext_w * 32));
+        LaunchScope scope(RBG_K_SEEDEXT, stream);
+        se_extend_kernel<<<ctas, ext_w * 32, ext_warp * ext_w, stream>>>(p, d, sc);
+      }
+      if ((rc = check_launch("se_extend_kernel"))) break;
+      {
+        const unsigned ctas = (unsigned)((max_boards + opt_w * 32 - 1) / (opt_w * 32));
+        LaunchScope scope(RBG_K_SEEDEXT, stream);
+        se_optimise_kernel<<<ctas, opt_w * 32, opt_warp * opt_w, stream>>>(p, d, sc);
+      }
+      rc = check_launch("se_optimise_kernel");
+    }
+    if (rc) break;
+    {
+      const size_t smem = (size_t)SE_FIN_WARPS * (2 * sc.CB + 8 * RBG_MAX_N);
+      const unsigned ctas = (unsigned)((max_boards + SE_FIN_WARPS - 1) / SE_FIN_WARPS);
+      LaunchScope scope(RBG_K_SEEDEXT, stream);
+      se_finish_kernel<<<ctas, SE_FIN_WARPS * 32, smem, stream>>>(p, d, sc, FastDiv::make((uint32_t)G));
+    }
+    rc = check_launch("se_finish_kernel");
+  } while (0);
+  cudaFreeAsync(base, stream);
+  return rc;
+}
+
 }  // namespace rbg

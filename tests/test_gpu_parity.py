@@ -154,6 +154,64 @@ def test_prw_full_size_invariants(rbg, G, N, B):
     assert bool(((hcode == 3 * i + 2) | zero_len).all())
 
 
+# ------------------------------------------------------------- SeedExtension
+SE_CONFIGS = [(2, 1), (4, 3), (5, 4), (6, 3), (9, 5), (10, 5), (14, 7), (20, 10), (32, 16), (40, 32)]
+
+
+@pytest.mark.parametrize("G,N", SE_CONFIGS)
+def test_seedext_solved_matches_oracle(rbg, orc, G, N):
+    B = 1024 if G <= 20 else 128
+    keys, kref = _keys(rbg, orc, 31 + G, B)
+    board = rbg.SeedExtensionBoard(G, G, N)
+    solved = board.return_solved_board(keys)
+    ref, stats = orc.seedext_solved_batch(kref, G, N)
+    assert np.array_equal(_np(solved), ref)
+    assert (stats[:, 2] == 0).all()  # the BFS never ran dry in the oracle either
+    (sr, sc), (er, ec) = board.generate_starts_ends(keys)
+    for b in range(0, B, max(1, B // 16)):
+        rs, re_ = orc.seedext_starts_ends(kref[b], G, N)
+        assert np.array_equal(_np(sr[b]), rs[0]) and np.array_equal(_np(sc[b]), rs[1])
+        assert np.array_equal(_np(er[b]), re_[0]) and np.array_equal(_np(ec[b]), re_[1])
+    training = board.return_training_board(keys)
+    assert np.array_equal(_np(training), ref * ((ref % 3) != 1))
+    if G >= 4:
+        assert int(rbg.engine.validate(solved, N).abs().max()) == 0
+
+
+@pytest.mark.parametrize("kw", [dict(randomness=0.5), dict(randomness=1.0), dict(two_sided=False), dict(extension_iterations=2),
+                                dict(extension_iterations=0), dict(extension_steps=3), dict(randomness=0.3, two_sided=False, extension_iterations=3, extension_steps=5)])
+def test_seedext_options_match_oracle(rbg, orc, kw):
+    G, N, B = 10, 5, 512
+    keys, kref = _keys(rbg, orc, 77, B)
+    solved = rbg.SeedExtensionBoard(G, G, N).return_solved_board(keys, **kw)
+    okw = dict(randomness=kw.get("randomness", 0.0), two_sided=kw.get("two_sided", True), iterations=kw.get("extension_iterations", 1), ext_steps=int(kw.get("extension_steps", -1)))
+    ref, _ = orc.seedext_solved_batch(kref, G, N, **okw)
+    assert np.array_equal(_np(solved), ref)
+
+
+def test_seedext_single_key_and_ragged(rbg, orc):
+    k = rbg.PRNGKey(0)
+    solved = rbg.SeedExtensionBoard(10, 10, 5).return_solved_board(k)
+    assert solved.shape == (10, 10)
+    assert np.array_equal(_np(solved), orc.seedext_solved(orc.PRNGKey(0), 10, 5))
+    for B in (1, 31, 33, 129):
+        keys, kref = _keys(rbg, orc, 13, B)
+        assert np.array_equal(_np(rbg.SeedExtensionBoard(10, 10, 5).return_solved_board(keys)), orc.seedext_solved_batch(kref, 10, 5)[0])
+
+
+def test_seedext_full_size_invariants(rbg):
+    """BASELINE config 4: SeedExtension 14x14 / 7 agents, 65 536 boards, all valid on the device."""
+    keys = rbg.split(rbg.PRNGKey(0), 65536)
+    solved = rbg.SeedExtensionBoard(14, 14, 7).return_solved_board(keys)
+    assert int(rbg.engine.validate(solved, 7).abs().max()) == 0
+    assert int((solved > 0).sum(dim=(1, 2)).min()) >= 14  # every wire has at least its two pins
+
+
+def test_seedext_too_many_agents_is_an_error(rbg):
+    with pytest.raises(rbg.RbgError):
+        rbg.SeedExtensionBoard(6, 6, 10).return_solved_board(rbg.split(rbg.PRNGKey(0), 4))  # lattice has 9 seed cells
+
+
 # ----------------------------------------------------------- generator State
 @pytest.mark.parametrize("kind", ["parallel_random_walk", "uniform"])
 @pytest.mark.parametrize("G,N", [(5, 3), (10, 5), (14, 7), (20, 10), (32, 16)])
@@ -163,6 +221,17 @@ def test_generator_state_matches_oracle(rbg, orc, kind, G, N):
     gen = {"parallel_random_walk": rbg.ParallelRandomWalkGenerator, "uniform": rbg.UniformRandomGenerator}[kind](G, N)
     st = gen(keys)
     _assert_state(st, orc.state_batch(kind, kref, G, N))
+
+
+@pytest.mark.parametrize("G,N", [(6, 3), (10, 5), (14, 7)])
+def test_seedext_generator_state_matches_oracle(rbg, orc, G, N):
+    keys, kref = _keys(rbg, orc, 5, 512)
+    _assert_state(rbg.SeedExtensionGenerator(G, N)(keys), orc.state_batch("seed_extension", kref, G, N))
+
+
+def test_seedext_connector_autoreset_matches_oracle(rbg, orc):
+    n_last = _rollout(rbg, orc, "seed_extension", 10, 5, B=512, steps=40, autoreset=True, time_limit=15)
+    assert n_last > 512
 
 
 # ------------------------------------------------------------------ Connector
@@ -182,7 +251,7 @@ def _rollout(rbg, orc, kind, G, N, B, steps, autoreset, time_limit=50, seed=3):
     import torch
 
     keys, kref = _keys(rbg, orc, seed, B)
-    gen = {"parallel_random_walk": rbg.ParallelRandomWalkGenerator, "uniform": rbg.UniformRandomGenerator}[kind](G, N)
+    gen = {"parallel_random_walk": rbg.ParallelRandomWalkGenerator, "uniform": rbg.UniformRandomGenerator, "seed_extension": rbg.SeedExtensionGenerator}[kind](G, N)
     env = rbg.Connector(generator=gen, time_limit=time_limit)
     st, ts = env.reset(keys)
     rst, rts = orc.connector_reset_batch(kind, kref, G, N)
