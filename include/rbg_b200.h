@@ -146,8 +146,15 @@ int rbg_connector_reset(int kind, const uint32_t *keys, int64_t B, int G, int N,
                         const rbg_state *state, const rbg_timestep *ts,
                         void *stream);
 
-/* bytes of device scratch rbg_connector_step needs when autoreset is on */
+/* bytes of device scratch rbg_connector_step needs when autoreset is on.  The
+ * workspace belongs to ONE env batch for as long as that batch is stepped: besides
+ * the reset lists it caches, per env, the next episode's start / target pins, which
+ * the library generates ahead of time on an internal side stream (the reset key of
+ * an episode is known when the episode starts).  16-byte aligned, need not be
+ * cleared.  Call rbg_workspace_release before freeing it. */
 int64_t rbg_step_workspace_bytes(int64_t B, int G, int N);
+/* waits for the side-stream work tied to `workspace` and forgets it */
+int rbg_workspace_release(void *workspace);
 
 /* Connector.step(state, action) (JUM env.py step), or with
  * params->autoreset_kind >= 0 VmapAutoResetWrapper(Connector).step (ST:166).

@@ -50,6 +50,7 @@ SYMBOLS = {
     "rbg_connector_observe": (_int, [_SP, _i64, _int, _int, _TP, _vp]),
     "rbg_connector_reset": (_int, [_int, _vp, _i64, _int, _int, _SP, _TP, _vp]),
     "rbg_step_workspace_bytes": (_i64, [_i64, _int, _int]),
+    "rbg_workspace_release": (_int, [_vp]),
     "rbg_connector_step": (_int, [_SP, _SP, _vp, _i64, _int, _int, _EP, _TP, _vp, _vp]),
     "rbg_random_actions": (_int, [_SP, _i64, _int, _int, _vp, _vp]),
     "rbg_connector_step_random": (_int, [_SP, _SP, _vp, _i64, _int, _int, _EP, _TP, _vp, _vp]),

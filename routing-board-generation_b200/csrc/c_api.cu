@@ -7,6 +7,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <unordered_map>
 #include <vector>
 
 #include "rbg_host.h"
@@ -158,6 +159,61 @@ static int generator_state_impl(int kind, const uint32_t *keys, int64_t B, int G
   return set_error(RBG_EINVAL, "unknown generator kind %d", kind);
 }
 
+// ---- auto-reset workspace ------------------------------------------------------
+// VmapAutoResetWrapper regenerates a board whenever an env finishes.  The reset key
+// of an episode is known as soon as the episode starts (split(state.key)[0]), so the
+// NEXT episode of every env that just reset is generated ahead of time on a side
+// stream ("refill") into a per-env cache; when the env finishes, env_kernel swaps the
+// cached episode in.  Only envs whose cache entry is not ready (first episode, or two
+// terminations in consecutive steps) take the synchronous reset kernel.  Results are
+// identical either way: a board is a pure function of its key.
+struct WsLayout {
+  size_t sync_list, refill_list[2], refill_keys[2], cache_tag, cache_key, cache_pins, total;
+};
+static WsLayout ws_layout(int64_t B, int N) {
+  auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  WsLayout w;
+  size_t off = 256;  // counters: sync @0, refill[0] @64, refill[1] @128
+  const size_t b = (size_t)(B > 0 ? B : 0);
+  w.sync_list = off;
+  off = up(off + 4 * b);
+  for (int i = 0; i < 2; ++i) {
+    w.refill_list[i] = off;
+    off = up(off + 4 * b);
+    w.refill_keys[i] = off;
+    off = up(off + 8 * b);
+  }
+  w.cache_tag = off;
+  off = up(off + 8 * b);
+  w.cache_key = off;
+  off = up(off + 8 * b);
+  w.cache_pins = off;
+  off = up(off + 4 * b * (size_t)N);
+  w.total = off;
+  return w;
+}
+
+struct AutoResetCtx {
+  int64_t B = 0;
+  int G = 0, N = 0, kind = -1;
+  uint64_t step = 0;
+  cudaStream_t side = nullptr;
+  cudaEvent_t env_done = nullptr;
+  cudaEvent_t refill_done[2] = {nullptr, nullptr};
+  bool refill_pending[2] = {false, false};
+};
+static std::mutex g_ar_mu;
+static std::unordered_map<void *, AutoResetCtx> g_ar;
+
+static bool speculative_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("RBG_NO_SPECULATIVE_RESET");
+    v = (e && atoi(e) != 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
 static int connector_step_impl(const rbg_state *in, const rbg_state *out, const int32_t *action, int32_t *action_out,
                                int random_policy, int64_t B, int G, int N, const rbg_env_params *params,
                                const rbg_timestep *ts, void *workspace, cudaStream_t stream) {
@@ -186,22 +242,105 @@ static int connector_step_impl(const rbg_state *in, const rbg_state *out, const 
   p.N = N;
   p.mode = ENV_MODE_STEP;
   p.env = *params;
-  int32_t *count = nullptr, *list = nullptr;
-  if (autoreset) {
-    count = reinterpret_cast<int32_t *>(workspace);
-    list = count + 4;
-    cudaError_t e = cudaMemsetAsync(count, 0, 16, stream);
-    if (e != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(reset count)");
-    p.list = list;
-    p.list_count = count;
+  if (!autoreset) return launch_env(p, env_int("RBG_ENV_E"), stream);
+
+  uint8_t *ws = reinterpret_cast<uint8_t *>(workspace);
+  if (!aligned16(ws)) return set_error(RBG_EALIGN, "workspace not 16-byte aligned");
+  const WsLayout wl = ws_layout(B, N);
+  const int kind = params->autoreset_kind;
+  const bool speculative = speculative_enabled() && (kind == RBG_GEN_PRW || kind == RBG_GEN_UNIFORM);
+  int32_t *sync_count = reinterpret_cast<int32_t *>(ws);
+  int32_t *sync_list = reinterpret_cast<int32_t *>(ws + wl.sync_list);
+  p.list = sync_list;
+  p.list_count = sync_count;
+  cudaError_t e;
+  AutoResetCtx *ctx = nullptr;
+  int par = 0;
+  if (speculative) {
+    std::lock_guard<std::mutex> lock(g_ar_mu);
+    ctx = &g_ar[workspace];
+    if (!ctx->side) {
+      if ((e = cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking)) != cudaSuccess) return set_cuda_error(e, "cudaStreamCreate(side)");
+      if ((e = cudaEventCreateWithFlags(&ctx->env_done, cudaEventDisableTiming)) != cudaSuccess) return set_cuda_error(e, "cudaEventCreate");
+      for (int i = 0; i < 2; ++i)
+        if ((e = cudaEventCreateWithFlags(&ctx->refill_done[i], cudaEventDisableTiming)) != cudaSuccess) return set_cuda_error(e, "cudaEventCreate");
+    }
+    if (ctx->B != B || ctx->G != G || ctx->N != N || ctx->kind != kind) {
+      // first use of this workspace (or a different batch in it): nothing cached yet.
+      // Pending refills of the previous occupant must not land after the clear.
+      for (int i = 0; i < 2; ++i)
+        if (ctx->refill_pending[i]) {
+          cudaStreamWaitEvent(stream, ctx->refill_done[i], 0);
+          ctx->refill_pending[i] = false;
+        }
+      // warm start: the next episode of EVERY env, one bulk generation keyed by the
+      // current State.key (a cold cache would send each env's first reset down the
+      // synchronous path)
+      PrwParams q;
+      memset(&q, 0, sizeof(q));
+      q.keys = in->key;
+      q.B = B;
+      q.G = G;
+      q.N = N;
+      q.mode = kind == RBG_GEN_PRW ? PRW_MODE_STATE : PRW_MODE_UNIFORM;
+      q.extra_split = (kind == RBG_GEN_PRW ? 1 : 0) + 1;
+      q.debug = debug_flags();
+      q.to_cache = 1;
+      q.cache_tag = reinterpret_cast<unsigned long long *>(ws + wl.cache_tag);
+      q.cache_key = reinterpret_cast<uint2 *>(ws + wl.cache_key);
+      q.cache_pins = reinterpret_cast<uint32_t *>(ws + wl.cache_pins);
+      if ((rc = launch_prw(q, B, env_int("RBG_PRW_M"), env_int("RBG_PRW_THREADS"), stream))) return rc;
+      ctx->B = B;
+      ctx->G = G;
+      ctx->N = N;
+      ctx->kind = kind;
+      ctx->step = 0;
+    }
+    par = (int)(ctx->step & 1);
+    // the refill launched two steps ago used this parity's list buffers
+    if (ctx->refill_pending[par]) {
+      if ((e = cudaStreamWaitEvent(stream, ctx->refill_done[par], 0)) != cudaSuccess) return set_cuda_error(e, "cudaStreamWaitEvent");
+      ctx->refill_pending[par] = false;
+    }
+    p.cache_tag = reinterpret_cast<const unsigned long long *>(ws + wl.cache_tag);
+    p.cache_key = reinterpret_cast<const uint2 *>(ws + wl.cache_key);
+    p.cache_pins = reinterpret_cast<const uint32_t *>(ws + wl.cache_pins);
+    p.refill_list = reinterpret_cast<int32_t *>(ws + wl.refill_list[par]);
+    p.refill_keys = reinterpret_cast<uint32_t *>(ws + wl.refill_keys[par]);
+    p.refill_count = reinterpret_cast<int32_t *>(ws + 64 + 64 * par);
   }
+  // counters: the other parity's refill counter may still be read by a refill in flight
+  if ((e = cudaMemsetAsync(ws, 0, 64, stream)) != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(reset counter)");
+  if (speculative && (e = cudaMemsetAsync(ws + 64 + 64 * par, 0, 64, stream)) != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(refill counter)");
   if ((rc = launch_env(p, env_int("RBG_ENV_E"), stream))) return rc;
-  if (autoreset) {
-    // VmapAutoResetWrapper._auto_reset: key, _ = split(state.key); reset(key):
-    // one more leading split()[0] than a plain generator call.
-    rc = generator_state_impl(params->autoreset_kind, out->key, B, G, N, out, ts, 1, list, count, stream);
+  // VmapAutoResetWrapper._auto_reset: key, _ = split(state.key); reset(key):
+  // one more leading split()[0] than a plain generator call.
+  if ((rc = generator_state_impl(kind, out->key, B, G, N, out, ts, 1, sync_list, sync_count, stream))) return rc;
+  if (speculative) {
+    if ((e = cudaEventRecord(ctx->env_done, stream)) != cudaSuccess) return set_cuda_error(e, "cudaEventRecord");
+    if ((e = cudaStreamWaitEvent(ctx->side, ctx->env_done, 0)) != cudaSuccess) return set_cuda_error(e, "cudaStreamWaitEvent(side)");
+    PrwParams q;
+    memset(&q, 0, sizeof(q));
+    q.keys = p.refill_keys;
+    q.keys_compact = 1;
+    q.B = B;
+    q.G = G;
+    q.N = N;
+    q.mode = kind == RBG_GEN_PRW ? PRW_MODE_STATE : PRW_MODE_UNIFORM;
+    q.extra_split = (kind == RBG_GEN_PRW ? 1 : 0) + 1;  // as the auto-reset call above
+    q.debug = debug_flags();
+    q.list = p.refill_list;
+    q.list_count = p.refill_count;
+    q.to_cache = 1;
+    q.cache_tag = reinterpret_cast<unsigned long long *>(ws + wl.cache_tag);
+    q.cache_key = reinterpret_cast<uint2 *>(ws + wl.cache_key);
+    q.cache_pins = reinterpret_cast<uint32_t *>(ws + wl.cache_pins);
+    if ((rc = launch_prw(q, B, env_int("RBG_PRW_M"), env_int("RBG_PRW_THREADS"), ctx->side))) return rc;
+    if ((e = cudaEventRecord(ctx->refill_done[par], ctx->side)) != cudaSuccess) return set_cuda_error(e, "cudaEventRecord(side)");
+    ctx->refill_pending[par] = true;
+    ctx->step++;
   }
-  return rc;
+  return RBG_OK;
 }
 
 // ---- device scratch for the _host variants --------------------------------
@@ -500,8 +639,23 @@ int rbg_connector_reset(int kind, const uint32_t *keys, int64_t B, int G, int N,
 
 int64_t rbg_step_workspace_bytes(int64_t B, int G, int N) {
   (void)G;
-  (void)N;
-  return 16 + 4 * (B > 0 ? B : 0);
+  return (int64_t)ws_layout(B, N).total;
+}
+
+int rbg_workspace_release(void *workspace) {
+  std::lock_guard<std::mutex> lock(g_ar_mu);
+  auto it = g_ar.find(workspace);
+  if (it == g_ar.end()) return RBG_OK;
+  AutoResetCtx &c = it->second;
+  if (c.side) {
+    cudaStreamSynchronize(c.side);
+    cudaStreamDestroy(c.side);
+    cudaEventDestroy(c.env_done);
+    cudaEventDestroy(c.refill_done[0]);
+    cudaEventDestroy(c.refill_done[1]);
+  }
+  g_ar.erase(it);
+  return RBG_OK;
 }
 
 int rbg_connector_step(const rbg_state *in, const rbg_state *out, const int32_t *action, int64_t B, int G, int N,
@@ -650,14 +804,15 @@ int rbg_connector_step_host(const rbg_state *in, const rbg_state *out, const int
   carve_state(size, B, G, N, &ds);
   carve_timestep(size, B, G, N, &dt);
   size.take<int32_t>((size_t)B * N);
-  size.take<uint8_t>((size_t)(nslices * (16 + 4 * sl)));
+  const size_t ws_bytes = (size_t)rbg_step_workspace_bytes(sl, G, N);
+  size.take<uint8_t>((size_t)nslices * ws_bytes);
   void *base;
   if ((rc = scratch_get(size.off + 256, dev, &base))) return rc;
   Carver c{reinterpret_cast<uint8_t *>(base)};
   carve_state(c, B, G, N, &ds);
   carve_timestep(c, B, G, N, &dt);
   int32_t *da = c.take<int32_t>((size_t)B * N);
-  uint8_t *ws = c.take<uint8_t>((size_t)(nslices * (16 + 4 * sl)));
+  uint8_t *ws = c.take<uint8_t>((size_t)nslices * ws_bytes);
   int si = 0;
   for (int64_t off = 0; off < B; off += sl, ++si) {
     const int64_t n = (B - off) < sl ? (B - off) : sl;
@@ -666,7 +821,7 @@ int rbg_connector_step_host(const rbg_state *in, const rbg_state *out, const int
     RBG_CPY(da + off * N, action + off * N, n * N * 4, cudaMemcpyHostToDevice, st);
     rbg_state dss = state_at(ds, off, G, N);
     rbg_timestep dts = timestep_at(dt, off, G, N);
-    if ((rc = rbg_connector_step(&dss, &dss, da + off * N, n, G, N, params, &dts, ws + (size_t)si * (16 + 4 * sl), st)))
+    if ((rc = rbg_connector_step(&dss, &dss, da + off * N, n, G, N, params, &dts, ws + (size_t)si * ws_bytes, st)))
       return rc;
     if ((rc = copy_state(out, &ds, off, n, G, N, cudaMemcpyDeviceToHost, off, st))) return rc;
     if ((rc = copy_timestep(ts, &dt, off, n, G, N, cudaMemcpyDeviceToHost, off, st))) return rc;

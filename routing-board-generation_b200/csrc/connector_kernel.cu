@@ -28,7 +28,8 @@ struct EnvSmem {
   int *flag;      // [E*N] bit0 was_connected, bit1 win, bit2 done, bits 4..7 mask
   float *rew;     // [E*N]
   int *cnt;       // [E*4] path cells, #done, #connected, #moved
-  int *term;      // [E]   bit0 terminal, bit1 skip (auto-reset takes over)
+  int *term;      // [E]   bit0 terminal, bit1 skip (the reset kernel takes over), bit2 cached episode swapped in
+  int *anyhit;    // [1]   some env of this CTA swaps in a cached episode
 };
 
 __host__ __device__ inline size_t env_carve(int E, int N, int cells,
@@ -43,7 +44,7 @@ __host__ __device__ inline size_t env_carve(int E, int N, int cells,
   size_t o_grid = take((size_t)E * cells);
   size_t o_pos = take(en * 4), o_tgt = take(en * 4), o_dest = take(en * 4);
   size_t o_flag = take(en * 4), o_rew = take(en * 4);
-  size_t o_cnt = take((size_t)E * 16), o_term = take((size_t)E * 4);
+  size_t o_cnt = take((size_t)E * 16), o_term = take((size_t)E * 4), o_any = take(16);
   if (s) {
     s->grid = base + o_grid;
     s->pos = reinterpret_cast<int *>(base + o_pos);
@@ -53,6 +54,7 @@ __host__ __device__ inline size_t env_carve(int E, int N, int cells,
     s->rew = reinterpret_cast<float *>(base + o_rew);
     s->cnt = reinterpret_cast<int *>(base + o_cnt);
     s->term = reinterpret_cast<int *>(base + o_term);
+    s->anyhit = reinterpret_cast<int *>(base + o_any);
   }
   return off;
 }
@@ -95,6 +97,7 @@ __global__ void __launch_bounds__(256) env_kernel(const EnvParams p) {
   env_carve(E, N, cells, smem_raw, &s);
 
   for (int i = tid; i < E * 4; i += nt) s.cnt[i] = 0;
+  if (tid == 0) *s.anyhit = 0;
   __syncthreads();
 
   // ---- phase 1: State.grid int32 -> uint8 shared memory, count PATH cells
@@ -200,23 +203,98 @@ __global__ void __launch_bounds__(256) env_kernel(const EnvParams p) {
     const int sc = p.in.step_count[e] + (is_step ? 1 : 0);
     const int nconn = s.cnt[4 * m + 2];
     const bool terminal = is_step && (s.cnt[4 * m + 1] == N || sc >= p.env.time_limit);
-    const bool skip = terminal && autoreset;
-    s.term[m] = (terminal ? 1 : 0) | (skip ? 2 : 0);
+    int tflag = terminal ? 1 : 0;
+    uint32_t k0 = 0, k1 = 0;
+    if (is_step) {
+      k0 = p.in.key[2 * e];
+      k1 = p.in.key[2 * e + 1];
+    }
+    if (terminal && autoreset) {
+      // VmapAutoResetWrapper: key, _ = split(state.key); reset(key).  If the next
+      // episode was generated ahead of time (tagged with this episode's key) it is
+      // swapped in below; otherwise the env goes to the reset kernel's list.
+      bool hit = false;
+      uint32_t nk0, nk1;
+      if (p.cache_tag) {
+        const unsigned long long tag = __ldcg(p.cache_tag + e);
+        if (tag == (((unsigned long long)k1 << 32) | k0)) {
+          __threadfence();
+          const uint2 nk = __ldcg(p.cache_key + e);
+          nk0 = nk.x;
+          nk1 = nk.y;
+          hit = true;
+        }
+      }
+      if (!hit) {  // State.key of the next episode: split(split(key)[0])[0]
+        uint32_t a0, a1, b0, b1;
+        split2(k0, k1, a0, a1, b0, b1);
+        split2(a0, a1, nk0, nk1, b0, b1);
+        p.list[atomicAdd(p.list_count, 1)] = (int32_t)e;
+      } else {
+        *s.anyhit = 1;
+        k0 = nk0;
+        k1 = nk1;
+      }
+      if (p.refill_list) {
+        const int slot = atomicAdd(p.refill_count, 1);
+        p.refill_list[slot] = (int32_t)e;
+        p.refill_keys[2 * slot] = nk0;
+        p.refill_keys[2 * slot + 1] = nk1;
+      }
+      tflag |= hit ? 4 : 2;
+    }
+    s.term[m] = tflag;
     p.ts.step_type[e] = (int8_t)(is_step ? (terminal ? 2 : 1) : 0);
     p.ts.num_connections[e] = nconn;
     p.ts.ratio_connections[e] = __fdiv_rn((float)nconn, (float)N);
     p.ts.total_path_length[e] = s.cnt[4 * m] + s.cnt[4 * m + 3] + N;
-    if (!skip) p.ts.obs_step_count[e] = sc;
+    if (!(tflag & 2)) p.ts.obs_step_count[e] = (tflag & 4) ? 0 : sc;
     if (is_step) {
-      p.out.step_count[e] = sc;
-      if (p.out.key != p.in.key) {
-        p.out.key[2 * e] = p.in.key[2 * e];
-        p.out.key[2 * e + 1] = p.in.key[2 * e + 1];
+      p.out.step_count[e] = (tflag & 4) ? 0 : sc;
+      if (p.out.key != p.in.key || (tflag & 4)) {
+        p.out.key[2 * e] = k0;
+        p.out.key[2 * e + 1] = k1;
       }
-      if (skip) p.list[atomicAdd(p.list_count, 1)] = (int32_t)e;
     }
   }
   __syncthreads();
+  if (*s.anyhit) {
+    // ---- phase 3b: swap in the cached episodes: pins-only grid (heads, then
+    // targets: PRWG:63-64), position = start, fresh action mask.  Reward, discount,
+    // step_type and extras stay those of the terminal step.
+    for (int i = tid; i < Ec * cells; i += nt) {
+      const int m = (int)p.divCells.div((uint32_t)i);
+      if (s.term[m] & 4) s.grid[i] = 0;
+    }
+    for (int t = tid; t < Ec * N; t += nt) {
+      const int m = (int)p.divN.div((uint32_t)t);
+      if (s.term[m] & 4) {
+        const uint32_t pin = __ldcg(p.cache_pins + env0 * N + t);
+        s.pos[t] = (int)(pin >> 16);
+        s.tgt[t] = (int)(pin & 0xffffu);
+      }
+    }
+    __syncthreads();
+    for (int t = tid; t < Ec * N; t += nt) {
+      const int m = (int)p.divN.div((uint32_t)t), a = t - m * N;
+      if (s.term[m] & 4) s.grid[(size_t)m * cells + (s.pos[t] >> 8) * G + (s.pos[t] & 255)] = (uint8_t)(3 * a + POSITION);
+    }
+    __syncthreads();
+    for (int t = tid; t < Ec * N; t += nt) {
+      const int m = (int)p.divN.div((uint32_t)t), a = t - m * N;
+      if (s.term[m] & 4) s.grid[(size_t)m * cells + (s.tgt[t] >> 8) * G + (s.tgt[t] & 255)] = (uint8_t)(3 * a + TARGET);
+    }
+    __syncthreads();
+    for (int t = tid; t < Ec * N; t += nt) {
+      const int m = (int)p.divN.div((uint32_t)t), a = t - m * N;
+      if (s.term[m] & 4) {
+        SmemGrid sg{s.grid + (size_t)m * cells, G, 0, G};
+        const uint32_t mk = move_mask(sg, s.pos[t] >> 8, s.pos[t] & 255, a, s.pos[t] == s.tgt[t]);
+        s.flag[t] = (s.flag[t] & 15) | (int)(mk << 4);
+      }
+    }
+    __syncthreads();
+  }
   for (int t = tid; t < Ec * N; t += nt) {
     const int m = (int)p.divN.div((uint32_t)t);
     const long long ga = env0 * N + t;
@@ -226,8 +304,13 @@ __global__ void __launch_bounds__(256) env_kernel(const EnvParams p) {
     p.ts.discount[ga] = is_step ? (((term & 1) || (fl & 4)) ? 0.0f : 1.0f) : 1.0f;
     if (!(term & 2)) store_mask5(p.ts.action_mask + ga * 5, (uint32_t)(fl >> 4) & 15u);
     if (is_step) {
-      reinterpret_cast<int2 *>(p.out.position)[ga] = make_int2(s.pos[t] >> 8, s.pos[t] & 255);
-      if (p.out.target != p.in.target) {
+      const int2 pos2 = make_int2(s.pos[t] >> 8, s.pos[t] & 255);
+      reinterpret_cast<int2 *>(p.out.position)[ga] = pos2;
+      if (term & 4) {
+        reinterpret_cast<int2 *>(p.out.target)[ga] = make_int2(s.tgt[t] >> 8, s.tgt[t] & 255);
+        reinterpret_cast<int2 *>(p.out.start)[ga] = pos2;
+        p.out.agent_id[ga] = t - m * N;
+      } else if (p.out.target != p.in.target) {
         reinterpret_cast<int2 *>(p.out.target)[ga] = make_int2(s.tgt[t] >> 8, s.tgt[t] & 255);
         reinterpret_cast<int2 *>(p.out.start)[ga] = reinterpret_cast<const int2 *>(p.in.start)[ga];
         p.out.agent_id[ga] = p.in.agent_id[ga];
@@ -238,26 +321,35 @@ __global__ void __launch_bounds__(256) env_kernel(const EnvParams p) {
   // ---- phase 4: bulk outputs: State.grid and observation.grid
   const int n3 = 3 * N;
   if (VEC) {
+    // A thread owns one packed word (4 cells) of one env: it writes the State
+    // row chunk once and then that chunk's N per-agent views.  Agent a+1's
+    // view is agent a's minus 3 with wrap-around (JUM env.py _obs_from_grid);
+    // EMPTY cells carry decrement 0 and an unreachable wrap bound, so they stay 0.
     const int c4 = cells >> 2;
     const uint32_t *g32 = reinterpret_cast<const uint32_t *>(s.grid);
-    if (is_step) {
-      int4 *dst = reinterpret_cast<int4 *>(p.out.grid) + env0 * c4;
-      for (int q = tid; q < Ec * c4; q += nt) {
-        const int m = (int)p.divC4.div((uint32_t)q);
-        if (s.term[m] & 2) continue;
-        dst[q] = bytes_to_int4(g32[q]);
-      }
-    }
+    int4 *gdst = reinterpret_cast<int4 *>(p.out.grid) + env0 * c4;
     int4 *odst = reinterpret_cast<int4 *>(p.ts.obs_grid) + env0 * N * c4;
-    for (int idx = tid; idx < Ec * N * c4; idx += nt) {
-      const uint32_t slice = p.divC4.div((uint32_t)idx);
-      const int q = idx - (int)slice * c4;
-      const int m = (int)p.divN.div(slice), a = (int)slice - m * N;
+    for (int idx = tid; idx < Ec * c4; idx += nt) {
+      const int m = (int)p.divC4.div((uint32_t)idx);
       if (s.term[m] & 2) continue;
-      const uint32_t w = g32[m * c4 + q];
-      const int a3 = 3 * a;
-      odst[idx] = make_int4(obs_value((int)(w & 0xffu), a3, n3), obs_value((int)((w >> 8) & 0xffu), a3, n3),
-                            obs_value((int)((w >> 16) & 0xffu), a3, n3), obs_value((int)(w >> 24), a3, n3));
+      const uint32_t w = g32[idx];
+      int t0 = (int)(w & 0xffu), t1 = (int)((w >> 8) & 0xffu), t2 = (int)((w >> 16) & 0xffu), t3 = (int)(w >> 24);
+      if (is_step) gdst[idx] = make_int4(t0, t1, t2, t3);
+      const int d0 = t0 ? 3 : 0, d1 = t1 ? 3 : 0, d2 = t2 ? 3 : 0, d3 = t3 ? 3 : 0;
+      const int l0 = t0 ? 1 : -4, l1 = t1 ? 1 : -4, l2 = t2 ? 1 : -4, l3 = t3 ? 1 : -4;
+      int4 *o = odst + (size_t)m * N * c4 + (idx - m * c4);
+#pragma unroll 4
+      for (int a = 0; a < N; ++a, o += c4) {
+        *o = make_int4(t0, t1, t2, t3);
+        t0 -= d0;
+        t1 -= d1;
+        t2 -= d2;
+        t3 -= d3;
+        t0 += (t0 < l0) ? n3 : 0;
+        t1 += (t1 < l1) ? n3 : 0;
+        t2 += (t2 < l2) ? n3 : 0;
+        t3 += (t3 < l3) ? n3 : 0;
+      }
     }
   } else {
     if (is_step) {
@@ -305,8 +397,8 @@ int launch_env(EnvParams p, int force_E, cudaStream_t stream) {
   const int G = p.G, N = p.N;
   p.cells = G * G;
   const bool vec = (p.cells & 3) == 0;
-  // ~32 KB of observation per CTA keeps the slab contiguous and the grid large
-  int E = (int)(32768 / ((int64_t)N * p.cells * 4));
+  // envs per CTA: about two packed words per thread in the bulk phases
+  int E = vec ? 512 / (p.cells >> 2) : (int)(32768 / ((int64_t)N * p.cells * 4));
   if (E < 1) E = 1;
   if (E > 32) E = 32;
   if (force_E > 0) E = force_E;

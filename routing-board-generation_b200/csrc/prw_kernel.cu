@@ -89,8 +89,9 @@ __global__ void __launch_bounds__(256) prw_kernel(const PrwParams p) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nthreads = blockDim.x, nwarps = nthreads >> 5;
   const long long total = p.list ? (long long)(*p.list_count) : p.B;
-  const long long base = (long long)blockIdx.x * p.M;
-  if (base >= total) return;
+  // CTAs stride over pools of M boards (list launches are sized for the worst case
+  // but usually hold a few percent of the batch)
+  for (long long base = (long long)blockIdx.x * p.M; base < total; base += (long long)gridDim.x * p.M) {
   const int Mc = (int)((total - base) < (long long)p.M ? (total - base) : (long long)p.M);
 
   PrwSmem s;
@@ -114,7 +115,8 @@ __global__ void __launch_bounds__(256) prw_kernel(const PrwParams p) {
     const uint32_t c = tid & 1u;
     const int mm = m < Mc ? m : Mc - 1;
     const long long e = p.list ? (long long)p.list[base + mm] : base + mm;
-    uint32_t k0 = p.keys[2 * e], k1 = p.keys[2 * e + 1];
+    const long long ki = p.keys_compact ? base + mm : e;
+    uint32_t k0 = p.keys[2 * ki], k1 = p.keys[2 * ki + 1];
     uint32_t o0, o1;
     for (int sp = 0; sp < p.extra_split; ++sp) {  // key = split(key)[0]
       tf_block(k0, k1, c, c + 2u, o0, o1);
@@ -316,6 +318,23 @@ __global__ void __launch_bounds__(256) prw_kernel(const PrwParams p) {
   for (int m = warp; m < Mc; m += nwarps) {
     const long long e = p.list ? (long long)p.list[base + m] : base + m;
     const uint8_t *g = s.grid + (size_t)m * SBp;
+    if (p.to_cache) {
+      // auto-reset cache entry: (start, target) pins + State.key of this episode,
+      // published under the key of the episode it succeeds (tag written last)
+      if (lane < N) {
+        const uint32_t st_ = s.start[m * Np + lane], fi = s.fin[m * Np + lane];
+        p.cache_pins[e * N + lane] = (st_ << 16) | fi;
+      }
+      if (lane == 0) p.cache_key[e] = make_uint2(s.k0[2 * m], s.k0[2 * m + 1]);
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) {
+        const long long ki = p.keys_compact ? base + m : e;
+        const unsigned long long tag = ((unsigned long long)p.keys[2 * ki + 1] << 32) | p.keys[2 * ki];
+        *reinterpret_cast<volatile unsigned long long *>(p.cache_tag + e) = tag;
+      }
+      continue;
+    }
     int32_t *gout = (p.mode == PRW_MODE_BOARD ? p.solved : p.st.grid) + e * cells;
     if (vec) {
       int4 *o = reinterpret_cast<int4 *>(gout);
@@ -378,6 +397,8 @@ __global__ void __launch_bounds__(256) prw_kernel(const PrwParams p) {
       warp_write_obs(sg, N, p.divG, p.ts.obs_grid + (size_t)e * N * cells, lane);
     }
   }
+  __syncthreads();  // shared memory is reused by the next pool
+  }
 }
 
 // ---------------------------------------------------------------- host side
@@ -425,8 +446,9 @@ int launch_prw(PrwParams p, int64_t max_boards, int force_M, int force_threads,
     cudaError_t e = cudaFuncSetAttribute(prw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(prw_kernel)");
   }
-  const int64_t ctas = (max_boards + M - 1) / M;
+  int64_t ctas = (max_boards + M - 1) / M;
   if (ctas <= 0) return RBG_OK;
+  if (p.list && ctas > 148 * 16) ctas = 148 * 16;  // the kernel strides; an empty list costs ~2 us
   {
     LaunchScope scope(RBG_K_PRW, stream);
     prw_kernel<<<(unsigned)ctas, threads, smem, stream>>>(p);

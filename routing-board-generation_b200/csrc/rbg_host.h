@@ -40,6 +40,12 @@ struct PrwParams {
   rbg_timestep ts;
   const int32_t *list;        // optional env list (auto-reset)
   const int32_t *list_count;  // device count of list entries
+  // auto-reset cache refill: keys[] is indexed by list slot (not env id) and the
+  // result goes to the env's cache entry instead of State / TimeStep
+  int keys_compact, to_cache;
+  unsigned long long *cache_tag;  // [B]   state.key this entry succeeds (k0 | k1 << 32)
+  uint2 *cache_key;               // [B]   State.key of the cached episode
+  uint32_t *cache_pins;           // [B,N] start_r<<24 | start_c<<16 | target_r<<8 | target_c
   // filled by launch_prw
   int W, S, SBp, cells, M, cap, Np, nsel;
   uint32_t thresh;
@@ -64,6 +70,14 @@ struct EnvParams {
   rbg_env_params env;
   int32_t *list;        // auto-reset list (device), may be NULL
   int32_t *list_count;  // device counter
+  // speculative auto-reset (c_api.cu "AutoReset"): envs whose next episode is
+  // already in the cache swap it in here; every finished env is queued for refill
+  const unsigned long long *cache_tag;
+  const uint2 *cache_key;
+  const uint32_t *cache_pins;
+  int32_t *refill_list;    // [B]
+  int32_t *refill_count;   // [1]
+  uint32_t *refill_keys;   // [B,2] State.key of the episode that just started
   // filled by launch_env
   int cells, E;
   FastDiv divN, divG, divC4, divCells;

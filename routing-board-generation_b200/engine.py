@@ -209,12 +209,14 @@ def connector_reset(kind, keys: torch.Tensor, G: int, N: int) -> Tuple[State, Ti
     return st, ts
 
 
-_workspaces: Dict[Tuple[int, int], torch.Tensor] = {}
+_workspaces: Dict[Tuple[int, int, int, int], torch.Tensor] = {}
 
 
 def _workspace(B: int, G: int, N: int) -> torch.Tensor:
+    """Auto-reset scratch of one env batch shape; kept alive for the process (the library's side
+    stream may still be filling it when the caller drops its last State)."""
     dev = _device()
-    k = (dev.index, B)
+    k = (dev.index, B, G, N)
     if k not in _workspaces:
         nbytes = int(_lib.load().rbg_step_workspace_bytes(B, G, N))
         _workspaces[k] = torch.empty((nbytes + 15) // 16 * 16, dtype=torch.uint8, device=dev)

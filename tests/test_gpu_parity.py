@@ -96,6 +96,38 @@ def test_reference_goldens_on_gpu(rbg, goldens):
     assert _np(st.key).tolist() == g["key"]
 
 
+def test_reference_runs_on_gpu(rbg):
+    """The CUDA path against outputs of the reference's own Python source (tests/golden/reference_runs.json,
+    made by tests/tools/make_reference_fixtures.py): collisions, SeedExtension options, generator States."""
+    import json
+    import os
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_runs.json")) as f:
+        runs = json.load(f)
+    for cfg in runs["prw_generate_board"]:
+        keys = rbg.split(rbg.PRNGKey(cfg["seed"]), cfg["n"])
+        heads, targets, solved = rbg.ParallelRandomWalkBoard(cfg["G"], cfg["G"], cfg["N"]).generate_board(keys)
+        assert _np(solved).tolist() == [r["solved"] for r in cfg["boards"]]
+        assert _np(heads).tolist() == [r["heads"] for r in cfg["boards"]]
+        assert _np(targets).tolist() == [r["targets"] for r in cfg["boards"]]
+    gens = {"parallel_random_walk": rbg.ParallelRandomWalkGenerator, "uniform": rbg.UniformRandomGenerator, "seed_extension": rbg.SeedExtensionGenerator}
+    for cfg in runs["generator_states"]:
+        keys = rbg.split(rbg.PRNGKey(cfg["seed"]), cfg["n"])
+        st = gens[cfg["kind"]](cfg["G"], cfg["N"])(keys)
+        assert _np(st.grid).tolist() == [r["grid"] for r in cfg["states"]], cfg["kind"]
+        assert _np(st.key).tolist() == [r["key"] for r in cfg["states"]]
+        assert _np(st.agents.start).tolist() == [r["start"] for r in cfg["states"]]
+        assert _np(st.agents.target).tolist() == [r["target"] for r in cfg["states"]]
+    for cfg in runs["seedext_solved"]:
+        keys = rbg.split(rbg.PRNGKey(cfg["seed"]), cfg["n"])
+        board = rbg.SeedExtensionBoard(cfg["G"], cfg["G"], cfg["N"])
+        solved = board.return_solved_board(keys, **cfg["options"])
+        assert _np(solved).tolist() == [r["solved"] for r in cfg["boards"]], cfg["options"]
+        (sr, sc), (er, ec) = board.generate_starts_ends(keys, **cfg["options"])
+        assert _np(sr).tolist() == [r["starts"][0] for r in cfg["boards"]] and _np(sc).tolist() == [r["starts"][1] for r in cfg["boards"]]
+        assert _np(er).tolist() == [r["ends"][0] for r in cfg["boards"]] and _np(ec).tolist() == [r["ends"][1] for r in cfg["boards"]]
+
+
 @pytest.mark.parametrize("G,N", PRW_CONFIGS)
 def test_prw_generate_matches_oracle(rbg, orc, G, N):
     B = 2048 if G <= 20 else 512
@@ -286,6 +318,34 @@ def test_connector_step_matches_oracle(rbg, orc, kind, G, N):
 def test_connector_autoreset_matches_oracle(rbg, orc, kind):
     n_last = _rollout(rbg, orc, kind, 10, 5, B=2048, steps=60, autoreset=True, time_limit=25)
     assert n_last > 2048  # every env has been through at least one auto-reset
+
+
+@pytest.mark.parametrize("kind", ["parallel_random_walk", "uniform", "seed_extension"])
+@pytest.mark.parametrize("time_limit", [1, 2, 3])
+def test_connector_autoreset_back_to_back_terminations(rbg, orc, kind, time_limit):
+    """Every env finishes every `time_limit` steps: the speculative next-episode cache is consumed
+    as fast as it can be refilled, so both the cached and the synchronous reset path run."""
+    _rollout(rbg, orc, kind, 10, 5, B=700, steps=12, autoreset=True, time_limit=time_limit, seed=17 + time_limit)
+
+
+def test_connector_autoreset_two_batches_share_nothing(rbg, orc):
+    """Two env batches stepped alternately (different workspaces by shape) stay independent."""
+    import torch
+
+    envs, states, refs = [], [], []
+    for (G, N, B, seed) in ((10, 5, 512, 1), (8, 4, 384, 2)):
+        keys, kref = _keys(rbg, orc, seed, B)
+        env = rbg.VmapAutoResetWrapper(rbg.Connector(generator=rbg.ParallelRandomWalkGenerator(G, N), time_limit=6))
+        st, _ = env.reset(keys)
+        rst, _ = orc.connector_reset_batch("parallel_random_walk", kref, G, N)
+        envs.append(env), states.append(st), refs.append(rst)
+    for t in range(20):
+        for i in range(2):
+            act = orc.random_actions_batch(refs[i])
+            states[i], ts = envs[i].step(states[i], torch.from_numpy(act).cuda())
+            refs[i], rts = orc.connector_step_batch(refs[i], act, time_limit=6, autoreset_kind="parallel_random_walk")
+            _assert_state(states[i], refs[i], f"batch {i} step {t}")
+            _assert_timestep(ts, rts, f"batch {i} step {t}")
 
 
 def test_connector_autoreset_32x32(rbg, orc):
