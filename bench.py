@@ -136,12 +136,21 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def step():
-        nonlocal state, ts
-        state, ts, _ = engine.connector_step(state, None, TIME_LIMIT, -0.03, 0.1, autoreset_kind="parallel_random_walk", inplace=True, random_policy=True, out=ts)
+    # The timed loop drives the engine the way the reference's training / benchmark loop does: a
+    # scan of `n_steps` = 20 env steps per call (configs/env/connector.yaml:27), here one
+    # rbg_connector_rollout_random call per chunk writing stacked [20, B, ...] TimeSteps.
+    chunk = args.chunk
+    ts = engine.alloc_timestep(B, G, N, chunk)
+    act = torch.empty((chunk, B, N), dtype=torch.int32, device=dev)
 
-    for _ in range(max(args.warmup, 3)):
-        step()
+    def run_steps(k):
+        nonlocal state
+        while k > 0:
+            n = min(k, chunk)
+            engine.connector_rollout_random(state, n, TIME_LIMIT, -0.03, 0.1, autoreset_kind="parallel_random_walk", out=ts, actions=act)
+            k -= n
+
+    run_steps(max(args.warmup, 3))
     sync_all()
 
     # ---- timed region: exactly K steps, device-timed, max over ranks
@@ -152,8 +161,7 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
     e0.record()
-    for _ in range(args.steps):
-        step()
+    run_steps(args.steps)
     e1.record()
     sync_all()
     launches = rbg.launch_count()
@@ -169,8 +177,7 @@ def run_ours(args):
     rbg._lib.kernel_timing(True)
     for k in ("env", "prw"):
         rbg._lib.kernel_time(k)
-    for _ in range(args.steps):
-        step()
+    run_steps(args.steps)
     torch.cuda.synchronize()
     n_env, ms_env = rbg._lib.kernel_time("env")
     n_prw, ms_prw = rbg._lib.kernel_time("prw")
@@ -201,6 +208,7 @@ def run_ours(args):
             "data": "synthetic (keys = split(PRNGKey(0), B), random-policy actions)",
             "config": {"workload": "connector_step_random_agent_autoreset_prw", "grid": G, "agents": N, "envs_per_gpu": B, "envs_total": total, "time_limit": TIME_LIMIT,
                        "generator": "ParallelRandomWalkGenerator", "parallelism": f"env-sharded x{world}",
+                       "api": f"rbg_connector_rollout_random, {chunk}-step chunks (the reference's n_steps scan), State in place, stacked TimeSteps",
                        "l2": f"no flush: per-step traffic {STEP_BYTES * B / 1e6:.0f} MB per GPU exceeds the 126 MB L2"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "secondary": secondary,
         }
@@ -288,6 +296,24 @@ def _secondary_prw(args, rbg, peak):
         bytes_ = PRW_BOARD_BYTES[(g, n)] * b
         out.append({"metric": "prw_solved_boards_per_sec", "workload": f"ParallelRandomWalkBoard.generate_board {g}x{g}/{n} B={b}", "value": round(b / (ms / 1e3), 1), "unit": "boards/s", "ms_per_batch": round(ms, 4),
                     "output_gbs": round(bytes_ / (ms / 1e3) / 1e9, 2), "hbm_frac": round(bytes_ / (ms / 1e3) / 1e9 / peak, 5), "bound": "integer issue (threefry2x32), see DESIGN.md"})
+    # SeedExtension 14x14/7 (BASELINE configs[3]): generation + on-device validity of every board
+    g, n, b = 14, 7, 65536
+    keys = rbg.split(rbg.PRNGKey(0), b)
+    board = rbg.SeedExtensionBoard(g, g, n)
+    for _ in range(2):
+        solved = board.return_solved_board(keys)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        solved = board.return_solved_board(keys)
+        flags = rbg.engine.validate(solved, n)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    out.append({"metric": "seedext_solved_boards_per_sec", "workload": f"SeedExtensionBoard.return_solved_board {g}x{g}/{n} B={b} + rbg_validate", "value": round(b / (ms / 1e3), 1), "unit": "boards/s",
+                "ms_per_batch": round(ms, 4), "invalid_boards": int((flags != 0).sum()), "bound": "sequential threefry chain per board (one lane per board), see DESIGN.md"})
     return out
 
 
@@ -296,12 +322,13 @@ def _cpu_workload(orc, B, nthreads):
     """reset B envs with the oracle and return a stepping closure (random policy + auto-reset step)."""
     kref = orc.split(orc.PRNGKey(0), B)
     st, _ = orc.connector_reset_batch("parallel_random_walk", kref, G, N, nthreads=nthreads)
-    box = {"st": st}
+    box = {"st": st, "ts": None}
 
     def step():
         act = orc.random_actions_batch(box["st"], nthreads=nthreads)
-        box["st"], ts = orc.connector_step_batch(box["st"], act, time_limit=TIME_LIMIT, autoreset_kind="parallel_random_walk", nthreads=nthreads, inplace=True)
-        return ts
+        # state updated in place, timestep buffers reused: no allocation inside the timed loop
+        box["st"], box["ts"] = orc.connector_step_batch(box["st"], act, time_limit=TIME_LIMIT, autoreset_kind="parallel_random_walk", nthreads=nthreads, inplace=True, out=box["ts"])
+        return box["ts"]
 
     return step
 
@@ -364,6 +391,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
+    ap.add_argument("--chunk", type=int, default=20, help="env steps per rollout call (the reference's n_steps)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")

@@ -182,6 +182,18 @@ int rbg_connector_step_random(const rbg_state *in, const rbg_state *out,
                               const rbg_timestep *ts, void *workspace,
                               void *stream);
 
+/* T consecutive rbg_connector_step_random calls in one call: the rollout of the
+ * reference's training / benchmark loop (`n_steps` scan, agent_training/configs/
+ * env/connector.yaml:27; benchmark_on_random_agent.py:59-102) with generation,
+ * reset and stepping fused into one launch sequence.  `state` is updated in place;
+ * every field of `ts` (and action_out, may be NULL) points to arrays with an extra
+ * LEADING axis T: obs_grid[T,B,N,G,G], reward[T,B,N], step_type[T,B] ... */
+int rbg_connector_rollout_random(const rbg_state *state, int32_t *action_out,
+                                 int64_t T, int64_t B, int G, int N,
+                                 const rbg_env_params *params,
+                                 const rbg_timestep *ts, void *workspace,
+                                 void *stream);
+
 /* Board validity (numpy_implementation/utils/post_processor_utils_numpy.py:34-155,
  * board_processor.py:111-162).  flags int32[B]: 0 valid; bit0 encoding out of
  * range, bit1 head/target count, bit2 neighbour-count rule, bit3 head and

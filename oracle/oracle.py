@@ -295,8 +295,9 @@ def connector_reset_batch(kind, keys, G: int, N: int, nthreads: int = 0):
     return st, connector_observe_batch(st, nthreads)
 
 
-def connector_step_batch(state: Dict[str, np.ndarray], action, time_limit: int = 50, timestep_reward: float = -0.03, connected_reward: float = 0.1, autoreset_kind=-1, nthreads: int = 0, inplace: bool = False):
-    """Connector.step (autoreset_kind < 0) or VmapAutoResetWrapper(Connector).step."""
+def connector_step_batch(state: Dict[str, np.ndarray], action, time_limit: int = 50, timestep_reward: float = -0.03, connected_reward: float = 0.1, autoreset_kind=-1, nthreads: int = 0, inplace: bool = False, out: Optional[Dict[str, np.ndarray]] = None):
+    """Connector.step (autoreset_kind < 0) or VmapAutoResetWrapper(Connector).step.
+    `out`: a timestep dict from a previous call to write into (no fresh allocation / page faults)."""
     if isinstance(autoreset_kind, str):
         autoreset_kind = GEN_KINDS[autoreset_kind]
     if not inplace:
@@ -304,7 +305,7 @@ def connector_step_batch(state: Dict[str, np.ndarray], action, time_limit: int =
     B, G, _ = state["grid"].shape
     N = state["target"].shape[1]
     action = _i32(action).reshape(B, N)
-    ts = _alloc_timestep(B, G, N)
+    ts = _alloc_timestep(B, G, N) if out is None else out
     lib().orc_connector_step_batch(
         C.c_int64(B), C.c_int(G), C.c_int(N), _p(state["grid"], i32p), _p(state["step_count"], i32p), _p(state["start"], i32p), _p(state["target"], i32p), _p(state["position"], i32p), _p(state["key"], u32p), _p(action, i32p),
         C.c_int(time_limit), C.c_float(timestep_reward), C.c_float(connected_reward), C.c_int(autoreset_kind),

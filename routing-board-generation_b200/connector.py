@@ -135,6 +135,14 @@ class VmapAutoResetWrapper:
         return engine.connector_step(state, None, e.time_limit, e._reward_fn.timestep_reward, e._reward_fn.connected_reward, autoreset_kind=e._generator.kind, inplace=inplace, random_policy=True)
 
 
+    def rollout_random(self, state: State, n_steps: int, out: Optional[TimeStep] = None):
+        """`n_steps` random-policy steps with auto-reset in one library call: generation, reset and
+        stepping fused into one launch sequence.  Updates `state` in place; returns
+        (state, TimeStep stacked [n_steps, B, ...], actions[n_steps, B, N])."""
+        e = self._env.unwrapped
+        return engine.connector_rollout_random(state, n_steps, e.time_limit, e._reward_fn.timestep_reward, e._reward_fn.connected_reward, autoreset_kind=e._generator.kind, out=out)
+
+
 class MultiToSingleWrapper:
     """jumanji.wrappers.MultiToSingleWrapper: reward -> sum over agents, discount -> max over agents."""
 

@@ -260,7 +260,10 @@ static int connector_step_impl(const rbg_state *in, const rbg_state *out, const 
     std::lock_guard<std::mutex> lock(g_ar_mu);
     ctx = &g_ar[workspace];
     if (!ctx->side) {
-      if ((e = cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking)) != cudaSuccess) return set_cuda_error(e, "cudaStreamCreate(side)");
+      // lowest priority: the refill has a whole step of slack, env_kernel's CTAs go first
+      int prio_lo = 0, prio_hi = 0;
+      cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+      if ((e = cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, prio_lo)) != cudaSuccess) return set_cuda_error(e, "cudaStreamCreate(side)");
       if ((e = cudaEventCreateWithFlags(&ctx->env_done, cudaEventDisableTiming)) != cudaSuccess) return set_cuda_error(e, "cudaEventCreate");
       for (int i = 0; i < 2; ++i)
         if ((e = cudaEventCreateWithFlags(&ctx->refill_done[i], cudaEventDisableTiming)) != cudaSuccess) return set_cuda_error(e, "cudaEventCreate");
@@ -666,6 +669,22 @@ int rbg_connector_step(const rbg_state *in, const rbg_state *out, const int32_t 
 int rbg_connector_step_random(const rbg_state *in, const rbg_state *out, int32_t *action_out, int64_t B, int G, int N,
                               const rbg_env_params *params, const rbg_timestep *ts, void *workspace, void *stream) {
   return connector_step_impl(in, out, nullptr, action_out, 1, B, G, N, params, ts, workspace, (cudaStream_t)stream);
+}
+
+int rbg_connector_rollout_random(const rbg_state *state, int32_t *action_out, int64_t T, int64_t B, int G, int N,
+                                 const rbg_env_params *params, const rbg_timestep *ts, void *workspace, void *stream) {
+  int rc;
+  if (T < 0) return set_error(RBG_EINVAL, "rollout length T=%lld", (long long)T);
+  if ((rc = check_dims(B, G, N, 1))) return rc;
+  if ((rc = check_timestep(ts))) return rc;
+  if (((int64_t)B * N * G * G * 4) % 16 != 0) return set_error(RBG_EALIGN, "rollout: one step of obs_grid (%lld bytes) is not a multiple of 16", (long long)B * N * G * G * 4);
+  for (int64_t t = 0; t < T; ++t) {
+    const rbg_timestep tt = timestep_at(*ts, t * B, G, N);
+    rc = connector_step_impl(state, state, nullptr, action_out ? action_out + t * B * N : nullptr, 1, B, G, N, params, &tt, workspace,
+                             (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return RBG_OK;
 }
 
 int rbg_random_actions(const rbg_state *state, int64_t B, int G, int N, int32_t *action, void *stream) {

@@ -15,6 +15,8 @@
 // State once (int32 -> uint8 into shared memory) and writes State +
 // observation [N,G,G] int32 exactly once, all bulk traffic as 128-bit
 // coalesced accesses over the CTA's contiguous slab of E envs.
+#include <stdlib.h>
+
 #include "connector_device.cuh"
 #include "rbg_host.h"
 
@@ -30,7 +32,12 @@ struct EnvSmem {
   int *cnt;       // [E*4] path cells, #done, #connected, #moved
   int *term;      // [E]   bit0 terminal, bit1 skip (the reset kernel takes over), bit2 cached episode swapped in
   int *anyhit;    // [1]   some env of this CTA swaps in a cached episode
+  uint8_t *lut;   // [N*RS + 256] per-agent observation codes: lut[a*RS + v] (JUM env.py _obs_from_grid)
+  int *env3;      // [E*4] State.key (2), step_count of the CTA's envs
 };
+
+// row stride of the observation table: codes 0..3N, rounded up to whole words
+__host__ __device__ inline int obs_lut_stride(int N) { return (3 * N + 1 + 3) & ~3; }
 
 __host__ __device__ inline size_t env_carve(int E, int N, int cells,
                                             uint8_t *base, EnvSmem *s) {
@@ -45,6 +52,8 @@ __host__ __device__ inline size_t env_carve(int E, int N, int cells,
   size_t o_pos = take(en * 4), o_tgt = take(en * 4), o_dest = take(en * 4);
   size_t o_flag = take(en * 4), o_rew = take(en * 4);
   size_t o_cnt = take((size_t)E * 16), o_term = take((size_t)E * 4), o_any = take(16);
+  size_t o_lut = take((size_t)N * obs_lut_stride(N) + 256);
+  size_t o_env3 = take((size_t)E * 16);
   if (s) {
     s->grid = base + o_grid;
     s->pos = reinterpret_cast<int *>(base + o_pos);
@@ -55,12 +64,24 @@ __host__ __device__ inline size_t env_carve(int E, int N, int cells,
     s->cnt = reinterpret_cast<int *>(base + o_cnt);
     s->term = reinterpret_cast<int *>(base + o_term);
     s->anyhit = reinterpret_cast<int *>(base + o_any);
+    s->lut = base + o_lut;
+    s->env3 = reinterpret_cast<int *>(base + o_env3);
   }
   return off;
 }
 
 __device__ __forceinline__ int is_path_code(int v) {
   return (v > 0 && (v - 1) % 3 == 0) ? 1 : 0;
+}
+
+// number of PATH codes (v % 3 == 1) among the four byte codes of a packed word,
+// two 16-bit lanes at a time: x / 3 == (x * 171) >> 9 for x < 256
+__device__ __forceinline__ int count_path_codes(uint32_t w) {
+  const uint32_t e = w & 0x00FF00FFu, o = (w >> 8) & 0x00FF00FFu;
+  const uint32_t re = e - 3u * (((e * 171u) >> 9) & 0x007F007Fu);
+  const uint32_t ro = o - 3u * (((o * 171u) >> 9) & 0x007F007Fu);
+  const uint32_t ie = re & ~(re >> 1) & 0x00010001u, io = ro & ~(ro >> 1) & 0x00010001u;
+  return __popc(ie | (io << 1));
 }
 
 // uniform pick over the legal actions, NOOP included (include/rbg_b200.h
@@ -84,7 +105,7 @@ __device__ __forceinline__ int random_action(uint32_t k0, uint32_t k1,
 }
 
 template <bool VEC>
-__global__ void __launch_bounds__(256) env_kernel(const EnvParams p) {
+__global__ void __launch_bounds__(256, 8) env_kernel(const EnvParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int tid = threadIdx.x, nt = blockDim.x;
   const int G = p.G, N = p.N, cells = p.cells, E = p.E;
@@ -93,23 +114,53 @@ __global__ void __launch_bounds__(256) env_kernel(const EnvParams p) {
   const int Ec = (int)((p.B - env0) < (long long)E ? (p.B - env0) : (long long)E);
   const bool is_step = (p.mode == ENV_MODE_STEP);
   const bool autoreset = is_step && p.env.autoreset_kind >= 0 && p.list != nullptr;
+  const bool inplace_grid = is_step && p.out.grid == p.in.grid;
+  // shared-memory carve-up: byte offsets come from the host (launch_env)
   EnvSmem s;
-  env_carve(E, N, cells, smem_raw, &s);
+  s.grid = smem_raw;
+  s.pos = reinterpret_cast<int *>(smem_raw + p.so[0]);
+  s.tgt = reinterpret_cast<int *>(smem_raw + p.so[1]);
+  s.dest = reinterpret_cast<int *>(smem_raw + p.so[2]);
+  s.flag = reinterpret_cast<int *>(smem_raw + p.so[3]);
+  s.rew = reinterpret_cast<float *>(smem_raw + p.so[4]);
+  s.cnt = reinterpret_cast<int *>(smem_raw + p.so[5]);
+  s.term = reinterpret_cast<int *>(smem_raw + p.so[6]);
+  s.anyhit = reinterpret_cast<int *>(smem_raw + p.so[7]);
+  s.lut = smem_raw + p.so[8];
+  s.env3 = reinterpret_cast<int *>(smem_raw + p.so[9]);
 
   for (int i = tid; i < E * 4; i += nt) s.cnt[i] = 0;
   if (tid == 0) *s.anyhit = 0;
+  const int RS = obs_lut_stride(N);
+  for (int a = tid >> 5; a < N; a += nt >> 5)  // one warp per table row
+    for (int v = tid & 31; v < RS; v += 32) s.lut[a * RS + v] = v <= 3 * N ? (uint8_t)obs_value(v, 3 * a, 3 * N) : (uint8_t)0;
   __syncthreads();
 
-  // ---- phase 1: State.grid int32 -> uint8 shared memory, count PATH cells
+  // ---- phase 1: State.grid int32 -> uint8 shared memory, count PATH cells; the
+  // agents' and envs' scalars ride the same DRAM round trip
+  for (int t = tid; t < Ec * N; t += nt) {
+    const int2 ps = __ldg(reinterpret_cast<const int2 *>(p.in.position) + env0 * N + t);
+    const int2 tg = __ldg(reinterpret_cast<const int2 *>(p.in.target) + env0 * N + t);
+    s.pos[t] = (ps.x << 8) | ps.y;
+    s.tgt[t] = (tg.x << 8) | tg.y;
+    if (is_step && !p.random_policy) s.dest[t] = __ldg(p.action + env0 * N + t);
+  }
+  if (is_step)
+    for (int m = tid; m < Ec; m += nt) {
+      s.env3[4 * m] = (int)p.in.key[2 * (env0 + m)];
+      s.env3[4 * m + 1] = (int)p.in.key[2 * (env0 + m) + 1];
+      s.env3[4 * m + 2] = p.in.step_count[env0 + m];
+    }
   if (VEC) {
     const int c4 = cells >> 2;
     const int4 *src = reinterpret_cast<const int4 *>(p.in.grid) + env0 * c4;
     uint32_t *g32 = reinterpret_cast<uint32_t *>(s.grid);
     for (int q = tid; q < Ec * c4; q += nt) {
       const int4 v = __ldg(src + q);
-      g32[q] = (uint32_t)(v.x & 0xff) | ((uint32_t)(v.y & 0xff) << 8) |
-               ((uint32_t)(v.z & 0xff) << 16) | ((uint32_t)(v.w & 0xff) << 24);
-      const int np = is_path_code(v.x) + is_path_code(v.y) + is_path_code(v.z) + is_path_code(v.w);
+      const uint32_t w = (uint32_t)(v.x & 0xff) | ((uint32_t)(v.y & 0xff) << 8) |
+                         ((uint32_t)(v.z & 0xff) << 16) | ((uint32_t)(v.w & 0xff) << 24);
+      g32[q] = w;
+      const int np = count_path_codes(w);
       if (np) atomicAdd(&s.cnt[4 * p.divC4.div((uint32_t)q)], np);
     }
   } else {
@@ -125,23 +176,18 @@ __global__ void __launch_bounds__(256) env_kernel(const EnvParams p) {
   // ---- phase 2: per agent: (sample action,) move_position, is_valid_position
   for (int t = tid; t < Ec * N; t += nt) {
     const int m = (int)p.divN.div((uint32_t)t), a = t - m * N;
-    const int2 ps = reinterpret_cast<const int2 *>(p.in.position)[env0 * N + t];
-    const int2 tg = reinterpret_cast<const int2 *>(p.in.target)[env0 * N + t];
-    const int r = ps.x, c = ps.y;
-    const bool was = (r == tg.x && c == tg.y);
-    s.pos[t] = (r << 8) | c;
-    s.tgt[t] = (tg.x << 8) | tg.y;
+    const int r = s.pos[t] >> 8, c = s.pos[t] & 255;
+    const bool was = s.pos[t] == s.tgt[t];
     int dest = -1 - t, fl = was ? 1 : 0;
     if (is_step) {
       SmemGrid sg{s.grid + (size_t)m * cells, G, 0, G};
       int action;
       if (p.random_policy) {
         const uint32_t mk = move_mask(sg, r, c, a, was);
-        action = random_action(p.in.key[2 * (env0 + m)], p.in.key[2 * (env0 + m) + 1],
-                               (uint32_t)p.in.step_count[env0 + m], (uint32_t)a, mk);
+        action = random_action((uint32_t)s.env3[4 * m], (uint32_t)s.env3[4 * m + 1], (uint32_t)s.env3[4 * m + 2], (uint32_t)a, mk);
         if (p.action_out) p.action_out[env0 * N + t] = action;
       } else {
-        action = p.action[env0 * N + t];
+        action = s.dest[t];
       }
       const int am = action < 0 ? 0 : (action > 4 ? 4 : action);  // lax.switch clamps
       const int nr = r + (am == UP ? -1 : (am == DOWN ? 1 : 0));
@@ -172,6 +218,11 @@ __global__ void __launch_bounds__(256) env_kernel(const EnvParams p) {
         uint8_t *g = s.grid + (size_t)m * cells;
         g[pr * G + pcol] = (uint8_t)(3 * a + PATH);
         g[d] = (uint8_t)(3 * a + POSITION);
+        if (inplace_grid) {  // State.grid updated in place: only these two cells change
+          int32_t *gg = p.out.grid + (env0 + m) * cells;
+          gg[pr * G + pcol] = 3 * a + PATH;
+          gg[d] = 3 * a + POSITION;
+        }
         uint32_t nr, nc;
         p.divG.divmod((uint32_t)d, nr, nc);
         s.pos[t] = (int)((nr << 8) | nc);
@@ -200,14 +251,14 @@ __global__ void __launch_bounds__(256) env_kernel(const EnvParams p) {
   __syncthreads();
   for (int m = tid; m < Ec; m += nt) {
     const long long e = env0 + m;
-    const int sc = p.in.step_count[e] + (is_step ? 1 : 0);
+    const int sc = is_step ? s.env3[4 * m + 2] + 1 : p.in.step_count[e];
     const int nconn = s.cnt[4 * m + 2];
     const bool terminal = is_step && (s.cnt[4 * m + 1] == N || sc >= p.env.time_limit);
     int tflag = terminal ? 1 : 0;
     uint32_t k0 = 0, k1 = 0;
     if (is_step) {
-      k0 = p.in.key[2 * e];
-      k1 = p.in.key[2 * e + 1];
+      k0 = (uint32_t)s.env3[4 * m];
+      k1 = (uint32_t)s.env3[4 * m + 1];
     }
     if (terminal && autoreset) {
       // VmapAutoResetWrapper: key, _ = split(state.key); reset(key).  If the next
@@ -259,38 +310,31 @@ __global__ void __launch_bounds__(256) env_kernel(const EnvParams p) {
   }
   __syncthreads();
   if (*s.anyhit) {
-    // ---- phase 3b: swap in the cached episodes: pins-only grid (heads, then
-    // targets: PRWG:63-64), position = start, fresh action mask.  Reward, discount,
-    // step_type and extras stay those of the terminal step.
-    for (int i = tid; i < Ec * cells; i += nt) {
-      const int m = (int)p.divCells.div((uint32_t)i);
-      if (s.term[m] & 4) s.grid[i] = 0;
-    }
-    for (int t = tid; t < Ec * N; t += nt) {
-      const int m = (int)p.divN.div((uint32_t)t);
-      if (s.term[m] & 4) {
-        const uint32_t pin = __ldcg(p.cache_pins + env0 * N + t);
-        s.pos[t] = (int)(pin >> 16);
-        s.tgt[t] = (int)(pin & 0xffffu);
+    // ---- phase 3b: swap in the cached episodes, one warp per finished env: pins-only
+    // grid (heads, then targets: PRWG:63-64), position = start, fresh action mask.
+    // Reward, discount, step_type and extras stay those of the terminal step.
+    const int lane = tid & 31, nwarps = nt >> 5;
+    for (int m = tid >> 5; m < Ec; m += nwarps) {
+      if (!(s.term[m] & 4)) continue;
+      uint8_t *g = s.grid + (size_t)m * cells;
+      for (int i = lane; i < cells; i += 32) g[i] = 0;
+      int ps = 0, tg = 0;
+      if (lane < N) {
+        const uint32_t pin = __ldcg(p.cache_pins + (env0 + m) * N + lane);
+        ps = (int)(pin >> 16);
+        tg = (int)(pin & 0xffffu);
+        s.pos[m * N + lane] = ps;
+        s.tgt[m * N + lane] = tg;
       }
-    }
-    __syncthreads();
-    for (int t = tid; t < Ec * N; t += nt) {
-      const int m = (int)p.divN.div((uint32_t)t), a = t - m * N;
-      if (s.term[m] & 4) s.grid[(size_t)m * cells + (s.pos[t] >> 8) * G + (s.pos[t] & 255)] = (uint8_t)(3 * a + POSITION);
-    }
-    __syncthreads();
-    for (int t = tid; t < Ec * N; t += nt) {
-      const int m = (int)p.divN.div((uint32_t)t), a = t - m * N;
-      if (s.term[m] & 4) s.grid[(size_t)m * cells + (s.tgt[t] >> 8) * G + (s.tgt[t] & 255)] = (uint8_t)(3 * a + TARGET);
-    }
-    __syncthreads();
-    for (int t = tid; t < Ec * N; t += nt) {
-      const int m = (int)p.divN.div((uint32_t)t), a = t - m * N;
-      if (s.term[m] & 4) {
-        SmemGrid sg{s.grid + (size_t)m * cells, G, 0, G};
-        const uint32_t mk = move_mask(sg, s.pos[t] >> 8, s.pos[t] & 255, a, s.pos[t] == s.tgt[t]);
-        s.flag[t] = (s.flag[t] & 15) | (int)(mk << 4);
+      __syncwarp();
+      if (lane < N) g[(ps >> 8) * G + (ps & 255)] = (uint8_t)(3 * lane + POSITION);
+      __syncwarp();
+      if (lane < N) g[(tg >> 8) * G + (tg & 255)] = (uint8_t)(3 * lane + TARGET);
+      __syncwarp();
+      if (lane < N) {
+        SmemGrid sg{g, G, 0, G};
+        const uint32_t mk = move_mask(sg, ps >> 8, ps & 255, lane, ps == tg);
+        s.flag[m * N + lane] = (s.flag[m * N + lane] & 15) | (int)(mk << 4);
       }
     }
     __syncthreads();
@@ -320,36 +364,27 @@ __global__ void __launch_bounds__(256) env_kernel(const EnvParams p) {
 
   // ---- phase 4: bulk outputs: State.grid and observation.grid
   const int n3 = 3 * N;
+  (void)n3;
   if (VEC) {
-    // A thread owns one packed word (4 cells) of one env: it writes the State
-    // row chunk once and then that chunk's N per-agent views.  Agent a+1's
-    // view is agent a's minus 3 with wrap-around (JUM env.py _obs_from_grid);
-    // EMPTY cells carry decrement 0 and an unreachable wrap bound, so they stay 0.
+    // A thread owns one packed word (4 cells) of one env: it writes the State row
+    // chunk (unless the grid is updated in place and only the moved cells changed)
+    // and then that chunk's N per-agent views through the observation table, one
+    // shared-memory byte read per cell (rows span <= 25 banks: conflict-free).
     const int c4 = cells >> 2;
     const uint32_t *g32 = reinterpret_cast<const uint32_t *>(s.grid);
     int4 *gdst = reinterpret_cast<int4 *>(p.out.grid) + env0 * c4;
     int4 *odst = reinterpret_cast<int4 *>(p.ts.obs_grid) + env0 * N * c4;
     for (int idx = tid; idx < Ec * c4; idx += nt) {
       const int m = (int)p.divC4.div((uint32_t)idx);
-      if (s.term[m] & 2) continue;
+      const int term = s.term[m];
+      if (term & 2) continue;
       const uint32_t w = g32[idx];
-      int t0 = (int)(w & 0xffu), t1 = (int)((w >> 8) & 0xffu), t2 = (int)((w >> 16) & 0xffu), t3 = (int)(w >> 24);
-      if (is_step) gdst[idx] = make_int4(t0, t1, t2, t3);
-      const int d0 = t0 ? 3 : 0, d1 = t1 ? 3 : 0, d2 = t2 ? 3 : 0, d3 = t3 ? 3 : 0;
-      const int l0 = t0 ? 1 : -4, l1 = t1 ? 1 : -4, l2 = t2 ? 1 : -4, l3 = t3 ? 1 : -4;
+      const uint32_t b0 = w & 0xffu, b1 = (w >> 8) & 0xffu, b2 = (w >> 16) & 0xffu, b3 = w >> 24;
+      if (is_step && (!inplace_grid || (term & 4))) gdst[idx] = make_int4((int)b0, (int)b1, (int)b2, (int)b3);
       int4 *o = odst + (size_t)m * N * c4 + (idx - m * c4);
-#pragma unroll 4
-      for (int a = 0; a < N; ++a, o += c4) {
-        *o = make_int4(t0, t1, t2, t3);
-        t0 -= d0;
-        t1 -= d1;
-        t2 -= d2;
-        t3 -= d3;
-        t0 += (t0 < l0) ? n3 : 0;
-        t1 += (t1 < l1) ? n3 : 0;
-        t2 += (t2 < l2) ? n3 : 0;
-        t3 += (t3 < l3) ? n3 : 0;
-      }
+      const uint8_t *lut = s.lut;
+#pragma unroll 2
+      for (int a = 0; a < N; ++a, o += c4, lut += RS) *o = make_int4(lut[b0], lut[b1], lut[b2], lut[b3]);
     }
   } else {
     if (is_step) {
@@ -394,11 +429,18 @@ __global__ void __launch_bounds__(256) random_actions_kernel(rbg_state st, long 
 }
 
 int launch_env(EnvParams p, int force_E, cudaStream_t stream) {
+  static int threads_env = -1;
+  if (threads_env < 0) {
+    const char *e = getenv("RBG_ENV_THREADS");
+    threads_env = e ? atoi(e) : 0;
+    if (threads_env != 64 && threads_env != 128 && threads_env != 256) threads_env = 256;
+  }
+  const int threads = threads_env;
   const int G = p.G, N = p.N;
   p.cells = G * G;
   const bool vec = (p.cells & 3) == 0;
   // envs per CTA: about two packed words per thread in the bulk phases
-  int E = vec ? 512 / (p.cells >> 2) : (int)(32768 / ((int64_t)N * p.cells * 4));
+  int E = vec ? (2 * threads) / (p.cells >> 2) : (int)(32768 / ((int64_t)N * p.cells * 4));
   if (E < 1) E = 1;
   if (E > 32) E = 32;
   if (force_E > 0) E = force_E;
@@ -409,6 +451,13 @@ int launch_env(EnvParams p, int force_E, cudaStream_t stream) {
   p.divC4 = FastDiv::make((uint32_t)(vec ? p.cells >> 2 : 1));
   p.divCells = FastDiv::make((uint32_t)p.cells);
   const size_t smem = env_carve(E, N, p.cells, nullptr, nullptr);
+  {
+    EnvSmem off;
+    env_carve(E, N, p.cells, nullptr, &off);
+    const uint8_t *z = nullptr;
+    const void *ptrs[10] = {off.pos, off.tgt, off.dest, off.flag, off.rew, off.cnt, off.term, off.anyhit, off.lut, off.env3};
+    for (int i = 0; i < 10; ++i) p.so[i] = (int)(reinterpret_cast<const uint8_t *>(ptrs[i]) - z);
+  }
   if (smem > 200 * 1024) return set_error(RBG_EINVAL, "connector: shared memory %zu too large", smem);
   const int64_t ctas = (p.B + E - 1) / E;
   if (ctas <= 0) return RBG_OK;
@@ -416,10 +465,10 @@ int launch_env(EnvParams p, int force_E, cudaStream_t stream) {
     LaunchScope scope(RBG_K_ENV, stream);
     if (vec) {
       if (smem > 48 * 1024) cudaFuncSetAttribute(env_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      env_kernel<true><<<(unsigned)ctas, 256, smem, stream>>>(p);
+      env_kernel<true><<<(unsigned)ctas, threads, smem, stream>>>(p);
     } else {
       if (smem > 48 * 1024) cudaFuncSetAttribute(env_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      env_kernel<false><<<(unsigned)ctas, 256, smem, stream>>>(p);
+      env_kernel<false><<<(unsigned)ctas, threads, smem, stream>>>(p);
     }
   }
   return check_launch("env_kernel");

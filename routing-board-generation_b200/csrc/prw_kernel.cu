@@ -448,7 +448,7 @@ int launch_prw(PrwParams p, int64_t max_boards, int force_M, int force_threads,
   }
   int64_t ctas = (max_boards + M - 1) / M;
   if (ctas <= 0) return RBG_OK;
-  if (p.list && ctas > 148 * 16) ctas = 148 * 16;  // the kernel strides; an empty list costs ~2 us
+  if (p.list && ctas > 148 * 4) ctas = 148 * 4;  // the kernel strides; an empty list costs ~2 us
   {
     LaunchScope scope(RBG_K_PRW, stream);
     prw_kernel<<<(unsigned)ctas, threads, smem, stream>>>(p);

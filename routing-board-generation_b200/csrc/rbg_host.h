@@ -80,6 +80,7 @@ struct EnvParams {
   uint32_t *refill_keys;   // [B,2] State.key of the episode that just started
   // filled by launch_env
   int cells, E;
+  int so[10];  // shared-memory byte offsets of EnvSmem's arrays after grid
   FastDiv divN, divG, divC4, divCells;
 };
 

@@ -107,21 +107,23 @@ def alloc_state(B: int, G: int, N: int) -> State:
     )
 
 
-def alloc_timestep(B: int, G: int, N: int) -> TimeStep:
+def alloc_timestep(B: int, G: int, N: int, T: Optional[int] = None) -> TimeStep:
+    """TimeStep buffers for a batch of B envs; with T, stacked [T, B, ...] (a rollout)."""
     dev = _device()
+    lead = (B,) if T is None else (T, B)
     return TimeStep(
-        step_type=torch.empty((B,), dtype=torch.int8, device=dev),
-        reward=torch.empty((B, N), dtype=torch.float32, device=dev),
-        discount=torch.empty((B, N), dtype=torch.float32, device=dev),
+        step_type=torch.empty(lead, dtype=torch.int8, device=dev),
+        reward=torch.empty(lead + (N,), dtype=torch.float32, device=dev),
+        discount=torch.empty(lead + (N,), dtype=torch.float32, device=dev),
         observation=Observation(
-            grid=torch.empty((B, N, G, G), dtype=torch.int32, device=dev),
-            action_mask=torch.empty((B, N, 5), dtype=torch.bool, device=dev),
-            step_count=torch.empty((B,), dtype=torch.int32, device=dev),
+            grid=torch.empty(lead + (N, G, G), dtype=torch.int32, device=dev),
+            action_mask=torch.empty(lead + (N, 5), dtype=torch.bool, device=dev),
+            step_count=torch.empty(lead, dtype=torch.int32, device=dev),
         ),
         extras={
-            "num_connections": torch.empty((B,), dtype=torch.int32, device=dev),
-            "ratio_connections": torch.empty((B,), dtype=torch.float32, device=dev),
-            "total_path_length": torch.empty((B,), dtype=torch.int32, device=dev),
+            "num_connections": torch.empty(lead, dtype=torch.int32, device=dev),
+            "ratio_connections": torch.empty(lead, dtype=torch.float32, device=dev),
+            "total_path_length": torch.empty(lead, dtype=torch.int32, device=dev),
         },
     )
 
@@ -246,6 +248,24 @@ def connector_step(st: State, action, time_limit: int = 50, timestep_reward: flo
     act = as_tensor(action, torch.int32).reshape(B, N)
     _lib.check(lib.rbg_connector_step(C.byref(s_in), C.byref(s_out), act.data_ptr(), B, G, N, C.byref(params), C.byref(t), ws.data_ptr() if ws is not None else None, _stream()))
     return new, ts
+
+
+def connector_rollout_random(st: State, n_steps: int, time_limit: int = 50, timestep_reward: float = -0.03, connected_reward: float = 0.1, autoreset_kind="parallel_random_walk", out: Optional[TimeStep] = None, actions: Optional[torch.Tensor] = None):
+    """n_steps auto-reset random-policy steps in ONE library call (the reference's `n_steps` scan).
+    `st` is updated in place; returns (st, TimeStep stacked [n_steps, B, ...], actions[n_steps, B, N])."""
+    if isinstance(autoreset_kind, str):
+        autoreset_kind = GENERATOR_KINDS[autoreset_kind]
+    B, G, N = _dims(st)
+    for t in (st.grid, st.step_count, st.key, st.agents.id, st.agents.start, st.agents.target, st.agents.position):
+        if not t.is_contiguous():
+            raise ValueError("rollout updates the State in place: its leaves must be contiguous")
+    ts = alloc_timestep(B, G, N, n_steps) if out is None else out
+    act = torch.empty((n_steps, B, N), dtype=torch.int32, device=_device()) if actions is None else actions
+    params = rbg_env_params(int(time_limit), float(timestep_reward), float(connected_reward), int(autoreset_kind))
+    ws = _workspace(B, G, N)
+    s, t = _state_struct(st), _timestep_struct(ts)
+    _lib.check(_lib.load().rbg_connector_rollout_random(C.byref(s), act.data_ptr(), n_steps, B, G, N, C.byref(params), C.byref(t), ws.data_ptr(), _stream()))
+    return st, ts, act
 
 
 def random_actions(st: State) -> torch.Tensor:

@@ -367,6 +367,22 @@ def test_fused_random_step_matches_two_calls(rbg, orc):
         _assert_timestep(ts, rts, f"at step {t}")
 
 
+@pytest.mark.parametrize("G,N,B,T", [(10, 5, 3000, 45), (32, 16, 96, 12)])
+def test_rollout_matches_stepwise_oracle(rbg, orc, G, N, B, T):
+    """rbg_connector_rollout_random (BASELINE configs[4] shape at 32x32/16) == T oracle steps."""
+    keys, kref = _keys(rbg, orc, 12, B)
+    env = rbg.VmapAutoResetWrapper(rbg.Connector(generator=rbg.ParallelRandomWalkGenerator(G, N), time_limit=9))
+    st, _ = env.reset(keys)
+    rst, _ = orc.connector_reset_batch("parallel_random_walk", kref, G, N)
+    st, ts, act = env.rollout_random(st, T)
+    for t in range(T):
+        a = orc.random_actions_batch(rst)
+        assert np.array_equal(_np(act[t]), a), f"actions differ at step {t}"
+        rst, rts = orc.connector_step_batch(rst, a, time_limit=9, autoreset_kind="parallel_random_walk")
+        _assert_timestep(ts[t], rts, f"at step {t}")
+    _assert_state(st, rst, "after the rollout")
+
+
 def test_multi_to_single_wrapper(rbg, orc):
     keys, kref = _keys(rbg, orc, 8, 64)
     env = rbg.MultiToSingleWrapper(rbg.Connector(generator=rbg.ParallelRandomWalkGenerator(10, 5)))
