@@ -41,7 +41,8 @@ def is_stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
+    extra = os.environ.get("RBG_NVCC_EXTRA", "").split()  # e.g. -DRBG_TF_PLAIN_ADD for A/B builds
+    if not force and not extra and not is_stale():
         return SO
     os.makedirs(LIBDIR, exist_ok=True)
     objs = []
@@ -49,7 +50,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     procs = []
     for s in SOURCES:
         obj = os.path.join(LIBDIR, s.replace(".cu", ".o"))
-        cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, s), "-o", obj]
+        cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, s), "-o", obj]
         procs.append((s, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for s, obj, pr in procs:
         out, _ = pr.communicate()

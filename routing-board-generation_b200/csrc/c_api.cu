@@ -112,7 +112,7 @@ static int env_int(const char *name) {
 
 static int generator_state_impl(int kind, const uint32_t *keys, int64_t B, int G, int N, const rbg_state *out,
                                 const rbg_timestep *ts, int extra_split, const int32_t *list,
-                                const int32_t *list_count, cudaStream_t stream) {
+                                const int32_t *list_count, cudaStream_t stream, int32_t *list_ticket = nullptr) {
   if (kind == RBG_GEN_PRW || kind == RBG_GEN_UNIFORM) {
     PrwParams p;
     memset(&p, 0, sizeof(p));
@@ -132,6 +132,7 @@ static int generator_state_impl(int kind, const uint32_t *keys, int64_t B, int G
     }
     p.list = list;
     p.list_count = list_count;
+    p.list_ticket = list_ticket;
     return launch_prw(p, B, env_int("RBG_PRW_M"), env_int("RBG_PRW_THREADS"), stream);
   }
   if (kind == RBG_GEN_SEEDEXT) {
@@ -276,6 +277,7 @@ static int connector_step_impl(const rbg_state *in, const rbg_state *out, const 
           cudaStreamWaitEvent(stream, ctx->refill_done[i], 0);
           ctx->refill_pending[i] = false;
         }
+      if ((e = cudaMemsetAsync(ws, 0, 256, stream)) != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(counters)");
       // warm start: the next episode of EVERY env, one bulk generation keyed by the
       // current State.key (a cold cache would send each env's first reset down the
       // synchronous path)
@@ -312,13 +314,13 @@ static int connector_step_impl(const rbg_state *in, const rbg_state *out, const 
     p.refill_keys = reinterpret_cast<uint32_t *>(ws + wl.refill_keys[par]);
     p.refill_count = reinterpret_cast<int32_t *>(ws + 64 + 64 * par);
   }
-  // counters: the other parity's refill counter may still be read by a refill in flight
-  if ((e = cudaMemsetAsync(ws, 0, 64, stream)) != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(reset counter)");
-  if (speculative && (e = cudaMemsetAsync(ws + 64 + 64 * par, 0, 64, stream)) != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(refill counter)");
+  // counters: with the speculative path the list kernels clear their own counter when
+  // they finish (prw_kernel list_ticket); they were zeroed once when the workspace was adopted
+  if (!speculative && (e = cudaMemsetAsync(ws, 0, 64, stream)) != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(reset counter)");
   if ((rc = launch_env(p, env_int("RBG_ENV_E"), stream))) return rc;
   // VmapAutoResetWrapper._auto_reset: key, _ = split(state.key); reset(key):
   // one more leading split()[0] than a plain generator call.
-  if ((rc = generator_state_impl(kind, out->key, B, G, N, out, ts, 1, sync_list, sync_count, stream))) return rc;
+  if ((rc = generator_state_impl(kind, out->key, B, G, N, out, ts, 1, sync_list, sync_count, stream, speculative ? sync_count + 1 : nullptr))) return rc;
   if (speculative) {
     if ((e = cudaEventRecord(ctx->env_done, stream)) != cudaSuccess) return set_cuda_error(e, "cudaEventRecord");
     if ((e = cudaStreamWaitEvent(ctx->side, ctx->env_done, 0)) != cudaSuccess) return set_cuda_error(e, "cudaStreamWaitEvent(side)");
@@ -334,6 +336,7 @@ static int connector_step_impl(const rbg_state *in, const rbg_state *out, const 
     q.debug = debug_flags();
     q.list = p.refill_list;
     q.list_count = p.refill_count;
+    q.list_ticket = p.refill_count + 1;
     q.to_cache = 1;
     q.cache_tag = reinterpret_cast<unsigned long long *>(ws + wl.cache_tag);
     q.cache_key = reinterpret_cast<uint2 *>(ws + wl.cache_key);

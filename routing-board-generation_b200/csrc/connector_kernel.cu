@@ -406,6 +406,249 @@ __global__ void __launch_bounds__(256, 8) env_kernel(const EnvParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// env_warp_kernel: the same step organised per WARP.  A warp owns K = 32 / Np envs
+// (Np = lanes per env, the next power of two >= N; lane = (env, agent)), keeps their
+// grids in its own slice of shared memory and runs every phase with __syncwarp only,
+// so warps in different phases overlap freely (the CTA-wide version above spends half
+// of its warp-time at barriers waiting for the agent phases).
+constexpr int EW_WARPS = 4;
+
+template <bool VEC>
+__global__ void __launch_bounds__(EW_WARPS * 32, 12) env_warp_kernel(const EnvParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int G = p.G, N = p.N, cells = p.cells;
+  const int Np = p.Np, K = 32 / Np, c4 = cells >> 2;
+  const int RS = obs_lut_stride(N);
+  uint8_t *lut = smem_raw;
+  for (int a = warp; a < N; a += EW_WARPS)
+    for (int v = lane; v < RS; v += 32) lut[a * RS + v] = v <= 3 * N ? (uint8_t)obs_value(v, 3 * a, 3 * N) : (uint8_t)0;
+  __syncthreads();  // the only CTA-wide barrier
+
+  const long long e0 = ((long long)blockIdx.x * EW_WARPS + warp) * K;
+  if (e0 >= p.B) return;
+  const int kc = (int)((p.B - e0) < (long long)K ? (p.B - e0) : (long long)K);
+  const bool is_step = (p.mode == ENV_MODE_STEP);
+  const bool autoreset = is_step && p.env.autoreset_kind >= 0 && p.list != nullptr;
+  const bool inplace_grid = is_step && p.out.grid == p.in.grid;
+  uint8_t *wg = smem_raw + p.so[0] + (size_t)warp * p.so[1];
+  uint32_t *wg32 = reinterpret_cast<uint32_t *>(wg);
+
+  const int j = lane / Np, a = lane & (Np - 1);
+  const bool env_ok = j < kc, agent = env_ok && a < N;
+  const long long e = e0 + (env_ok ? j : 0);
+  const uint32_t gmask = Np == 32 ? FULL : (((1u << Np) - 1u) << (j * Np));
+
+  // ---- load: State.grid int32 -> uint8 (one packed word per int4), agent and env scalars
+  if (VEC) {
+    const int4 *src = reinterpret_cast<const int4 *>(p.in.grid) + e0 * c4;
+    for (int q = lane; q < kc * c4; q += 32) {
+      const int4 v = __ldg(src + q);
+      wg32[q] = (uint32_t)(v.x & 0xff) | ((uint32_t)(v.y & 0xff) << 8) | ((uint32_t)(v.z & 0xff) << 16) | ((uint32_t)(v.w & 0xff) << 24);
+    }
+  } else {
+    const int32_t *src = p.in.grid + e0 * cells;
+    for (int i = lane; i < kc * cells; i += 32) wg[i] = (uint8_t)__ldg(src + i);
+  }
+  int pos = 0, tgt = 0, action = 0, sc0 = 0;
+  uint32_t k0 = 0, k1 = 0;
+  if (agent) {
+    const int2 ps = __ldg(reinterpret_cast<const int2 *>(p.in.position) + e * N + a);
+    const int2 tg = __ldg(reinterpret_cast<const int2 *>(p.in.target) + e * N + a);
+    pos = (ps.x << 8) | ps.y;
+    tgt = (tg.x << 8) | tg.y;
+    if (is_step && !p.random_policy) action = __ldg(p.action + e * N + a);
+  }
+  if (env_ok) {
+    sc0 = p.in.step_count[e];
+    if (is_step) {
+      k0 = p.in.key[2 * e];
+      k1 = p.in.key[2 * e + 1];
+    }
+  }
+  __syncwarp();
+
+  uint8_t *g = wg + (size_t)j * cells;
+  const SmemGrid sg{g, G, 0, G};
+  // PATH cells of the env before the move (extras: total_path_length)
+  int paths = 0;
+  if (env_ok) {
+    if (VEC) {
+      for (int q = a; q < c4; q += Np) paths += count_path_codes(wg32[j * c4 + q]);
+    } else {
+      for (int i = a; i < cells; i += Np) paths += (g[i] % 3u == 1u) ? 1 : 0;
+    }
+  }
+  for (int off = Np >> 1; off; off >>= 1) paths += __shfl_xor_sync(FULL, paths, off);
+
+  // ---- agents: (sample action,) move_position, is_valid_position, collisions
+  const bool was = agent && pos == tgt;
+  int r = pos >> 8, c = pos & 255, dest = -1;
+  if (is_step && agent) {
+    if (p.random_policy) {
+      const uint32_t mk = move_mask(sg, r, c, a, was);
+      action = random_action(k0, k1, (uint32_t)sc0, (uint32_t)a, mk);
+      if (p.action_out) p.action_out[e * N + a] = action;
+    }
+    const int am = action < 0 ? 0 : (action > 4 ? 4 : action);  // lax.switch clamps
+    const int nr = r + (am == UP ? -1 : (am == DOWN ? 1 : 0));
+    const int nc = c + (am == RIGHT ? 1 : (am == LEFT ? -1 : 0));
+    const bool inb = (unsigned)nr < (unsigned)G && (unsigned)nc < (unsigned)G;
+    const uint32_t v = inb ? sg.at(nr, nc) : 0xFFu;
+    if (inb && (v == 0u || v == 3u * a + TARGET) && !was && action != NOOP) dest = nr * G + nc;
+  }
+  // same destination in the same env -> only the highest agent id moves
+  const uint32_t mval = dest >= 0 ? (((uint32_t)j << 16) | (uint32_t)dest) : (0x80000000u | (uint32_t)lane);
+  const uint32_t mm = __match_any_sync(FULL, mval);
+  const bool win = dest >= 0 && lane == 31 - __clz(mm);
+  __syncwarp();  // every read of the pre-move grid is done
+  if (win) {  // move_agent: old head -> PATH, new cell -> POSITION
+    g[r * G + c] = (uint8_t)(3 * a + PATH);
+    g[dest] = (uint8_t)(3 * a + POSITION);
+    if (inplace_grid) {  // State.grid updated in place: only these two cells change
+      int32_t *gg = p.out.grid + e * cells;
+      gg[r * G + c] = 3 * a + PATH;
+      gg[dest] = 3 * a + POSITION;
+    }
+    uint32_t nr, nc;
+    p.divG.divmod((uint32_t)dest, nr, nc);
+    pos = (int)((nr << 8) | nc);
+  }
+  __syncwarp();
+
+  // ---- action mask, connected / done, reward on the new grid
+  const bool now = agent && pos == tgt;
+  uint32_t mk3 = 0;
+  if (agent) mk3 = move_mask(sg, pos >> 8, pos & 255, a, now);
+  const bool done = now || mk3 == 0u;  // connected_or_blocked
+  const float rew = __fadd_rn(__fmul_rn(p.env.connected_reward, (!was && now) ? 1.0f : 0.0f), __fmul_rn(p.env.timestep_reward, was ? 0.0f : 1.0f));
+  const int ndone = __popc(__ballot_sync(FULL, agent && done) & gmask);
+  const int nconn = __popc(__ballot_sync(FULL, now) & gmask);
+  const int nmoved = __popc(__ballot_sync(FULL, win) & gmask);
+
+  // ---- per env: termination, auto-reset bookkeeping (group-uniform values)
+  const int sc = sc0 + (is_step ? 1 : 0);
+  const bool terminal = is_step && env_ok && (ndone == N || sc >= p.env.time_limit);
+  int tflag = terminal ? 1 : 0;
+  if (terminal && autoreset) {
+    bool hit = false;
+    uint32_t nk0, nk1;
+    if (p.cache_tag) {
+      const unsigned long long tag = __ldcg(p.cache_tag + e);
+      if (tag == (((unsigned long long)k1 << 32) | k0)) {
+        __threadfence();
+        const uint2 nk = __ldcg(p.cache_key + e);
+        nk0 = nk.x;
+        nk1 = nk.y;
+        hit = true;
+      }
+    }
+    if (!hit) {  // State.key of the next episode: split(split(key)[0])[0]
+      uint32_t a0, a1, b0, b1;
+      split2(k0, k1, a0, a1, b0, b1);
+      split2(a0, a1, nk0, nk1, b0, b1);
+    }
+    if (a == 0) {
+      if (!hit) p.list[atomicAdd(p.list_count, 1)] = (int32_t)e;
+      if (p.refill_list) {
+        const int slot = atomicAdd(p.refill_count, 1);
+        p.refill_list[slot] = (int32_t)e;
+        p.refill_keys[2 * slot] = nk0;
+        p.refill_keys[2 * slot + 1] = nk1;
+      }
+    }
+    if (hit) {
+      k0 = nk0;
+      k1 = nk1;
+    }
+    tflag |= hit ? 4 : 2;
+  }
+  if (tflag & 4) {
+    // swap in the cached episode: pins-only grid (heads, then targets: PRWG:63-64),
+    // position = start, fresh action mask; reward / discount / step_type / extras stay
+    // those of the terminal step
+    for (int i = a; i < cells; i += Np) g[i] = 0;
+    if (a < N) {
+      const uint32_t pin = __ldcg(p.cache_pins + e * N + a);
+      pos = (int)(pin >> 16);
+      tgt = (int)(pin & 0xffffu);
+    }
+    __syncwarp(gmask);
+    if (a < N) g[(pos >> 8) * G + (pos & 255)] = (uint8_t)(3 * a + POSITION);
+    __syncwarp(gmask);
+    if (a < N) g[(tgt >> 8) * G + (tgt & 255)] = (uint8_t)(3 * a + TARGET);
+    __syncwarp(gmask);
+    if (a < N) mk3 = move_mask(sg, pos >> 8, pos & 255, a, pos == tgt);
+  }
+  __syncwarp();
+
+  // ---- small outputs
+  if (env_ok && a == 0) {
+    p.ts.step_type[e] = (int8_t)(is_step ? (terminal ? 2 : 1) : 0);
+    p.ts.num_connections[e] = nconn;
+    p.ts.ratio_connections[e] = __fdiv_rn((float)nconn, (float)N);
+    p.ts.total_path_length[e] = paths + nmoved + N;
+    if (!(tflag & 2)) p.ts.obs_step_count[e] = (tflag & 4) ? 0 : sc;
+    if (is_step) {
+      p.out.step_count[e] = (tflag & 4) ? 0 : sc;
+      if (p.out.key != p.in.key || (tflag & 4)) {
+        p.out.key[2 * e] = k0;
+        p.out.key[2 * e + 1] = k1;
+      }
+    }
+  }
+  if (agent) {
+    const long long ga = e * N + a;
+    p.ts.reward[ga] = is_step ? rew : 0.0f;
+    p.ts.discount[ga] = is_step ? ((terminal || done) ? 0.0f : 1.0f) : 1.0f;
+    if (!(tflag & 2)) store_mask5(p.ts.action_mask + ga * 5, mk3);
+    if (is_step) {
+      const int2 pos2 = make_int2(pos >> 8, pos & 255);
+      reinterpret_cast<int2 *>(p.out.position)[ga] = pos2;
+      if (tflag & 4) {
+        reinterpret_cast<int2 *>(p.out.target)[ga] = make_int2(tgt >> 8, tgt & 255);
+        reinterpret_cast<int2 *>(p.out.start)[ga] = pos2;
+        p.out.agent_id[ga] = a;
+      } else if (p.out.target != p.in.target) {
+        reinterpret_cast<int2 *>(p.out.target)[ga] = make_int2(tgt >> 8, tgt & 255);
+        reinterpret_cast<int2 *>(p.out.start)[ga] = reinterpret_cast<const int2 *>(p.in.start)[ga];
+        p.out.agent_id[ga] = p.in.agent_id[ga];
+      }
+    }
+  }
+
+  // ---- bulk outputs: State.grid and observation.grid (see env_kernel phase 4)
+  const uint32_t skipm = __ballot_sync(FULL, a == 0 && (tflag & 2));  // bit j*Np: env j is rewritten by the reset kernel
+  const uint32_t hitm = __ballot_sync(FULL, a == 0 && (tflag & 4));
+  if (VEC) {
+    int4 *gdst = reinterpret_cast<int4 *>(p.out.grid) + e0 * c4;
+    int4 *odst = reinterpret_cast<int4 *>(p.ts.obs_grid) + e0 * N * c4;
+    for (int q = lane; q < kc * c4; q += 32) {
+      const int m = (int)p.divC4.div((uint32_t)q);
+      if ((skipm >> (m * Np)) & 1u) continue;
+      const uint32_t w = wg32[q];
+      const uint32_t b0 = w & 0xffu, b1 = (w >> 8) & 0xffu, b2 = (w >> 16) & 0xffu, b3 = w >> 24;
+      if (is_step && (!inplace_grid || ((hitm >> (m * Np)) & 1u))) gdst[q] = make_int4((int)b0, (int)b1, (int)b2, (int)b3);
+      int4 *o = odst + (size_t)m * N * c4 + (q - m * c4);
+      const uint8_t *row = lut;
+#pragma unroll 2
+      for (int x = 0; x < N; ++x, o += c4, row += RS) *o = make_int4(row[b0], row[b1], row[b2], row[b3]);
+    }
+  } else {
+    int32_t *gdst = p.out.grid + e0 * cells;
+    int32_t *odst = p.ts.obs_grid + e0 * N * cells;
+    for (int i = lane; i < kc * cells; i += 32) {
+      const int m = (int)p.divCells.div((uint32_t)i);
+      if ((skipm >> (m * Np)) & 1u) continue;
+      const uint32_t v = wg[i];
+      if (is_step) gdst[i] = (int)v;
+      int32_t *o = odst + (size_t)m * N * cells + (i - m * cells);
+      for (int x = 0; x < N; ++x, o += cells) *o = lut[x * RS + v];
+    }
+  }
+}
+
 // standalone random policy: one thread per (env, agent), grid read from global
 __global__ void __launch_bounds__(256) random_actions_kernel(rbg_state st, long long B, int G, int N,
                                                              FastDiv divN, int32_t *action) {
@@ -429,16 +672,43 @@ __global__ void __launch_bounds__(256) random_actions_kernel(rbg_state st, long 
 }
 
 int launch_env(EnvParams p, int force_E, cudaStream_t stream) {
-  static int threads_env = -1;
+  static int threads_env = -1, use_cta = -1;
   if (threads_env < 0) {
     const char *e = getenv("RBG_ENV_THREADS");
     threads_env = e ? atoi(e) : 0;
     if (threads_env != 64 && threads_env != 128 && threads_env != 256) threads_env = 256;
+    const char *k = getenv("RBG_ENV_KERNEL");  // "cta": the CTA-wide kernel (A/B comparisons)
+    use_cta = (k && k[0] == 'c') ? 1 : 0;
   }
-  const int threads = threads_env;
   const int G = p.G, N = p.N;
   p.cells = G * G;
   const bool vec = (p.cells & 3) == 0;
+  p.divN = FastDiv::make((uint32_t)N);
+  p.divG = FastDiv::make((uint32_t)G);
+  p.divC4 = FastDiv::make((uint32_t)(vec ? p.cells >> 2 : 1));
+  p.divCells = FastDiv::make((uint32_t)p.cells);
+  if (p.B <= 0) return RBG_OK;
+  if (!use_cta) {
+    // warp-per-K-envs kernel
+    int Np = 1;
+    while (Np < N) Np <<= 1;
+    p.Np = Np;
+    const int K = 32 / Np;
+    p.E = EW_WARPS * K;
+    const size_t lutB = ((size_t)N * obs_lut_stride(N) + 256 + 15) & ~(size_t)15;
+    const size_t wgrid = ((size_t)K * p.cells + 15) & ~(size_t)15;
+    p.so[0] = (int)lutB;
+    p.so[1] = (int)wgrid;
+    const size_t smem = lutB + EW_WARPS * wgrid;
+    const int64_t ctas = (p.B + p.E - 1) / p.E;
+    LaunchScope scope(RBG_K_ENV, stream);
+    if (vec)
+      env_warp_kernel<true><<<(unsigned)ctas, EW_WARPS * 32, smem, stream>>>(p);
+    else
+      env_warp_kernel<false><<<(unsigned)ctas, EW_WARPS * 32, smem, stream>>>(p);
+    return check_launch("env_warp_kernel");
+  }
+  const int threads = threads_env;
   // envs per CTA: about two packed words per thread in the bulk phases
   int E = vec ? (2 * threads) / (p.cells >> 2) : (int)(32768 / ((int64_t)N * p.cells * 4));
   if (E < 1) E = 1;
@@ -446,10 +716,6 @@ int launch_env(EnvParams p, int force_E, cudaStream_t stream) {
   if (force_E > 0) E = force_E;
   if (!vec) E = (E + 3) & ~3;  // scalar path: keep slabs 16-byte aligned anyway
   p.E = E;
-  p.divN = FastDiv::make((uint32_t)N);
-  p.divG = FastDiv::make((uint32_t)G);
-  p.divC4 = FastDiv::make((uint32_t)(vec ? p.cells >> 2 : 1));
-  p.divCells = FastDiv::make((uint32_t)p.cells);
   const size_t smem = env_carve(E, N, p.cells, nullptr, nullptr);
   {
     EnvSmem off;
@@ -460,7 +726,6 @@ int launch_env(EnvParams p, int force_E, cudaStream_t stream) {
   }
   if (smem > 200 * 1024) return set_error(RBG_EINVAL, "connector: shared memory %zu too large", smem);
   const int64_t ctas = (p.B + E - 1) / E;
-  if (ctas <= 0) return RBG_OK;
   {
     LaunchScope scope(RBG_K_ENV, stream);
     if (vec) {

@@ -399,6 +399,19 @@ __global__ void __launch_bounds__(256) prw_kernel(const PrwParams p) {
   }
   __syncthreads();  // shared memory is reused by the next pool
   }
+  // list launches recycle their counter: the last CTA to finish clears it (every CTA
+  // has read it by then), so the host needs no memset between steps
+  if (p.list_ticket) {
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      if (atomicAdd(p.list_ticket, 1) == (int)gridDim.x - 1) {
+        *const_cast<int32_t *>(p.list_count) = 0;
+        *p.list_ticket = 0;
+        __threadfence();
+      }
+    }
+  }
 }
 
 // ---------------------------------------------------------------- host side
@@ -448,7 +461,7 @@ int launch_prw(PrwParams p, int64_t max_boards, int force_M, int force_threads,
   }
   int64_t ctas = (max_boards + M - 1) / M;
   if (ctas <= 0) return RBG_OK;
-  if (p.list && ctas > 148 * 4) ctas = 148 * 4;  // the kernel strides; an empty list costs ~2 us
+  if (p.list && ctas > 148 * (p.to_cache ? 4 : 2)) ctas = 148 * (p.to_cache ? 4 : 2);  // refills are ~4% of the batch; the synchronous list is near-empty  // the kernel strides; an empty list costs ~2 us
   {
     LaunchScope scope(RBG_K_PRW, stream);
     prw_kernel<<<(unsigned)ctas, threads, smem, stream>>>(p);

@@ -22,33 +22,51 @@ __device__ __forceinline__ uint32_t rotl(uint32_t x, int r) {
   return __funnelshift_l(x, x, r);
 }
 
-#define RBG_TF_ROUND(r) \
-  x0 += x1;             \
-  x1 = rotl(x1, r);     \
+// Pipe balance experiment (kept behind -DRBG_TF_IMAD_ADD): on sm_100 IADD3 / SHF /
+// LOP3 all issue to the ALU pipe while IMAD goes to the FMA pipe, so multiplying by a 1
+// the compiler cannot see through turns the 30 additions of a block into IMADs and
+// splits the block 40 / 30 between the pipes.  MEASURED SLOWER on B200 (r01:
+// ParallelRandomWalk 10x10/5 267 M vs 283 M boards/s, SeedExtension 14x14/7 7.26 M vs
+// 7.68 M boards/s): these kernels are bound by the dependent-issue latency of the
+// add -> rotate -> xor chain, not by ALU-pipe throughput, and the cross-pipe RAW costs
+// one extra cycle per round.  Plain additions are the default.
+static __constant__ uint32_t c_rbg_one = 1u;
+
+#ifdef RBG_TF_IMAD_ADD
+#define RBG_TF_ADD(a, b) ((b) * one + (a))
+#else
+#define RBG_TF_ADD(a, b) ((a) + (b))
+#endif
+
+#define RBG_TF_ROUND(r)    \
+  x0 = RBG_TF_ADD(x0, x1); \
+  x1 = rotl(x1, r);        \
   x1 ^= x0;
 
 // One threefry2x32 block: key (k0,k1), counter (x0,x1) -> (o0,o1).
 __device__ __forceinline__ void tf_block(uint32_t k0, uint32_t k1, uint32_t x0,
                                          uint32_t x1, uint32_t &o0,
                                          uint32_t &o1) {
+  const uint32_t one = c_rbg_one;
+  (void)one;
   const uint32_t ks2 = k0 ^ k1 ^ 0x1BD11BDAu;
-  x0 += k0;
-  x1 += k1;
+  x0 = RBG_TF_ADD(x0, k0);
+  x1 = RBG_TF_ADD(x1, k1);
   RBG_TF_ROUND(13) RBG_TF_ROUND(15) RBG_TF_ROUND(26) RBG_TF_ROUND(6)
-  x0 += k1;
-  x1 += ks2 + 1u;
+  x0 = RBG_TF_ADD(x0, k1);
+  x1 = RBG_TF_ADD(x1, ks2 + 1u);
   RBG_TF_ROUND(17) RBG_TF_ROUND(29) RBG_TF_ROUND(16) RBG_TF_ROUND(24)
-  x0 += ks2;
-  x1 += k0 + 2u;
+  x0 = RBG_TF_ADD(x0, ks2);
+  x1 = RBG_TF_ADD(x1, k0 + 2u);
   RBG_TF_ROUND(13) RBG_TF_ROUND(15) RBG_TF_ROUND(26) RBG_TF_ROUND(6)
-  x0 += k0;
-  x1 += k1 + 3u;
+  x0 = RBG_TF_ADD(x0, k0);
+  x1 = RBG_TF_ADD(x1, k1 + 3u);
   RBG_TF_ROUND(17) RBG_TF_ROUND(29) RBG_TF_ROUND(16) RBG_TF_ROUND(24)
-  x0 += k1;
-  x1 += ks2 + 4u;
+  x0 = RBG_TF_ADD(x0, k1);
+  x1 = RBG_TF_ADD(x1, ks2 + 4u);
   RBG_TF_ROUND(13) RBG_TF_ROUND(15) RBG_TF_ROUND(26) RBG_TF_ROUND(6)
-  x0 += ks2;
-  x1 += k0 + 5u;
+  x0 = RBG_TF_ADD(x0, ks2);
+  x1 = RBG_TF_ADD(x1, k0 + 5u);
   o0 = x0;
   o1 = x1;
 }

@@ -40,6 +40,7 @@ struct PrwParams {
   rbg_timestep ts;
   const int32_t *list;        // optional env list (auto-reset)
   const int32_t *list_count;  // device count of list entries
+  int32_t *list_ticket;       // optional: CTAs-done ticket; the last CTA zeroes list_count and the ticket
   // auto-reset cache refill: keys[] is indexed by list slot (not env id) and the
   // result goes to the env's cache entry instead of State / TimeStep
   int keys_compact, to_cache;
@@ -79,7 +80,7 @@ struct EnvParams {
   int32_t *refill_count;   // [1]
   uint32_t *refill_keys;   // [B,2] State.key of the episode that just started
   // filled by launch_env
-  int cells, E;
+  int cells, E, Np;
   int so[10];  // shared-memory byte offsets of EnvSmem's arrays after grid
   FastDiv divN, divG, divC4, divCells;
 };
