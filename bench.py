@@ -150,6 +150,10 @@ def run_ours(args):
             engine.connector_rollout_random(state, n, TIME_LIMIT, -0.03, 0.1, autoreset_kind="parallel_random_walk", out=ts, actions=act)
             k -= n
 
+    # Burn-in to the stationary regime: right after reset() every env is at step 0, so the
+    # first episodes end in lock-step (all survivors hit time_limit together); a few episode
+    # lengths later terminations are spread evenly (about 4 % of the envs per step).
+    run_steps(args.burnin)
     run_steps(max(args.warmup, 3))
     sync_all()
 
@@ -207,7 +211,7 @@ def run_ours(args):
             "ms_per_step": round(ms_max / args.steps, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
             "data": "synthetic (keys = split(PRNGKey(0), B), random-policy actions)",
             "config": {"workload": "connector_step_random_agent_autoreset_prw", "grid": G, "agents": N, "envs_per_gpu": B, "envs_total": total, "time_limit": TIME_LIMIT,
-                       "generator": "ParallelRandomWalkGenerator", "parallelism": f"env-sharded x{world}",
+                       "generator": "ParallelRandomWalkGenerator", "parallelism": f"env-sharded x{world}", "burnin_steps": args.burnin,
                        "api": f"rbg_connector_rollout_random, {chunk}-step chunks (the reference's n_steps scan), State in place, stacked TimeSteps",
                        "l2": f"no flush: per-step traffic {STEP_BYTES * B / 1e6:.0f} MB per GPU exceeds the 126 MB L2"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "secondary": secondary,
@@ -391,6 +395,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
+    ap.add_argument("--burnin", type=int, default=160, help="untimed steps after reset() so that episode ends are desynchronised")
     ap.add_argument("--chunk", type=int, default=20, help="env steps per rollout call (the reference's n_steps)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--skip-e2e", action="store_true")
