@@ -232,7 +232,8 @@ int64_t rbg_launch_count(int reset);
 #define RBG_K_SPLIT 3      /* split_keys_kernel */
 #define RBG_K_VALIDATE 4   /* validate_kernel */
 #define RBG_K_SEEDEXT 5    /* seedext_kernel */
-#define RBG_K_COUNT 6
+#define RBG_K_ROLLOUT 6    /* rollout_warp_kernel: T fused steps */
+#define RBG_K_COUNT 7
 int rbg_kernel_timing(int enable);
 int rbg_kernel_time(int kernel, int64_t *launches, double *total_ms);
 

@@ -96,7 +96,7 @@ def launch_count(reset: bool = False) -> int:
     return int(load().rbg_launch_count(1 if reset else 0))
 
 
-KERNELS = {"prw": 0, "env": 1, "random_actions": 2, "split": 3, "validate": 4, "seedext": 5}
+KERNELS = {"prw": 0, "env": 1, "random_actions": 2, "split": 3, "validate": 4, "seedext": 5, "rollout": 6}
 
 
 def kernel_timing(enable: bool) -> None:

@@ -674,14 +674,108 @@ int rbg_connector_step_random(const rbg_state *in, const rbg_state *out, int32_t
   return connector_step_impl(in, out, nullptr, action_out, 1, B, G, N, params, ts, workspace, (cudaStream_t)stream);
 }
 
+// Fused rollout (rollout_warp_kernel): one launch per chunk of steps plus one refill of
+// the next-episode cache for the envs that reset during the chunk.
+static int rollout_fused(const rbg_state *state, int32_t *action_out, int64_t T, int64_t B, int G, int N,
+                         const rbg_env_params *params, const rbg_timestep *ts, void *workspace, cudaStream_t stream) {
+  uint8_t *ws = reinterpret_cast<uint8_t *>(workspace);
+  const WsLayout wl = ws_layout(B, N);
+  const int kind = params->autoreset_kind;
+  cudaError_t e;
+  int rc;
+  AutoResetCtx *ctx;
+  {
+    std::lock_guard<std::mutex> lock(g_ar_mu);
+    ctx = &g_ar[workspace];
+  }
+  // refills launched by the step-wise path on the side stream must have landed
+  for (int i = 0; i < 2; ++i)
+    if (ctx->refill_pending[i]) {
+      if ((e = cudaStreamWaitEvent(stream, ctx->refill_done[i], 0)) != cudaSuccess) return set_cuda_error(e, "cudaStreamWaitEvent");
+      ctx->refill_pending[i] = false;
+    }
+  auto cache_params = [&](PrwParams &q) {
+    memset(&q, 0, sizeof(q));
+    q.B = B;
+    q.G = G;
+    q.N = N;
+    q.mode = kind == RBG_GEN_PRW ? PRW_MODE_STATE : PRW_MODE_UNIFORM;
+    q.extra_split = (kind == RBG_GEN_PRW ? 1 : 0) + 1;
+    q.debug = debug_flags();
+    q.to_cache = 1;
+    q.cache_tag = reinterpret_cast<unsigned long long *>(ws + wl.cache_tag);
+    q.cache_key = reinterpret_cast<uint2 *>(ws + wl.cache_key);
+    q.cache_pins = reinterpret_cast<uint32_t *>(ws + wl.cache_pins);
+  };
+  if (ctx->B != B || ctx->G != G || ctx->N != N || ctx->kind != kind) {
+    if ((e = cudaMemsetAsync(ws, 0, 256, stream)) != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(counters)");
+    PrwParams q;  // warm start: the next episode of every env
+    cache_params(q);
+    q.keys = state->key;
+    if ((rc = launch_prw(q, B, env_int("RBG_PRW_M"), env_int("RBG_PRW_THREADS"), stream))) return rc;
+    ctx->B = B;
+    ctx->G = G;
+    ctx->N = N;
+    ctx->kind = kind;
+    ctx->step = 0;
+  }
+  static int chunk_env = -1;
+  if (chunk_env < 0) {
+    chunk_env = env_int("RBG_ROLLOUT_CHUNK");
+    if (chunk_env <= 0) chunk_env = 20;  // the reference's n_steps (agent_training/configs/env/connector.yaml:27)
+  }
+  EnvParams p;
+  memset(&p, 0, sizeof(p));
+  p.in = *state;
+  p.out = *state;
+  p.B = B;
+  p.G = G;
+  p.N = N;
+  p.mode = ENV_MODE_STEP;
+  p.random_policy = 1;
+  p.env = *params;
+  p.cache_tag = reinterpret_cast<const unsigned long long *>(ws + wl.cache_tag);
+  p.cache_key = reinterpret_cast<const uint2 *>(ws + wl.cache_key);
+  p.cache_pins = reinterpret_cast<const uint32_t *>(ws + wl.cache_pins);
+  p.refill_list = reinterpret_cast<int32_t *>(ws + wl.refill_list[0]);
+  p.refill_keys = reinterpret_cast<uint32_t *>(ws + wl.refill_keys[0]);
+  p.refill_count = reinterpret_cast<int32_t *>(ws + 64);
+  for (int64_t t0 = 0; t0 < T; t0 += chunk_env) {
+    const int n = (int)((T - t0) < chunk_env ? (T - t0) : chunk_env);
+    p.ts = timestep_at(*ts, t0 * B, G, N);
+    if ((rc = launch_rollout(p, kind, n, action_out ? action_out + t0 * B * N : nullptr, stream))) return rc;
+    PrwParams q;  // refill the cache entries consumed in this chunk (the kernel clears the counter when done)
+    cache_params(q);
+    q.keys = p.refill_keys;
+    q.keys_compact = 1;
+    q.list = p.refill_list;
+    q.list_count = p.refill_count;
+    q.list_ticket = p.refill_count + 1;
+    q.bulk_list = 1;
+    if ((rc = launch_prw(q, B, env_int("RBG_PRW_M"), env_int("RBG_PRW_THREADS"), stream))) return rc;
+  }
+  return RBG_OK;
+}
+
 int rbg_connector_rollout_random(const rbg_state *state, int32_t *action_out, int64_t T, int64_t B, int G, int N,
                                  const rbg_env_params *params, const rbg_timestep *ts, void *workspace, void *stream) {
   int rc;
   if (T < 0) return set_error(RBG_EINVAL, "rollout length T=%lld", (long long)T);
   if ((rc = check_dims(B, G, N, 1))) return rc;
+  if ((rc = check_state(state, "state"))) return rc;
   if ((rc = check_timestep(ts))) return rc;
-  if (((int64_t)B * N * G * G * 4) % 16 != 0) return set_error(RBG_EALIGN, "rollout: one step of obs_grid (%lld bytes) is not a multiple of 16", (long long)B * N * G * G * 4);
-  for (int64_t t = 0; t < T; ++t) {
+  if (!params) return set_error(RBG_EINVAL, "params is NULL");
+  // (when G*G % 4 == 0 every step slice of the stacked arrays keeps the 16-byte alignment the
+  // vector path needs; otherwise the kernels use scalar accesses)
+  if (B == 0 || T == 0) return RBG_OK;
+  const int kind = params->autoreset_kind;
+  static int fused = -1;
+  if (fused < 0) fused = env_int("RBG_NO_FUSED_ROLLOUT") ? 0 : 1;
+  if (fused && speculative_enabled() && workspace && (kind == RBG_GEN_PRW || kind == RBG_GEN_UNIFORM)) {
+    if (!aligned16(workspace)) return set_error(RBG_EALIGN, "workspace not 16-byte aligned");
+    return rollout_fused(state, action_out, T, B, G, N, params, ts, workspace, (cudaStream_t)stream);
+  }
+  for (int64_t t = 0; t < T; ++t) {  // step-wise: SeedExtension resets, or the fused kernel switched off
     const rbg_timestep tt = timestep_at(*ts, t * B, G, N);
     rc = connector_step_impl(state, state, nullptr, action_out ? action_out + t * B * N : nullptr, 1, B, G, N, params, &tt, workspace,
                              (cudaStream_t)stream);

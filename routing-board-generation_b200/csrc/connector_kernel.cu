@@ -18,6 +18,7 @@
 #include <stdlib.h>
 
 #include "connector_device.cuh"
+#include "prw_warp.cuh"
 #include "rbg_host.h"
 
 namespace rbg {
@@ -649,6 +650,263 @@ __global__ void __launch_bounds__(EW_WARPS * 32, 12) env_warp_kernel(const EnvPa
   }
 }
 
+// ---------------------------------------------------------------------------
+// rollout_warp_kernel: T random-policy steps with auto-reset in ONE launch (the
+// reference's `n_steps` scan: generation, reset and stepping fused).  Same lane layout
+// as env_warp_kernel, but the warp keeps its K envs on chip for the whole rollout: the
+// State is read once and written once per launch, so a step only pays for what it must
+// emit (observation, mask, reward, discount, step_type, extras, action); PATH counts are
+// carried instead of recounted.  Finished envs swap in their pre-generated next episode
+// (cache, see c_api.cu "AutoReset"); an env that finishes AGAIN before the host has had
+// a chance to refill its cache entry gets its episode generated right here by the warp
+// (prw_warp.cuh).  Envs that reset are queued for one refill after the launch.
+struct RolloutParams {
+  int T;
+  int kind;              // RBG_GEN_PRW / RBG_GEN_UNIFORM
+  int gen_off;           // smem byte offset of the per-warp generator scratch
+  int gen_stride;        // bytes per warp
+  int gen_cand_bytes;    // cand region size within the scratch
+  int gen_sel_bytes;
+  int cap;
+  uint32_t thresh;
+  int32_t *action_out;   // [T,B,N] or NULL
+};
+
+template <bool VEC>
+__global__ void __launch_bounds__(EW_WARPS * 32, 8) rollout_warp_kernel(const EnvParams p, const RolloutParams rp) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int G = p.G, N = p.N, cells = p.cells;
+  const int Np = p.Np, K = 32 / Np, c4 = cells >> 2;
+  const int RS = obs_lut_stride(N);
+  uint8_t *lut = smem_raw;
+  for (int a = warp; a < N; a += EW_WARPS)
+    for (int v = lane; v < RS; v += 32) lut[a * RS + v] = v <= 3 * N ? (uint8_t)obs_value(v, 3 * a, 3 * N) : (uint8_t)0;
+  __syncthreads();  // the only CTA-wide barrier
+
+  const long long e0 = ((long long)blockIdx.x * EW_WARPS + warp) * K;
+  if (e0 >= p.B) return;
+  const int kc = (int)((p.B - e0) < (long long)K ? (p.B - e0) : (long long)K);
+  uint8_t *wg = smem_raw + p.so[0] + (size_t)warp * p.so[1];
+  uint32_t *wg32 = reinterpret_cast<uint32_t *>(wg);
+  WarpGenScratch gs;
+  {
+    uint8_t *gb = smem_raw + rp.gen_off + (size_t)warp * rp.gen_stride;
+    gs.cand = reinterpret_cast<uint64_t *>(gb);
+    gs.sel = reinterpret_cast<uint16_t *>(gb + rp.gen_cand_bytes);
+    gs.board = gb + rp.gen_cand_bytes + rp.gen_sel_bytes;
+    gs.cap = rp.cap;
+    gs.thresh = rp.thresh;
+  }
+
+  const int j = lane / Np, a = lane & (Np - 1);
+  const bool env_ok = j < kc, agent = env_ok && a < N;
+  const long long e = e0 + (env_ok ? j : 0);
+  const uint32_t gmask = Np == 32 ? FULL : (((1u << Np) - 1u) << (j * Np));
+
+  // ---- load the State once
+  if (VEC) {
+    const int4 *src = reinterpret_cast<const int4 *>(p.in.grid) + e0 * c4;
+    for (int q = lane; q < kc * c4; q += 32) {
+      const int4 v = __ldg(src + q);
+      wg32[q] = (uint32_t)(v.x & 0xff) | ((uint32_t)(v.y & 0xff) << 8) | ((uint32_t)(v.z & 0xff) << 16) | ((uint32_t)(v.w & 0xff) << 24);
+    }
+  } else {
+    const int32_t *src = p.in.grid + e0 * cells;
+    for (int i = lane; i < kc * cells; i += 32) wg[i] = (uint8_t)__ldg(src + i);
+  }
+  int pos = 0, tgt = 0, start = 0, sc = 0;
+  uint32_t k0 = 0, k1 = 0;
+  if (agent) {
+    const int2 ps = __ldg(reinterpret_cast<const int2 *>(p.in.position) + e * N + a);
+    const int2 tg = __ldg(reinterpret_cast<const int2 *>(p.in.target) + e * N + a);
+    const int2 st = __ldg(reinterpret_cast<const int2 *>(p.in.start) + e * N + a);
+    pos = (ps.x << 8) | ps.y;
+    tgt = (tg.x << 8) | tg.y;
+    start = (st.x << 8) | st.y;
+  }
+  if (env_ok) {
+    sc = p.in.step_count[e];
+    k0 = p.in.key[2 * e];
+    k1 = p.in.key[2 * e + 1];
+  }
+  __syncwarp();
+  uint8_t *g = wg + (size_t)j * cells;
+  const SmemGrid sg{g, G, 0, G};
+  int paths = 0;  // PATH cells of the env (extras: total_path_length), carried across steps
+  if (env_ok) {
+    if (VEC) {
+      for (int q = a; q < c4; q += Np) paths += count_path_codes(wg32[j * c4 + q]);
+    } else {
+      for (int i = a; i < cells; i += Np) paths += (g[i] % 3u == 1u) ? 1 : 0;
+    }
+  }
+  for (int off = Np >> 1; off; off >>= 1) paths += __shfl_xor_sync(FULL, paths, off);
+  bool did_reset = false;
+
+  for (int t = 0; t < rp.T; ++t) {
+    const long long tb = (long long)t * p.B;  // row offset of step t in the stacked outputs
+    // ---- agents: sample action, move_position, is_valid_position, collisions
+    const bool was = agent && pos == tgt;
+    const int r = pos >> 8, c = pos & 255;
+    int dest = -1;
+    if (agent) {
+      const uint32_t mk = move_mask(sg, r, c, a, was);
+      const int action = random_action(k0, k1, (uint32_t)sc, (uint32_t)a, mk);
+      if (rp.action_out) rp.action_out[(tb + e) * N + a] = action;
+      const int nr = r + (action == UP ? -1 : (action == DOWN ? 1 : 0));
+      const int nc = c + (action == RIGHT ? 1 : (action == LEFT ? -1 : 0));
+      const bool inb = (unsigned)nr < (unsigned)G && (unsigned)nc < (unsigned)G;
+      const uint32_t v = inb ? sg.at(nr, nc) : 0xFFu;
+      if (inb && (v == 0u || v == 3u * a + TARGET) && !was && action != NOOP) dest = nr * G + nc;
+    }
+    const uint32_t mval = dest >= 0 ? (((uint32_t)j << 16) | (uint32_t)dest) : (0x80000000u | (uint32_t)lane);
+    const uint32_t mm = __match_any_sync(FULL, mval);
+    const bool win = dest >= 0 && lane == 31 - __clz(mm);
+    __syncwarp();
+    if (win) {
+      g[r * G + c] = (uint8_t)(3 * a + PATH);
+      g[dest] = (uint8_t)(3 * a + POSITION);
+      uint32_t nr, nc;
+      p.divG.divmod((uint32_t)dest, nr, nc);
+      pos = (int)((nr << 8) | nc);
+    }
+    __syncwarp();
+    // ---- action mask, connected / done, reward on the new grid
+    const bool now = agent && pos == tgt;
+    uint32_t mk3 = 0;
+    if (agent) mk3 = move_mask(sg, pos >> 8, pos & 255, a, now);
+    const bool done = now || mk3 == 0u;
+    const float rew = __fadd_rn(__fmul_rn(p.env.connected_reward, (!was && now) ? 1.0f : 0.0f), __fmul_rn(p.env.timestep_reward, was ? 0.0f : 1.0f));
+    const int ndone = __popc(__ballot_sync(FULL, agent && done) & gmask);
+    const int nconn = __popc(__ballot_sync(FULL, now) & gmask);
+    paths += __popc(__ballot_sync(FULL, win) & gmask);
+    sc += 1;
+    const bool terminal = env_ok && (ndone == N || sc >= p.env.time_limit);
+    const int tpl = paths + N;
+
+    // ---- auto-reset: cached episode, else generate it here
+    bool hit = false;
+    uint32_t nk0 = 0, nk1 = 0;
+    if (terminal && p.cache_tag) {
+      const unsigned long long tag = __ldcg(p.cache_tag + e);
+      if (tag == (((unsigned long long)k1 << 32) | k0)) {
+        __threadfence();
+        const uint2 nk = __ldcg(p.cache_key + e);
+        nk0 = nk.x;
+        nk1 = nk.y;
+        hit = true;
+      }
+    }
+    int npos = pos, ntgt = tgt;
+    if (hit && a < N) {
+      const uint32_t pin = __ldcg(p.cache_pins + e * N + a);
+      npos = (int)(pin >> 16);
+      ntgt = (int)(pin & 0xffffu);
+    }
+    uint32_t missm = __ballot_sync(FULL, terminal && !hit && a == 0);
+    while (missm) {  // warp-uniform: generate the episode of env `jj` with the whole warp
+      const int src_lane = __ffs(missm) - 1;
+      missm &= missm - 1;
+      const uint32_t gk0 = __shfl_sync(FULL, k0, src_lane), gk1 = __shfl_sync(FULL, k1, src_lane);
+      uint32_t x0, x1;
+      int gstart, gfin;
+      warp_generate_pins(rp.kind, gk0, gk1, G, N, p.divG, gs, lane, x0, x1, gstart, gfin);
+      // lane i < N holds agent i's pins; hand them to env jj's lanes
+      const int from = a < N ? a : 0;
+      const int hs = __shfl_sync(FULL, gstart, from), hf = __shfl_sync(FULL, gfin, from);
+      if (lane >= src_lane && lane < src_lane + Np) {
+        nk0 = x0;
+        nk1 = x1;
+        if (a < N) {
+          npos = hs;
+          ntgt = hf;
+        }
+      }
+    }
+    // ---- small outputs of step t (terminal step's reward / discount / step_type / extras)
+    if (env_ok && a == 0) {
+      p.ts.step_type[tb + e] = (int8_t)(terminal ? 2 : 1);
+      p.ts.num_connections[tb + e] = nconn;
+      p.ts.ratio_connections[tb + e] = __fdiv_rn((float)nconn, (float)N);
+      p.ts.total_path_length[tb + e] = tpl;
+      p.ts.obs_step_count[tb + e] = terminal ? 0 : sc;
+    }
+    if (agent) {
+      p.ts.reward[(tb + e) * N + a] = rew;
+      p.ts.discount[(tb + e) * N + a] = (terminal || done) ? 0.0f : 1.0f;
+    }
+    if (terminal) {  // group-uniform: swap in the new episode (pins-only grid, heads then targets)
+      for (int i = a; i < cells; i += Np) g[i] = 0;
+      pos = npos;
+      tgt = ntgt;
+      start = npos;
+      k0 = nk0;
+      k1 = nk1;
+      sc = 0;
+      paths = 0;
+      did_reset = true;
+      __syncwarp(gmask);
+      if (a < N) g[(pos >> 8) * G + (pos & 255)] = (uint8_t)(3 * a + POSITION);
+      __syncwarp(gmask);
+      if (a < N) g[(tgt >> 8) * G + (tgt & 255)] = (uint8_t)(3 * a + TARGET);
+      __syncwarp(gmask);
+      if (a < N) mk3 = move_mask(sg, pos >> 8, pos & 255, a, pos == tgt);
+    }
+    __syncwarp();
+    if (agent) store_mask5(p.ts.action_mask + ((tb + e) * N + a) * 5, mk3);
+    // ---- observation of step t
+    if (VEC) {
+      int4 *odst = reinterpret_cast<int4 *>(p.ts.obs_grid) + (tb + e0) * N * c4;
+      for (int q = lane; q < kc * c4; q += 32) {
+        const int m = (int)p.divC4.div((uint32_t)q);
+        const uint32_t w = wg32[q];
+        const uint32_t b0 = w & 0xffu, b1 = (w >> 8) & 0xffu, b2 = (w >> 16) & 0xffu, b3 = w >> 24;
+        int4 *o = odst + (size_t)m * N * c4 + (q - m * c4);
+        const uint8_t *row = lut;
+#pragma unroll 2
+        for (int x = 0; x < N; ++x, o += c4, row += RS) *o = make_int4(row[b0], row[b1], row[b2], row[b3]);
+      }
+    } else {
+      int32_t *odst = p.ts.obs_grid + (tb + e0) * N * cells;
+      for (int i = lane; i < kc * cells; i += 32) {
+        const int m = (int)p.divCells.div((uint32_t)i);
+        const uint32_t v = wg[i];
+        int32_t *o = odst + (size_t)m * N * cells + (i - m * cells);
+        for (int x = 0; x < N; ++x, o += cells) *o = lut[x * RS + v];
+      }
+    }
+    __syncwarp();  // the next step's writes must not overtake these reads
+  }
+
+  // ---- write the State once; queue the envs that reset for a cache refill
+  if (VEC) {
+    int4 *gdst = reinterpret_cast<int4 *>(p.out.grid) + e0 * c4;
+    for (int q = lane; q < kc * c4; q += 32) gdst[q] = bytes_to_int4(wg32[q]);
+  } else {
+    int32_t *gdst = p.out.grid + e0 * cells;
+    for (int i = lane; i < kc * cells; i += 32) gdst[i] = wg[i];
+  }
+  if (env_ok && a == 0) {
+    p.out.step_count[e] = sc;
+    p.out.key[2 * e] = k0;
+    p.out.key[2 * e + 1] = k1;
+    if (did_reset && p.refill_list) {
+      const int slot = atomicAdd(p.refill_count, 1);
+      p.refill_list[slot] = (int32_t)e;
+      p.refill_keys[2 * slot] = k0;
+      p.refill_keys[2 * slot + 1] = k1;
+    }
+  }
+  if (agent) {
+    const long long ga = e * N + a;
+    reinterpret_cast<int2 *>(p.out.position)[ga] = make_int2(pos >> 8, pos & 255);
+    reinterpret_cast<int2 *>(p.out.target)[ga] = make_int2(tgt >> 8, tgt & 255);
+    reinterpret_cast<int2 *>(p.out.start)[ga] = make_int2(start >> 8, start & 255);
+    p.out.agent_id[ga] = a;
+  }
+}
+
 // standalone random policy: one thread per (env, agent), grid read from global
 __global__ void __launch_bounds__(256) random_actions_kernel(rbg_state st, long long B, int G, int N,
                                                              FastDiv divN, int32_t *action) {
@@ -737,6 +995,53 @@ int launch_env(EnvParams p, int force_E, cudaStream_t stream) {
     }
   }
   return check_launch("env_kernel");
+}
+
+int launch_rollout(EnvParams p, int kind, int T, int32_t *action_out, cudaStream_t stream) {
+  const int G = p.G, N = p.N;
+  p.cells = G * G;
+  const bool vec = (p.cells & 3) == 0;
+  p.divN = FastDiv::make((uint32_t)N);
+  p.divG = FastDiv::make((uint32_t)G);
+  p.divC4 = FastDiv::make((uint32_t)(vec ? p.cells >> 2 : 1));
+  p.divCells = FastDiv::make((uint32_t)p.cells);
+  if (p.B <= 0 || T <= 0) return RBG_OK;
+  int Np = 1;
+  while (Np < N) Np <<= 1;
+  p.Np = Np;
+  const int K = 32 / Np;
+  p.E = EW_WARPS * K;
+  const size_t lutB = ((size_t)N * obs_lut_stride(N) + 256 + 15) & ~(size_t)15;
+  const size_t wgrid = ((size_t)K * p.cells + 15) & ~(size_t)15;
+  p.so[0] = (int)lutB;
+  p.so[1] = (int)wgrid;
+  RolloutParams rp;
+  rp.T = T;
+  rp.kind = kind;
+  rp.action_out = action_out;
+  const int nsel = kind == RBG_GEN_PRW ? N : 2 * N;
+  rp.cap = 4 * nsel + 32;
+  {
+    const double frac = (2.0 * nsel + 16.0) / (double)p.cells;
+    rp.thresh = frac >= 1.0 ? 0xffffffffu : (uint32_t)(frac * 4294967296.0);
+  }
+  rp.gen_cand_bytes = (int)(((size_t)rp.cap * 8 + 15) & ~(size_t)15);
+  rp.gen_sel_bytes = (int)(((size_t)(2 * N + 2) * 2 + 15) & ~(size_t)15);
+  const size_t board = (((size_t)(G + 4) * (G + 4) + 15) / 16) * 16;
+  rp.gen_stride = (int)(rp.gen_cand_bytes + rp.gen_sel_bytes + board);
+  rp.gen_off = (int)(lutB + EW_WARPS * wgrid);
+  const size_t smem = (size_t)rp.gen_off + (size_t)EW_WARPS * rp.gen_stride;
+  if (smem > 200 * 1024) return set_error(RBG_EINVAL, "rollout: shared memory %zu too large", smem);
+  const int64_t ctas = (p.B + p.E - 1) / p.E;
+  LaunchScope scope(RBG_K_ROLLOUT, stream);
+  if (vec) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(rollout_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    rollout_warp_kernel<true><<<(unsigned)ctas, EW_WARPS * 32, smem, stream>>>(p, rp);
+  } else {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(rollout_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    rollout_warp_kernel<false><<<(unsigned)ctas, EW_WARPS * 32, smem, stream>>>(p, rp);
+  }
+  return check_launch("rollout_warp_kernel");
 }
 
 int launch_random_actions(const rbg_state &st, int64_t B, int G, int N, int32_t *action, cudaStream_t stream) {

@@ -439,7 +439,7 @@ int launch_prw(PrwParams p, int64_t max_boards, int force_M, int force_threads,
     threads = 64;
     M = 2 * gpw * 2;  // one board per group + one refill
   }
-  if (p.list) {
+  if (p.list && !p.bulk_list) {  // per-step lists: a few percent of the batch, latency matters
     threads = 64;
     M = 2 * gpw;
   }
@@ -461,7 +461,7 @@ int launch_prw(PrwParams p, int64_t max_boards, int force_M, int force_threads,
   }
   int64_t ctas = (max_boards + M - 1) / M;
   if (ctas <= 0) return RBG_OK;
-  if (p.list && ctas > 148 * (p.to_cache ? 4 : 2)) ctas = 148 * (p.to_cache ? 4 : 2);  // refills are ~4% of the batch; the synchronous list is near-empty  // the kernel strides; an empty list costs ~2 us
+  if (p.list && !p.bulk_list && ctas > 148 * (p.to_cache ? 4 : 2)) ctas = 148 * (p.to_cache ? 4 : 2);  // refills are ~4% of the batch; the synchronous list is near-empty  // the kernel strides; an empty list costs ~2 us
   {
     LaunchScope scope(RBG_K_PRW, stream);
     prw_kernel<<<(unsigned)ctas, threads, smem, stream>>>(p);

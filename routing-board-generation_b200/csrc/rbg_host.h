@@ -44,6 +44,7 @@ struct PrwParams {
   // auto-reset cache refill: keys[] is indexed by list slot (not env id) and the
   // result goes to the env's cache entry instead of State / TimeStep
   int keys_compact, to_cache;
+  int bulk_list;  // the list is large (a rollout chunk's resets): use the bulk launch shape
   unsigned long long *cache_tag;  // [B]   state.key this entry succeeds (k0 | k1 << 32)
   uint2 *cache_key;               // [B]   State.key of the cached episode
   uint32_t *cache_pins;           // [B,N] start_r<<24 | start_c<<16 | target_r<<8 | target_c
@@ -86,6 +87,8 @@ struct EnvParams {
 };
 
 int launch_env(EnvParams p, int force_E, cudaStream_t stream);
+// T random-policy auto-reset steps in one launch (kind: RBG_GEN_PRW / RBG_GEN_UNIFORM); ts fields stacked [T,B,...]
+int launch_rollout(EnvParams p, int kind, int T, int32_t *action_out, cudaStream_t stream);
 int launch_random_actions(const rbg_state &st, int64_t B, int G, int N,
                           int32_t *action, cudaStream_t stream);
 

@@ -367,20 +367,62 @@ def test_fused_random_step_matches_two_calls(rbg, orc):
         _assert_timestep(ts, rts, f"at step {t}")
 
 
-@pytest.mark.parametrize("G,N,B,T", [(10, 5, 3000, 45), (32, 16, 96, 12)])
-def test_rollout_matches_stepwise_oracle(rbg, orc, G, N, B, T):
-    """rbg_connector_rollout_random (BASELINE configs[4] shape at 32x32/16) == T oracle steps."""
+@pytest.mark.parametrize("kind,G,N,B,T,time_limit", [
+    ("parallel_random_walk", 10, 5, 3000, 45, 9),     # resets inside every chunk, some envs twice (in-kernel generation)
+    ("parallel_random_walk", 32, 16, 96, 12, 9),      # BASELINE configs[4] shape
+    ("parallel_random_walk", 10, 5, 1000, 25, 1),     # every step is terminal: the in-kernel generator runs constantly
+    ("parallel_random_walk", 10, 5, 1000, 25, 2),
+    ("parallel_random_walk", 5, 3, 777, 23, 6),       # cells % 4 != 0: scalar path, ragged last warp
+    ("parallel_random_walk", 9, 9, 301, 14, 5),       # N > 8: two envs per warp
+    ("parallel_random_walk", 12, 20, 130, 14, 7),     # N > 16: one env per warp
+    ("parallel_random_walk", 40, 32, 40, 8, 5),       # largest supported shape
+    ("uniform", 10, 5, 2000, 30, 7),
+    ("uniform", 7, 6, 500, 21, 3),
+    ("seed_extension", 10, 5, 300, 12, 5),            # no fused kernel for this generator: step-wise path
+])
+def test_rollout_matches_stepwise_oracle(rbg, orc, kind, G, N, B, T, time_limit):
+    """rbg_connector_rollout_random (fused generate + reset + rollout) == T oracle steps."""
     keys, kref = _keys(rbg, orc, 12, B)
-    env = rbg.VmapAutoResetWrapper(rbg.Connector(generator=rbg.ParallelRandomWalkGenerator(G, N), time_limit=9))
+    gen = {"parallel_random_walk": rbg.ParallelRandomWalkGenerator, "uniform": rbg.UniformRandomGenerator, "seed_extension": rbg.SeedExtensionGenerator}[kind](G, N)
+    env = rbg.VmapAutoResetWrapper(rbg.Connector(generator=gen, time_limit=time_limit))
     st, _ = env.reset(keys)
-    rst, _ = orc.connector_reset_batch("parallel_random_walk", kref, G, N)
+    rst, _ = orc.connector_reset_batch(kind, kref, G, N)
     st, ts, act = env.rollout_random(st, T)
     for t in range(T):
         a = orc.random_actions_batch(rst)
         assert np.array_equal(_np(act[t]), a), f"actions differ at step {t}"
-        rst, rts = orc.connector_step_batch(rst, a, time_limit=9, autoreset_kind="parallel_random_walk")
+        rst, rts = orc.connector_step_batch(rst, a, time_limit=time_limit, autoreset_kind=kind)
         _assert_timestep(ts[t], rts, f"at step {t}")
     _assert_state(st, rst, "after the rollout")
+    # a second rollout continues from the in-place State (and a warm cache)
+    st, ts, act = env.rollout_random(st, 7)
+    for t in range(7):
+        a = orc.random_actions_batch(rst)
+        rst, rts = orc.connector_step_batch(rst, a, time_limit=time_limit, autoreset_kind=kind)
+        _assert_timestep(ts[t], rts, f"at step {t} of the second rollout")
+    _assert_state(st, rst, "after the second rollout")
+
+
+def test_rollout_and_stepwise_calls_interleave(rbg, orc):
+    """The fused rollout and the per-step API share one workspace (cache, refill lists)."""
+    import torch
+
+    keys, kref = _keys(rbg, orc, 33, 1500)
+    env = rbg.VmapAutoResetWrapper(rbg.Connector(generator=rbg.ParallelRandomWalkGenerator(10, 5), time_limit=6))
+    st, _ = env.reset(keys)
+    rst, _ = orc.connector_reset_batch("parallel_random_walk", kref, 10, 5)
+    for rnd in range(4):
+        for _ in range(5):
+            a = orc.random_actions_batch(rst)
+            st, ts = env.step(st, torch.from_numpy(a).cuda(), inplace=True)
+            rst, rts = orc.connector_step_batch(rst, a, time_limit=6, autoreset_kind="parallel_random_walk")
+            _assert_timestep(ts, rts, f"step-wise, round {rnd}")
+        st, ts, act = env.rollout_random(st, 11)
+        for t in range(11):
+            a = orc.random_actions_batch(rst)
+            rst, rts = orc.connector_step_batch(rst, a, time_limit=6, autoreset_kind="parallel_random_walk")
+            _assert_timestep(ts[t], rts, f"rollout step {t}, round {rnd}")
+        _assert_state(st, rst, f"round {rnd}")
 
 
 def test_multi_to_single_wrapper(rbg, orc):
