@@ -670,10 +670,14 @@ struct RolloutParams {
   int cap;
   uint32_t thresh;
   int32_t *action_out;   // [T,B,N] or NULL
+  int ratio_off;         // smem byte offset of the n / N table
 };
 
+#ifndef RBG_ROLLOUT_MIN_CTAS
+#define RBG_ROLLOUT_MIN_CTAS 8
+#endif
 template <bool VEC>
-__global__ void __launch_bounds__(EW_WARPS * 32, 8) rollout_warp_kernel(const EnvParams p, const RolloutParams rp) {
+__global__ void __launch_bounds__(EW_WARPS * 32, RBG_ROLLOUT_MIN_CTAS) rollout_warp_kernel(const EnvParams p, const RolloutParams rp) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = p.G, N = p.N, cells = p.cells;
@@ -682,6 +686,8 @@ __global__ void __launch_bounds__(EW_WARPS * 32, 8) rollout_warp_kernel(const En
   uint8_t *lut = smem_raw;
   for (int a = warp; a < N; a += EW_WARPS)
     for (int v = lane; v < RS; v += 32) lut[a * RS + v] = v <= 3 * N ? (uint8_t)obs_value(v, 3 * a, 3 * N) : (uint8_t)0;
+  float *ratio_lut = reinterpret_cast<float *>(smem_raw + rp.ratio_off);  // n / N for n = 0..N (extras: ratio_connections)
+  if (tid <= N) ratio_lut[tid] = __fdiv_rn((float)tid, (float)N);
   __syncthreads();  // the only CTA-wide barrier
 
   const long long e0 = ((long long)blockIdx.x * EW_WARPS + warp) * K;
@@ -743,6 +749,9 @@ __global__ void __launch_bounds__(EW_WARPS * 32, 8) rollout_warp_kernel(const En
   }
   for (int off = Np >> 1; off; off >>= 1) paths += __shfl_xor_sync(FULL, paths, off);
   bool did_reset = false;
+  // the action mask of the state an env is in: what step t emits is what step t+1's policy samples from
+  uint32_t mk3 = 0;
+  if (agent) mk3 = move_mask(sg, pos >> 8, pos & 255, a, pos == tgt);
 
   for (int t = 0; t < rp.T; ++t) {
     const long long tb = (long long)t * p.B;  // row offset of step t in the stacked outputs
@@ -751,8 +760,7 @@ __global__ void __launch_bounds__(EW_WARPS * 32, 8) rollout_warp_kernel(const En
     const int r = pos >> 8, c = pos & 255;
     int dest = -1;
     if (agent) {
-      const uint32_t mk = move_mask(sg, r, c, a, was);
-      const int action = random_action(k0, k1, (uint32_t)sc, (uint32_t)a, mk);
+      const int action = random_action(k0, k1, (uint32_t)sc, (uint32_t)a, mk3);
       if (rp.action_out) rp.action_out[(tb + e) * N + a] = action;
       const int nr = r + (action == UP ? -1 : (action == DOWN ? 1 : 0));
       const int nc = c + (action == RIGHT ? 1 : (action == LEFT ? -1 : 0));
@@ -774,7 +782,7 @@ __global__ void __launch_bounds__(EW_WARPS * 32, 8) rollout_warp_kernel(const En
     __syncwarp();
     // ---- action mask, connected / done, reward on the new grid
     const bool now = agent && pos == tgt;
-    uint32_t mk3 = 0;
+    mk3 = 0;
     if (agent) mk3 = move_mask(sg, pos >> 8, pos & 255, a, now);
     const bool done = now || mk3 == 0u;
     const float rew = __fadd_rn(__fmul_rn(p.env.connected_reward, (!was && now) ? 1.0f : 0.0f), __fmul_rn(p.env.timestep_reward, was ? 0.0f : 1.0f));
@@ -786,23 +794,22 @@ __global__ void __launch_bounds__(EW_WARPS * 32, 8) rollout_warp_kernel(const En
     const int tpl = paths + N;
 
     // ---- auto-reset: cached episode, else generate it here
+    // (the host refills the cache on this stream BEFORE the launch, so unlike the per-step
+    // kernel no acquire fence is needed and the three reads go out together)
     bool hit = false;
     uint32_t nk0 = 0, nk1 = 0;
+    int npos = pos, ntgt = tgt;
     if (terminal && p.cache_tag) {
       const unsigned long long tag = __ldcg(p.cache_tag + e);
+      const uint2 nk = __ldcg(p.cache_key + e);
+      const uint32_t pin = a < N ? __ldcg(p.cache_pins + e * N + a) : 0u;
       if (tag == (((unsigned long long)k1 << 32) | k0)) {
-        __threadfence();
-        const uint2 nk = __ldcg(p.cache_key + e);
         nk0 = nk.x;
         nk1 = nk.y;
+        npos = (int)(pin >> 16);
+        ntgt = (int)(pin & 0xffffu);
         hit = true;
       }
-    }
-    int npos = pos, ntgt = tgt;
-    if (hit && a < N) {
-      const uint32_t pin = __ldcg(p.cache_pins + e * N + a);
-      npos = (int)(pin >> 16);
-      ntgt = (int)(pin & 0xffffu);
     }
     uint32_t missm = __ballot_sync(FULL, terminal && !hit && a == 0);
     while (missm) {  // warp-uniform: generate the episode of env `jj` with the whole warp
@@ -828,7 +835,7 @@ __global__ void __launch_bounds__(EW_WARPS * 32, 8) rollout_warp_kernel(const En
     if (env_ok && a == 0) {
       p.ts.step_type[tb + e] = (int8_t)(terminal ? 2 : 1);
       p.ts.num_connections[tb + e] = nconn;
-      p.ts.ratio_connections[tb + e] = __fdiv_rn((float)nconn, (float)N);
+      p.ts.ratio_connections[tb + e] = ratio_lut[nconn];
       p.ts.total_path_length[tb + e] = tpl;
       p.ts.obs_step_count[tb + e] = terminal ? 0 : sc;
     }
@@ -1030,7 +1037,8 @@ int launch_rollout(EnvParams p, int kind, int T, int32_t *action_out, cudaStream
   const size_t board = (((size_t)(G + 4) * (G + 4) + 15) / 16) * 16;
   rp.gen_stride = (int)(rp.gen_cand_bytes + rp.gen_sel_bytes + board);
   rp.gen_off = (int)(lutB + EW_WARPS * wgrid);
-  const size_t smem = (size_t)rp.gen_off + (size_t)EW_WARPS * rp.gen_stride;
+  rp.ratio_off = rp.gen_off + EW_WARPS * rp.gen_stride;
+  const size_t smem = (size_t)rp.ratio_off + 4 * (RBG_MAX_N + 4);
   if (smem > 200 * 1024) return set_error(RBG_EINVAL, "rollout: shared memory %zu too large", smem);
   const int64_t ctas = (p.B + p.E - 1) / p.E;
   LaunchScope scope(RBG_K_ROLLOUT, stream);
