@@ -39,6 +39,7 @@ struct SeScratch {
   uint32_t *keys;   // [B, 4]   loop key (2), optkey of the current iteration (2)
   uint32_t *gkey;   // [B, 2]   State.key (random_seed_generator.py:34,57)
   int32_t *status;  // [B]      bit0 BFS ran dry / pop limit (never seen), bits 8.. sweeps
+  uint32_t *snap;   // [ceil(B/32), SB2w, 32]  pre-sweep board of every lane, word-interleaved per warp
   int CB;
 };
 
@@ -48,7 +49,7 @@ struct SeDims {
   uint32_t thresh;    // selection filter
   int cap;
   int S2, SB2w;       // extend: padded stride (G+4), words per padded board
-  int lane_words_ext; // extend: words per lane (board + snapshot), odd
+  int lane_words_ext; // extend: words per lane (the padded board), odd
   int S1, SB1;        // optimise: padded stride (G+2), bytes per padded board
   int lane_bytes_opt; // optimise: bytes per lane (board, parents, fifo, pins), multiple of 4 with odd word count
 };
@@ -140,7 +141,10 @@ __global__ void __launch_bounds__(128) se_extend_kernel(const SeedExtParams p, c
   const int G = d.G, S = d.S2;
   uint8_t *mine = smem_raw + ((size_t)warp * 32 + lane) * d.lane_words_ext * 4;
   uint8_t *board = mine;
-  uint8_t *snap = mine + d.SB2w * 4;
+  // the pre-sweep snapshot lives in global memory (L2), word q of this lane at [q * 32 + lane] of
+  // its warp's region: written and read once per mirrored sweep, coalesced, and it halves the
+  // shared-memory footprint (twice the resident warps)
+  uint32_t *snap = sc.snap + (size_t)(m >> 5) * d.SB2w * 32 + lane;
 
   // key, extkey, optkey = split(key, 3)   SE:189
   uint32_t key0 = 0, key1 = 0;
@@ -178,8 +182,7 @@ __global__ void __launch_bounds__(128) se_extend_kernel(const SeedExtParams p, c
     const bool mirrored = flip || flop;
     if (mirrored) {  // the convergence test needs the pre-sweep board  PPU:70,186-189
       const uint32_t *a = reinterpret_cast<const uint32_t *>(board);
-      uint32_t *b = reinterpret_cast<uint32_t *>(snap);
-      for (int q = 0; q < d.SB2w; ++q) b[q] = a[q];
+      for (int q = 0; q < d.SB2w; ++q) snap[q * 32] = a[q];
     }
     bool modified = false;
     // walking the FLIPPED board row-major == walking the board with mirrored
@@ -255,8 +258,11 @@ __global__ void __launch_bounds__(128) se_extend_kernel(const SeedExtParams p, c
       bool diff = false;
       for (int r = 0; r < G; ++r) {
         const uint8_t *a = board + (r + 2) * S + 2;
-        const uint8_t *b = snap + ((flip ? G - 1 - r : r) + 2) * S + 2 + (flop ? G - 1 : 0);
-        for (int c = 0; c < G; ++c, b += scol) diff |= (a[c] != b[0]);
+        int o = ((flip ? G - 1 - r : r) + 2) * S + 2 + (flop ? G - 1 : 0);  // byte offset in the snapshot
+        for (int c = 0; c < G; ++c, o += scol) {
+          const uint32_t w = snap[(o >> 2) * 32];
+          diff |= (uint32_t)a[c] != ((w >> (8 * (o & 3))) & 0xffu);
+        }
       }
       again = diff;
     }
@@ -519,7 +525,7 @@ int launch_seedext(SeedExtParams p, int64_t max_boards, cudaStream_t stream) {
   }
   d.S2 = G + 4;
   d.SB2w = (int)(round_up((size_t)d.S2 * d.S2, 4) / 4);
-  d.lane_words_ext = 2 * d.SB2w + 1;  // odd: lanes on the same cell hit 32 different banks
+  d.lane_words_ext = d.SB2w | 1;  // odd: lanes on the same cell hit 32 different banks
   d.S1 = G + 2;
   d.SB1 = (int)round_up((size_t)d.S1 * d.S1, 4);
   {
@@ -532,7 +538,8 @@ int launch_seedext(SeedExtParams p, int64_t max_boards, cudaStream_t stream) {
   sc.CB = (int)round_up((size_t)d.cells, 16);
   const size_t n = (size_t)max_boards;
   const size_t o_keys = round_up(n * sc.CB, 256), o_gkey = o_keys + round_up(n * 16, 256), o_status = o_gkey + round_up(n * 8, 256);
-  const size_t total = o_status + round_up(n * 4, 256);
+  const size_t o_snap = o_status + round_up(n * 4, 256);
+  const size_t total = o_snap + round_up(((n + 31) / 32) * 32 * (size_t)d.SB2w * 4, 256);
   uint8_t *base = nullptr;
   {  // keep the stream-ordered pool's memory cached between calls (default: released at every sync)
     static bool pool_ready = false;
@@ -552,6 +559,7 @@ int launch_seedext(SeedExtParams p, int64_t max_boards, cudaStream_t stream) {
   sc.keys = reinterpret_cast<uint32_t *>(base + o_keys);
   sc.gkey = reinterpret_cast<uint32_t *>(base + o_gkey);
   sc.status = reinterpret_cast<int32_t *>(base + o_status);
+  sc.snap = reinterpret_cast<uint32_t *>(base + o_snap);
 
   int rc = RBG_OK;
   do {
