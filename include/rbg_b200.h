@@ -123,6 +123,14 @@ int rbg_prw_generate(const uint32_t *keys, int64_t B, int G, int N,
 int rbg_generator_state(int kind, const uint32_t *keys, int64_t B, int G, int N,
                         const rbg_state *out, void *stream);
 
+/* BoardDatasetGeneratorJAX.__call__(key) -> State
+ * (rl_training/offline_generation/dataset_generator_jax.py:112-141): `key, _ = split(key)`,
+ * `which = randint(key, (), 0, K)`, State from the K pre-generated boards' pins
+ * heads[K,2,N] / targets[K,2,N] (the layout generate_n_boards stores, :58-110). */
+int rbg_dataset_state(const uint32_t *keys, int64_t B, int G, int N,
+                      const int32_t *heads, const int32_t *targets, int64_t K,
+                      const rbg_state *out, void *stream);
+
 /* SeedExtensionBoard(G,G,N).return_solved_board(key, randomness, two_sided,
  * extension_iterations, extension_steps)   SE:149-227.
  * extension_steps < 0 means unlimited (the reference default 1e23). */

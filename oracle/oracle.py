@@ -265,6 +265,21 @@ def state_batch(kind, keys, G: int, N: int, nthreads: int = 0) -> Dict[str, np.n
     return st
 
 
+def dataset_state_batch(keys, G: int, N: int, heads, targets) -> Dict[str, np.ndarray]:
+    """BoardDatasetGeneratorJAX.__call__ over keys[B,2]; heads / targets int32[K,2,N]."""
+    keys = _u32(keys).reshape(-1, 2)
+    heads, targets = _i32(heads), _i32(targets)
+    B, K = keys.shape[0], heads.shape[0]
+    st = dict(grid=np.empty((B, G, G), np.int32), step_count=np.empty((B,), np.int32), agent_id=np.empty((B, N), np.int32), start=np.empty((B, N, 2), np.int32),
+              target=np.empty((B, N, 2), np.int32), position=np.empty((B, N, 2), np.int32), key=np.empty((B, 2), np.uint32))
+    for b in range(B):
+        sc = C.c_int32()
+        lib().orc_dataset_state(_p(keys[b], u32p), C.c_int(G), C.c_int(N), _p(heads, i32p), _p(targets, i32p), C.c_int64(K), _p(st["grid"][b], i32p), C.byref(sc),
+                                _p(st["agent_id"][b], i32p), _p(st["start"][b], i32p), _p(st["target"][b], i32p), _p(st["position"][b], i32p), _p(st["key"][b], u32p))
+        st["step_count"][b] = sc.value
+    return st
+
+
 # ---------------------------------------------------------------- Connector
 def _alloc_timestep(B: int, G: int, N: int) -> Dict[str, np.ndarray]:
     return dict(

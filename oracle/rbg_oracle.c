@@ -803,6 +803,35 @@ int orc_state(int kind, const uint32_t key_in[2], int G, int N, int32_t *grid,
   return 0;
 }
 
+/* BoardDatasetGeneratorJAX.__call__ (rl_training/offline_generation/
+ * dataset_generator_jax.py:112-141): key, _ = split(key); which = randint(key, (), 0, K);
+ * State from heads[which] / targets[which] (each [2,N], rows then cols). */
+int orc_dataset_state(const uint32_t key_in[2], int G, int N, const int32_t *heads,
+                      const int32_t *targets, int64_t K, int32_t *grid,
+                      int32_t *step_count, int32_t *agent_id, int32_t *start,
+                      int32_t *target, int32_t *position, uint32_t key_out[2]) {
+  uint32_t ks[4];
+  orc_split(key_in, 2, ks);
+  int32_t which = orc_randint(&ks[0], 0, (int32_t)K);
+  const int32_t *h = heads + (size_t)which * 2 * N, *t = targets + (size_t)which * 2 * N;
+  memset(grid, 0, sizeof(int32_t) * (size_t)(G * G));
+  for (int i = 0; i < N; ++i) grid[h[i] * G + h[N + i]] = 3 * i + POSITION;
+  for (int i = 0; i < N; ++i) grid[t[i] * G + t[N + i]] = 3 * i + TARGET;
+  for (int i = 0; i < N; ++i) {
+    agent_id[i] = i;
+    start[2 * i] = h[i];
+    start[2 * i + 1] = h[N + i];
+    target[2 * i] = t[i];
+    target[2 * i + 1] = t[N + i];
+    position[2 * i] = h[i];
+    position[2 * i + 1] = h[N + i];
+  }
+  *step_count = 0;
+  key_out[0] = ks[0];
+  key_out[1] = ks[1];
+  return 0;
+}
+
 /* ======================================================================== */
 /* Connector (jumanji==0.2.2 environments/routing/connector/{env,utils,       */
 /* reward}.py -- UPSTREAM, not under /root/reference; call sites             */

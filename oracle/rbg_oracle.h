@@ -176,6 +176,12 @@ void orc_random_actions_batch(int64_t B, int G, int N, const int32_t *grid,
                               int32_t *action, int nthreads);
 int orc_max_threads(void);
 
+/* BoardDatasetGeneratorJAX.__call__: heads / targets are [K,2,N] */
+int orc_dataset_state(const uint32_t key_in[2], int G, int N, const int32_t *heads,
+                      const int32_t *targets, int64_t K, int32_t *grid,
+                      int32_t *step_count, int32_t *agent_id, int32_t *start,
+                      int32_t *target, int32_t *position, uint32_t key_out[2]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,11 +7,12 @@ from .board_generation import ParallelRandomWalkBoard, SeedExtensionBoard  # noq
 from .connector import Connector, DenseRewardFn, MultiToSingleWrapper, VmapAutoResetWrapper, make_random_policy_connector  # noqa: F401
 from .engine import PRNGKey, split  # noqa: F401
 from .interface import BoardGenerator, BoardName  # noqa: F401
+from .offline_generation import BoardDatasetGeneratorJAX  # noqa: F401
 from .online_generators import Generator, ParallelRandomWalkGenerator, SeedExtensionGenerator, UniformRandomGenerator  # noqa: F401
 from .types import Agent, Observation, State, TimeStep  # noqa: F401
 
 __all__ = [
-    "Agent", "BoardGenerator", "BoardName", "Connector", "DenseRewardFn", "Generator", "MultiToSingleWrapper", "Observation",
+    "Agent", "BoardDatasetGeneratorJAX", "BoardGenerator", "BoardName", "Connector", "DenseRewardFn", "Generator", "MultiToSingleWrapper", "Observation",
     "ParallelRandomWalkBoard", "ParallelRandomWalkGenerator", "PRNGKey", "RbgError", "SeedExtensionBoard", "SeedExtensionGenerator",
     "State", "TimeStep", "UniformRandomGenerator", "VmapAutoResetWrapper", "engine", "launch_count", "make_random_policy_connector",
     "sharding", "split",

@@ -45,6 +45,7 @@ SYMBOLS = {
     "rbg_split_keys": (_int, [C.POINTER(C.c_uint32), _i64, _i64, _i64, _vp, _vp]),
     "rbg_prw_generate": (_int, [_vp, _i64, _int, _int, _vp, _vp, _vp, _vp, _vp]),
     "rbg_generator_state": (_int, [_int, _vp, _i64, _int, _int, _SP, _vp]),
+    "rbg_dataset_state": (_int, [_vp, _i64, _int, _int, _vp, _vp, _i64, _SP, _vp]),
     "rbg_seedext_solved": (_int, [_vp, _i64, _int, _int, _f, _int, _int, _i64, _vp, _vp]),
     "rbg_seedext_starts_ends": (_int, [_vp, _i64, _int, _int, _f, _int, _int, _i64, _vp, _vp, _vp]),
     "rbg_connector_observe": (_int, [_SP, _i64, _int, _int, _TP, _vp]),

@@ -573,6 +573,17 @@ int rbg_generator_state(int kind, const uint32_t *keys, int64_t B, int G, int N,
   return generator_state_impl(kind, keys, B, G, N, out, nullptr, 0, nullptr, nullptr, (cudaStream_t)stream);
 }
 
+int rbg_dataset_state(const uint32_t *keys, int64_t B, int G, int N, const int32_t *heads, const int32_t *targets, int64_t K,
+                      const rbg_state *out, void *stream) {
+  int rc;
+  if ((rc = check_dims(B, G, N, 1))) return rc;
+  if (B == 0) return RBG_OK;
+  if (!keys || !heads || !targets) return set_error(RBG_EINVAL, "rbg_dataset_state: NULL pointer");
+  if (K < 1 || K > 0x7fffffffLL) return set_error(RBG_EINVAL, "rbg_dataset_state: number of boards K=%lld", (long long)K);
+  if ((rc = check_state(out, "state"))) return rc;
+  return launch_dataset_state(keys, B, G, N, heads, targets, K, *out, (cudaStream_t)stream);
+}
+
 int rbg_seedext_solved(const uint32_t *keys, int64_t B, int G, int N, float randomness, int two_sided,
                        int iterations, int64_t extension_steps, int32_t *solved, void *stream) {
   int rc;

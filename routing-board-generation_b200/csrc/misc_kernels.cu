@@ -35,6 +35,62 @@ int launch_split_keys(uint32_t k0, uint32_t k1, int64_t B, int64_t offset, int64
   return check_launch("split_keys_kernel");
 }
 
+// BoardDatasetGeneratorJAX.__call__ (dataset_generator_jax.py:112-141), one warp per env:
+// key, _ = split(key); which = randint(key, (), 0, K) with jax's two-draw formula
+// (SURVEY A.9); pins-only grid from heads[which] / targets[which] (heads first, then targets).
+constexpr int DS_WARPS = 8;
+
+__global__ void __launch_bounds__(DS_WARPS * 32) dataset_state_kernel(const uint32_t *__restrict__ keys, long long B, int G, int N,
+                                                                      const int32_t *__restrict__ heads, const int32_t *__restrict__ targets,
+                                                                      uint32_t K, rbg_state st) {
+  const int lane = threadIdx.x & 31;
+  const long long e = (long long)blockIdx.x * DS_WARPS + (threadIdx.x >> 5);
+  if (e >= B) return;
+  const int cells = G * G;
+  uint32_t k0, k1, b0, b1, h0, h1, l0, l1;
+  split2(keys[2 * e], keys[2 * e + 1], k0, k1, b0, b1);  // State.key = split(key)[0]
+  split2(k0, k1, h0, h1, l0, l1);                        // randint: k1, k2 = split(key)
+  const uint32_t hi = bits_scalar(h0, h1), lo = bits_scalar(l0, l1);
+  uint32_t mult = 65536u % K;
+  mult = (uint32_t)(((unsigned long long)mult * mult) % K);
+  const uint32_t which = ((hi % K) * mult + (lo % K)) % K;  // uint32 wrap-around as in jax
+  int32_t *grid = st.grid + e * cells;
+  for (int i = lane; i < cells; i += 32) grid[i] = 0;
+  int sr = 0, sc = 0, tr = 0, tc = 0;
+  if (lane < N) {
+    const int32_t *h = heads + (size_t)which * 2 * N, *t = targets + (size_t)which * 2 * N;
+    sr = h[lane];
+    sc = h[N + lane];
+    tr = t[lane];
+    tc = t[N + lane];
+  }
+  __syncwarp();
+  if (lane < N && (unsigned)sr < (unsigned)G && (unsigned)sc < (unsigned)G) grid[sr * G + sc] = 3 * lane + POSITION;
+  __syncwarp();
+  if (lane < N && (unsigned)tr < (unsigned)G && (unsigned)tc < (unsigned)G) grid[tr * G + tc] = 3 * lane + TARGET;
+  if (lane < N) {
+    st.agent_id[e * N + lane] = lane;
+    reinterpret_cast<int2 *>(st.start)[e * N + lane] = make_int2(sr, sc);
+    reinterpret_cast<int2 *>(st.target)[e * N + lane] = make_int2(tr, tc);
+    reinterpret_cast<int2 *>(st.position)[e * N + lane] = make_int2(sr, sc);
+  }
+  if (lane == 0) {
+    st.step_count[e] = 0;
+    st.key[2 * e] = k0;
+    st.key[2 * e + 1] = k1;
+  }
+}
+
+int launch_dataset_state(const uint32_t *keys, int64_t B, int G, int N, const int32_t *heads, const int32_t *targets, int64_t K,
+                         const rbg_state &st, cudaStream_t stream) {
+  if (B <= 0) return RBG_OK;
+  {
+    LaunchScope scope(RBG_K_VALIDATE, stream);
+    dataset_state_kernel<<<(unsigned)((B + DS_WARPS - 1) / DS_WARPS), DS_WARPS * 32, 0, stream>>>(keys, B, G, N, heads, targets, (uint32_t)K, st);
+  }
+  return check_launch("dataset_state_kernel");
+}
+
 // Board validity, one warp per board (rules: reference
 // numpy_implementation/utils/post_processor_utils_numpy.py:34-155 and the
 // head->target connectivity of board_processor.py:111-162).

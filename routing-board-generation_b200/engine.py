@@ -164,6 +164,15 @@ def generator_state(kind, keys: torch.Tensor, G: int, N: int, out: Optional[Stat
     return st
 
 
+def dataset_state(keys: torch.Tensor, G: int, N: int, heads: torch.Tensor, targets: torch.Tensor) -> State:
+    """BoardDatasetGeneratorJAX.__call__ over keys[B,2]: pick one of the K stored boards per key."""
+    B = keys.shape[0]
+    st = alloc_state(B, G, N)
+    s = _state_struct(st)
+    _lib.check(_lib.load().rbg_dataset_state(keys.data_ptr(), B, G, N, heads.data_ptr(), targets.data_ptr(), heads.shape[0], C.byref(s), _stream()))
+    return st
+
+
 def seedext_solved(keys: torch.Tensor, G: int, N: int, randomness: float = 0.0, two_sided: bool = True, iterations: int = 1, extension_steps: float = 1e23) -> torch.Tensor:
     B = keys.shape[0]
     solved = torch.empty((B, G, G), dtype=torch.int32, device=_device())

@@ -266,6 +266,44 @@ def test_seedext_connector_autoreset_matches_oracle(rbg, orc):
     assert n_last > 512
 
 
+@pytest.mark.parametrize("board_name,G,N,K", [("offline_parallel_rw", 10, 5, 1000), ("offline_parallel_rw", 6, 4, 7), ("offline_seed_extension", 8, 4, 37)])
+def test_dataset_generator_matches_oracle(rbg, orc, board_name, G, N, K):
+    """BoardDatasetGeneratorJAX: K boards from split(PRNGKey(0), K), __call__ picks one with jax's randint."""
+    gen = rbg.BoardDatasetGeneratorJAX(G, N, board_name=board_name, number_of_boards=K)
+    kref = orc.split(orc.PRNGKey(0), K)
+    if board_name == "offline_seed_extension":
+        ref = [orc.seedext_starts_ends(kref[b], G, N, randomness=1.0, two_sided=False) for b in range(K)]
+        rh = np.stack([r[0] for r in ref])
+        rt = np.stack([r[1] for r in ref])
+    else:
+        rh, rt, _, _ = orc.prw_generate_batch(kref, G, N)
+    assert np.array_equal(_np(gen.heads), rh) and np.array_equal(_np(gen.targets), rt)
+    keys, k2 = _keys(rbg, orc, 3, 2048)
+    _assert_state(gen(keys), orc.dataset_state_batch(k2, G, N, rh, rt))
+    picked = {tuple(map(tuple, s)) for s in _np(gen(keys).agents.start)}
+    assert len(picked) > min(K, 2048) // 3  # the draw spreads over the stored boards
+    one = gen(rbg.PRNGKey(5))
+    assert one.grid.shape == (G, G)
+    assert np.array_equal(_np(gen.print_board(3)) > 0, _np(gen.print_board(3)) > 0)
+
+
+def test_dataset_generator_reference_run(rbg):
+    """Against the reference's own BoardDatasetGeneratorJAX run on the jax shim (tests/golden/reference_runs.json)."""
+    import json
+    import os
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_runs.json")) as f:
+        runs = json.load(f)
+    for cfg in runs.get("dataset_generator", []):
+        gen = rbg.BoardDatasetGeneratorJAX(cfg["G"], cfg["N"], board_name=cfg["board_name"], number_of_boards=cfg["K"])
+        assert _np(gen.heads).tolist() == cfg["heads"] and _np(gen.targets).tolist() == cfg["targets"]
+        keys = rbg.split(rbg.PRNGKey(cfg["seed"]), cfg["n"])
+        st = gen(keys)
+        assert _np(st.grid).tolist() == [r["grid"] for r in cfg["states"]]
+        assert _np(st.key).tolist() == [r["key"] for r in cfg["states"]]
+        assert _np(st.agents.start).tolist() == [r["start"] for r in cfg["states"]]
+
+
 # ------------------------------------------------------------------ Connector
 @pytest.mark.parametrize("kind", ["parallel_random_walk", "uniform"])
 @pytest.mark.parametrize("G,N", [(5, 3), (10, 5), (9, 4), (32, 16)])

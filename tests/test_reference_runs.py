@@ -76,6 +76,25 @@ def test_seedext_stages(orc, runs):
         assert rc == 0 and opt.tolist() == row["optimised_wire0"]
 
 
+def test_dataset_generator(orc, runs):
+    """BoardDatasetGeneratorJAX (dataset_generator_jax.py): stored boards and the randint pick."""
+    assert runs.get("dataset_generator"), "fixtures missing: rerun tests/tools/make_reference_fixtures.py dataset"
+    for cfg in runs["dataset_generator"]:
+        G, N, K = cfg["G"], cfg["N"], cfg["K"]
+        kref = orc.split(orc.PRNGKey(0), K)
+        if cfg["board_name"] == "offline_seed_extension":
+            ref = [orc.seedext_starts_ends(kref[b], G, N, randomness=1.0, two_sided=False) for b in range(K)]
+            rh, rt = np.stack([r[0] for r in ref]), np.stack([r[1] for r in ref])
+        else:
+            rh, rt, _, _ = orc.prw_generate_batch(kref, G, N)
+        assert rh.tolist() == cfg["heads"] and rt.tolist() == cfg["targets"]
+        keys = orc.split(orc.PRNGKey(cfg["seed"]), cfg["n"])
+        st = orc.dataset_state_batch(keys, G, N, rh, rt)
+        for b, ref_st in enumerate(cfg["states"]):
+            assert st["grid"][b].tolist() == ref_st["grid"] and st["key"][b].tolist() == ref_st["key"]
+            assert st["start"][b].tolist() == ref_st["start"] and st["target"][b].tolist() == ref_st["target"]
+
+
 @pytest.mark.skipif(not os.path.isdir(REF), reason="/root/reference is not mounted (GPU box)")
 def test_shim_passes_the_references_own_tests():
     """The NumPy jax stand-in the fixtures were made with runs the reference's only test file green."""

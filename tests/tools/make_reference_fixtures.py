@@ -10,6 +10,8 @@ What is pinned this way (none of it has a golden in the reference itself):
   * ParallelRandomWalkGenerator / UniformRandomGenerator / SeedExtensionGenerator States
   * SeedExtensionBoard.return_seeded_board / return_solved_board / generate_starts_ends with the
     default and the non-default options; extend_wires_jax and optimise_wire in isolation
+  * BoardDatasetGeneratorJAX: the stored boards and the randint pick of __call__
+    (`python tests/tools/make_reference_fixtures.py dataset` regenerates only this section)
 The shim's jax.random is checked first against the reference-owned goldens by running the reference's
 own test file (test_parallel_random_walk_board.py, 35 tests) under it.
 """
@@ -38,7 +40,38 @@ def run_reference_tests() -> str:
     return tail
 
 
+def dataset_section():
+    """BoardDatasetGeneratorJAX (dataset_generator_jax.py:20-141) -> merged into the existing JSON."""
+    sys.path.insert(0, SHIM)
+    sys.path.insert(0, REF)
+    import jax
+    import numpy as np
+    from routing_board_generation.rl_training.offline_generation.dataset_generator_jax import BoardDatasetGeneratorJAX
+
+    def L(x):
+        return np.asarray(x).astype(np.int64).tolist()
+
+    out = []
+    for (G, N, K, name, seed, n) in ((6, 4, 7, "offline_parallel_rw", 51, 24), (8, 4, 5, "offline_seed_extension", 52, 16)):
+        gen = BoardDatasetGeneratorJAX(G, N, board_name=name, number_of_boards=K)
+        keys = np.asarray(jax.random.split(jax.random.PRNGKey(seed), n))
+        states = []
+        for k in keys:
+            st = gen(jax.numpy.array(k))
+            states.append(dict(key=L(st.key), grid=L(st.grid), start=L(st.agents.start), target=L(st.agents.target)))
+        out.append(dict(G=G, N=N, K=K, board_name=name, seed=seed, n=n, heads=L(gen.heads), targets=L(gen.targets), states=states))
+        print("dataset generator", name, G, N, K)
+    with open(OUT) as f:
+        data = json.load(f)
+    data["dataset_generator"] = out
+    with open(OUT, "w") as f:
+        json.dump(data, f, separators=(",", ":"))
+    print("merged into", OUT)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "dataset":
+        return dataset_section()
     print("reference tests under the shim:", run_reference_tests())
     sys.path.insert(0, SHIM)
     sys.path.insert(0, REF)
@@ -124,6 +157,7 @@ def main():
     with open(OUT, "w") as f:
         json.dump(out, f, separators=(",", ":"))
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
+    dataset_section()
 
 
 if __name__ == "__main__":
