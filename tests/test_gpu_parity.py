@@ -502,6 +502,36 @@ def test_host_variants(rbg, orc):
     assert np.array_equal(solved, rs) and np.array_equal(heads, rh) and np.array_equal(targets, rt)
 
 
+def test_dlpack_and_numpy_keys(rbg, orc):
+    """Keys may come from any DLPack producer (JAX / CuPy arrays in the reference's world) or NumPy;
+    results leave as DLPack capsules without a copy."""
+    import torch
+    from torch.utils import dlpack as tdl
+
+    class Foreign:  # a minimal non-torch DLPack producer
+        def __init__(self, t):
+            self._t = t
+
+        def __dlpack__(self, stream=None):
+            return self._t.__dlpack__()
+
+        def __dlpack_device__(self):
+            return self._t.__dlpack_device__()
+
+    kref = orc.split(orc.PRNGKey(9), 300)
+    ref = orc.prw_generate_batch(kref, 10, 5)[2]
+    board = rbg.ParallelRandomWalkBoard(10, 10, 5)
+    dev_keys = torch.from_numpy(kref.view(np.int32)).cuda()
+    for keys in (kref, kref.view(np.int32), Foreign(dev_keys), dev_keys, kref.astype(np.int64)):
+        assert np.array_equal(_np(board.generate_board(keys)[2]), ref)
+    solved = board.generate_board(kref)[2]
+    back = tdl.from_dlpack(tdl.to_dlpack(solved))
+    assert back.data_ptr() == solved.data_ptr() and np.array_equal(_np(back), ref)
+    # single key as a Python list / NumPy vector -> un-batched result, like the reference
+    one = board.generate_board([int(kref[0][0]), int(kref[0][1])])[2]
+    assert one.shape == (10, 10) and np.array_equal(_np(one), ref[0])
+
+
 def test_errors_are_reported_not_swallowed(rbg):
     import torch
 
