@@ -1004,6 +1004,27 @@ int launch_env(EnvParams p, int force_E, cudaStream_t stream) {
   return check_launch("env_kernel");
 }
 
+// Wave balance: a launch of `ctas` CTAs runs in ceil(ctas / (148 * c)) rounds when c CTAs fit on an
+// SM; pick the residency c in [cmin, cmax] with the smallest rounds * c and enforce it by padding
+// the dynamic shared memory (4096 CTAs: 8 per SM = 3.46 -> 4 rounds of 8; 7 per SM = 3.95 -> 4
+// rounds of 7, measured 3 % faster).
+static size_t balance_waves(int64_t ctas, int cmax, int cmin, size_t smem_needed) {
+  int best = cmax;
+  int64_t best_cost = -1;
+  for (int c = cmax; c >= cmin; --c) {
+    const int64_t rounds = (ctas + 148LL * c - 1) / (148LL * c);
+    const int64_t cost = rounds * c;
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best = c;
+    }
+  }
+  if (best == cmax) return smem_needed;
+  // per-SM shared memory 228 KB, 1 KB reserved per CTA: c CTAs fit, c + 1 do not
+  const size_t pad = (size_t)(228 * 1024) / (size_t)(best + 1) + 1024;
+  return pad > smem_needed ? pad : smem_needed;
+}
+
 int launch_rollout(EnvParams p, int kind, int T, int32_t *action_out, cudaStream_t stream) {
   const int G = p.G, N = p.N;
   p.cells = G * G;
@@ -1038,9 +1059,10 @@ int launch_rollout(EnvParams p, int kind, int T, int32_t *action_out, cudaStream
   rp.gen_stride = (int)(rp.gen_cand_bytes + rp.gen_sel_bytes + board);
   rp.gen_off = (int)(lutB + EW_WARPS * wgrid);
   rp.ratio_off = rp.gen_off + EW_WARPS * rp.gen_stride;
-  const size_t smem = (size_t)rp.ratio_off + 4 * (RBG_MAX_N + 4);
+  size_t smem = (size_t)rp.ratio_off + 4 * (RBG_MAX_N + 4);
   if (smem > 200 * 1024) return set_error(RBG_EINVAL, "rollout: shared memory %zu too large", smem);
   const int64_t ctas = (p.B + p.E - 1) / p.E;
+  if (smem <= 24 * 1024) smem = balance_waves(ctas, RBG_ROLLOUT_MIN_CTAS, 5, smem);  // registers allow RBG_ROLLOUT_MIN_CTAS per SM
   LaunchScope scope(RBG_K_ROLLOUT, stream);
   if (vec) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(rollout_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
