@@ -243,7 +243,7 @@ static int connector_step_impl(const rbg_state *in, const rbg_state *out, const 
   p.N = N;
   p.mode = ENV_MODE_STEP;
   p.env = *params;
-  if (!autoreset) return launch_env(p, env_int("RBG_ENV_E"), stream);
+  if (!autoreset) return launch_env(p, stream);
 
   uint8_t *ws = reinterpret_cast<uint8_t *>(workspace);
   if (!aligned16(ws)) return set_error(RBG_EALIGN, "workspace not 16-byte aligned");
@@ -317,7 +317,7 @@ static int connector_step_impl(const rbg_state *in, const rbg_state *out, const 
   // counters: with the speculative path the list kernels clear their own counter when
   // they finish (prw_kernel list_ticket); they were zeroed once when the workspace was adopted
   if (!speculative && (e = cudaMemsetAsync(ws, 0, 64, stream)) != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(reset counter)");
-  if ((rc = launch_env(p, env_int("RBG_ENV_E"), stream))) return rc;
+  if ((rc = launch_env(p, stream))) return rc;
   // VmapAutoResetWrapper._auto_reset: key, _ = split(state.key); reset(key):
   // one more leading split()[0] than a plain generator call.
   if ((rc = generator_state_impl(kind, out->key, B, G, N, out, ts, 1, sync_list, sync_count, stream, speculative ? sync_count + 1 : nullptr))) return rc;
@@ -644,7 +644,7 @@ int rbg_connector_observe(const rbg_state *state, int64_t B, int G, int N, const
   p.N = N;
   p.mode = ENV_MODE_OBSERVE;
   p.env.autoreset_kind = -1;
-  return launch_env(p, env_int("RBG_ENV_E"), (cudaStream_t)stream);
+  return launch_env(p, (cudaStream_t)stream);
 }
 
 int rbg_connector_reset(int kind, const uint32_t *keys, int64_t B, int G, int N, const rbg_state *state,

@@ -11,10 +11,10 @@
 // discount / step_type, extras, the per-agent observation and (with
 // auto-reset) the compaction of finished envs into a reset list.
 //
-// The kernel is HBM-write bound (DESIGN.md "K2"): per env-step it reads the
-// State once (int32 -> uint8 into shared memory) and writes State +
-// observation [N,G,G] int32 exactly once, all bulk traffic as 128-bit
-// coalesced accesses over the CTA's contiguous slab of E envs.
+// The kernels are HBM-write bound by bytes (DESIGN.md "K2", "K2b"): the per-step
+// kernel reads the State once (int32 -> uint8 into shared memory) and writes State +
+// observation [N,G,G] int32 exactly once; the fused rollout kernel keeps the State on
+// chip for a whole chunk of steps.  All bulk traffic is 128-bit coalesced.
 #include <stdlib.h>
 
 #include "connector_device.cuh"
@@ -23,57 +23,8 @@
 
 namespace rbg {
 
-struct EnvSmem {
-  uint8_t *grid;  // [E*cells] flat, same layout as the int32 input
-  int *pos;       // [E*N] (r<<8|c)
-  int *tgt;       // [E*N]
-  int *dest;      // [E*N] destination flat cell or unique negative
-  int *flag;      // [E*N] bit0 was_connected, bit1 win, bit2 done, bits 4..7 mask
-  float *rew;     // [E*N]
-  int *cnt;       // [E*4] path cells, #done, #connected, #moved
-  int *term;      // [E]   bit0 terminal, bit1 skip (the reset kernel takes over), bit2 cached episode swapped in
-  int *anyhit;    // [1]   some env of this CTA swaps in a cached episode
-  uint8_t *lut;   // [N*RS + 256] per-agent observation codes: lut[a*RS + v] (JUM env.py _obs_from_grid)
-  int *env3;      // [E*4] State.key (2), step_count of the CTA's envs
-};
-
 // row stride of the observation table: codes 0..3N, rounded up to whole words
 __host__ __device__ inline int obs_lut_stride(int N) { return (3 * N + 1 + 3) & ~3; }
-
-__host__ __device__ inline size_t env_carve(int E, int N, int cells,
-                                            uint8_t *base, EnvSmem *s) {
-  size_t off = 0;
-  auto take = [&](size_t bytes) {
-    size_t o = off;
-    off += (bytes + 15) / 16 * 16;
-    return o;
-  };
-  const size_t en = (size_t)E * N;
-  size_t o_grid = take((size_t)E * cells);
-  size_t o_pos = take(en * 4), o_tgt = take(en * 4), o_dest = take(en * 4);
-  size_t o_flag = take(en * 4), o_rew = take(en * 4);
-  size_t o_cnt = take((size_t)E * 16), o_term = take((size_t)E * 4), o_any = take(16);
-  size_t o_lut = take((size_t)N * obs_lut_stride(N) + 256);
-  size_t o_env3 = take((size_t)E * 16);
-  if (s) {
-    s->grid = base + o_grid;
-    s->pos = reinterpret_cast<int *>(base + o_pos);
-    s->tgt = reinterpret_cast<int *>(base + o_tgt);
-    s->dest = reinterpret_cast<int *>(base + o_dest);
-    s->flag = reinterpret_cast<int *>(base + o_flag);
-    s->rew = reinterpret_cast<float *>(base + o_rew);
-    s->cnt = reinterpret_cast<int *>(base + o_cnt);
-    s->term = reinterpret_cast<int *>(base + o_term);
-    s->anyhit = reinterpret_cast<int *>(base + o_any);
-    s->lut = base + o_lut;
-    s->env3 = reinterpret_cast<int *>(base + o_env3);
-  }
-  return off;
-}
-
-__device__ __forceinline__ int is_path_code(int v) {
-  return (v > 0 && (v - 1) % 3 == 0) ? 1 : 0;
-}
 
 // number of PATH codes (v % 3 == 1) among the four byte codes of a packed word,
 // two 16-bit lanes at a time: x / 3 == (x * 171) >> 9 for x < 256
@@ -105,314 +56,13 @@ __device__ __forceinline__ int random_action(uint32_t k0, uint32_t k1,
   return act;
 }
 
-template <bool VEC>
-__global__ void __launch_bounds__(256, 8) env_kernel(const EnvParams p) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  const int tid = threadIdx.x, nt = blockDim.x;
-  const int G = p.G, N = p.N, cells = p.cells, E = p.E;
-  const long long env0 = (long long)blockIdx.x * E;
-  if (env0 >= p.B) return;
-  const int Ec = (int)((p.B - env0) < (long long)E ? (p.B - env0) : (long long)E);
-  const bool is_step = (p.mode == ENV_MODE_STEP);
-  const bool autoreset = is_step && p.env.autoreset_kind >= 0 && p.list != nullptr;
-  const bool inplace_grid = is_step && p.out.grid == p.in.grid;
-  // shared-memory carve-up: byte offsets come from the host (launch_env)
-  EnvSmem s;
-  s.grid = smem_raw;
-  s.pos = reinterpret_cast<int *>(smem_raw + p.so[0]);
-  s.tgt = reinterpret_cast<int *>(smem_raw + p.so[1]);
-  s.dest = reinterpret_cast<int *>(smem_raw + p.so[2]);
-  s.flag = reinterpret_cast<int *>(smem_raw + p.so[3]);
-  s.rew = reinterpret_cast<float *>(smem_raw + p.so[4]);
-  s.cnt = reinterpret_cast<int *>(smem_raw + p.so[5]);
-  s.term = reinterpret_cast<int *>(smem_raw + p.so[6]);
-  s.anyhit = reinterpret_cast<int *>(smem_raw + p.so[7]);
-  s.lut = smem_raw + p.so[8];
-  s.env3 = reinterpret_cast<int *>(smem_raw + p.so[9]);
-
-  for (int i = tid; i < E * 4; i += nt) s.cnt[i] = 0;
-  if (tid == 0) *s.anyhit = 0;
-  const int RS = obs_lut_stride(N);
-  for (int a = tid >> 5; a < N; a += nt >> 5)  // one warp per table row
-    for (int v = tid & 31; v < RS; v += 32) s.lut[a * RS + v] = v <= 3 * N ? (uint8_t)obs_value(v, 3 * a, 3 * N) : (uint8_t)0;
-  __syncthreads();
-
-  // ---- phase 1: State.grid int32 -> uint8 shared memory, count PATH cells; the
-  // agents' and envs' scalars ride the same DRAM round trip
-  for (int t = tid; t < Ec * N; t += nt) {
-    const int2 ps = __ldg(reinterpret_cast<const int2 *>(p.in.position) + env0 * N + t);
-    const int2 tg = __ldg(reinterpret_cast<const int2 *>(p.in.target) + env0 * N + t);
-    s.pos[t] = (ps.x << 8) | ps.y;
-    s.tgt[t] = (tg.x << 8) | tg.y;
-    if (is_step && !p.random_policy) s.dest[t] = __ldg(p.action + env0 * N + t);
-  }
-  if (is_step)
-    for (int m = tid; m < Ec; m += nt) {
-      s.env3[4 * m] = (int)p.in.key[2 * (env0 + m)];
-      s.env3[4 * m + 1] = (int)p.in.key[2 * (env0 + m) + 1];
-      s.env3[4 * m + 2] = p.in.step_count[env0 + m];
-    }
-  if (VEC) {
-    const int c4 = cells >> 2;
-    const int4 *src = reinterpret_cast<const int4 *>(p.in.grid) + env0 * c4;
-    uint32_t *g32 = reinterpret_cast<uint32_t *>(s.grid);
-    for (int q = tid; q < Ec * c4; q += nt) {
-      const int4 v = __ldg(src + q);
-      const uint32_t w = (uint32_t)(v.x & 0xff) | ((uint32_t)(v.y & 0xff) << 8) |
-                         ((uint32_t)(v.z & 0xff) << 16) | ((uint32_t)(v.w & 0xff) << 24);
-      g32[q] = w;
-      const int np = count_path_codes(w);
-      if (np) atomicAdd(&s.cnt[4 * p.divC4.div((uint32_t)q)], np);
-    }
-  } else {
-    const int32_t *src = p.in.grid + env0 * cells;
-    for (int i = tid; i < Ec * cells; i += nt) {
-      const int v = __ldg(src + i);
-      s.grid[i] = (uint8_t)v;
-      if (is_path_code(v)) atomicAdd(&s.cnt[4 * p.divCells.div((uint32_t)i)], 1);
-    }
-  }
-  __syncthreads();
-
-  // ---- phase 2: per agent: (sample action,) move_position, is_valid_position
-  for (int t = tid; t < Ec * N; t += nt) {
-    const int m = (int)p.divN.div((uint32_t)t), a = t - m * N;
-    const int r = s.pos[t] >> 8, c = s.pos[t] & 255;
-    const bool was = s.pos[t] == s.tgt[t];
-    int dest = -1 - t, fl = was ? 1 : 0;
-    if (is_step) {
-      SmemGrid sg{s.grid + (size_t)m * cells, G, 0, G};
-      int action;
-      if (p.random_policy) {
-        const uint32_t mk = move_mask(sg, r, c, a, was);
-        action = random_action((uint32_t)s.env3[4 * m], (uint32_t)s.env3[4 * m + 1], (uint32_t)s.env3[4 * m + 2], (uint32_t)a, mk);
-        if (p.action_out) p.action_out[env0 * N + t] = action;
-      } else {
-        action = s.dest[t];
-      }
-      const int am = action < 0 ? 0 : (action > 4 ? 4 : action);  // lax.switch clamps
-      const int nr = r + (am == UP ? -1 : (am == DOWN ? 1 : 0));
-      const int nc = c + (am == RIGHT ? 1 : (am == LEFT ? -1 : 0));
-      const bool inb = (unsigned)nr < (unsigned)G && (unsigned)nc < (unsigned)G;
-      const uint32_t v = inb ? sg.at(nr, nc) : 0xFFu;
-      const bool valid = inb && (v == 0u || v == 3u * a + TARGET) && !was && action != NOOP;
-      if (valid) dest = nr * G + nc;
-    }
-    s.dest[t] = dest;
-    s.flag[t] = fl;
-  }
-  __syncthreads();
-  if (is_step) {
-    // collisions: same destination -> only the highest agent id moves
-    for (int t = tid; t < Ec * N; t += nt) {
-      const int m = (int)p.divN.div((uint32_t)t), a = t - m * N;
-      const int d = s.dest[t];
-      bool win = d >= 0;
-      for (int j = a + 1; j < N && win; ++j) win = (s.dest[m * N + j] != d);
-      if (win) s.flag[t] |= 2;
-    }
-    __syncthreads();
-    for (int t = tid; t < Ec * N; t += nt) {
-      if (s.flag[t] & 2) {  // move_agent: old head -> PATH, new cell -> POSITION
-        const int m = (int)p.divN.div((uint32_t)t), a = t - m * N;
-        const int pr = s.pos[t] >> 8, pcol = s.pos[t] & 255, d = s.dest[t];
-        uint8_t *g = s.grid + (size_t)m * cells;
-        g[pr * G + pcol] = (uint8_t)(3 * a + PATH);
-        g[d] = (uint8_t)(3 * a + POSITION);
-        if (inplace_grid) {  // State.grid updated in place: only these two cells change
-          int32_t *gg = p.out.grid + (env0 + m) * cells;
-          gg[pr * G + pcol] = 3 * a + PATH;
-          gg[d] = 3 * a + POSITION;
-        }
-        uint32_t nr, nc;
-        p.divG.divmod((uint32_t)d, nr, nc);
-        s.pos[t] = (int)((nr << 8) | nc);
-        atomicAdd(&s.cnt[4 * m + 3], 1);
-      }
-    }
-    __syncthreads();
-  }
-
-  // ---- phase 3: action mask, connected / done, reward on the new grid
-  for (int t = tid; t < Ec * N; t += nt) {
-    const int m = (int)p.divN.div((uint32_t)t), a = t - m * N;
-    const int r = s.pos[t] >> 8, c = s.pos[t] & 255;
-    const bool now = (s.pos[t] == s.tgt[t]);
-    const bool was = s.flag[t] & 1;
-    SmemGrid sg{s.grid + (size_t)m * cells, G, 0, G};
-    const uint32_t mk = move_mask(sg, r, c, a, now);
-    const bool done = now || mk == 0u;  // connected_or_blocked
-    if (done) atomicAdd(&s.cnt[4 * m + 1], 1);
-    if (now) atomicAdd(&s.cnt[4 * m + 2], 1);
-    s.flag[t] |= (done ? 4 : 0) | (int)(mk << 4);
-    // DenseRewardFn: connected_reward*(~was & now) + timestep_reward*(~was)
-    s.rew[t] = __fadd_rn(__fmul_rn(p.env.connected_reward, (!was && now) ? 1.0f : 0.0f),
-                         __fmul_rn(p.env.timestep_reward, was ? 0.0f : 1.0f));
-  }
-  __syncthreads();
-  for (int m = tid; m < Ec; m += nt) {
-    const long long e = env0 + m;
-    const int sc = is_step ? s.env3[4 * m + 2] + 1 : p.in.step_count[e];
-    const int nconn = s.cnt[4 * m + 2];
-    const bool terminal = is_step && (s.cnt[4 * m + 1] == N || sc >= p.env.time_limit);
-    int tflag = terminal ? 1 : 0;
-    uint32_t k0 = 0, k1 = 0;
-    if (is_step) {
-      k0 = (uint32_t)s.env3[4 * m];
-      k1 = (uint32_t)s.env3[4 * m + 1];
-    }
-    if (terminal && autoreset) {
-      // VmapAutoResetWrapper: key, _ = split(state.key); reset(key).  If the next
-      // episode was generated ahead of time (tagged with this episode's key) it is
-      // swapped in below; otherwise the env goes to the reset kernel's list.
-      bool hit = false;
-      uint32_t nk0, nk1;
-      if (p.cache_tag) {
-        const unsigned long long tag = __ldcg(p.cache_tag + e);
-        if (tag == (((unsigned long long)k1 << 32) | k0)) {
-          __threadfence();
-          const uint2 nk = __ldcg(p.cache_key + e);
-          nk0 = nk.x;
-          nk1 = nk.y;
-          hit = true;
-        }
-      }
-      if (!hit) {  // State.key of the next episode: split(split(key)[0])[0]
-        uint32_t a0, a1, b0, b1;
-        split2(k0, k1, a0, a1, b0, b1);
-        split2(a0, a1, nk0, nk1, b0, b1);
-        p.list[atomicAdd(p.list_count, 1)] = (int32_t)e;
-      } else {
-        *s.anyhit = 1;
-        k0 = nk0;
-        k1 = nk1;
-      }
-      if (p.refill_list) {
-        const int slot = atomicAdd(p.refill_count, 1);
-        p.refill_list[slot] = (int32_t)e;
-        p.refill_keys[2 * slot] = nk0;
-        p.refill_keys[2 * slot + 1] = nk1;
-      }
-      tflag |= hit ? 4 : 2;
-    }
-    s.term[m] = tflag;
-    p.ts.step_type[e] = (int8_t)(is_step ? (terminal ? 2 : 1) : 0);
-    p.ts.num_connections[e] = nconn;
-    p.ts.ratio_connections[e] = __fdiv_rn((float)nconn, (float)N);
-    p.ts.total_path_length[e] = s.cnt[4 * m] + s.cnt[4 * m + 3] + N;
-    if (!(tflag & 2)) p.ts.obs_step_count[e] = (tflag & 4) ? 0 : sc;
-    if (is_step) {
-      p.out.step_count[e] = (tflag & 4) ? 0 : sc;
-      if (p.out.key != p.in.key || (tflag & 4)) {
-        p.out.key[2 * e] = k0;
-        p.out.key[2 * e + 1] = k1;
-      }
-    }
-  }
-  __syncthreads();
-  if (*s.anyhit) {
-    // ---- phase 3b: swap in the cached episodes, one warp per finished env: pins-only
-    // grid (heads, then targets: PRWG:63-64), position = start, fresh action mask.
-    // Reward, discount, step_type and extras stay those of the terminal step.
-    const int lane = tid & 31, nwarps = nt >> 5;
-    for (int m = tid >> 5; m < Ec; m += nwarps) {
-      if (!(s.term[m] & 4)) continue;
-      uint8_t *g = s.grid + (size_t)m * cells;
-      for (int i = lane; i < cells; i += 32) g[i] = 0;
-      int ps = 0, tg = 0;
-      if (lane < N) {
-        const uint32_t pin = __ldcg(p.cache_pins + (env0 + m) * N + lane);
-        ps = (int)(pin >> 16);
-        tg = (int)(pin & 0xffffu);
-        s.pos[m * N + lane] = ps;
-        s.tgt[m * N + lane] = tg;
-      }
-      __syncwarp();
-      if (lane < N) g[(ps >> 8) * G + (ps & 255)] = (uint8_t)(3 * lane + POSITION);
-      __syncwarp();
-      if (lane < N) g[(tg >> 8) * G + (tg & 255)] = (uint8_t)(3 * lane + TARGET);
-      __syncwarp();
-      if (lane < N) {
-        SmemGrid sg{g, G, 0, G};
-        const uint32_t mk = move_mask(sg, ps >> 8, ps & 255, lane, ps == tg);
-        s.flag[m * N + lane] = (s.flag[m * N + lane] & 15) | (int)(mk << 4);
-      }
-    }
-    __syncthreads();
-  }
-  for (int t = tid; t < Ec * N; t += nt) {
-    const int m = (int)p.divN.div((uint32_t)t);
-    const long long ga = env0 * N + t;
-    const int term = s.term[m];
-    const int fl = s.flag[t];
-    p.ts.reward[ga] = is_step ? s.rew[t] : 0.0f;
-    p.ts.discount[ga] = is_step ? (((term & 1) || (fl & 4)) ? 0.0f : 1.0f) : 1.0f;
-    if (!(term & 2)) store_mask5(p.ts.action_mask + ga * 5, (uint32_t)(fl >> 4) & 15u);
-    if (is_step) {
-      const int2 pos2 = make_int2(s.pos[t] >> 8, s.pos[t] & 255);
-      reinterpret_cast<int2 *>(p.out.position)[ga] = pos2;
-      if (term & 4) {
-        reinterpret_cast<int2 *>(p.out.target)[ga] = make_int2(s.tgt[t] >> 8, s.tgt[t] & 255);
-        reinterpret_cast<int2 *>(p.out.start)[ga] = pos2;
-        p.out.agent_id[ga] = t - m * N;
-      } else if (p.out.target != p.in.target) {
-        reinterpret_cast<int2 *>(p.out.target)[ga] = make_int2(s.tgt[t] >> 8, s.tgt[t] & 255);
-        reinterpret_cast<int2 *>(p.out.start)[ga] = reinterpret_cast<const int2 *>(p.in.start)[ga];
-        p.out.agent_id[ga] = p.in.agent_id[ga];
-      }
-    }
-  }
-
-  // ---- phase 4: bulk outputs: State.grid and observation.grid
-  const int n3 = 3 * N;
-  (void)n3;
-  if (VEC) {
-    // A thread owns one packed word (4 cells) of one env: it writes the State row
-    // chunk (unless the grid is updated in place and only the moved cells changed)
-    // and then that chunk's N per-agent views through the observation table, one
-    // shared-memory byte read per cell (rows span <= 25 banks: conflict-free).
-    const int c4 = cells >> 2;
-    const uint32_t *g32 = reinterpret_cast<const uint32_t *>(s.grid);
-    int4 *gdst = reinterpret_cast<int4 *>(p.out.grid) + env0 * c4;
-    int4 *odst = reinterpret_cast<int4 *>(p.ts.obs_grid) + env0 * N * c4;
-    for (int idx = tid; idx < Ec * c4; idx += nt) {
-      const int m = (int)p.divC4.div((uint32_t)idx);
-      const int term = s.term[m];
-      if (term & 2) continue;
-      const uint32_t w = g32[idx];
-      const uint32_t b0 = w & 0xffu, b1 = (w >> 8) & 0xffu, b2 = (w >> 16) & 0xffu, b3 = w >> 24;
-      if (is_step && (!inplace_grid || (term & 4))) gdst[idx] = make_int4((int)b0, (int)b1, (int)b2, (int)b3);
-      int4 *o = odst + (size_t)m * N * c4 + (idx - m * c4);
-      const uint8_t *lut = s.lut;
-#pragma unroll 2
-      for (int a = 0; a < N; ++a, o += c4, lut += RS) *o = make_int4(lut[b0], lut[b1], lut[b2], lut[b3]);
-    }
-  } else {
-    if (is_step) {
-      int32_t *dst = p.out.grid + env0 * cells;
-      for (int i = tid; i < Ec * cells; i += nt) {
-        const int m = (int)p.divCells.div((uint32_t)i);
-        if (s.term[m] & 2) continue;
-        dst[i] = s.grid[i];
-      }
-    }
-    int32_t *odst = p.ts.obs_grid + env0 * N * cells;
-    for (int idx = tid; idx < Ec * N * cells; idx += nt) {
-      const uint32_t slice = p.divCells.div((uint32_t)idx);
-      const int cell = idx - (int)slice * cells;
-      const int m = (int)p.divN.div(slice), a = (int)slice - m * N;
-      if (s.term[m] & 2) continue;
-      odst[idx] = obs_value((int)s.grid[m * cells + cell], 3 * a, n3);
-    }
-  }
-}
-
 // ---------------------------------------------------------------------------
-// env_warp_kernel: the same step organised per WARP.  A warp owns K = 32 / Np envs
+// env_warp_kernel: one Connector step (or observe) per WARP.  A warp owns K = 32 / Np envs
 // (Np = lanes per env, the next power of two >= N; lane = (env, agent)), keeps their
 // grids in its own slice of shared memory and runs every phase with __syncwarp only,
-// so warps in different phases overlap freely (the CTA-wide version above spends half
-// of its warp-time at barriers waiting for the agent phases).
+// so warps in different phases overlap freely (the first, CTA-wide version of this
+// kernel spent half of its warp-time at __syncthreads waiting for the agent phases;
+// it is in the history, profiles/r01a_env_full.csv is its ncu capture).
 constexpr int EW_WARPS = 4;
 
 template <bool VEC>
@@ -936,15 +586,7 @@ __global__ void __launch_bounds__(256) random_actions_kernel(rbg_state st, long 
   action[t] = random_action(st.key[2 * e], st.key[2 * e + 1], (uint32_t)st.step_count[e], (uint32_t)a, mk);
 }
 
-int launch_env(EnvParams p, int force_E, cudaStream_t stream) {
-  static int threads_env = -1, use_cta = -1;
-  if (threads_env < 0) {
-    const char *e = getenv("RBG_ENV_THREADS");
-    threads_env = e ? atoi(e) : 0;
-    if (threads_env != 64 && threads_env != 128 && threads_env != 256) threads_env = 256;
-    const char *k = getenv("RBG_ENV_KERNEL");  // "cta": the CTA-wide kernel (A/B comparisons)
-    use_cta = (k && k[0] == 'c') ? 1 : 0;
-  }
+int launch_env(EnvParams p, cudaStream_t stream) {
   const int G = p.G, N = p.N;
   p.cells = G * G;
   const bool vec = (p.cells & 3) == 0;
@@ -953,55 +595,23 @@ int launch_env(EnvParams p, int force_E, cudaStream_t stream) {
   p.divC4 = FastDiv::make((uint32_t)(vec ? p.cells >> 2 : 1));
   p.divCells = FastDiv::make((uint32_t)p.cells);
   if (p.B <= 0) return RBG_OK;
-  if (!use_cta) {
-    // warp-per-K-envs kernel
-    int Np = 1;
-    while (Np < N) Np <<= 1;
-    p.Np = Np;
-    const int K = 32 / Np;
-    p.E = EW_WARPS * K;
-    const size_t lutB = ((size_t)N * obs_lut_stride(N) + 256 + 15) & ~(size_t)15;
-    const size_t wgrid = ((size_t)K * p.cells + 15) & ~(size_t)15;
-    p.so[0] = (int)lutB;
-    p.so[1] = (int)wgrid;
-    const size_t smem = lutB + EW_WARPS * wgrid;
-    const int64_t ctas = (p.B + p.E - 1) / p.E;
-    LaunchScope scope(RBG_K_ENV, stream);
-    if (vec)
-      env_warp_kernel<true><<<(unsigned)ctas, EW_WARPS * 32, smem, stream>>>(p);
-    else
-      env_warp_kernel<false><<<(unsigned)ctas, EW_WARPS * 32, smem, stream>>>(p);
-    return check_launch("env_warp_kernel");
-  }
-  const int threads = threads_env;
-  // envs per CTA: about two packed words per thread in the bulk phases
-  int E = vec ? (2 * threads) / (p.cells >> 2) : (int)(32768 / ((int64_t)N * p.cells * 4));
-  if (E < 1) E = 1;
-  if (E > 32) E = 32;
-  if (force_E > 0) E = force_E;
-  if (!vec) E = (E + 3) & ~3;  // scalar path: keep slabs 16-byte aligned anyway
-  p.E = E;
-  const size_t smem = env_carve(E, N, p.cells, nullptr, nullptr);
-  {
-    EnvSmem off;
-    env_carve(E, N, p.cells, nullptr, &off);
-    const uint8_t *z = nullptr;
-    const void *ptrs[10] = {off.pos, off.tgt, off.dest, off.flag, off.rew, off.cnt, off.term, off.anyhit, off.lut, off.env3};
-    for (int i = 0; i < 10; ++i) p.so[i] = (int)(reinterpret_cast<const uint8_t *>(ptrs[i]) - z);
-  }
-  if (smem > 200 * 1024) return set_error(RBG_EINVAL, "connector: shared memory %zu too large", smem);
-  const int64_t ctas = (p.B + E - 1) / E;
-  {
-    LaunchScope scope(RBG_K_ENV, stream);
-    if (vec) {
-      if (smem > 48 * 1024) cudaFuncSetAttribute(env_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      env_kernel<true><<<(unsigned)ctas, threads, smem, stream>>>(p);
-    } else {
-      if (smem > 48 * 1024) cudaFuncSetAttribute(env_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      env_kernel<false><<<(unsigned)ctas, threads, smem, stream>>>(p);
-    }
-  }
-  return check_launch("env_kernel");
+  int Np = 1;
+  while (Np < N) Np <<= 1;
+  p.Np = Np;
+  const int K = 32 / Np;
+  p.E = EW_WARPS * K;
+  const size_t lutB = ((size_t)N * obs_lut_stride(N) + 256 + 15) & ~(size_t)15;
+  const size_t wgrid = ((size_t)K * p.cells + 15) & ~(size_t)15;
+  p.so[0] = (int)lutB;
+  p.so[1] = (int)wgrid;
+  const size_t smem = lutB + EW_WARPS * wgrid;
+  const int64_t ctas = (p.B + p.E - 1) / p.E;
+  LaunchScope scope(RBG_K_ENV, stream);
+  if (vec)
+    env_warp_kernel<true><<<(unsigned)ctas, EW_WARPS * 32, smem, stream>>>(p);
+  else
+    env_warp_kernel<false><<<(unsigned)ctas, EW_WARPS * 32, smem, stream>>>(p);
+  return check_launch("env_warp_kernel");
 }
 
 // Wave balance: a launch of `ctas` CTAs runs in ceil(ctas / (148 * c)) rounds when c CTAs fit on an

@@ -443,6 +443,7 @@ int launch_prw(PrwParams p, int64_t max_boards, int force_M, int force_threads,
     threads = 64;
     M = 2 * gpw;
   }
+  if (p.bulk_list) M = 32;  // a rollout chunk's refill is ~0.8 x the batch: smaller pools balance the CTA waves (measured)
   if (force_threads > 0) threads = force_threads;
   if (force_M > 0) M = force_M;
   // keep shared memory per CTA moderate so several CTAs share an SM

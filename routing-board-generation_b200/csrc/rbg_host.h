@@ -81,12 +81,12 @@ struct EnvParams {
   int32_t *refill_count;   // [1]
   uint32_t *refill_keys;   // [B,2] State.key of the episode that just started
   // filled by launch_env
-  int cells, E, Np;
-  int so[10];  // shared-memory byte offsets of EnvSmem's arrays after grid
+  int cells, E, Np;  // E envs per CTA, Np lanes per env
+  int so[2];         // shared memory: [0] bytes of the observation table, [1] bytes of one warp's grid slice
   FastDiv divN, divG, divC4, divCells;
 };
 
-int launch_env(EnvParams p, int force_E, cudaStream_t stream);
+int launch_env(EnvParams p, cudaStream_t stream);
 // T random-policy auto-reset steps in one launch (kind: RBG_GEN_PRW / RBG_GEN_UNIFORM); ts fields stacked [T,B,...]
 int launch_rollout(EnvParams p, int kind, int T, int32_t *action_out, cudaStream_t stream);
 int launch_random_actions(const rbg_state &st, int64_t B, int G, int N,
