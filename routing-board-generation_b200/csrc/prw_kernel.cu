@@ -462,7 +462,7 @@ int launch_prw(PrwParams p, int64_t max_boards, int force_M, int force_threads,
   }
   int64_t ctas = (max_boards + M - 1) / M;
   if (ctas <= 0) return RBG_OK;
-  if (p.list && !p.bulk_list && ctas > 148 * (p.to_cache ? 4 : 2)) ctas = 148 * (p.to_cache ? 4 : 2);  // refills are ~4% of the batch; the synchronous list is near-empty  // the kernel strides; an empty list costs ~2 us
+  if (p.list && !p.bulk_list && ctas > 148 * (p.to_cache ? 4 : 2)) ctas = 148 * (p.to_cache ? 4 : 2);  // per-step lists hold a few percent of the batch and the kernel strides over them
   {
     LaunchScope scope(RBG_K_PRW, stream);
     prw_kernel<<<(unsigned)ctas, threads, smem, stream>>>(p);
