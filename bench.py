@@ -206,8 +206,8 @@ def run_ours(args):
                     "algorithmic_bytes_per_launch": STEP_BYTES * B, "avg_launch_ms": round(env_ms, 5), "peak_source": peak_src,
                     "kernel_share_of_step": round(ms_env / max(ms_env + ms_prw, 1e-9), 4), "prw_reset_kernel_avg_ms": round(ms_prw / max(n_prw, 1), 5)}
 
-    # ---- e2e: the env-step call with HOST buffers through the C-ABI (rbg_connector_step_host):
-    # State + actions H2D from pinned memory, step, State + TimeStep D2H, every step.
+    # ---- e2e: the env-step call with HOST buffers through the C-ABI (rbg_connector_step_host_io):
+    # actions H2D from pinned memory, step, whole TimeStep D2H, every step.
     e2e = None
     secondary = []
     cpu_baseline = None
@@ -245,6 +245,10 @@ def _traffic_from_profile(kernel: str):
 
 
 def _e2e_host(args, rbg, lib, state, B, world, rank, dev):
+    """The env step as a host-side consumer sees it (rbg_connector_step_host_io): every step the
+    actions are copied H2D from pinned memory and the whole TimeStep (observation, mask, reward,
+    discount, step_type, extras) is copied back D2H; the State is the env's own device-resident
+    state, exactly as in the reference's loop."""
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -254,31 +258,27 @@ def _e2e_host(args, rbg, lib, state, B, world, rank, dev):
     def pinned(shape, dtype):
         return torch.empty(shape, dtype=dtype).pin_memory()
 
-    hs = dict(grid=pinned((B, G, G), torch.int32), step_count=pinned((B,), torch.int32), agent_id=pinned((B, N), torch.int32), start=pinned((B, N, 2), torch.int32),
-              target=pinned((B, N, 2), torch.int32), position=pinned((B, N, 2), torch.int32), key=pinned((B, 2), torch.int32))
-    a = state.agents
-    for k, t in dict(grid=state.grid, step_count=state.step_count, agent_id=a.id, start=a.start, target=a.target, position=a.position, key=state.key.view(torch.int32)).items():
-        hs[k].copy_(t.cpu())
     hts = dict(obs=pinned((B, N, G, G), torch.int32), mask=pinned((B, N, 5), torch.uint8), sc=pinned((B,), torch.int32), reward=pinned((B, N), torch.float32), discount=pinned((B, N), torch.float32),
                step_type=pinned((B,), torch.int8), nc=pinned((B,), torch.int32), rc=pinned((B,), torch.float32), tpl=pinned((B,), torch.int32))
     act = pinned((B, N), torch.int32)
     rng = np.random.default_rng(rank)
     act.copy_(torch.from_numpy(rng.integers(0, 5, size=(B, N)).astype(np.int32)))
-    s = L.rbg_state(*(hs[k].data_ptr() for k in ("grid", "step_count", "agent_id", "start", "target", "position", "key")))
+    a = state.agents
+    s = L.rbg_state(state.grid.data_ptr(), state.step_count.data_ptr(), a.id.data_ptr(), a.start.data_ptr(), a.target.data_ptr(), a.position.data_ptr(), state.key.data_ptr())
     t = L.rbg_timestep(*(hts[k].data_ptr() for k in ("obs", "mask", "sc", "reward", "discount", "step_type", "nc", "rc", "tpl")))
     params = L.rbg_env_params(TIME_LIMIT, -0.03, 0.1, 0)
-    h2d = sum(v.numel() * v.element_size() for v in hs.values()) + act.numel() * 4
-    d2h = sum(v.numel() * v.element_size() for v in hs.values()) + sum(v.numel() * v.element_size() for v in hts.values())
+    h2d = act.numel() * 4
+    d2h = sum(v.numel() * v.element_size() for v in hts.values())
 
     def step():
-        L.check(lib.rbg_connector_step_host(C.byref(s), C.byref(s), act.data_ptr(), B, G, N, C.byref(params), C.byref(t), -1))
+        L.check(lib.rbg_connector_step_host_io(C.byref(s), act.data_ptr(), B, G, N, C.byref(params), C.byref(t), -1))
 
     for _ in range(3):
         step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    k = max(3, min(args.steps, 20))
+    k = max(3, min(args.steps, 30))
     t0 = time.perf_counter()
     for _ in range(k):
         step()  # synchronous: returns after the D2H copies have landed
@@ -288,7 +288,8 @@ def _e2e_host(args, rbg, lib, state, B, world, rank, dev):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     dt = float(tt.item())
     return {"value": round(B * world * k / dt, 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": k,
-            "api": "rbg_connector_step_host (pinned host State + actions in, State + TimeStep out, auto-reset on)", "timer": "host wall clock around synchronous calls, max over ranks"}
+            "api": "rbg_connector_step_host_io (pinned host actions in, full TimeStep out to pinned host memory, State device-resident, auto-reset on)",
+            "timer": "host wall clock around synchronous calls, max over ranks"}
 
 
 def _secondary_prw(args, rbg, peak):

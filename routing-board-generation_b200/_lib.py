@@ -60,6 +60,7 @@ SYMBOLS = {
     "rbg_prw_generate_host": (_int, [_vp, _i64, _int, _int, _vp, _vp, _vp, _int]),
     "rbg_connector_reset_host": (_int, [_int, _vp, _i64, _int, _int, _SP, _TP, _int]),
     "rbg_connector_step_host": (_int, [_SP, _SP, _vp, _i64, _int, _int, _EP, _TP, _int]),
+    "rbg_connector_step_host_io": (_int, [_SP, _vp, _i64, _int, _int, _EP, _TP, _int]),
     "rbg_host_alloc": (_vp, [_i64]),
     "rbg_host_free": (None, [_vp]),
     "rbg_launch_count": (_i64, [_int]),

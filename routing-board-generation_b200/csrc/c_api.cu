@@ -960,4 +960,49 @@ int rbg_connector_step_host(const rbg_state *in, const rbg_state *out, const int
   return RBG_OK;
 }
 
+// Env-pool style step: the State stays on the device (updated in place), the actions come from and
+// the TimeStep goes to HOST buffers, pipelined over env slices on three streams.
+int rbg_connector_step_host_io(const rbg_state *state, const int32_t *action, int64_t B, int G, int N,
+                               const rbg_env_params *params, const rbg_timestep *ts, int device) {
+  int rc, dev;
+  if ((rc = check_dims(B, G, N, 1))) return rc;
+  if (!action || !params || !ts) return set_error(RBG_EINVAL, "rbg_connector_step_host_io: NULL pointer");
+  if ((rc = check_state(state, "state"))) return rc;
+  if (B == 0) return RBG_OK;
+  if ((rc = use_device(device, &dev))) return rc;
+  cudaError_t e = cudaDeviceSynchronize();  // the State may have been produced on any stream of the caller
+  if (e != cudaSuccess) return set_cuda_error(e, "cudaDeviceSynchronize");
+  std::lock_guard<std::mutex> lock(g_scratch_mu);
+  const int nsl = B >= 4096 ? 8 : 1;
+  const int64_t sl = slice_size(B, nsl);
+  const int64_t nslices = (B + sl - 1) / sl;
+  Carver size{nullptr};
+  rbg_timestep dt;
+  carve_timestep(size, B, G, N, &dt);
+  size.take<int32_t>((size_t)B * N);
+  const size_t ws_bytes = (size_t)rbg_step_workspace_bytes(sl, G, N);
+  size.take<uint8_t>((size_t)nslices * ws_bytes);
+  void *base;
+  if ((rc = scratch_get(size.off + 256, dev, &base))) return rc;
+  Carver c{reinterpret_cast<uint8_t *>(base)};
+  carve_timestep(c, B, G, N, &dt);
+  int32_t *da = c.take<int32_t>((size_t)B * N);
+  uint8_t *ws = c.take<uint8_t>((size_t)nslices * ws_bytes);
+  int si = 0;
+  for (int64_t off = 0; off < B; off += sl, ++si) {
+    const int64_t n = (B - off) < sl ? (B - off) : sl;
+    cudaStream_t st = g_streams[si % 3];
+    RBG_CPY(da + off * N, action + off * N, n * N * 4, cudaMemcpyHostToDevice, st);
+    rbg_state dss = state_at(*state, off, G, N);
+    rbg_timestep dts = timestep_at(dt, off, G, N);
+    if ((rc = rbg_connector_step(&dss, &dss, da + off * N, n, G, N, params, &dts, ws + (size_t)si * ws_bytes, st))) return rc;
+    if ((rc = copy_timestep(ts, &dt, off, n, G, N, cudaMemcpyDeviceToHost, off, st))) return rc;
+  }
+  for (int i = 0; i < 3; ++i) {
+    e = cudaStreamSynchronize(g_streams[i]);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaStreamSynchronize");
+  }
+  return RBG_OK;
+}
+
 }  // extern "C"

@@ -532,6 +532,32 @@ def test_dlpack_and_numpy_keys(rbg, orc):
     assert one.shape == (10, 10) and np.array_equal(_np(one), ref[0])
 
 
+def test_step_host_io_matches_oracle(rbg, orc):
+    """rbg_connector_step_host_io: device-resident State, host actions in, host TimeStep out."""
+    import torch
+
+    L, lib = rbg._lib, rbg._lib.load()
+    G, N, B = 10, 5, 5000
+    keys, kref = _keys(rbg, orc, 44, B)
+    env = rbg.VmapAutoResetWrapper(rbg.Connector(generator=rbg.ParallelRandomWalkGenerator(G, N), time_limit=7))
+    st, _ = env.reset(keys)
+    rst, _ = orc.connector_reset_batch("parallel_random_walk", kref, G, N)
+    h = dict(obs=np.empty((B, N, G, G), np.int32), mask=np.empty((B, N, 5), np.uint8), sc=np.empty(B, np.int32), reward=np.empty((B, N), np.float32), discount=np.empty((B, N), np.float32),
+             step_type=np.empty(B, np.int8), nc=np.empty(B, np.int32), rc=np.empty(B, np.float32), tpl=np.empty(B, np.int32))
+    a = st.agents
+    s = L.rbg_state(st.grid.data_ptr(), st.step_count.data_ptr(), a.id.data_ptr(), a.start.data_ptr(), a.target.data_ptr(), a.position.data_ptr(), st.key.data_ptr())
+    t = L.rbg_timestep(*(h[k].ctypes.data for k in ("obs", "mask", "sc", "reward", "discount", "step_type", "nc", "rc", "tpl")))
+    params = L.rbg_env_params(7, -0.03, 0.1, 0)
+    for step in range(20):
+        act = orc.random_actions_batch(rst)
+        L.check(lib.rbg_connector_step_host_io(C.byref(s), act.ctypes.data, B, G, N, C.byref(params), C.byref(t), -1))
+        rst, rts = orc.connector_step_batch(rst, act, time_limit=7, autoreset_kind="parallel_random_walk")
+        assert np.array_equal(h["obs"], rts["obs"]) and np.array_equal(h["mask"], rts["action_mask"]), f"step {step}"
+        assert np.array_equal(h["reward"].view(np.uint32), rts["reward"].view(np.uint32)) and np.array_equal(h["step_type"], rts["step_type"])
+        assert np.array_equal(h["tpl"], rts["total_path_length"]) and np.array_equal(h["sc"], rts["obs_step_count"])
+        _assert_state(st, rst, f"step {step}")
+
+
 def test_errors_are_reported_not_swallowed(rbg):
     import torch
 
