@@ -314,6 +314,27 @@ def _secondary_prw(args, rbg, peak):
         bytes_ = PRW_BOARD_BYTES[(g, n)] * b
         out.append({"metric": "prw_solved_boards_per_sec", "workload": f"ParallelRandomWalkBoard.generate_board {g}x{g}/{n} B={b}", "value": round(b / (ms / 1e3), 1), "unit": "boards/s", "ms_per_batch": round(ms, 4),
                     "output_gbs": round(bytes_ / (ms / 1e3) / 1e9, 2), "hbm_frac": round(bytes_ / (ms / 1e3) / 1e9 / peak, 5), "bound": "integer issue (threefry2x32), see DESIGN.md"})
+    # fused generate + reset + rollout at the A2C rollout shape (BASELINE configs[4]): 32x32 / 16 agents, 20 steps
+    g, n, b, T = 32, 16, 8192, 20
+    env = rbg.VmapAutoResetWrapper(rbg.Connector(generator=rbg.ParallelRandomWalkGenerator(g, n), time_limit=TIME_LIMIT))
+    st, _ = env.reset(rbg.split(rbg.PRNGKey(0), b))
+    ts_big = rbg.engine.alloc_timestep(b, g, n, T)
+    for _ in range(6):  # past the first episodes
+        st, _, _ = env.rollout_random(st, T, out=ts_big)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        st, _, _ = env.rollout_random(st, T, out=ts_big)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    step_bytes = 4 * n * g * g + 5 * n + 4 + 8 * n + 1 + 12 + 4 * n  # what a fused step must emit (65 825 B)
+    out.append({"metric": "connector_env_steps_per_sec", "workload": f"fused generate+reset+rollout {g}x{g}/{n} B={b}, {T} steps per call", "value": round(b * T / (ms / 1e3), 1), "unit": "env-steps/s",
+                "ms_per_step": round(ms / T, 4), "output_gbs": round(step_bytes * b * T / (ms / 1e3) / 1e9, 1), "hbm_frac": round(step_bytes * b * T / (ms / 1e3) / 1e9 / peak, 4)})
+    del ts_big, st
+    torch.cuda.empty_cache()
     # SeedExtension 14x14/7 (BASELINE configs[3]): generation + on-device validity of every board
     g, n, b = 14, 7, 65536
     keys = rbg.split(rbg.PRNGKey(0), b)
