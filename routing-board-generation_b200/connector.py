@@ -127,12 +127,12 @@ class VmapAutoResetWrapper:
 
     def step(self, state: State, action, inplace: bool = False):
         e = self._env.unwrapped
-        return engine.connector_step(state, action, e.time_limit, e._reward_fn.timestep_reward, e._reward_fn.connected_reward, autoreset_kind=e._generator.kind, inplace=inplace)
+        return engine.connector_step(state, action, e.time_limit, e._reward_fn.timestep_reward, e._reward_fn.connected_reward, autoreset_kind=e._generator.kind, inplace=inplace, owner=e)
 
     def step_random(self, state: State, inplace: bool = False):
         """Random-policy step in the same launch (the agent=random benchmark loop)."""
         e = self._env.unwrapped
-        return engine.connector_step(state, None, e.time_limit, e._reward_fn.timestep_reward, e._reward_fn.connected_reward, autoreset_kind=e._generator.kind, inplace=inplace, random_policy=True)
+        return engine.connector_step(state, None, e.time_limit, e._reward_fn.timestep_reward, e._reward_fn.connected_reward, autoreset_kind=e._generator.kind, inplace=inplace, random_policy=True, owner=e)
 
 
     def rollout_random(self, state: State, n_steps: int, out: Optional[TimeStep] = None):
@@ -140,7 +140,7 @@ class VmapAutoResetWrapper:
         stepping fused into one launch sequence.  Updates `state` in place; returns
         (state, TimeStep stacked [n_steps, B, ...], actions[n_steps, B, N])."""
         e = self._env.unwrapped
-        return engine.connector_rollout_random(state, n_steps, e.time_limit, e._reward_fn.timestep_reward, e._reward_fn.connected_reward, autoreset_kind=e._generator.kind, out=out)
+        return engine.connector_rollout_random(state, n_steps, e.time_limit, e._reward_fn.timestep_reward, e._reward_fn.connected_reward, autoreset_kind=e._generator.kind, out=out, owner=e)
 
 
 class MultiToSingleWrapper:

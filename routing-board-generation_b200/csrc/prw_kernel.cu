@@ -455,7 +455,7 @@ int launch_prw(PrwParams p, int64_t max_boards, int force_M, int force_threads,
   }
   p.M = M;
   const size_t smem = prw_carve(p, threads / 32, nullptr, nullptr);
-  if (smem > 200 * 1024) return RBG_EINVAL;
+  if (smem > 200 * 1024) return set_error(RBG_EINVAL, "prw_kernel: %zu bytes of shared memory per CTA", smem);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(prw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(prw_kernel)");

@@ -220,21 +220,23 @@ def connector_reset(kind, keys: torch.Tensor, G: int, N: int) -> Tuple[State, Ti
     return st, ts
 
 
-_workspaces: Dict[Tuple[int, int, int, int], torch.Tensor] = {}
+_workspaces: Dict[Tuple, torch.Tensor] = {}
 
 
-def _workspace(B: int, G: int, N: int) -> torch.Tensor:
-    """Auto-reset scratch of one env batch shape; kept alive for the process (the library's side
-    stream may still be filling it when the caller drops its last State)."""
+def _workspace(B: int, G: int, N: int, owner=None) -> torch.Tensor:
+    """Auto-reset scratch (reset lists + the next-episode cache) of one env batch.  Keyed by the
+    owning wrapper when there is one, so two batches of the same shape do not evict each other's
+    cache entries; kept alive for the process (the library's side stream may still be filling it
+    when the caller drops its last State)."""
     dev = _device()
-    k = (dev.index, B, G, N)
+    k = (dev.index, B, G, N, id(owner) if owner is not None else None)
     if k not in _workspaces:
         nbytes = int(_lib.load().rbg_step_workspace_bytes(B, G, N))
         _workspaces[k] = torch.empty((nbytes + 15) // 16 * 16, dtype=torch.uint8, device=dev)
     return _workspaces[k]
 
 
-def connector_step(st: State, action, time_limit: int = 50, timestep_reward: float = -0.03, connected_reward: float = 0.1, autoreset_kind=-1, inplace: bool = False, random_policy: bool = False, out: Optional[TimeStep] = None):
+def connector_step(st: State, action, time_limit: int = 50, timestep_reward: float = -0.03, connected_reward: float = 0.1, autoreset_kind=-1, inplace: bool = False, random_policy: bool = False, out: Optional[TimeStep] = None, owner=None):
     """Connector.step (autoreset_kind < 0) or VmapAutoResetWrapper(Connector).step over a batch.
 
     random_policy=True ignores `action`, samples the uniform-over-legal-actions policy in the
@@ -247,7 +249,7 @@ def connector_step(st: State, action, time_limit: int = 50, timestep_reward: flo
     new = st if inplace else alloc_state(B, G, N)
     ts = alloc_timestep(B, G, N) if out is None else out
     params = rbg_env_params(int(time_limit), float(timestep_reward), float(connected_reward), int(autoreset_kind))
-    ws = _workspace(B, G, N) if autoreset_kind >= 0 else None
+    ws = _workspace(B, G, N, owner) if autoreset_kind >= 0 else None
     s_in, s_out, t = _state_struct(st), _state_struct(new), _timestep_struct(ts)
     lib = _lib.load()
     if random_policy:
@@ -259,7 +261,7 @@ def connector_step(st: State, action, time_limit: int = 50, timestep_reward: flo
     return new, ts
 
 
-def connector_rollout_random(st: State, n_steps: int, time_limit: int = 50, timestep_reward: float = -0.03, connected_reward: float = 0.1, autoreset_kind="parallel_random_walk", out: Optional[TimeStep] = None, actions: Optional[torch.Tensor] = None):
+def connector_rollout_random(st: State, n_steps: int, time_limit: int = 50, timestep_reward: float = -0.03, connected_reward: float = 0.1, autoreset_kind="parallel_random_walk", out: Optional[TimeStep] = None, actions: Optional[torch.Tensor] = None, owner=None):
     """n_steps auto-reset random-policy steps in ONE library call (the reference's `n_steps` scan).
     `st` is updated in place; returns (st, TimeStep stacked [n_steps, B, ...], actions[n_steps, B, N])."""
     if isinstance(autoreset_kind, str):
@@ -271,7 +273,7 @@ def connector_rollout_random(st: State, n_steps: int, time_limit: int = 50, time
     ts = alloc_timestep(B, G, N, n_steps) if out is None else out
     act = torch.empty((n_steps, B, N), dtype=torch.int32, device=_device()) if actions is None else actions
     params = rbg_env_params(int(time_limit), float(timestep_reward), float(connected_reward), int(autoreset_kind))
-    ws = _workspace(B, G, N)
+    ws = _workspace(B, G, N, owner)
     s, t = _state_struct(st), _timestep_struct(ts)
     _lib.check(_lib.load().rbg_connector_rollout_random(C.byref(s), act.data_ptr(), n_steps, B, G, N, C.byref(params), C.byref(t), ws.data_ptr(), _stream()))
     return st, ts, act
