@@ -502,6 +502,37 @@ def test_host_variants(rbg, orc):
     assert np.array_equal(solved, rs) and np.array_equal(heads, rh) and np.array_equal(targets, rt)
 
 
+def test_random_shapes_sweep(rbg, orc):
+    """Random (G, N, B) shapes: generators, reset and a short fused rollout against the oracle."""
+    rng = np.random.default_rng(2024)
+    for it in range(24):
+        G = int(rng.integers(2, 25))
+        N = int(rng.integers(1, min(32, G * G // 2) + 1))
+        B = int(rng.integers(1, 200))
+        keys, kref = _keys(rbg, orc, 100 + it, B)
+        heads, targets, solved = rbg.ParallelRandomWalkBoard(G, G, N).generate_board(keys)
+        rh, rt, rs, _ = orc.prw_generate_batch(kref, G, N)
+        assert np.array_equal(_np(solved), rs) and np.array_equal(_np(heads), rh) and np.array_equal(_np(targets), rt), (G, N, B)
+        kind = "uniform" if it % 3 == 0 else "parallel_random_walk"
+        gen = (rbg.UniformRandomGenerator if kind == "uniform" else rbg.ParallelRandomWalkGenerator)(G, N)
+        tl = int(rng.integers(1, 9))
+        env = rbg.VmapAutoResetWrapper(rbg.Connector(generator=gen, time_limit=tl))
+        st, ts = env.reset(keys)
+        rst, rts = orc.connector_reset_batch(kind, kref, G, N)
+        _assert_state(st, rst, (G, N, B))
+        _assert_timestep(ts, rts, (G, N, B))
+        T = int(rng.integers(1, 12))
+        st, tss, act = env.rollout_random(st, T)
+        for t in range(T):
+            a = orc.random_actions_batch(rst)
+            rst, rts = orc.connector_step_batch(rst, a, time_limit=tl, autoreset_kind=kind)
+            _assert_timestep(tss[t], rts, (G, N, B, kind, tl, t))
+        _assert_state(st, rst, (G, N, B, kind))
+        if N <= (G // 2) ** 2:
+            sb = rbg.SeedExtensionBoard(G, G, N).return_solved_board(keys)
+            assert np.array_equal(_np(sb), orc.seedext_solved_batch(kref, G, N)[0]), ("seed extension", G, N, B)
+
+
 def test_dlpack_and_numpy_keys(rbg, orc):
     """Keys may come from any DLPack producer (JAX / CuPy arrays in the reference's world) or NumPy;
     results leave as DLPack capsules without a copy."""
