@@ -34,6 +34,9 @@ def rbg():
 
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
+    import __graft_entry__ as ge
+
+    ge.build_library()  # no-op when routing-board-generation_b200/lib/librbg_b200.so is up to date
     import routing_board_generation_b200 as pkg
 
     pkg._lib.load()
