@@ -589,6 +589,34 @@ def test_step_host_io_matches_oracle(rbg, orc):
         _assert_state(st, rst, f"step {step}")
 
 
+def test_cabi_argument_errors(rbg):
+    """Bad arguments come back as negative codes with a message, never as a crash or a silent fallback."""
+    import torch
+
+    lib = rbg._lib.load()
+    keys = rbg.split(rbg.PRNGKey(0), 8)
+    out = torch.empty(8 * 100 + 1, dtype=torch.int32, device="cuda")
+    h = torch.empty((8, 2, 5), dtype=torch.int32, device="cuda")
+    # solved not 16-byte aligned
+    assert lib.rbg_prw_generate(keys.data_ptr(), 8, 10, 5, h.data_ptr(), h.data_ptr(), out.data_ptr() + 4, None, None) == -2
+    assert b"aligned" in lib.rbg_last_error()
+    assert lib.rbg_prw_generate(keys.data_ptr(), -1, 10, 5, h.data_ptr(), h.data_ptr(), out.data_ptr(), None, None) == -1
+    assert lib.rbg_prw_generate(keys.data_ptr(), 8, 10, 33, h.data_ptr(), h.data_ptr(), out.data_ptr(), None, None) == -1
+    assert lib.rbg_seedext_solved(keys.data_ptr(), 8, 6, 10, 0.0, 1, 1, -1, out.data_ptr(), None) == -1  # lattice too small
+    st = rbg.ParallelRandomWalkGenerator(10, 5)(keys)
+    ts = rbg.engine.alloc_timestep(8, 10, 5)
+    s, t = rbg.engine._state_struct(st), rbg.engine._timestep_struct(ts)
+    params = rbg._lib.rbg_env_params(50, -0.03, 0.1, 0)
+    act = torch.zeros((8, 5), dtype=torch.int32, device="cuda")
+    # auto-reset without a workspace
+    assert lib.rbg_connector_step(C.byref(s), C.byref(s), act.data_ptr(), 8, 10, 5, C.byref(params), C.byref(t), None, None) == -1
+    assert b"workspace" in lib.rbg_last_error()
+    params = rbg._lib.rbg_env_params(50, -0.03, 0.1, 7)  # unknown generator kind
+    ws = torch.zeros(1 << 16, dtype=torch.uint8, device="cuda")
+    assert lib.rbg_connector_step(C.byref(s), C.byref(s), act.data_ptr(), 8, 10, 5, C.byref(params), C.byref(t), ws.data_ptr(), None) == -1
+    assert lib.rbg_kernel_time(99, None, None) == -1
+
+
 def test_errors_are_reported_not_swallowed(rbg):
     import torch
 
