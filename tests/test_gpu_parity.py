@@ -158,6 +158,31 @@ def test_prw_large_batch_10x10(rbg, orc):
     assert np.array_equal(_np(solved), rs) and np.array_equal(_np(heads), rh) and np.array_equal(_np(targets), rt)
 
 
+def test_prw_exact_selection_fallback(rbg):
+    """The start-cell selection normally filters sort keys by a threshold and ranks the survivors; when
+    the filter keeps too few / too many it falls back to an exact N-round selection.  RBG_DEBUG_FLAGS=1
+    forces that path (read once per process, hence the subprocess)."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r)\n"
+        "import routing_board_generation_b200 as rbg\n"
+        "from oracle import oracle as orc\n"
+        "for (G, N, B) in ((10, 5, 777), (5, 3, 300), (20, 10, 200)):\n"
+        "    k = rbg.split(rbg.PRNGKey(3), B); kr = orc.split(orc.PRNGKey(3), B)\n"
+        "    s = rbg.ParallelRandomWalkBoard(G, G, N).generate_board(k)[2].cpu().numpy()\n"
+        "    assert np.array_equal(s, orc.prw_generate_batch(kr, G, N)[2]), (G, N)\n"
+        "    st = rbg.UniformRandomGenerator(G, N)(k)\n"
+        "    assert np.array_equal(st.grid.cpu().numpy(), orc.state_batch('uniform', kr, G, N)['grid'])\n"
+        "print('exact ok')\n"
+    ) % root
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, RBG_DEBUG_FLAGS="1"), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "exact ok" in r.stdout, r.stderr[-2000:]
+
+
 def test_prw_empty_batch(rbg):
     import torch
 
@@ -439,6 +464,33 @@ def test_rollout_matches_stepwise_oracle(rbg, orc, kind, G, N, B, T, time_limit)
         rst, rts = orc.connector_step_batch(rst, a, time_limit=time_limit, autoreset_kind=kind)
         _assert_timestep(ts[t], rts, f"at step {t} of the second rollout")
     _assert_state(st, rst, "after the second rollout")
+
+
+def test_rollout_long_horizon(rbg, orc):
+    """1 480 steps over 4 096 envs (6 M env-steps, ~240 k resets) in odd-sized fused chunks: every
+    TimeStep leaf of every step and the final State against the oracle."""
+    B, G, N, T = 4096, 10, 5, 37
+    keys, kref = _keys(rbg, orc, 77, B)
+    env = rbg.VmapAutoResetWrapper(rbg.Connector(generator=rbg.ParallelRandomWalkGenerator(G, N), time_limit=50))
+    st, _ = env.reset(keys)
+    rst, _ = orc.connector_reset_batch("parallel_random_walk", kref, G, N)
+    ts_buf = rbg.engine.alloc_timestep(B, G, N, T)
+    resets = 0
+    for chunk in range(40):
+        st, ts, act = env.rollout_random(st, T, out=ts_buf)
+        acts = _np(act)
+        obs, mask, rew = _np(ts.observation.grid), _np(ts.observation.action_mask), _np(ts.reward)
+        stype, tpl, disc = _np(ts.step_type), _np(ts.extras["total_path_length"]), _np(ts.discount)
+        for t in range(T):
+            a = orc.random_actions_batch(rst)
+            assert np.array_equal(acts[t], a), (chunk, t)
+            rst, rts = orc.connector_step_batch(rst, a, time_limit=50, autoreset_kind="parallel_random_walk", inplace=True)
+            assert np.array_equal(obs[t], rts["obs"]) and np.array_equal(mask[t], rts["action_mask"]), (chunk, t)
+            assert np.array_equal(rew[t].view(np.uint32), rts["reward"].view(np.uint32)) and np.array_equal(disc[t].view(np.uint32), rts["discount"].view(np.uint32)), (chunk, t)
+            assert np.array_equal(stype[t], rts["step_type"]) and np.array_equal(tpl[t], rts["total_path_length"]), (chunk, t)
+            resets += int((rts["step_type"] == 2).sum())
+        _assert_state(st, rst, f"after chunk {chunk}")
+    assert resets > 150000
 
 
 def test_rollout_and_stepwise_calls_interleave(rbg, orc):
