@@ -160,25 +160,48 @@ __global__ void __launch_bounds__(VAL_WARPS * 32) validate_kernel(const int32_t 
       nb += (c < G - 1 && same(i + 1, w));
       if (t == PATH ? nb != 2 : nb != 1) fl |= 4;
     }
-    // connectivity: flood from every eligible head through own-wire cells
-    if (eligible) reached[hpos[lane]] = 1;
-    __syncwarp();
-    for (int it = 0; it < cells; ++it) {
-      bool changed = false;
-      for (int i = lane; i < cells; i += 32) {
-        const int v = grid[i];
-        if (v == 0 || reached[i]) continue;
-        const int w = (v - 1) / 3;
-        const int r = i / G, c = i - r * G;
-        const bool hit = (r > 0 && reached[i - G] && same(i - G, w)) || (r < G - 1 && reached[i + G] && same(i + G, w)) ||
-                         (c > 0 && reached[i - 1] && same(i - 1, w)) || (c < G - 1 && reached[i + 1] && same(i + 1, w));
-        if (hit) {
-          reached[i] = 1;
-          changed = true;
+    // connectivity head -> target through own-wire cells.  When the neighbour-count rule holds
+    // (warp-uniform test) every wire cell has at most two same-wire neighbours, so a wire is a simple
+    // chain and lane w can just walk it from its head; otherwise flood from every head.
+    const bool chains = __reduce_or_sync(FULL, fl & 4) == 0;
+    if (chains) {
+      if (eligible) {
+        int cur = hpos[lane], prev = -1;
+        reached[cur] = 1;
+        for (int step = 0; step < cells && cur != tpos[lane]; ++step) {
+          const int r = cur / G, c = cur - r * G;
+          int nxt = -1;
+          if (r > 0 && cur - G != prev && same(cur - G, lane)) nxt = cur - G;
+          if (r < G - 1 && cur + G != prev && same(cur + G, lane)) nxt = cur + G;
+          if (c > 0 && cur - 1 != prev && same(cur - 1, lane)) nxt = cur - 1;
+          if (c < G - 1 && cur + 1 != prev && same(cur + 1, lane)) nxt = cur + 1;
+          if (nxt < 0) break;
+          prev = cur;
+          cur = nxt;
+          reached[cur] = 1;
         }
       }
       __syncwarp();
-      if (!__any_sync(FULL, changed)) break;
+    } else {
+      if (eligible) reached[hpos[lane]] = 1;
+      __syncwarp();
+      for (int it = 0; it < cells; ++it) {
+        bool changed = false;
+        for (int i = lane; i < cells; i += 32) {
+          const int v = grid[i];
+          if (v == 0 || reached[i]) continue;
+          const int w = (v - 1) / 3;
+          const int r = i / G, c = i - r * G;
+          const bool hit = (r > 0 && reached[i - G] && same(i - G, w)) || (r < G - 1 && reached[i + G] && same(i + G, w)) ||
+                           (c > 0 && reached[i - 1] && same(i - 1, w)) || (c < G - 1 && reached[i + 1] && same(i + 1, w));
+          if (hit) {
+            reached[i] = 1;
+            changed = true;
+          }
+        }
+        __syncwarp();
+        if (!__any_sync(FULL, changed)) break;
+      }
     }
     if (eligible && !reached[tpos[lane]]) fl |= 8;
     fl = __reduce_or_sync(FULL, fl);
