@@ -241,7 +241,10 @@ int64_t rbg_launch_count(int reset);
  * every kernel launch is bracketed by a pair of CUDA events recorded on the
  * launching stream.  rbg_kernel_time synchronises on the recorded events,
  * returns the number of launches of `kernel` (RBG_K_*) and their summed device
- * time since the last call, and clears that kernel's record. */
+ * time since the last call, and clears that kernel's record.  The fused rollout
+ * normally runs slices of the batch on several streams so that their kernels
+ * overlap; while timing is enabled it launches everything on the caller's
+ * stream, one kernel at a time, so that a pair of events times one kernel. */
 #define RBG_K_PRW 0        /* prw_kernel: ParallelRandomWalk / Uniform generator */
 #define RBG_K_ENV 1        /* env_kernel: Connector step / observe */
 #define RBG_K_RANDACT 2    /* random_actions_kernel */

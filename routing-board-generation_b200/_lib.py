@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "lib", "librbg_b200.so")
+SO_PATH = os.environ.get("RBG_B200_LIB") or os.path.join(_HERE, "lib", "librbg_b200.so")  # override: A/B builds of the same CUDA library
 
 GEN_PRW, GEN_UNIFORM, GEN_SEEDEXT = 0, 1, 2
 MAX_G, MAX_N = 40, 32

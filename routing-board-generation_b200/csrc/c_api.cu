@@ -202,6 +202,9 @@ struct AutoResetCtx {
   cudaEvent_t env_done = nullptr;
   cudaEvent_t refill_done[2] = {nullptr, nullptr};
   bool refill_pending[2] = {false, false};
+  // fused rollout: slices 1.. of the batch run on their own streams
+  cudaStream_t slice_stream[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t slice_fork = nullptr, slice_done[3] = {nullptr, nullptr, nullptr};
 };
 static std::mutex g_ar_mu;
 static std::unordered_map<void *, AutoResetCtx> g_ar;
@@ -671,6 +674,13 @@ int rbg_workspace_release(void *workspace) {
     cudaEventDestroy(c.refill_done[0]);
     cudaEventDestroy(c.refill_done[1]);
   }
+  for (int i = 0; i < 3; ++i)
+    if (c.slice_stream[i]) {
+      cudaStreamSynchronize(c.slice_stream[i]);
+      cudaStreamDestroy(c.slice_stream[i]);
+      cudaEventDestroy(c.slice_done[i]);
+    }
+  if (c.slice_fork) cudaEventDestroy(c.slice_fork);
   g_ar.erase(it);
   return RBG_OK;
 }
@@ -748,22 +758,60 @@ static int rollout_fused(const rbg_state *state, int32_t *action_out, int64_t T,
   p.cache_tag = reinterpret_cast<const unsigned long long *>(ws + wl.cache_tag);
   p.cache_key = reinterpret_cast<const uint2 *>(ws + wl.cache_key);
   p.cache_pins = reinterpret_cast<const uint32_t *>(ws + wl.cache_pins);
-  p.refill_list = reinterpret_cast<int32_t *>(ws + wl.refill_list[0]);
-  p.refill_keys = reinterpret_cast<uint32_t *>(ws + wl.refill_keys[0]);
-  p.refill_count = reinterpret_cast<int32_t *>(ws + 64);
+  // Slices of the batch on their own streams: each slice alternates rollout chunk -> cache
+  // refill, and while one slice's (memory-bound) rollout drains, another slice's (issue-bound)
+  // refill and the ramp of its next chunk fill the SMs.  Slices never share an env, a list or
+  // a cache entry, so the result does not depend on how they interleave.
+  static int slices_env = -1;
+  if (slices_env < 0) {
+    slices_env = env_int("RBG_ROLLOUT_SLICES");
+    if (slices_env <= 0) slices_env = 2;
+    if (slices_env > 4) slices_env = 4;
+  }
+  int nsl = slices_env;
+  while (nsl > 1 && B < (int64_t)nsl * 2048) --nsl;
+  if (g_timing.load(std::memory_order_relaxed)) nsl = 1;  // event pairs must time one kernel at a time
+  int64_t cuts[5];
+  cuts[0] = 0;
+  for (int s = 1; s < nsl; ++s) cuts[s] = ((B * s / nsl) + 127) & ~(int64_t)127;  // whole CTAs on either side
+  cuts[nsl] = B;
+  if (nsl > 1) {
+    if (!ctx->slice_fork && (e = cudaEventCreateWithFlags(&ctx->slice_fork, cudaEventDisableTiming)) != cudaSuccess) return set_cuda_error(e, "cudaEventCreate");
+    if ((e = cudaEventRecord(ctx->slice_fork, stream)) != cudaSuccess) return set_cuda_error(e, "cudaEventRecord(fork)");
+    for (int s = 1; s < nsl; ++s) {
+      if (!ctx->slice_stream[s - 1]) {
+        if ((e = cudaStreamCreateWithFlags(&ctx->slice_stream[s - 1], cudaStreamNonBlocking)) != cudaSuccess) return set_cuda_error(e, "cudaStreamCreate(slice)");
+        if ((e = cudaEventCreateWithFlags(&ctx->slice_done[s - 1], cudaEventDisableTiming)) != cudaSuccess) return set_cuda_error(e, "cudaEventCreate");
+      }
+      if ((e = cudaStreamWaitEvent(ctx->slice_stream[s - 1], ctx->slice_fork, 0)) != cudaSuccess) return set_cuda_error(e, "cudaStreamWaitEvent(fork)");
+    }
+  }
   for (int64_t t0 = 0; t0 < T; t0 += chunk_env) {
     const int n = (int)((T - t0) < chunk_env ? (T - t0) : chunk_env);
     p.ts = timestep_at(*ts, t0 * B, G, N);
-    if ((rc = launch_rollout(p, kind, n, action_out ? action_out + t0 * B * N : nullptr, stream))) return rc;
-    PrwParams q;  // refill the cache entries consumed in this chunk (the kernel clears the counter when done)
-    cache_params(q);
-    q.keys = p.refill_keys;
-    q.keys_compact = 1;
-    q.list = p.refill_list;
-    q.list_count = p.refill_count;
-    q.list_ticket = p.refill_count + 1;
-    q.bulk_list = 1;
-    if ((rc = launch_prw(q, B, env_int("RBG_PRW_M"), env_int("RBG_PRW_THREADS"), stream))) return rc;
+    for (int s = 0; s < nsl; ++s) {
+      cudaStream_t st = s == 0 ? stream : ctx->slice_stream[s - 1];
+      p.env_lo = cuts[s];
+      p.env_hi = cuts[s + 1];
+      // the slice's share of the list buffers; counter + ticket pairs 16 bytes apart from ws + 64
+      p.refill_list = reinterpret_cast<int32_t *>(ws + wl.refill_list[0]) + p.env_lo;
+      p.refill_keys = reinterpret_cast<uint32_t *>(ws + wl.refill_keys[0]) + 2 * p.env_lo;
+      p.refill_count = reinterpret_cast<int32_t *>(ws + 64 + 16 * s);
+      if ((rc = launch_rollout(p, kind, n, action_out ? action_out + t0 * B * N : nullptr, st))) return rc;
+      PrwParams q;  // refill the cache entries consumed in this chunk (the kernel clears the counter when done)
+      cache_params(q);
+      q.keys = p.refill_keys;
+      q.keys_compact = 1;
+      q.list = p.refill_list;
+      q.list_count = p.refill_count;
+      q.list_ticket = p.refill_count + 1;
+      q.bulk_list = 1;
+      if ((rc = launch_prw(q, p.env_hi - p.env_lo, env_int("RBG_PRW_M"), env_int("RBG_PRW_THREADS"), st))) return rc;
+    }
+  }
+  for (int s = 1; s < nsl; ++s) {
+    if ((e = cudaEventRecord(ctx->slice_done[s - 1], ctx->slice_stream[s - 1])) != cudaSuccess) return set_cuda_error(e, "cudaEventRecord(join)");
+    if ((e = cudaStreamWaitEvent(stream, ctx->slice_done[s - 1], 0)) != cudaSuccess) return set_cuda_error(e, "cudaStreamWaitEvent(join)");
   }
   return RBG_OK;
 }

@@ -26,6 +26,40 @@ namespace rbg {
 // row stride of the observation table: codes 0..3N, rounded up to whole words
 __host__ __device__ inline int obs_lut_stride(int N) { return (3 * N + 1 + 3) & ~3; }
 
+// The fused rollout kernel uses ONE stride for every N (codes 0..96), so that the per-agent
+// table rows sit at compile-time offsets from the four cell addresses of a packed word.
+constexpr int OBS_RS = 100;
+
+// four cells (one packed word) -> the same four cells in every agent's view: per agent four
+// table bytes and one 128-bit store, nothing else (views are c4 int4 apart).
+__device__ __forceinline__ void emit_views(const uint8_t *lut, uint32_t w, int N, int4 *o, int c4) {
+  const uint8_t *l0 = lut + (w & 0xffu), *l1 = lut + ((w >> 8) & 0xffu), *l2 = lut + ((w >> 16) & 0xffu), *l3 = lut + (w >> 24);
+  int x = N;
+  for (; x >= 4; x -= 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      *o = make_int4(l0[u * OBS_RS], l1[u * OBS_RS], l2[u * OBS_RS], l3[u * OBS_RS]);
+      o += c4;
+    }
+    l0 += 4 * OBS_RS;
+    l1 += 4 * OBS_RS;
+    l2 += 4 * OBS_RS;
+    l3 += 4 * OBS_RS;
+  }
+  if (x & 2) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      *o = make_int4(l0[u * OBS_RS], l1[u * OBS_RS], l2[u * OBS_RS], l3[u * OBS_RS]);
+      o += c4;
+    }
+    l0 += 2 * OBS_RS;
+    l1 += 2 * OBS_RS;
+    l2 += 2 * OBS_RS;
+    l3 += 2 * OBS_RS;
+  }
+  if (x & 1) *o = make_int4(l0[0], l1[0], l2[0], l3[0]);
+}
+
 // number of PATH codes (v % 3 == 1) among the four byte codes of a packed word,
 // two 16-bit lanes at a time: x / 3 == (x * 171) >> 9 for x < 256
 __device__ __forceinline__ int count_path_codes(uint32_t w) {
@@ -321,10 +355,26 @@ struct RolloutParams {
   uint32_t thresh;
   int32_t *action_out;   // [T,B,N] or NULL
   int ratio_off;         // smem byte offset of the n / N table
+  int stage_off;         // smem byte offset of the per-warp observation staging
+  int stage_bytes;       // bytes per buffer
+  int stage_nbuf;        // 1: one chunk per step (a whole step passes before it is refilled); 2: alternate
+  int stage_warp;        // bytes per warp (>= stage_nbuf * stage_bytes; the generator scratch aliases it)
+  int ce, cv;            // a staged chunk = ce whole envs (cv == N) or cv views of one env (ce == 1)
 };
 
+// Bulk asynchronous copy shared -> global (the TMA unit moves the bytes, the LSU queue does not
+// see them).  Issued by one lane; the buffer may be rewritten once its group has been READ.
+__device__ __forceinline__ void bulk_store(void *gdst, uint32_t ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int PENDING>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PENDING) : "memory");
+}
+
 #ifndef RBG_ROLLOUT_MIN_CTAS
-#define RBG_ROLLOUT_MIN_CTAS 8
+#define RBG_ROLLOUT_MIN_CTAS 6
 #endif
 template <bool VEC>
 __global__ void __launch_bounds__(EW_WARPS * 32, RBG_ROLLOUT_MIN_CTAS) rollout_warp_kernel(const EnvParams p, const RolloutParams rp) {
@@ -332,7 +382,7 @@ __global__ void __launch_bounds__(EW_WARPS * 32, RBG_ROLLOUT_MIN_CTAS) rollout_w
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = p.G, N = p.N, cells = p.cells;
   const int Np = p.Np, K = 32 / Np, c4 = cells >> 2;
-  const int RS = obs_lut_stride(N);
+  constexpr int RS = OBS_RS;
   uint8_t *lut = smem_raw;
   for (int a = warp; a < N; a += EW_WARPS)
     for (int v = lane; v < RS; v += 32) lut[a * RS + v] = v <= 3 * N ? (uint8_t)obs_value(v, 3 * a, 3 * N) : (uint8_t)0;
@@ -340,14 +390,14 @@ __global__ void __launch_bounds__(EW_WARPS * 32, RBG_ROLLOUT_MIN_CTAS) rollout_w
   if (tid <= N) ratio_lut[tid] = __fdiv_rn((float)tid, (float)N);
   __syncthreads();  // the only CTA-wide barrier
 
-  const long long e0 = ((long long)blockIdx.x * EW_WARPS + warp) * K;
-  if (e0 >= p.B) return;
-  const int kc = (int)((p.B - e0) < (long long)K ? (p.B - e0) : (long long)K);
+  const long long e0 = p.env_lo + ((long long)blockIdx.x * EW_WARPS + warp) * K;
+  if (e0 >= p.env_hi) return;
+  const int kc = (int)((p.env_hi - e0) < (long long)K ? (p.env_hi - e0) : (long long)K);
   uint8_t *wg = smem_raw + p.so[0] + (size_t)warp * p.so[1];
   uint32_t *wg32 = reinterpret_cast<uint32_t *>(wg);
   WarpGenScratch gs;
   {
-    uint8_t *gb = smem_raw + rp.gen_off + (size_t)warp * rp.gen_stride;
+    uint8_t *gb = VEC ? smem_raw + rp.stage_off + (size_t)warp * rp.stage_warp : smem_raw + rp.gen_off + (size_t)warp * rp.gen_stride;
     gs.cand = reinterpret_cast<uint64_t *>(gb);
     gs.sel = reinterpret_cast<uint16_t *>(gb + rp.gen_cand_bytes);
     gs.board = gb + rp.gen_cand_bytes + rp.gen_sel_bytes;
@@ -402,6 +452,25 @@ __global__ void __launch_bounds__(EW_WARPS * 32, RBG_ROLLOUT_MIN_CTAS) rollout_w
   // the action mask of the state an env is in: what step t emits is what step t+1's policy samples from
   uint32_t mk3 = 0;
   if (agent) mk3 = move_mask(sg, pos >> 8, pos & 255, a, pos == tgt);
+
+  // observation addressing, hoisted out of the step loop: word q = m * c4 + rem of the warp's
+  // envs goes to int4 slot m * N * c4 + rem of its first env's first view
+  int rem0 = 0, off0 = 0, q_rem = 0, q_off = 0, q_wrap = 0;
+  int4 *obs_t = nullptr;
+  long long obs_step = 0;
+  if (VEC) {
+    const int m0 = (int)p.divC4.div((uint32_t)lane), qm = (int)p.divC4.div(32u);
+    rem0 = lane - m0 * c4;
+    off0 = m0 * N * c4 + rem0;
+    q_rem = 32 - qm * c4;
+    q_off = qm * N * c4 + q_rem;
+    q_wrap = (N - 1) * c4;
+    obs_t = reinterpret_cast<int4 *>(p.ts.obs_grid) + e0 * N * c4;
+    obs_step = p.B * N * c4;
+  }
+  uint8_t *stage = smem_raw + rp.stage_off + (size_t)warp * rp.stage_warp;
+  const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
+  int buf = 0;
 
   for (int t = 0; t < rp.T; ++t) {
     const long long tb = (long long)t * p.B;  // row offset of step t in the stacked outputs
@@ -468,6 +537,12 @@ __global__ void __launch_bounds__(EW_WARPS * 32, RBG_ROLLOUT_MIN_CTAS) rollout_w
       const uint32_t gk0 = __shfl_sync(FULL, k0, src_lane), gk1 = __shfl_sync(FULL, k1, src_lane);
       uint32_t x0, x1;
       int gstart, gfin;
+#ifndef RBG_OBS_DIRECT
+      if (VEC) {  // the generator scratch aliases the observation staging
+        if (lane == 0) bulk_wait_read<0>();
+        __syncwarp();
+      }
+#endif
       warp_generate_pins(rp.kind, gk0, gk1, G, N, p.divG, gs, lane, x0, x1, gstart, gfin);
       // lane i < N holds agent i's pins; hand them to env jj's lanes
       const int from = a < N ? a : 0;
@@ -514,16 +589,56 @@ __global__ void __launch_bounds__(EW_WARPS * 32, RBG_ROLLOUT_MIN_CTAS) rollout_w
     if (agent) store_mask5(p.ts.action_mask + ((tb + e) * N + a) * 5, mk3);
     // ---- observation of step t
     if (VEC) {
-      int4 *odst = reinterpret_cast<int4 *>(p.ts.obs_grid) + (tb + e0) * N * c4;
-      for (int q = lane; q < kc * c4; q += 32) {
-        const int m = (int)p.divC4.div((uint32_t)q);
-        const uint32_t w = wg32[q];
-        const uint32_t b0 = w & 0xffu, b1 = (w >> 8) & 0xffu, b2 = (w >> 16) & 0xffu, b3 = w >> 24;
-        int4 *o = odst + (size_t)m * N * c4 + (q - m * c4);
-        const uint8_t *row = lut;
-#pragma unroll 2
-        for (int x = 0; x < N; ++x, o += c4, row += RS) *o = make_int4(row[b0], row[b1], row[b2], row[b3]);
+      // The views are built in shared memory in their global layout and leave as bulk copies:
+      // with direct 128-bit stores the LSU queue filled up with stores draining at the L1->L2
+      // rate and every other warp's shared-memory access queued behind them.
+      int4 *odst = obs_t;
+      obs_t += obs_step;
+#ifdef RBG_OBS_DIRECT
+      {
+        int rem = rem0, off = off0;
+        for (int q = lane; q < kc * c4; q += 32) {
+          emit_views(lut, wg32[q], N, odst + off, c4);
+          rem += q_rem;
+          off += q_off;
+          if (rem >= c4) {
+            rem -= c4;
+            off += q_wrap;
+          }
+        }
       }
+#else
+      for (int m0 = 0; m0 < kc; m0 += rp.ce) {
+        const int nenv = min(rp.ce, kc - m0), nw = nenv * c4;
+        const uint32_t *src = wg32 + m0 * c4;
+        for (int x0 = 0; x0 < N; x0 += rp.cv) {
+          const int nv = min(rp.cv, N - x0);
+          if (lane == 0) {  // the buffer about to be filled has been read
+            if (rp.stage_nbuf == 1)
+              bulk_wait_read<0>();
+            else
+              bulk_wait_read<1>();
+          }
+          __syncwarp();
+          int4 *sb = reinterpret_cast<int4 *>(stage + buf * rp.stage_bytes);
+          int rem = rem0, off = off0;
+          for (int q = lane; q < nw; q += 32) {
+            emit_views(lut + x0 * OBS_RS, src[q], nv, sb + off, c4);
+            rem += q_rem;  // word q + 32: same env or the next one(s)
+            off += q_off;
+            if (rem >= c4) {
+              rem -= c4;
+              off += q_wrap;
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0)
+            bulk_store(odst + (size_t)(m0 * N + x0) * c4, stage_s + (uint32_t)(buf * rp.stage_bytes), (uint32_t)(((nenv - 1) * N + nv) * c4) * 16u);
+          buf ^= rp.stage_nbuf - 1;
+        }
+      }
+#endif
     } else {
       int32_t *odst = p.ts.obs_grid + (tb + e0) * N * cells;
       for (int i = lane; i < kc * cells; i += 32) {
@@ -538,6 +653,7 @@ __global__ void __launch_bounds__(EW_WARPS * 32, RBG_ROLLOUT_MIN_CTAS) rollout_w
 
   // ---- write the State once; queue the envs that reset for a cache refill
   if (VEC) {
+    if (lane == 0) bulk_wait_read<0>();  // shared memory must outlive the last bulk copies
     int4 *gdst = reinterpret_cast<int4 *>(p.out.grid) + e0 * c4;
     for (int q = lane; q < kc * c4; q += 32) gdst[q] = bytes_to_int4(wg32[q]);
   } else {
@@ -644,12 +760,16 @@ int launch_rollout(EnvParams p, int kind, int T, int32_t *action_out, cudaStream
   p.divC4 = FastDiv::make((uint32_t)(vec ? p.cells >> 2 : 1));
   p.divCells = FastDiv::make((uint32_t)p.cells);
   if (p.B <= 0 || T <= 0) return RBG_OK;
+  if (p.env_hi <= p.env_lo) {
+    p.env_lo = 0;
+    p.env_hi = p.B;
+  }
   int Np = 1;
   while (Np < N) Np <<= 1;
   p.Np = Np;
   const int K = 32 / Np;
   p.E = EW_WARPS * K;
-  const size_t lutB = ((size_t)N * obs_lut_stride(N) + 256 + 15) & ~(size_t)15;
+  const size_t lutB = ((size_t)N * OBS_RS + 256 + 15) & ~(size_t)15;
   const size_t wgrid = ((size_t)K * p.cells + 15) & ~(size_t)15;
   p.so[0] = (int)lutB;
   p.so[1] = (int)wgrid;
@@ -668,11 +788,51 @@ int launch_rollout(EnvParams p, int kind, int T, int32_t *action_out, cudaStream
   const size_t board = (((size_t)(G + 4) * (G + 4) + 15) / 16) * 16;
   rp.gen_stride = (int)(rp.gen_cand_bytes + rp.gen_sel_bytes + board);
   rp.gen_off = (int)(lutB + EW_WARPS * wgrid);
-  rp.ratio_off = rp.gen_off + EW_WARPS * rp.gen_stride;
-  size_t smem = (size_t)rp.ratio_off + 4 * (RBG_MAX_N + 4);
+  rp.ratio_off = rp.gen_off + (vec ? 0 : EW_WARPS * rp.gen_stride);
+  size_t smem = (((size_t)rp.ratio_off + 4 * (RBG_MAX_N + 4)) + 15) & ~(size_t)15;
+  rp.stage_off = (int)smem;
+  rp.stage_bytes = 0;
+  rp.stage_nbuf = 1;
+  rp.stage_warp = 0;
+  rp.ce = 1;
+  rp.cv = N;
+  if (vec) {
+    // observation staging: the warp's whole step if that is at most 8 KB (one buffer), else two
+    // buffers of about 4 KB, each a whole number of envs or of views of one env
+    size_t target = 4096, whole = 8192;
+    if (const char *ex = getenv("RBG_EXP_STAGE")) target = (size_t)atoi(ex);
+    if (const char *ex = getenv("RBG_EXP_WHOLE")) whole = (size_t)atoi(ex);
+    const size_t view = (size_t)p.cells * 4, envb = view * N;
+    if ((size_t)K * envb <= whole) {
+      rp.ce = K;
+      rp.stage_bytes = (int)(K * envb);
+    } else if (envb <= target) {
+      rp.stage_nbuf = 2;
+      rp.ce = (int)(target / envb) < K ? (int)(target / envb) : K;
+      rp.stage_bytes = (int)(rp.ce * envb);
+    } else {
+      rp.stage_nbuf = 2;
+      rp.cv = view >= target ? 1 : (int)(target / view);
+      if (rp.cv > N) rp.cv = N;
+      rp.stage_bytes = (int)(rp.cv * view);
+    }
+    rp.stage_warp = rp.stage_nbuf * rp.stage_bytes;
+    if (rp.stage_warp < rp.gen_stride) rp.stage_warp = rp.gen_stride;
+    rp.stage_warp = (rp.stage_warp + 15) & ~15;
+    smem += (size_t)EW_WARPS * rp.stage_warp;
+  }
   if (smem > 200 * 1024) return set_error(RBG_EINVAL, "rollout: shared memory %zu too large", smem);
-  const int64_t ctas = (p.B + p.E - 1) / p.E;
-  if (smem <= 24 * 1024) smem = balance_waves(ctas, RBG_ROLLOUT_MIN_CTAS, 5, smem);  // registers allow RBG_ROLLOUT_MIN_CTAS per SM
+  const int64_t ctas = (p.env_hi - p.env_lo + p.E - 1) / p.E;
+  {  // residency: registers allow RBG_ROLLOUT_MIN_CTAS per SM, shared memory (1 KB reserved per CTA) maybe fewer
+    int cmax = (int)((228 * 1024) / (smem + 1024));
+    if (cmax > RBG_ROLLOUT_MIN_CTAS) cmax = RBG_ROLLOUT_MIN_CTAS;
+    if (cmax >= 3) smem = balance_waves(ctas, cmax, cmax - 2, smem);
+  }
+  if (const char *ex = getenv("RBG_EXP_CTAS")) {
+    const int c = atoi(ex);
+    const size_t pad = (size_t)(228 * 1024) / (size_t)(c + 1) + 1024;
+    if (c >= 1 && c < 8 && pad > smem) smem = pad;
+  }
   LaunchScope scope(RBG_K_ROLLOUT, stream);
   if (vec) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(rollout_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -66,6 +66,7 @@ struct EnvParams {
   const int32_t *action;  // [B,N] (STEP)
   int32_t *action_out;    // optional (random policy)
   long long B;
+  long long env_lo, env_hi;  // rollout: the slice [env_lo, env_hi) of the batch this launch covers (0, 0 = all)
   int G, N;
   int mode;           // ENV_MODE_*
   int random_policy;  // sample actions in-kernel
