@@ -362,6 +362,73 @@ struct RolloutParams {
   int ce, cv;            // a staged chunk = ce whole envs (cv == N) or cv views of one env (ce == 1)
 };
 
+// Shared-memory accesses by 32-bit shared address: the staged observation loop keeps its three
+// base addresses (packed grid words, table, staging) in registers instead of letting the
+// compiler rebuild them from threadIdx in every iteration.
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF));
+  return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ uint32_t opaque(uint32_t v) {  // the compiler may not re-derive v
+  asm volatile("" : "+r"(v));
+  return v;
+}
+template <int U>
+__device__ __forceinline__ void stage_view(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t o) {
+  sts_v4(o, lds_u8<U * OBS_RS>(a0), lds_u8<U * OBS_RS>(a1), lds_u8<U * OBS_RS>(a2), lds_u8<U * OBS_RS>(a3));
+}
+// four cells (packed word w) -> the same four cells of nv consecutive agents' views, staged at
+// shared address o with views vs bytes apart; lut_s = shared address of the first agent's table row
+__device__ __forceinline__ void stage_views(uint32_t lut_s, uint32_t w, int nv, uint32_t o, uint32_t vs) {
+  uint32_t a0 = lut_s + (w & 0xffu), a1 = lut_s + ((w >> 8) & 0xffu), a2 = lut_s + ((w >> 16) & 0xffu), a3 = lut_s + (w >> 24);
+  int x = nv;
+  for (; x >= 4; x -= 4) {
+    stage_view<0>(a0, a1, a2, a3, o);
+    stage_view<1>(a0, a1, a2, a3, o + vs);
+    stage_view<2>(a0, a1, a2, a3, o + 2 * vs);
+    stage_view<3>(a0, a1, a2, a3, o + 3 * vs);
+    a0 += 4 * OBS_RS;
+    a1 += 4 * OBS_RS;
+    a2 += 4 * OBS_RS;
+    a3 += 4 * OBS_RS;
+    o += 4 * vs;
+  }
+  if (x & 2) {
+    stage_view<0>(a0, a1, a2, a3, o);
+    stage_view<1>(a0, a1, a2, a3, o + vs);
+    a0 += 2 * OBS_RS;
+    a1 += 2 * OBS_RS;
+    a2 += 2 * OBS_RS;
+    a3 += 2 * OBS_RS;
+    o += 2 * vs;
+  }
+  if (x & 1) stage_view<0>(a0, a1, a2, a3, o);
+}
+
+// the same with the agent count known at compile time: straight-line code
+template <int NV>
+__device__ __forceinline__ void stage_views_fixed(uint32_t lut_s, uint32_t w, uint32_t o, uint32_t vs) {
+  const uint32_t a0 = lut_s + (w & 0xffu), a1 = lut_s + ((w >> 8) & 0xffu), a2 = lut_s + ((w >> 16) & 0xffu), a3 = lut_s + (w >> 24);
+  stage_view<0>(a0, a1, a2, a3, o);
+  if (NV > 1) stage_view<1>(a0, a1, a2, a3, o += vs);
+  if (NV > 2) stage_view<2>(a0, a1, a2, a3, o += vs);
+  if (NV > 3) stage_view<3>(a0, a1, a2, a3, o += vs);
+  if (NV > 4) stage_view<4>(a0, a1, a2, a3, o += vs);
+  if (NV > 5) stage_view<5>(a0, a1, a2, a3, o += vs);
+  if (NV > 6) stage_view<6>(a0, a1, a2, a3, o += vs);
+  if (NV > 7) stage_view<7>(a0, a1, a2, a3, o += vs);
+}
+
 // Bulk asynchronous copy shared -> global (the TMA unit moves the bytes, the LSU queue does not
 // see them).  Issued by one lane; the buffer may be rewritten once its group has been READ.
 __device__ __forceinline__ void bulk_store(void *gdst, uint32_t ssrc, uint32_t bytes) {
@@ -468,8 +535,10 @@ __global__ void __launch_bounds__(EW_WARPS * 32, RBG_ROLLOUT_MIN_CTAS) rollout_w
     obs_t = reinterpret_cast<int4 *>(p.ts.obs_grid) + e0 * N * c4;
     obs_step = p.B * N * c4;
   }
-  uint8_t *stage = smem_raw + rp.stage_off + (size_t)warp * rp.stage_warp;
-  const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
+  const uint32_t stage_s = opaque((uint32_t)__cvta_generic_to_shared(smem_raw + rp.stage_off + (size_t)warp * rp.stage_warp));
+  const uint32_t lut_s = opaque((uint32_t)__cvta_generic_to_shared(lut));
+  const uint32_t wq_s = opaque((uint32_t)__cvta_generic_to_shared(wg32) + 4u * (uint32_t)lane);
+  const uint32_t view_b = (uint32_t)c4 * 16u;
   int buf = 0;
 
   for (int t = 0; t < rp.T; ++t) {
@@ -610,7 +679,6 @@ __global__ void __launch_bounds__(EW_WARPS * 32, RBG_ROLLOUT_MIN_CTAS) rollout_w
 #else
       for (int m0 = 0; m0 < kc; m0 += rp.ce) {
         const int nenv = min(rp.ce, kc - m0), nw = nenv * c4;
-        const uint32_t *src = wg32 + m0 * c4;
         for (int x0 = 0; x0 < N; x0 += rp.cv) {
           const int nv = min(rp.cv, N - x0);
           if (lane == 0) {  // the buffer about to be filled has been read
@@ -620,21 +688,34 @@ __global__ void __launch_bounds__(EW_WARPS * 32, RBG_ROLLOUT_MIN_CTAS) rollout_w
               bulk_wait_read<1>();
           }
           __syncwarp();
-          int4 *sb = reinterpret_cast<int4 *>(stage + buf * rp.stage_bytes);
-          int rem = rem0, off = off0;
+          const uint32_t sb = stage_s + (uint32_t)(buf * rp.stage_bytes);
+          const uint32_t row = lut_s + (uint32_t)(x0 * OBS_RS);
+          uint32_t wq = wq_s + 4u * (uint32_t)(m0 * c4), o = sb + 16u * (uint32_t)off0;
+          int rem = rem0;
           for (int q = lane; q < nw; q += 32) {
-            emit_views(lut + x0 * OBS_RS, src[q], nv, sb + off, c4);
+            const uint32_t w = lds_u32(wq);
+            switch (nv) {  // warp-uniform
+              case 2: stage_views_fixed<2>(row, w, o, view_b); break;
+              case 3: stage_views_fixed<3>(row, w, o, view_b); break;
+              case 4: stage_views_fixed<4>(row, w, o, view_b); break;
+              case 5: stage_views_fixed<5>(row, w, o, view_b); break;
+              case 6: stage_views_fixed<6>(row, w, o, view_b); break;
+              case 7: stage_views_fixed<7>(row, w, o, view_b); break;
+              case 8: stage_views_fixed<8>(row, w, o, view_b); break;
+              default: stage_views(row, w, nv, o, view_b);
+            }
+            wq += 128u;
             rem += q_rem;  // word q + 32: same env or the next one(s)
-            off += q_off;
+            o += 16u * (uint32_t)q_off;
             if (rem >= c4) {
               rem -= c4;
-              off += q_wrap;
+              o += 16u * (uint32_t)q_wrap;
             }
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0)
-            bulk_store(odst + (size_t)(m0 * N + x0) * c4, stage_s + (uint32_t)(buf * rp.stage_bytes), (uint32_t)(((nenv - 1) * N + nv) * c4) * 16u);
+            bulk_store(odst + (size_t)(m0 * N + x0) * c4, sb, (uint32_t)(((nenv - 1) * N + nv) * c4) * 16u);
           buf ^= rp.stage_nbuf - 1;
         }
       }

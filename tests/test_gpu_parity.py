@@ -439,8 +439,13 @@ def test_fused_random_step_matches_two_calls(rbg, orc):
     ("parallel_random_walk", 9, 9, 301, 14, 5),       # N > 8: two envs per warp
     ("parallel_random_walk", 12, 20, 130, 14, 7),     # N > 16: one env per warp
     ("parallel_random_walk", 40, 32, 40, 8, 5),       # largest supported shape
+    ("parallel_random_walk", 8, 4, 4611, 24, 6),      # two batch slices on two streams, ragged cut and ragged last warp
+    ("parallel_random_walk", 12, 10, 4099, 22, 7),    # staged views in two alternating buffers (5.7 KB per env), two slices
+    ("parallel_random_walk", 6, 12, 310, 21, 4),      # c4 = 9 < 32 lanes, one env per warp
+    ("parallel_random_walk", 4, 2, 1300, 21, 3),      # 16 envs per warp, 2 KB of views per step
     ("uniform", 10, 5, 2000, 30, 7),
     ("uniform", 7, 6, 500, 21, 3),
+    ("uniform", 8, 8, 4200, 21, 5),                   # two slices, Uniform in-kernel generation
     ("seed_extension", 10, 5, 300, 12, 5),            # no fused kernel for this generator: step-wise path
 ])
 def test_rollout_matches_stepwise_oracle(rbg, orc, kind, G, N, B, T, time_limit):
@@ -464,6 +469,38 @@ def test_rollout_matches_stepwise_oracle(rbg, orc, kind, G, N, B, T, time_limit)
         rst, rts = orc.connector_step_batch(rst, a, time_limit=time_limit, autoreset_kind=kind)
         _assert_timestep(ts[t], rts, f"at step {t} of the second rollout")
     _assert_state(st, rst, "after the second rollout")
+
+
+@pytest.mark.parametrize("slices", [1, 3, 4])
+def test_rollout_slice_counts(rbg, slices):
+    """The fused rollout splits the batch into slices that run on separate streams (2 by default);
+    RBG_ROLLOUT_SLICES (read once per process, hence the subprocess) selects 1, 3 or 4: same results."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r)\n"
+        "import routing_board_generation_b200 as rbg\n"
+        "from oracle import oracle as orc\n"
+        "G, N, B, T = 10, 5, 8200, 21\n"
+        "k = rbg.split(rbg.PRNGKey(5), B); kr = orc.split(orc.PRNGKey(5), B)\n"
+        "env = rbg.VmapAutoResetWrapper(rbg.Connector(generator=rbg.ParallelRandomWalkGenerator(G, N), time_limit=6))\n"
+        "st, _ = env.reset(k); rst, _ = orc.connector_reset_batch('parallel_random_walk', kr, G, N)\n"
+        "for rep in range(2):\n"
+        "    st, ts, act = env.rollout_random(st, T)\n"
+        "    obs, rew, stype = ts.observation.grid.cpu().numpy(), ts.reward.cpu().numpy(), ts.step_type.cpu().numpy()\n"
+        "    for t in range(T):\n"
+        "        a = orc.random_actions_batch(rst)\n"
+        "        assert np.array_equal(act[t].cpu().numpy(), a), t\n"
+        "        rst, rts = orc.connector_step_batch(rst, a, time_limit=6, autoreset_kind='parallel_random_walk')\n"
+        "        assert np.array_equal(obs[t], rts['obs']) and np.array_equal(rew[t], rts['reward']) and np.array_equal(stype[t], rts['step_type']), t\n"
+        "    assert np.array_equal(st.grid.cpu().numpy(), rst['grid']) and np.array_equal(st.key.cpu().numpy(), rst['key'])\n"
+        "print('slices ok')\n"
+    ) % root
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, RBG_ROLLOUT_SLICES=str(slices)), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "slices ok" in r.stdout, (r.stdout[-500:], r.stderr[-2000:])
 
 
 def test_rollout_long_horizon(rbg, orc):

@@ -17,7 +17,8 @@ out = None
 for _ in range(burn):
     st, out, _ = env.rollout_random(st, T, out=out)
 torch.cuda.synchronize()
-rbg._lib.kernel_timing(True)
+timing = not os.environ.get('NOTIMING')  # kernel timing serialises the slices (one kernel at a time)
+rbg._lib.kernel_timing(timing)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(calls):
