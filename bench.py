@@ -293,9 +293,22 @@ def _e2e_host(args, rbg, lib, state, B, world, rank, dev):
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     dt = float(tt.item())
+    # context: what the bus gives a plain pinned D2H copy of the observation buffer alone
+    dobs = torch.empty((B, N, G, G), dtype=torch.int32, device=dev)
+    hts["obs"].copy_(dobs, non_blocking=True)
+    torch.cuda.synchronize()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(5):
+        hts["obs"].copy_(dobs, non_blocking=True)
+    c1.record()
+    torch.cuda.synchronize()
+    bus = dobs.numel() * 4 * 5 / (c0.elapsed_time(c1) / 1e3) / 1e9
+    mine = d2h * k / dt / 1e9
     return {"value": round(B * world * k / dt, 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": k,
             "api": "rbg_connector_step_host_io (pinned host actions in, full TimeStep out to pinned host memory, State device-resident, auto-reset on)",
-            "timer": "host wall clock around synchronous calls, max over ranks"}
+            "timer": "host wall clock around synchronous calls, max over ranks",
+            "d2h_gbs": round(mine, 1), "pinned_d2h_copy_gbs": round(bus, 1), "frac_of_bus": round(mine / bus, 3)}
 
 
 def _secondary_prw(args, rbg, peak):

@@ -361,6 +361,7 @@ struct Scratch {
 static std::mutex g_scratch_mu;
 static Scratch g_scratch;
 static cudaStream_t g_streams[3] = {nullptr, nullptr, nullptr};
+static cudaEvent_t g_stream_ev[3] = {nullptr, nullptr, nullptr};
 
 static int scratch_get(size_t bytes, int device, void **out) {
   if (g_scratch.ptr && (g_scratch.bytes < bytes || g_scratch.device != device)) {
@@ -380,6 +381,7 @@ static int scratch_get(size_t bytes, int device, void **out) {
     if (!g_streams[i]) {
       cudaError_t e = cudaStreamCreateWithFlags(&g_streams[i], cudaStreamNonBlocking);
       if (e != cudaSuccess) return set_cuda_error(e, "cudaStreamCreate");
+      if ((e = cudaEventCreateWithFlags(&g_stream_ev[i], cudaEventDisableTiming)) != cudaSuccess) return set_cuda_error(e, "cudaEventCreate");
     }
   *out = g_scratch.ptr;
   return RBG_OK;
@@ -436,10 +438,12 @@ static int copy_state(const rbg_state *dst, const rbg_state *src, int64_t off, i
   RBG_CPY(dst->key + dst_off * 2, src->key + off * 2, n * 8, kind, st);
   return RBG_OK;
 }
+// `parts`: 1 = observation.grid (the bulk), 2 = every other leaf, 3 = both
 static int copy_timestep(const rbg_timestep *dst, const rbg_timestep *src, int64_t off, int64_t n, int G, int N,
-                         cudaMemcpyKind kind, int64_t dst_off, cudaStream_t st) {
+                         cudaMemcpyKind kind, int64_t dst_off, cudaStream_t st, int parts = 3) {
   const size_t c = (size_t)G * G * N;
-  RBG_CPY(dst->obs_grid + dst_off * c, src->obs_grid + off * c, n * c * 4, kind, st);
+  if (parts & 1) RBG_CPY(dst->obs_grid + dst_off * c, src->obs_grid + off * c, n * c * 4, kind, st);
+  if (!(parts & 2)) return RBG_OK;
   RBG_CPY(dst->action_mask + dst_off * N * 5, src->action_mask + off * N * 5, n * N * 5, kind, st);
   RBG_CPY(dst->obs_step_count + dst_off, src->obs_step_count + off, n * 4, kind, st);
   RBG_CPY(dst->reward + dst_off * N, src->reward + off * N, n * N * 4, kind, st);
@@ -1036,16 +1040,26 @@ int rbg_connector_step_host_io(const rbg_state *state, const int32_t *action, in
   carve_timestep(c, B, G, N, &dt);
   int32_t *da = c.take<int32_t>((size_t)B * N);
   uint8_t *ws = c.take<uint8_t>((size_t)nslices * ws_bytes);
+  // One compute stream runs the slices' kernels back to back (the whole batch is ~0.1 ms of
+  // kernels, the copies 2.4 ms); the two copy streams take the observation (96 % of the bytes)
+  // of each slice as soon as its kernel is done, so the bus is busy from the first slice on.
+  // The small leaves go once for the whole batch: 8 copies instead of 8 per slice.
+  static cudaEvent_t slice_ev[16] = {nullptr};
+  cudaStream_t cs = g_streams[0];
+  RBG_CPY(da, action, (size_t)B * N * 4, cudaMemcpyHostToDevice, cs);
   int si = 0;
   for (int64_t off = 0; off < B; off += sl, ++si) {
     const int64_t n = (B - off) < sl ? (B - off) : sl;
-    cudaStream_t st = g_streams[si % 3];
-    RBG_CPY(da + off * N, action + off * N, n * N * 4, cudaMemcpyHostToDevice, st);
     rbg_state dss = state_at(*state, off, G, N);
     rbg_timestep dts = timestep_at(dt, off, G, N);
-    if ((rc = rbg_connector_step(&dss, &dss, da + off * N, n, G, N, params, &dts, ws + (size_t)si * ws_bytes, st))) return rc;
-    if ((rc = copy_timestep(ts, &dt, off, n, G, N, cudaMemcpyDeviceToHost, off, st))) return rc;
+    if ((rc = rbg_connector_step(&dss, &dss, da + off * N, n, G, N, params, &dts, ws + (size_t)si * ws_bytes, cs))) return rc;
+    if (!slice_ev[si] && (e = cudaEventCreateWithFlags(&slice_ev[si], cudaEventDisableTiming)) != cudaSuccess) return set_cuda_error(e, "cudaEventCreate");
+    if ((e = cudaEventRecord(slice_ev[si], cs)) != cudaSuccess) return set_cuda_error(e, "cudaEventRecord");
+    cudaStream_t xs = g_streams[1 + (si & 1)];
+    if ((e = cudaStreamWaitEvent(xs, slice_ev[si], 0)) != cudaSuccess) return set_cuda_error(e, "cudaStreamWaitEvent");
+    if ((rc = copy_timestep(ts, &dt, off, n, G, N, cudaMemcpyDeviceToHost, off, xs, 1))) return rc;
   }
+  if ((rc = copy_timestep(ts, &dt, 0, B, G, N, cudaMemcpyDeviceToHost, 0, cs, 2))) return rc;
   for (int i = 0; i < 3; ++i) {
     e = cudaStreamSynchronize(g_streams[i]);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaStreamSynchronize");
