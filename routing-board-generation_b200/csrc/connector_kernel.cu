@@ -18,47 +18,14 @@
 #include <stdlib.h>
 
 #include "connector_device.cuh"
+#include "obs_stage.cuh"
 #include "prw_warp.cuh"
 #include "rbg_host.h"
 
 namespace rbg {
 
-// row stride of the observation table: codes 0..3N, rounded up to whole words
+// row stride of the per-step kernel's observation table: codes 0..3N, rounded up to whole words
 __host__ __device__ inline int obs_lut_stride(int N) { return (3 * N + 1 + 3) & ~3; }
-
-// The fused rollout kernel uses ONE stride for every N (codes 0..96), so that the per-agent
-// table rows sit at compile-time offsets from the four cell addresses of a packed word.
-constexpr int OBS_RS = 100;
-
-// four cells (one packed word) -> the same four cells in every agent's view: per agent four
-// table bytes and one 128-bit store, nothing else (views are c4 int4 apart).
-__device__ __forceinline__ void emit_views(const uint8_t *lut, uint32_t w, int N, int4 *o, int c4) {
-  const uint8_t *l0 = lut + (w & 0xffu), *l1 = lut + ((w >> 8) & 0xffu), *l2 = lut + ((w >> 16) & 0xffu), *l3 = lut + (w >> 24);
-  int x = N;
-  for (; x >= 4; x -= 4) {
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      *o = make_int4(l0[u * OBS_RS], l1[u * OBS_RS], l2[u * OBS_RS], l3[u * OBS_RS]);
-      o += c4;
-    }
-    l0 += 4 * OBS_RS;
-    l1 += 4 * OBS_RS;
-    l2 += 4 * OBS_RS;
-    l3 += 4 * OBS_RS;
-  }
-  if (x & 2) {
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      *o = make_int4(l0[u * OBS_RS], l1[u * OBS_RS], l2[u * OBS_RS], l3[u * OBS_RS]);
-      o += c4;
-    }
-    l0 += 2 * OBS_RS;
-    l1 += 2 * OBS_RS;
-    l2 += 2 * OBS_RS;
-    l3 += 2 * OBS_RS;
-  }
-  if (x & 1) *o = make_int4(l0[0], l1[0], l2[0], l3[0]);
-}
 
 // number of PATH codes (v % 3 == 1) among the four byte codes of a packed word,
 // two 16-bit lanes at a time: x / 3 == (x * 171) >> 9 for x < 256
@@ -98,9 +65,12 @@ __device__ __forceinline__ int random_action(uint32_t k0, uint32_t k1,
 // kernel spent half of its warp-time at __syncthreads waiting for the agent phases;
 // it is in the history, profiles/r01a_env_full.csv is its ncu capture).
 constexpr int EW_WARPS = 4;
+#ifndef RBG_ENV_MIN_CTAS
+#define RBG_ENV_MIN_CTAS 12
+#endif
 
 template <bool VEC>
-__global__ void __launch_bounds__(EW_WARPS * 32, 12) env_warp_kernel(const EnvParams p) {
+__global__ void __launch_bounds__(EW_WARPS * 32, RBG_ENV_MIN_CTAS) env_warp_kernel(const EnvParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = p.G, N = p.N, cells = p.cells;
@@ -307,6 +277,9 @@ __global__ void __launch_bounds__(EW_WARPS * 32, 12) env_warp_kernel(const EnvPa
   const uint32_t skipm = __ballot_sync(FULL, a == 0 && (tflag & 2));  // bit j*Np: env j is rewritten by the reset kernel
   const uint32_t hitm = __ballot_sync(FULL, a == 0 && (tflag & 4));
   if (VEC) {
+    // (Staging + bulk copies as in the rollout kernel measured SLOWER here, 77 vs 50 us per step: a
+    // warp of this kernel lives for one step, so it would wait for its own copy to be read before
+    // it may exit; the rollout kernel's hoisted store loop measured the same as this one.)
     int4 *gdst = reinterpret_cast<int4 *>(p.out.grid) + e0 * c4;
     int4 *odst = reinterpret_cast<int4 *>(p.ts.obs_grid) + e0 * N * c4;
     for (int q = lane; q < kc * c4; q += 32) {
@@ -361,84 +334,6 @@ struct RolloutParams {
   int stage_warp;        // bytes per warp (>= stage_nbuf * stage_bytes; the generator scratch aliases it)
   int ce, cv;            // a staged chunk = ce whole envs (cv == N) or cv views of one env (ce == 1)
 };
-
-// Shared-memory accesses by 32-bit shared address: the staged observation loop keeps its three
-// base addresses (packed grid words, table, staging) in registers instead of letting the
-// compiler rebuild them from threadIdx in every iteration.
-__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
-  uint32_t v;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
-  return v;
-}
-template <int OFF>
-__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
-  uint32_t v;
-  asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF));
-  return v;
-}
-__device__ __forceinline__ void sts_v4(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
-  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
-}
-__device__ __forceinline__ uint32_t opaque(uint32_t v) {  // the compiler may not re-derive v
-  asm volatile("" : "+r"(v));
-  return v;
-}
-template <int U>
-__device__ __forceinline__ void stage_view(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t o) {
-  sts_v4(o, lds_u8<U * OBS_RS>(a0), lds_u8<U * OBS_RS>(a1), lds_u8<U * OBS_RS>(a2), lds_u8<U * OBS_RS>(a3));
-}
-// four cells (packed word w) -> the same four cells of nv consecutive agents' views, staged at
-// shared address o with views vs bytes apart; lut_s = shared address of the first agent's table row
-__device__ __forceinline__ void stage_views(uint32_t lut_s, uint32_t w, int nv, uint32_t o, uint32_t vs) {
-  uint32_t a0 = lut_s + (w & 0xffu), a1 = lut_s + ((w >> 8) & 0xffu), a2 = lut_s + ((w >> 16) & 0xffu), a3 = lut_s + (w >> 24);
-  int x = nv;
-  for (; x >= 4; x -= 4) {
-    stage_view<0>(a0, a1, a2, a3, o);
-    stage_view<1>(a0, a1, a2, a3, o + vs);
-    stage_view<2>(a0, a1, a2, a3, o + 2 * vs);
-    stage_view<3>(a0, a1, a2, a3, o + 3 * vs);
-    a0 += 4 * OBS_RS;
-    a1 += 4 * OBS_RS;
-    a2 += 4 * OBS_RS;
-    a3 += 4 * OBS_RS;
-    o += 4 * vs;
-  }
-  if (x & 2) {
-    stage_view<0>(a0, a1, a2, a3, o);
-    stage_view<1>(a0, a1, a2, a3, o + vs);
-    a0 += 2 * OBS_RS;
-    a1 += 2 * OBS_RS;
-    a2 += 2 * OBS_RS;
-    a3 += 2 * OBS_RS;
-    o += 2 * vs;
-  }
-  if (x & 1) stage_view<0>(a0, a1, a2, a3, o);
-}
-
-// the same with the agent count known at compile time: straight-line code
-template <int NV>
-__device__ __forceinline__ void stage_views_fixed(uint32_t lut_s, uint32_t w, uint32_t o, uint32_t vs) {
-  const uint32_t a0 = lut_s + (w & 0xffu), a1 = lut_s + ((w >> 8) & 0xffu), a2 = lut_s + ((w >> 16) & 0xffu), a3 = lut_s + (w >> 24);
-  stage_view<0>(a0, a1, a2, a3, o);
-  if (NV > 1) stage_view<1>(a0, a1, a2, a3, o += vs);
-  if (NV > 2) stage_view<2>(a0, a1, a2, a3, o += vs);
-  if (NV > 3) stage_view<3>(a0, a1, a2, a3, o += vs);
-  if (NV > 4) stage_view<4>(a0, a1, a2, a3, o += vs);
-  if (NV > 5) stage_view<5>(a0, a1, a2, a3, o += vs);
-  if (NV > 6) stage_view<6>(a0, a1, a2, a3, o += vs);
-  if (NV > 7) stage_view<7>(a0, a1, a2, a3, o += vs);
-}
-
-// Bulk asynchronous copy shared -> global (the TMA unit moves the bytes, the LSU queue does not
-// see them).  Issued by one lane; the buffer may be rewritten once its group has been READ.
-__device__ __forceinline__ void bulk_store(void *gdst, uint32_t ssrc, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-template <int PENDING>
-__device__ __forceinline__ void bulk_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PENDING) : "memory");
-}
 
 #ifndef RBG_ROLLOUT_MIN_CTAS
 #define RBG_ROLLOUT_MIN_CTAS 6
@@ -520,26 +415,15 @@ __global__ void __launch_bounds__(EW_WARPS * 32, RBG_ROLLOUT_MIN_CTAS) rollout_w
   uint32_t mk3 = 0;
   if (agent) mk3 = move_mask(sg, pos >> 8, pos & 255, a, pos == tgt);
 
-  // observation addressing, hoisted out of the step loop: word q = m * c4 + rem of the warp's
-  // envs goes to int4 slot m * N * c4 + rem of its first env's first view
-  int rem0 = 0, off0 = 0, q_rem = 0, q_off = 0, q_wrap = 0;
+  // observation: staged in shared memory, written by bulk copies (obs_stage.cuh)
+  ObsStager os;
   int4 *obs_t = nullptr;
   long long obs_step = 0;
   if (VEC) {
-    const int m0 = (int)p.divC4.div((uint32_t)lane), qm = (int)p.divC4.div(32u);
-    rem0 = lane - m0 * c4;
-    off0 = m0 * N * c4 + rem0;
-    q_rem = 32 - qm * c4;
-    q_off = qm * N * c4 + q_rem;
-    q_wrap = (N - 1) * c4;
+    os.init(smem_raw + rp.stage_off + (size_t)warp * rp.stage_warp, lut, wg32, N, c4, p.divC4, lane, rp.stage_bytes, rp.stage_nbuf, rp.ce, rp.cv);
     obs_t = reinterpret_cast<int4 *>(p.ts.obs_grid) + e0 * N * c4;
     obs_step = p.B * N * c4;
   }
-  const uint32_t stage_s = opaque((uint32_t)__cvta_generic_to_shared(smem_raw + rp.stage_off + (size_t)warp * rp.stage_warp));
-  const uint32_t lut_s = opaque((uint32_t)__cvta_generic_to_shared(lut));
-  const uint32_t wq_s = opaque((uint32_t)__cvta_generic_to_shared(wg32) + 4u * (uint32_t)lane);
-  const uint32_t view_b = (uint32_t)c4 * 16u;
-  int buf = 0;
 
   for (int t = 0; t < rp.T; ++t) {
     const long long tb = (long long)t * p.B;  // row offset of step t in the stacked outputs
@@ -606,12 +490,7 @@ __global__ void __launch_bounds__(EW_WARPS * 32, RBG_ROLLOUT_MIN_CTAS) rollout_w
       const uint32_t gk0 = __shfl_sync(FULL, k0, src_lane), gk1 = __shfl_sync(FULL, k1, src_lane);
       uint32_t x0, x1;
       int gstart, gfin;
-#ifndef RBG_OBS_DIRECT
-      if (VEC) {  // the generator scratch aliases the observation staging
-        if (lane == 0) bulk_wait_read<0>();
-        __syncwarp();
-      }
-#endif
+      if (VEC) os.drain(lane);  // the generator scratch aliases the observation staging
       warp_generate_pins(rp.kind, gk0, gk1, G, N, p.divG, gs, lane, x0, x1, gstart, gfin);
       // lane i < N holds agent i's pins; hand them to env jj's lanes
       const int from = a < N ? a : 0;
@@ -658,67 +537,23 @@ __global__ void __launch_bounds__(EW_WARPS * 32, RBG_ROLLOUT_MIN_CTAS) rollout_w
     if (agent) store_mask5(p.ts.action_mask + ((tb + e) * N + a) * 5, mk3);
     // ---- observation of step t
     if (VEC) {
-      // The views are built in shared memory in their global layout and leave as bulk copies:
-      // with direct 128-bit stores the LSU queue filled up with stores draining at the L1->L2
-      // rate and every other warp's shared-memory access queued behind them.
       int4 *odst = obs_t;
       obs_t += obs_step;
 #ifdef RBG_OBS_DIRECT
-      {
-        int rem = rem0, off = off0;
+      {  // A/B build: direct 128-bit stores
+        int rem = os.rem0, off = os.off0;
         for (int q = lane; q < kc * c4; q += 32) {
           emit_views(lut, wg32[q], N, odst + off, c4);
-          rem += q_rem;
-          off += q_off;
+          rem += os.q_rem;
+          off += os.q_off;
           if (rem >= c4) {
             rem -= c4;
-            off += q_wrap;
+            off += os.q_wrap;
           }
         }
       }
 #else
-      for (int m0 = 0; m0 < kc; m0 += rp.ce) {
-        const int nenv = min(rp.ce, kc - m0), nw = nenv * c4;
-        for (int x0 = 0; x0 < N; x0 += rp.cv) {
-          const int nv = min(rp.cv, N - x0);
-          if (lane == 0) {  // the buffer about to be filled has been read
-            if (rp.stage_nbuf == 1)
-              bulk_wait_read<0>();
-            else
-              bulk_wait_read<1>();
-          }
-          __syncwarp();
-          const uint32_t sb = stage_s + (uint32_t)(buf * rp.stage_bytes);
-          const uint32_t row = lut_s + (uint32_t)(x0 * OBS_RS);
-          uint32_t wq = wq_s + 4u * (uint32_t)(m0 * c4), o = sb + 16u * (uint32_t)off0;
-          int rem = rem0;
-          for (int q = lane; q < nw; q += 32) {
-            const uint32_t w = lds_u32(wq);
-            switch (nv) {  // warp-uniform
-              case 2: stage_views_fixed<2>(row, w, o, view_b); break;
-              case 3: stage_views_fixed<3>(row, w, o, view_b); break;
-              case 4: stage_views_fixed<4>(row, w, o, view_b); break;
-              case 5: stage_views_fixed<5>(row, w, o, view_b); break;
-              case 6: stage_views_fixed<6>(row, w, o, view_b); break;
-              case 7: stage_views_fixed<7>(row, w, o, view_b); break;
-              case 8: stage_views_fixed<8>(row, w, o, view_b); break;
-              default: stage_views(row, w, nv, o, view_b);
-            }
-            wq += 128u;
-            rem += q_rem;  // word q + 32: same env or the next one(s)
-            o += 16u * (uint32_t)q_off;
-            if (rem >= c4) {
-              rem -= c4;
-              o += 16u * (uint32_t)q_wrap;
-            }
-          }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          __syncwarp();
-          if (lane == 0)
-            bulk_store(odst + (size_t)(m0 * N + x0) * c4, sb, (uint32_t)(((nenv - 1) * N + nv) * c4) * 16u);
-          buf ^= rp.stage_nbuf - 1;
-        }
-      }
+      os.emit(kc, N, c4, lane, odst);
 #endif
     } else {
       int32_t *odst = p.ts.obs_grid + (tb + e0) * N * cells;
@@ -734,7 +569,7 @@ __global__ void __launch_bounds__(EW_WARPS * 32, RBG_ROLLOUT_MIN_CTAS) rollout_w
 
   // ---- write the State once; queue the envs that reset for a cache refill
   if (VEC) {
-    if (lane == 0) bulk_wait_read<0>();  // shared memory must outlive the last bulk copies
+    os.drain(lane);
     int4 *gdst = reinterpret_cast<int4 *>(p.out.grid) + e0 * c4;
     for (int q = lane; q < kc * c4; q += 32) gdst[q] = bytes_to_int4(wg32[q]);
   } else {
@@ -878,25 +713,11 @@ int launch_rollout(EnvParams p, int kind, int T, int32_t *action_out, cudaStream
   rp.ce = 1;
   rp.cv = N;
   if (vec) {
-    // observation staging: the warp's whole step if that is at most 8 KB (one buffer), else two
-    // buffers of about 4 KB, each a whole number of envs or of views of one env
-    size_t target = 4096, whole = 8192;
-    if (const char *ex = getenv("RBG_EXP_STAGE")) target = (size_t)atoi(ex);
-    if (const char *ex = getenv("RBG_EXP_WHOLE")) whole = (size_t)atoi(ex);
-    const size_t view = (size_t)p.cells * 4, envb = view * N;
-    if ((size_t)K * envb <= whole) {
-      rp.ce = K;
-      rp.stage_bytes = (int)(K * envb);
-    } else if (envb <= target) {
-      rp.stage_nbuf = 2;
-      rp.ce = (int)(target / envb) < K ? (int)(target / envb) : K;
-      rp.stage_bytes = (int)(rp.ce * envb);
-    } else {
-      rp.stage_nbuf = 2;
-      rp.cv = view >= target ? 1 : (int)(target / view);
-      if (rp.cv > N) rp.cv = N;
-      rp.stage_bytes = (int)(rp.cv * view);
-    }
+    const ObsStagePlan pl = obs_stage_plan(K, N, p.cells, 4096, 8192);
+    rp.stage_bytes = pl.bytes;
+    rp.stage_nbuf = pl.nbuf;
+    rp.ce = pl.ce;
+    rp.cv = pl.cv;
     rp.stage_warp = rp.stage_nbuf * rp.stage_bytes;
     if (rp.stage_warp < rp.gen_stride) rp.stage_warp = rp.gen_stride;
     rp.stage_warp = (rp.stage_warp + 15) & ~15;

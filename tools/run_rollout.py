@@ -28,5 +28,6 @@ torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / calls
 n_ro, ms_ro = rbg._lib.kernel_time("rollout")
 n_pw, ms_pw = rbg._lib.kernel_time("prw")
+n_env, ms_env = rbg._lib.kernel_time("env")
 print(f"{G}x{G}/{N} B={B} T={T}: {ms:.4f} ms/call  {B * T / ms / 1e3:.1f} M env-steps/s | rollout kernel {ms_ro / max(n_ro, 1):.4f} ms x{n_ro}"
-      f" | refill {ms_pw / max(n_pw, 1):.4f} ms x{n_pw} | checksum {int(out.reward.sum() * 100)} {int(st.grid.sum())}")
+      f" | refill {ms_pw / max(n_pw, 1):.4f} ms x{n_pw} | env {ms_env / max(n_env, 1):.4f} ms x{n_env} | checksum {int(out.reward.sum() * 100)} {int(st.grid.sum())}")
