@@ -730,11 +730,6 @@ int launch_rollout(EnvParams p, int kind, int T, int32_t *action_out, cudaStream
     if (cmax > RBG_ROLLOUT_MIN_CTAS) cmax = RBG_ROLLOUT_MIN_CTAS;
     if (cmax >= 3) smem = balance_waves(ctas, cmax, cmax - 2, smem);
   }
-  if (const char *ex = getenv("RBG_EXP_CTAS")) {
-    const int c = atoi(ex);
-    const size_t pad = (size_t)(228 * 1024) / (size_t)(c + 1) + 1024;
-    if (c >= 1 && c < 8 && pad > smem) smem = pad;
-  }
   LaunchScope scope(RBG_K_ROLLOUT, stream);
   if (vec) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(rollout_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

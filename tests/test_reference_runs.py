@@ -104,3 +104,22 @@ def test_shim_passes_the_references_own_tests():
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", test], cwd="/tmp", env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:]
     assert "35 passed" in r.stdout
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="/root/reference is not mounted (GPU box)")
+def test_sequential_random_walk_is_not_instantiable():
+    """SequentialRandomWalkBoard subclasses the NumPy AbstractBoard without implementing
+    its abstract methods, so the reference cannot construct it (nor the generator built on it): there
+    is no behaviour to reproduce, which is why the engine has no such generator."""
+    shim = os.path.join(ROOT, "tests", "tools", "jax_shim")
+    code = (
+        "from routing_board_generation.board_generation_methods.jax_implementation.board_generation.sequential_random_walk import SequentialRandomWalkBoard\n"
+        "try:\n"
+        "    SequentialRandomWalkBoard(6, 6, 3)\n"
+        "except TypeError as e:\n"
+        "    print('TypeError:', e)\n"
+    )
+    env = dict(os.environ, PYTHONPATH=shim + os.pathsep + REF)
+    r = subprocess.run([sys.executable, "-c", code], cwd="/tmp", env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "TypeError" in r.stdout and "abstract" in r.stdout
