@@ -503,6 +503,47 @@ def test_rollout_slice_counts(rbg, slices):
     assert r.returncode == 0 and "slices ok" in r.stdout, (r.stdout[-500:], r.stderr[-2000:])
 
 
+@pytest.mark.parametrize("G,N,B,T,time_limit", [(10, 5, 65536, 45, 50), (32, 16, 8192, 22, 9)])
+def test_rollout_full_size_two_paths_agree(rbg, G, N, B, T, time_limit):
+    """BASELINE configs[1] and [4] at full size, where the oracle would take minutes: the fused rollout
+    (rollout_warp_kernel, bulk refill, two batch slices on two streams) and the step-by-step path
+    (env_warp_kernel, speculative + synchronous reset kernels) are independent implementations and must
+    produce the same State and the same TimeStep leaves at every step; plus invariants of the stream."""
+    import torch
+
+    keys = rbg.split(rbg.PRNGKey(0), B)
+    gen = rbg.ParallelRandomWalkGenerator(G, N)
+    env_a = rbg.VmapAutoResetWrapper(rbg.Connector(generator=gen, time_limit=time_limit))
+    env_b = rbg.VmapAutoResetWrapper(rbg.Connector(generator=gen, time_limit=time_limit))
+    sa, _ = env_a.reset(keys)
+    sb, _ = env_b.reset(keys)
+    sa, ts, act = env_a.rollout_random(sa, T)
+    resets = 0
+    for t in range(T):
+        sb, tb, ab = env_b.step_random(sb, inplace=True)
+        assert torch.equal(act[t], ab), f"actions differ at step {t}"
+        for name, x, y in (("obs", ts.observation.grid[t], tb.observation.grid), ("mask", ts.observation.action_mask[t], tb.observation.action_mask),
+                           ("step_count", ts.observation.step_count[t], tb.observation.step_count), ("reward", ts.reward[t], tb.reward),
+                           ("discount", ts.discount[t], tb.discount), ("step_type", ts.step_type[t], tb.step_type),
+                           ("num_connections", ts.extras["num_connections"][t], tb.extras["num_connections"]),
+                           ("ratio_connections", ts.extras["ratio_connections"][t], tb.extras["ratio_connections"]),
+                           ("total_path_length", ts.extras["total_path_length"][t], tb.extras["total_path_length"])):
+            assert torch.equal(x, y), f"{name} differs at step {t}"
+        last = ts.step_type[t] == 2
+        resets += int(last.sum())
+        # a terminal step restarts the episode: step_count 0 and every agent free to NOOP
+        assert int(ts.observation.step_count[t][last].abs().sum()) == 0
+        assert bool((ts.observation.action_mask[t][..., 0] == 1).all())
+        # each agent sees itself as wire 0: exactly one POSITION (2) per view unless it sits on its target
+        heads = (ts.observation.grid[t] == 2).sum(dim=(2, 3))
+        assert int(heads.max()) <= 1
+    assert resets > B // 2, "the run must exercise the auto-reset"
+    for name in ("grid", "step_count", "key"):
+        assert torch.equal(getattr(sa, name), getattr(sb, name)), name
+    for name in ("id", "start", "target", "position"):
+        assert torch.equal(getattr(sa.agents, name), getattr(sb.agents, name)), name
+
+
 def test_rollout_long_horizon(rbg, orc):
     """1 480 steps over 4 096 envs (6 M env-steps, ~240 k resets) in odd-sized fused chunks: every
     TimeStep leaf of every step and the final State against the oracle."""
