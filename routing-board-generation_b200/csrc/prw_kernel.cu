@@ -84,7 +84,11 @@ __host__ __device__ inline size_t prw_carve(const PrwParams &p, int nwarps,
   return align_up(off, 16);
 }
 
+#ifdef RBG_PRW_MIN_CTAS
+__global__ void __launch_bounds__(256, RBG_PRW_MIN_CTAS) prw_kernel(const PrwParams p) {
+#else
 __global__ void __launch_bounds__(256) prw_kernel(const PrwParams p) {
+#endif
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nthreads = blockDim.x, nwarps = nthreads >> 5;
