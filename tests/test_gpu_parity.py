@@ -632,13 +632,14 @@ def test_host_variants(rbg, orc):
     assert np.array_equal(solved, rs) and np.array_equal(heads, rh) and np.array_equal(targets, rt)
 
 
-def test_random_shapes_sweep(rbg, orc):
+@pytest.mark.parametrize("seed,iters,glo,ghi,bhi", [(2024, 24, 2, 25, 200), (2025, 10, 25, 41, 40)])
+def test_random_shapes_sweep(rbg, orc, seed, iters, glo, ghi, bhi):
     """Random (G, N, B) shapes: generators, reset and a short fused rollout against the oracle."""
-    rng = np.random.default_rng(2024)
-    for it in range(24):
-        G = int(rng.integers(2, 25))
+    rng = np.random.default_rng(seed)
+    for it in range(iters):
+        G = int(rng.integers(glo, ghi))
         N = int(rng.integers(1, min(32, G * G // 2) + 1))
-        B = int(rng.integers(1, 200))
+        B = int(rng.integers(1, bhi))
         keys, kref = _keys(rbg, orc, 100 + it, B)
         heads, targets, solved = rbg.ParallelRandomWalkBoard(G, G, N).generate_board(keys)
         rh, rt, rs, _ = orc.prw_generate_batch(kref, G, N)
