@@ -540,20 +540,12 @@ __global__ void __launch_bounds__(EW_WARPS * 32, RBG_ROLLOUT_MIN_CTAS) rollout_w
       int4 *odst = obs_t;
       obs_t += obs_step;
 #ifdef RBG_OBS_DIRECT
-      {  // A/B build: direct 128-bit stores
-        int rem = os.rem0, off = os.off0;
-        for (int q = lane; q < kc * c4; q += 32) {
-          emit_views(lut, wg32[q], N, odst + off, c4);
-          rem += os.q_rem;
-          off += os.q_off;
-          if (rem >= c4) {
-            rem -= c4;
-            off += os.q_wrap;
-          }
-        }
-      }
+      os.emit_direct(lut, wg32, kc, N, c4, lane, odst);  // A/B build: always direct 128-bit stores
 #else
-      os.emit(kc, N, c4, lane, odst);
+      if (os.nbuf)
+        os.emit(kc, N, c4, lane, odst);
+      else
+        os.emit_direct(lut, wg32, kc, N, c4, lane, odst);
 #endif
     } else {
       int32_t *odst = p.ts.obs_grid + (tb + e0) * N * cells;

@@ -133,7 +133,7 @@ __device__ __forceinline__ void bulk_wait_read() {
 // bytes holding a whole number of envs, or of views of one env.
 struct ObsStagePlan {
   int bytes;  // per buffer
-  int nbuf;   // 1 or 2
+  int nbuf;   // 1 or 2; 0 = do not stage, store directly (a chunk would be a single view)
   int ce;     // envs per chunk (cv == N)
   int cv;     // views per chunk (ce == 1) or N
 };
@@ -155,6 +155,10 @@ inline ObsStagePlan obs_stage_plan(int K, int N, int cells, size_t target, size_
     pl.cv = view >= target ? 1 : (int)(target / view);
     if (pl.cv > N) pl.cv = N;
     pl.bytes = (int)(pl.cv * view);
+    if (pl.cv < 2 && N > 1) {
+      pl.nbuf = 0;
+      pl.bytes = 0;
+    }
   }
   return pl;
 }
@@ -227,6 +231,23 @@ struct ObsStager {
         __syncwarp();
         if (lane == 0) bulk_store(odst + (size_t)(m0 * N + x0) * c4, sb, (uint32_t)(((nenv - 1) * N + nv) * c4) * 16u);
         buf ^= nbuf - 1;
+      }
+    }
+  }
+
+  // the same views by direct 128-bit stores: for boards whose views are so large that a staged chunk
+  // would hold a single view (32x32: 4 KB), where re-reading the packed words once per view costs
+  // more than the bulk copies save (measured: 32x32/16 82.6 M env-steps/s direct, 69 M staged;
+  // 20x20/10 with two views per chunk 356 M staged, 321 M direct)
+  __device__ __forceinline__ void emit_direct(const uint8_t *lut, const uint32_t *wg32, int kc, int N, int c4, int lane, int4 *odst) const {
+    int rem = rem0, off = off0;
+    for (int q = lane; q < kc * c4; q += 32) {
+      emit_views(lut, wg32[q], N, odst + off, c4);
+      rem += q_rem;
+      off += q_off;
+      if (rem >= c4) {
+        rem -= c4;
+        off += q_wrap;
       }
     }
   }
