@@ -338,8 +338,10 @@ struct RolloutParams {
 #ifndef RBG_ROLLOUT_MIN_CTAS
 #define RBG_ROLLOUT_MIN_CTAS 6
 #endif
-template <bool VEC>
+// OBS: 0 scalar stores (cells % 4 != 0), 1 direct 128-bit stores, 2 staged + bulk copies (obs_stage.cuh)
+template <int OBS>
 __global__ void __launch_bounds__(EW_WARPS * 32, RBG_ROLLOUT_MIN_CTAS) rollout_warp_kernel(const EnvParams p, const RolloutParams rp) {
+  constexpr bool VEC = OBS != 0;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = p.G, N = p.N, cells = p.cells;
@@ -490,7 +492,7 @@ __global__ void __launch_bounds__(EW_WARPS * 32, RBG_ROLLOUT_MIN_CTAS) rollout_w
       const uint32_t gk0 = __shfl_sync(FULL, k0, src_lane), gk1 = __shfl_sync(FULL, k1, src_lane);
       uint32_t x0, x1;
       int gstart, gfin;
-      if (VEC) os.drain(lane);  // the generator scratch aliases the observation staging
+      if (OBS == 2) os.drain(lane);  // the generator scratch aliases the observation staging
       warp_generate_pins(rp.kind, gk0, gk1, G, N, p.divG, gs, lane, x0, x1, gstart, gfin);
       // lane i < N holds agent i's pins; hand them to env jj's lanes
       const int from = a < N ? a : 0;
@@ -539,14 +541,10 @@ __global__ void __launch_bounds__(EW_WARPS * 32, RBG_ROLLOUT_MIN_CTAS) rollout_w
     if (VEC) {
       int4 *odst = obs_t;
       obs_t += obs_step;
-#ifdef RBG_OBS_DIRECT
-      os.emit_direct(lut, wg32, kc, N, c4, lane, odst);  // A/B build: always direct 128-bit stores
-#else
-      if (os.nbuf)
+      if (OBS == 2)
         os.emit(kc, N, c4, lane, odst);
       else
         os.emit_direct(lut, wg32, kc, N, c4, lane, odst);
-#endif
     } else {
       int32_t *odst = p.ts.obs_grid + (tb + e0) * N * cells;
       for (int i = lane; i < kc * cells; i += 32) {
@@ -561,7 +559,7 @@ __global__ void __launch_bounds__(EW_WARPS * 32, RBG_ROLLOUT_MIN_CTAS) rollout_w
 
   // ---- write the State once; queue the envs that reset for a cache refill
   if (VEC) {
-    os.drain(lane);
+    if (OBS == 2) os.drain(lane);
     int4 *gdst = reinterpret_cast<int4 *>(p.out.grid) + e0 * c4;
     for (int q = lane; q < kc * c4; q += 32) gdst[q] = bytes_to_int4(wg32[q]);
   } else {
@@ -723,12 +721,20 @@ int launch_rollout(EnvParams p, int kind, int T, int32_t *action_out, cudaStream
     if (cmax >= 3) smem = balance_waves(ctas, cmax, cmax - 2, smem);
   }
   LaunchScope scope(RBG_K_ROLLOUT, stream);
-  if (vec) {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(rollout_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    rollout_warp_kernel<true><<<(unsigned)ctas, EW_WARPS * 32, smem, stream>>>(p, rp);
+#ifdef RBG_OBS_DIRECT
+  const bool staged = false;  // A/B build: never stage
+#else
+  const bool staged = vec && rp.stage_nbuf != 0;
+#endif
+  if (staged) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(rollout_warp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    rollout_warp_kernel<2><<<(unsigned)ctas, EW_WARPS * 32, smem, stream>>>(p, rp);
+  } else if (vec) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(rollout_warp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    rollout_warp_kernel<1><<<(unsigned)ctas, EW_WARPS * 32, smem, stream>>>(p, rp);
   } else {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(rollout_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    rollout_warp_kernel<false><<<(unsigned)ctas, EW_WARPS * 32, smem, stream>>>(p, rp);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(rollout_warp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    rollout_warp_kernel<0><<<(unsigned)ctas, EW_WARPS * 32, smem, stream>>>(p, rp);
   }
   return check_launch("rollout_warp_kernel");
 }
