@@ -97,10 +97,18 @@ __global__ void __launch_bounds__(EW_WARPS * 32, RBG_ENV_MIN_CTAS) env_warp_kern
 
   // ---- load: State.grid int32 -> uint8 (one packed word per int4), agent and env scalars
   if (VEC) {
+    // four loads in flight per lane before the first one is used (a load-use pair per iteration
+    // made a warp pay one L2 round trip per 32 words: 19 % of the kernel's stall samples)
     const int4 *src = reinterpret_cast<const int4 *>(p.in.grid) + e0 * c4;
-    for (int q = lane; q < kc * c4; q += 32) {
-      const int4 v = __ldg(src + q);
-      wg32[q] = (uint32_t)(v.x & 0xff) | ((uint32_t)(v.y & 0xff) << 8) | ((uint32_t)(v.z & 0xff) << 16) | ((uint32_t)(v.w & 0xff) << 24);
+    const int nq = kc * c4;
+    for (int q0 = lane; q0 < nq; q0 += 128) {
+      int4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = (q0 + 32 * u < nq) ? __ldg(src + q0 + 32 * u) : make_int4(0, 0, 0, 0);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (q0 + 32 * u < nq)
+          wg32[q0 + 32 * u] = (uint32_t)(v[u].x & 0xff) | ((uint32_t)(v[u].y & 0xff) << 8) | ((uint32_t)(v[u].z & 0xff) << 16) | ((uint32_t)(v[u].w & 0xff) << 24);
     }
   } else {
     const int32_t *src = p.in.grid + e0 * cells;
@@ -376,10 +384,18 @@ __global__ void __launch_bounds__(EW_WARPS * 32, RBG_ROLLOUT_MIN_CTAS) rollout_w
 
   // ---- load the State once
   if (VEC) {
+    // four loads in flight per lane before the first one is used (a load-use pair per iteration
+    // made a warp pay one L2 round trip per 32 words: 19 % of the kernel's stall samples)
     const int4 *src = reinterpret_cast<const int4 *>(p.in.grid) + e0 * c4;
-    for (int q = lane; q < kc * c4; q += 32) {
-      const int4 v = __ldg(src + q);
-      wg32[q] = (uint32_t)(v.x & 0xff) | ((uint32_t)(v.y & 0xff) << 8) | ((uint32_t)(v.z & 0xff) << 16) | ((uint32_t)(v.w & 0xff) << 24);
+    const int nq = kc * c4;
+    for (int q0 = lane; q0 < nq; q0 += 128) {
+      int4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = (q0 + 32 * u < nq) ? __ldg(src + q0 + 32 * u) : make_int4(0, 0, 0, 0);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (q0 + 32 * u < nq)
+          wg32[q0 + 32 * u] = (uint32_t)(v[u].x & 0xff) | ((uint32_t)(v[u].y & 0xff) << 8) | ((uint32_t)(v[u].z & 0xff) << 16) | ((uint32_t)(v[u].w & 0xff) << 24);
     }
   } else {
     const int32_t *src = p.in.grid + e0 * cells;
