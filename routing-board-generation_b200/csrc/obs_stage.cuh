@@ -190,6 +190,27 @@ struct ObsStager {
     buf = 0;
   }
 
+  // the words of one chunk -> its staging buffer; NV = views per word when known at compile time, else 0
+  template <int NV>
+  __device__ __forceinline__ void fill(uint32_t row, uint32_t wq, uint32_t sb, int nw, int nv, int c4, int lane) const {
+    uint32_t o = sb + 16u * (uint32_t)off0;
+    int rem = rem0;
+    for (int q = lane; q < nw; q += 32) {
+      const uint32_t w = lds_u32(wq);
+      if (NV > 0)
+        stage_views_fixed<(NV > 0 ? NV : 1)>(row, w, o, view_b);
+      else
+        stage_views(row, w, nv, o, view_b);
+      wq += 128u;
+      rem += q_rem;  // word q + 32: same env or the next one(s)
+      o += 16u * (uint32_t)q_off;
+      if (rem >= c4) {
+        rem -= c4;
+        o += 16u * (uint32_t)q_wrap;
+      }
+    }
+  }
+
   // all 32 lanes: stage and send the views of the warp's kc envs to odst (int4 units, 16-byte aligned)
   __device__ __forceinline__ void emit(int kc, int N, int c4, int lane, int4 *odst) {
     for (int m0 = 0; m0 < kc; m0 += ce) {
@@ -205,27 +226,16 @@ struct ObsStager {
         __syncwarp();
         const uint32_t sb = stage_s + (uint32_t)(buf * stage_bytes);
         const uint32_t row = lut_s + (uint32_t)(x0 * OBS_RS);
-        uint32_t wq = wq_s + 4u * (uint32_t)(m0 * c4), o = sb + 16u * (uint32_t)off0;
-        int rem = rem0;
-        for (int q = lane; q < nw; q += 32) {
-          const uint32_t w = lds_u32(wq);
-          switch (nv) {  // warp-uniform
-            case 2: stage_views_fixed<2>(row, w, o, view_b); break;
-            case 3: stage_views_fixed<3>(row, w, o, view_b); break;
-            case 4: stage_views_fixed<4>(row, w, o, view_b); break;
-            case 5: stage_views_fixed<5>(row, w, o, view_b); break;
-            case 6: stage_views_fixed<6>(row, w, o, view_b); break;
-            case 7: stage_views_fixed<7>(row, w, o, view_b); break;
-            case 8: stage_views_fixed<8>(row, w, o, view_b); break;
-            default: stage_views(row, w, nv, o, view_b);
-          }
-          wq += 128u;
-          rem += q_rem;  // word q + 32: same env or the next one(s)
-          o += 16u * (uint32_t)q_off;
-          if (rem >= c4) {
-            rem -= c4;
-            o += 16u * (uint32_t)q_wrap;
-          }
+        const uint32_t wq = wq_s + 4u * (uint32_t)(m0 * c4);
+        switch (nv) {  // warp-uniform; the agent count of the common cases is a compile-time constant
+          case 2: fill<2>(row, wq, sb, nw, 2, c4, lane); break;
+          case 3: fill<3>(row, wq, sb, nw, 3, c4, lane); break;
+          case 4: fill<4>(row, wq, sb, nw, 4, c4, lane); break;
+          case 5: fill<5>(row, wq, sb, nw, 5, c4, lane); break;
+          case 6: fill<6>(row, wq, sb, nw, 6, c4, lane); break;
+          case 7: fill<7>(row, wq, sb, nw, 7, c4, lane); break;
+          case 8: fill<8>(row, wq, sb, nw, 8, c4, lane); break;
+          default: fill<0>(row, wq, sb, nw, nv, c4, lane);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
