@@ -32,8 +32,10 @@ struct SmemGrid {
 __device__ __forceinline__ uint32_t move_mask(const SmemGrid &g, int r, int c,
                                               int agent, bool connected) {
   const uint32_t tgt = 3u * agent + TARGET;
-  const uint32_t u = g.at_checked(r - 1, c), ri = g.at_checked(r, c + 1),
-                 d = g.at_checked(r + 1, c), l = g.at_checked(r, c - 1);
+  // (r, c) is on the grid; a neighbour off the grid reads as 0xFF (never empty, nobody's target)
+  const uint8_t *pc = g.base + (r + g.pad) * g.S + (c + g.pad);
+  const uint32_t u = r > 0 ? pc[-g.S] : 0xFFu, ri = c < g.G - 1 ? pc[1] : 0xFFu;
+  const uint32_t d = r < g.G - 1 ? pc[g.S] : 0xFFu, l = c > 0 ? pc[-1] : 0xFFu;
   uint32_t m = 0;
   m |= (u == 0u || u == tgt) ? 1u : 0u;
   m |= (ri == 0u || ri == tgt) ? 2u : 0u;

@@ -45,16 +45,13 @@ __device__ __forceinline__ int random_action(uint32_t k0, uint32_t k1,
   uint32_t o0, o1;
   tf_block(k0, k1, step, agent, o0, o1);
   const uint32_t n = 1u + __popc(mk);
-  int pick = (int)__umulhi(o0, n);
+  const int pick = (int)__umulhi(o0, n);  // 0 = NOOP, k = the k-th legal move in action order
   if (pick == 0) return NOOP;
-  int act = 0;
-#pragma unroll
-  for (int a = 1; a <= 4; ++a) {
-    if ((mk >> (a - 1)) & 1u) {
-      if (--pick == 0 && act == 0) act = a;
-    }
-  }
-  return act;
+  uint32_t b = mk;
+  if (pick > 1) b &= b - 1u;
+  if (pick > 2) b &= b - 1u;
+  if (pick > 3) b &= b - 1u;
+  return __ffs((int)b);
 }
 
 // ---------------------------------------------------------------------------
@@ -448,15 +445,14 @@ __global__ void __launch_bounds__(EW_WARPS * 32, RBG_ROLLOUT_MIN_CTAS) rollout_w
     // ---- agents: sample action, move_position, is_valid_position, collisions
     const bool was = agent && pos == tgt;
     const int r = pos >> 8, c = pos & 255;
+    const long long row_e = tb + e, row_a = row_e * N + a;  // this lane's rows in the stacked per-env / per-agent outputs
     int dest = -1;
     if (agent) {
+      // the action comes from mk3 = is_valid_position of the four moves on this very grid (empty mask
+      // for a connected agent), so a non-NOOP action needs no second validity test
       const int action = random_action(k0, k1, (uint32_t)sc, (uint32_t)a, mk3);
-      if (rp.action_out) rp.action_out[(tb + e) * N + a] = action;
-      const int nr = r + (action == UP ? -1 : (action == DOWN ? 1 : 0));
-      const int nc = c + (action == RIGHT ? 1 : (action == LEFT ? -1 : 0));
-      const bool inb = (unsigned)nr < (unsigned)G && (unsigned)nc < (unsigned)G;
-      const uint32_t v = inb ? sg.at(nr, nc) : 0xFFu;
-      if (inb && (v == 0u || v == 3u * a + TARGET) && !was && action != NOOP) dest = nr * G + nc;
+      if (rp.action_out) rp.action_out[row_a] = action;
+      if (action != NOOP) dest = r * G + c + (action == UP ? -G : (action == DOWN ? G : (action == RIGHT ? 1 : -1)));
     }
     const uint32_t mval = dest >= 0 ? (((uint32_t)j << 16) | (uint32_t)dest) : (0x80000000u | (uint32_t)lane);
     const uint32_t mm = __match_any_sync(FULL, mval);
@@ -524,15 +520,15 @@ __global__ void __launch_bounds__(EW_WARPS * 32, RBG_ROLLOUT_MIN_CTAS) rollout_w
     }
     // ---- small outputs of step t (terminal step's reward / discount / step_type / extras)
     if (env_ok && a == 0) {
-      p.ts.step_type[tb + e] = (int8_t)(terminal ? 2 : 1);
-      p.ts.num_connections[tb + e] = nconn;
-      p.ts.ratio_connections[tb + e] = ratio_lut[nconn];
-      p.ts.total_path_length[tb + e] = tpl;
-      p.ts.obs_step_count[tb + e] = terminal ? 0 : sc;
+      p.ts.step_type[row_e] = (int8_t)(terminal ? 2 : 1);
+      p.ts.num_connections[row_e] = nconn;
+      p.ts.ratio_connections[row_e] = ratio_lut[nconn];
+      p.ts.total_path_length[row_e] = tpl;
+      p.ts.obs_step_count[row_e] = terminal ? 0 : sc;
     }
     if (agent) {
-      p.ts.reward[(tb + e) * N + a] = rew;
-      p.ts.discount[(tb + e) * N + a] = (terminal || done) ? 0.0f : 1.0f;
+      p.ts.reward[row_a] = rew;
+      p.ts.discount[row_a] = (terminal || done) ? 0.0f : 1.0f;
     }
     if (terminal) {  // group-uniform: swap in the new episode (pins-only grid, heads then targets)
       for (int i = a; i < cells; i += Np) g[i] = 0;
@@ -552,7 +548,7 @@ __global__ void __launch_bounds__(EW_WARPS * 32, RBG_ROLLOUT_MIN_CTAS) rollout_w
       if (a < N) mk3 = move_mask(sg, pos >> 8, pos & 255, a, pos == tgt);
     }
     __syncwarp();
-    if (agent) store_mask5(p.ts.action_mask + ((tb + e) * N + a) * 5, mk3);
+    if (agent) store_mask5(p.ts.action_mask + row_a * 5, mk3);
     // ---- observation of step t
     if (VEC) {
       int4 *odst = obs_t;
