@@ -730,7 +730,16 @@ int launch_rollout(EnvParams p, int kind, int T, int32_t *action_out, cudaStream
   {  // residency: registers allow RBG_ROLLOUT_MIN_CTAS per SM, shared memory (1 KB reserved per CTA) maybe fewer
     int cmax = (int)((228 * 1024) / (smem + 1024));
     if (cmax > RBG_ROLLOUT_MIN_CTAS) cmax = RBG_ROLLOUT_MIN_CTAS;
-    if (cmax >= 3) smem = balance_waves(ctas, cmax, cmax - 2, smem);
+    static int force = -1;  // RBG_ROLLOUT_CTAS=n: n CTAs per SM instead of the wave-balanced choice (experiments)
+    if (force < 0) {
+      const char *ex = getenv("RBG_ROLLOUT_CTAS");
+      force = ex ? atoi(ex) : 0;
+    }
+    if (force > 0) {
+      const size_t pad = (size_t)(228 * 1024) / (size_t)(force + 1) + 1024;
+      if (force < cmax && pad > smem) smem = pad;
+    } else if (cmax >= 3)
+      smem = balance_waves(ctas, cmax, cmax - 2, smem);
   }
   LaunchScope scope(RBG_K_ROLLOUT, stream);
 #ifdef RBG_OBS_DIRECT
