@@ -28,6 +28,8 @@
 //                       starts/ends extraction, State / observation / action mask
 // Boards travel between the kernels as uint8 in a stream-ordered scratch
 // allocation (1 byte per cell, L2-resident for any realistic batch).
+#include <stdlib.h>
+
 #include "connector_device.cuh"
 #include "rbg_host.h"
 #include "select.cuh"
@@ -133,6 +135,51 @@ __device__ __forceinline__ void split3(uint32_t k0, uint32_t k1, uint32_t out[6]
   tf_block(k0, k1, 2u, 5u, out[2], out[5]);
 }
 
+// The random pick of extend_wires_jax (PPU:127-144) for the lanes in `needm`, computed by the whole
+// warp.  One lane alone would run, per draw, split(k) -> split(ck) -> random_bits: five threefry
+// blocks in three dependent levels, and only 1-3 lanes of a warp need a pick at the same cell.
+// Here five worker lanes serve each needing lane (six at a time): roles 0, 1 the two blocks of
+// `k, ck = split(k)`, roles 2, 3 the two blocks of randint's `split(ck)`, role 4 the block of
+// random_bits(k2); the levels are pipelined across draws, so every pass of ONE block per lane
+// completes one draw of every needing lane (draw t comes out of pass t + 2).  The first draw that
+// lands on a valid candidate wins, exactly as in the sequential loop.
+__device__ __forceinline__ uint32_t warp_pick(uint32_t needm, bool need, uint32_t k0, uint32_t k1, uint32_t ok, uint32_t pick, int lane) {
+  const int my_rank = __popc(needm & ((1u << lane) - 1u)), total = __popc(needm);
+  const int s = lane / 5, r = lane - 5 * s;  // slot and role of this lane as a worker (lanes 30, 31 have none)
+  const uint32_t c0 = (r == 1 || r == 3) ? 1u : 0u, c1 = r == 4 ? 0u : c0 + 2u;  // (0,2) (1,3) (0,2) (1,3) (0,0)
+  const int src_a = 5 * s + (r == 4 ? 2 : 0);
+  for (int base = 0; base < total; base += 6) {
+    const int ns = total - base < 6 ? total - base : 6;
+    const bool worker = s < ns;
+    const int owner = worker ? (int)__fns(needm, 0, base + s + 1) : 0;  // the lane this slot works for
+    uint32_t x0 = __shfl_sync(FULL, k0, owner), x1 = __shfl_sync(FULL, k1, owner);
+    const uint32_t slot_ok = __shfl_sync(FULL, ok, owner);
+    bool done = !(worker && r == 4);
+    uint32_t result = 0;
+    for (int t = 0;; ++t) {
+      uint32_t o0, o1;
+      tf_block(x0, x1, c0, c1, o0, o1);
+      if (!done && t >= 2) {  // role 4: random_bits of draw t - 2
+        const uint32_t pk = 1u << (o0 & 3u);
+        if (slot_ok & pk) {
+          result = pk;
+          done = true;
+        }
+      }
+      if (!__any_sync(FULL, !done)) break;
+      // roles 0, 1 <- split(k)[0]; roles 2, 3 <- ck = split(k)[1]; role 4 <- k2 = split(ck)[1]
+      const uint32_t a0 = __shfl_sync(FULL, o0, src_a), a1 = __shfl_sync(FULL, o1, src_a);
+      const uint32_t b0 = __shfl_sync(FULL, o0, src_a + 1), b1 = __shfl_sync(FULL, o1, src_a + 1);
+      x0 = r < 2 ? a0 : a1;
+      x1 = r < 2 ? b0 : b1;
+    }
+    const bool mine = need && my_rank >= base && my_rank < base + ns;
+    const uint32_t got = __shfl_sync(FULL, result, mine ? 5 * (my_rank - base) + 4 : 0);
+    if (mine) pick = got;
+  }
+  return pick;
+}
+
 __global__ void __launch_bounds__(128) se_extend_kernel(const SeedExtParams p, const SeDims d, const SeScratch sc) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -169,16 +216,23 @@ __global__ void __launch_bounds__(128) se_extend_kernel(const SeedExtParams p, c
   bool again = live;  // prev_layout differs from the board by construction  PPU:47
   long long step_num = 0;
   int sweeps = 0;
-  while (again && (p.ext_steps < 0 || step_num < p.ext_steps)) {
-    ++step_num;
-    ++sweeps;
-    // key, flipkey, flopkey = split(key, 3); choice over [True, False]  PPU:63-67
-    uint32_t f[6];
-    split3(key0, key1, f);
-    key0 = f[0];
-    key1 = f[1];
-    const bool flip = randint_pow2(f[2], f[3], 2u) == 0u;
-    const bool flop = randint_pow2(f[4], f[5], 2u) == 0u;
+  // The sweep is warp-synchronous: all 32 lanes walk the cells together (lanes whose board has
+  // converged idle through it), so that the random picks can be computed by the whole warp.
+  for (;;) {
+    const bool act = again && (p.ext_steps < 0 || step_num < p.ext_steps);
+    if (!__any_sync(FULL, act)) break;
+    bool flip = false, flop = false;
+    if (act) {
+      ++step_num;
+      ++sweeps;
+      // key, flipkey, flopkey = split(key, 3); choice over [True, False]  PPU:63-67
+      uint32_t f[6];
+      split3(key0, key1, f);
+      key0 = f[0];
+      key1 = f[1];
+      flip = randint_pow2(f[2], f[3], 2u) == 0u;
+      flop = randint_pow2(f[4], f[5], 2u) == 0u;
+    }
     const bool mirrored = flip || flop;
     if (mirrored) {  // the convergence test needs the pre-sweep board  PPU:70,186-189
       const uint32_t *a = reinterpret_cast<const uint32_t *>(board);
@@ -196,75 +250,77 @@ __global__ void __launch_bounds__(128) se_extend_kernel(const SeedExtParams p, c
         uint32_t n0, r0, n1, r1;
         tf_block(key0, key1, 0u, 2u, n0, r0);
         tf_block(key0, key1, 1u, 3u, n1, r1);
-        const uint32_t v = pc[0];
-        const uint32_t wv = v - 1u;           // v == 0 wraps: type test below fails
-        const uint32_t w3 = (wv / 3u) * 3u;   // 3 * wire
-        const uint32_t ctype = wv - w3 + 1u;  // PATH 1, POSITION 2, TARGET 3
-        const bool extendable = v != 0u && (two_sided ? ctype != PATH : ctype == TARGET);  // PPU:109-116
-        if (extendable) {
-          const uint32_t b3 = w3 + 1u;
-          // candidates in list order up, left, down, right (PPU:322-369); a
-          // candidate is dropped when it touches the wire anywhere but through
-          // the current cell (PPU:86-97)
-          const uint32_t u = pc[-sr], l = pc[-scol], dn = pc[sr], r = pc[scol];
-          const bool oul = own_wire(pc[-sr - scol], b3), our = own_wire(pc[-sr + scol], b3);
-          const bool odl = own_wire(pc[sr - scol], b3), odr = own_wire(pc[sr + scol], b3);
-          uint32_t ok = 0;
-          ok |= (u == 0u && !own_wire(pc[-2 * sr], b3) && !oul && !our) ? 1u : 0u;
-          ok |= (l == 0u && !own_wire(pc[-2 * scol], b3) && !oul && !odl) ? 2u : 0u;
-          ok |= (dn == 0u && !own_wire(pc[2 * sr], b3) && !odl && !odr) ? 4u : 0u;
-          ok |= (r == 0u && !own_wire(pc[2 * scol], b3) && !our && !odr) ? 8u : 0u;
-          if (ok) {
-            // previous neighbour: last match among up, down, left (PPU:200-234);
-            // the priority cell mirrors it through the current cell (PPU:99-103)
-            uint32_t pri = 0;
-            if (own_wire(u, b3)) pri = 4u;   // came from above -> continue down
-            if (own_wire(dn, b3)) pri = 1u;  // from below -> up
-            if (own_wire(l, b3)) pri = 8u;   // from the left -> right
-            bool take_pri = (ok & pri) != 0u;
-            if (take_pri && use_rand) {  // PPU:157-162
-              const float uni = bits_to_uniform(bits_scalar(r0, r1));
-              take_pri = !(p.randomness > uni);
-            }
-            uint32_t pick = pri;
-            if (!take_pri) {
-              // repeat `k, ck = split(k); pos = list[randint(ck, 0, 4)]` until valid,
-              // from the cell's key, which is NOT advanced by this loop  PPU:127-144
-              uint32_t lk0 = key0, lk1 = key1;
-              for (;;) {
-                uint32_t x0, x1, c0, c1;
-                split2(lk0, lk1, x0, x1, c0, c1);
-                lk0 = x0;
-                lk1 = x1;
-                pick = 1u << randint_pow2(c0, c1, 4u);
-                if (ok & pick) break;
+        uint32_t v = 0, b3 = 0, ok = 0, pick = 0;
+        bool need = false;
+        if (act) {
+          v = pc[0];
+          const uint32_t wv = v - 1u;           // v == 0 wraps: type test below fails
+          const uint32_t w3 = (wv / 3u) * 3u;   // 3 * wire
+          const uint32_t ctype = wv - w3 + 1u;  // PATH 1, POSITION 2, TARGET 3
+          const bool extendable = v != 0u && (two_sided ? ctype != PATH : ctype == TARGET);  // PPU:109-116
+          if (extendable) {
+            b3 = w3 + 1u;
+            // candidates in list order up, left, down, right (PPU:322-369); a
+            // candidate is dropped when it touches the wire anywhere but through
+            // the current cell (PPU:86-97)
+            const uint32_t u = pc[-sr], l = pc[-scol], dn = pc[sr], r = pc[scol];
+            const bool oul = own_wire(pc[-sr - scol], b3), our = own_wire(pc[-sr + scol], b3);
+            const bool odl = own_wire(pc[sr - scol], b3), odr = own_wire(pc[sr + scol], b3);
+            ok |= (u == 0u && !own_wire(pc[-2 * sr], b3) && !oul && !our) ? 1u : 0u;
+            ok |= (l == 0u && !own_wire(pc[-2 * scol], b3) && !oul && !odl) ? 2u : 0u;
+            ok |= (dn == 0u && !own_wire(pc[2 * sr], b3) && !odl && !odr) ? 4u : 0u;
+            ok |= (r == 0u && !own_wire(pc[2 * scol], b3) && !our && !odr) ? 8u : 0u;
+            if (ok) {
+              // previous neighbour: last match among up, down, left (PPU:200-234);
+              // the priority cell mirrors it through the current cell (PPU:99-103)
+              uint32_t pri = 0;
+              if (own_wire(u, b3)) pri = 4u;   // came from above -> continue down
+              if (own_wire(dn, b3)) pri = 1u;  // from below -> up
+              if (own_wire(l, b3)) pri = 8u;   // from the left -> right
+              bool take_pri = (ok & pri) != 0u;
+              if (take_pri && use_rand) {  // PPU:157-162
+                const float uni = bits_to_uniform(bits_scalar(r0, r1));
+                take_pri = !(p.randomness > uni);
               }
+              pick = pri;
+              need = !take_pri;
             }
-            const int delta = pick == 1u ? -sr : (pick == 2u ? -scol : (pick == 4u ? sr : scol));
-            pc[delta] = (uint8_t)v;   // the head / target moves      PPU:165-167
-            pc[0] = (uint8_t)b3;      // and leaves PATH behind       PPU:168-173
-            modified = true;
           }
         }
-        key0 = n0;
-        key1 = n1;
+        // repeat `k, ck = split(k); pos = list[randint(ck, 0, 4)]` until valid, from the cell's
+        // key, which is NOT advanced by this loop (PPU:127-144): the lanes that need it are few
+        // (1-3 per cell), so the whole warp computes their draws (warp_pick)
+        const uint32_t needm = __ballot_sync(FULL, need);
+        if (needm) pick = warp_pick(needm, need, key0, key1, ok, pick, lane);
+        if (ok) {
+          const int delta = pick == 1u ? -sr : (pick == 2u ? -scol : (pick == 4u ? sr : scol));
+          pc[delta] = (uint8_t)v;   // the head / target moves      PPU:165-167
+          pc[0] = (uint8_t)b3;      // and leaves PATH behind       PPU:168-173
+          modified = true;
+        }
+        if (act) {
+          key0 = n0;
+          key1 = n1;
+        }
       }
     }
     // PPU:186-189: un-flip the board (a no-op here) and loop while the FLIPPED
     // pre-sweep layout differs from the un-flipped result
-    if (!mirrored) {
-      again = modified;
-    } else {
-      bool diff = false;
-      for (int r = 0; r < G; ++r) {
-        const uint8_t *a = board + (r + 2) * S + 2;
-        int o = ((flip ? G - 1 - r : r) + 2) * S + 2 + (flop ? G - 1 : 0);  // byte offset in the snapshot
-        for (int c = 0; c < G; ++c, o += scol) {
-          const uint32_t w = snap[(o >> 2) * 32];
-          diff |= (uint32_t)a[c] != ((w >> (8 * (o & 3))) & 0xffu);
+    if (act) {
+      if (!mirrored) {
+        again = modified;
+      } else {
+        bool diff = false;
+        for (int r = 0; r < G; ++r) {
+          const uint8_t *a = board + (r + 2) * S + 2;
+          int o = ((flip ? G - 1 - r : r) + 2) * S + 2 + (flop ? G - 1 : 0);  // byte offset in the snapshot
+          for (int c = 0; c < G; ++c, o += scol) {
+            const uint32_t w = snap[(o >> 2) * 32];
+            diff |= (uint32_t)a[c] != ((w >> (8 * (o & 3))) & 0xffu);
+          }
         }
+        again = diff;
       }
-      again = diff;
     }
   }
   if (live) {
@@ -570,14 +626,16 @@ int launch_seedext(SeedExtParams p, int64_t max_boards, cudaStream_t stream) {
       se_seed_kernel<<<ctas, SE_SEED_WARPS * 32, smem, stream>>>(p, d, sc);
     }
     if ((rc = check_launch("se_seed_kernel"))) break;
-    // lane-per-board kernels: as many warps per CTA as ~100 KB of shared memory allow
-    auto warps_for = [](size_t per_warp) {
-      int w = 4;
+    // lane-per-board kernels: small CTAs (2 warps / 1 warp), so that a batch that is a single wave
+    // spreads evenly over the SMs (65 536 boards 14x14/7: 4 + 2 warps per CTA 6.97 ms, 2 + 1 6.45 ms)
+    auto warps_for = [](size_t per_warp, int w) {
       while (w > 1 && per_warp * w > 100 * 1024) w >>= 1;
       return w;
     };
     const size_t ext_warp = (size_t)32 * d.lane_words_ext * 4, opt_warp = (size_t)32 * d.lane_bytes_opt;
-    const int ext_w = warps_for(ext_warp), opt_w = warps_for(opt_warp);
+    int ext_w = warps_for(ext_warp, 2), opt_w = warps_for(opt_warp, 1);
+    if (const char *ex = getenv("RBG_SE_EXT_WARPS")) ext_w = atoi(ex) >= 1 && atoi(ex) <= 4 ? warps_for(ext_warp, atoi(ex)) : ext_w;
+    if (const char *ex = getenv("RBG_SE_OPT_WARPS")) opt_w = atoi(ex) >= 1 && atoi(ex) <= 4 ? warps_for(opt_warp, atoi(ex)) : opt_w;
     if ((rc = set_smem(reinterpret_cast<const void *>(se_extend_kernel), ext_warp * ext_w, "se_extend_kernel"))) break;
     if ((rc = set_smem(reinterpret_cast<const void *>(se_optimise_kernel), opt_warp * opt_w, "se_optimise_kernel"))) break;
     for (int it = 0; it < p.iterations && rc == RBG_OK; ++it) {  // SE:180-200 while_loop over extension_iterations
