@@ -191,19 +191,27 @@ __global__ void __launch_bounds__(EW_WARPS * 32, RBG_ENV_MIN_CTAS) env_warp_kern
   const int sc = sc0 + (is_step ? 1 : 0);
   const bool terminal = is_step && env_ok && (ndone == N || sc >= p.env.time_limit);
   int tflag = terminal ? 1 : 0;
-  if (terminal && autoreset) {
-    bool hit = false;
-    uint32_t nk0, nk1;
-    if (p.cache_tag) {
-      const unsigned long long tag = __ldcg(p.cache_tag + e);
-      if (tag == (((unsigned long long)k1 << 32) | k0)) {
-        __threadfence();
-        const uint2 nk = __ldcg(p.cache_key + e);
-        nk0 = nk.x;
-        nk1 = nk.y;
-        hit = true;
-      }
+  // The cache entry may be published by the refill kernel (side stream) while this kernel runs:
+  // ONE lane per env reads the tag and decides, the others take its verdict (lanes that each read
+  // the tag themselves could disagree on hit / miss if the tag lands between their loads).
+  int hit_i = 0;
+  uint32_t ck0 = 0, ck1 = 0;
+  if (terminal && autoreset && a == 0 && p.cache_tag) {
+    const unsigned long long tag = __ldcg(p.cache_tag + e);
+    if (tag == (((unsigned long long)k1 << 32) | k0)) {
+      __threadfence();
+      const uint2 nk = __ldcg(p.cache_key + e);
+      ck0 = nk.x;
+      ck1 = nk.y;
+      hit_i = 1;
     }
+  }
+  hit_i = __shfl_sync(FULL, hit_i, j * Np);
+  ck0 = __shfl_sync(FULL, ck0, j * Np);
+  ck1 = __shfl_sync(FULL, ck1, j * Np);
+  if (terminal && autoreset) {
+    const bool hit = hit_i != 0;
+    uint32_t nk0 = ck0, nk1 = ck1;
     if (!hit) {  // State.key of the next episode: split(split(key)[0])[0]
       uint32_t a0, a1, b0, b1;
       split2(k0, k1, a0, a1, b0, b1);
