@@ -319,7 +319,22 @@ static int connector_step_impl(const rbg_state *in, const rbg_state *out, const 
   }
   // counters: with the speculative path the list kernels clear their own counter when
   // they finish (prw_kernel list_ticket); they were zeroed once when the workspace was adopted
-  if (!speculative && (e = cudaMemsetAsync(ws, 0, 64, stream)) != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(reset counter)");
+  if (!speculative) {
+    if ((e = cudaMemsetAsync(ws, 0, 64, stream)) != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(reset counter)");
+    // This path leaves its reset count in the counter.  If the same workspace has served (or will
+    // serve) a speculative batch, that batch must adopt it afresh: its kernels rely on counters
+    // that are zero between steps.
+    std::lock_guard<std::mutex> lock(g_ar_mu);
+    auto it = g_ar.find(workspace);
+    if (it != g_ar.end()) {
+      for (int i = 0; i < 2; ++i)
+        if (it->second.refill_pending[i]) {
+          cudaStreamWaitEvent(stream, it->second.refill_done[i], 0);
+          it->second.refill_pending[i] = false;
+        }
+      it->second.B = 0;
+    }
+  }
   if ((rc = launch_env(p, stream))) return rc;
   // VmapAutoResetWrapper._auto_reset: key, _ = split(state.key); reset(key):
   // one more leading split()[0] than a plain generator call.

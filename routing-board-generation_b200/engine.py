@@ -8,6 +8,8 @@ through DLPack (`as_tensor`), results can go back out the same way
 from __future__ import annotations
 
 import ctypes as C
+import itertools
+import weakref
 from typing import Dict, Optional, Tuple
 
 import numpy as np
@@ -221,6 +223,7 @@ def connector_reset(kind, keys: torch.Tensor, G: int, N: int) -> Tuple[State, Ti
 
 
 _workspaces: Dict[Tuple, torch.Tensor] = {}
+_ws_tokens = itertools.count(1)
 
 
 def _workspace(B: int, G: int, N: int, owner=None) -> torch.Tensor:
@@ -229,11 +232,32 @@ def _workspace(B: int, G: int, N: int, owner=None) -> torch.Tensor:
     cache entries; kept alive for the process (the library's side stream may still be filling it
     when the caller drops its last State)."""
     dev = _device()
-    k = (dev.index, B, G, N, id(owner) if owner is not None else None)
+    token = None
+    if owner is not None:  # id(owner) can be reused by a later env: give every owner its own token
+        token = getattr(owner, "_rbg_ws_token", None)
+        if token is None:
+            token = next(_ws_tokens)
+            try:
+                owner._rbg_ws_token = token
+            except AttributeError:
+                token = ("id", id(owner))
+    k = (dev.index, B, G, N, token)
     if k not in _workspaces:
         nbytes = int(_lib.load().rbg_step_workspace_bytes(B, G, N))
         _workspaces[k] = torch.empty((nbytes + 15) // 16 * 16, dtype=torch.uint8, device=dev)
+        if owner is not None and not isinstance(token, tuple):
+            weakref.finalize(owner, _drop_workspace, k)
     return _workspaces[k]
+
+
+def _drop_workspace(k) -> None:
+    """The owning env is gone: let the library forget the workspace (waits for its side stream) and free it."""
+    ws = _workspaces.pop(k, None)
+    if ws is not None:
+        try:
+            _lib.load().rbg_workspace_release(ws.data_ptr())
+        except Exception:
+            pass
 
 
 def connector_step(st: State, action, time_limit: int = 50, timestep_reward: float = -0.03, connected_reward: float = 0.1, autoreset_kind=-1, inplace: bool = False, random_policy: bool = False, out: Optional[TimeStep] = None, owner=None):

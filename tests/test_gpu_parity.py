@@ -391,6 +391,33 @@ def test_connector_autoreset_back_to_back_terminations(rbg, orc, kind, time_limi
     _rollout(rbg, orc, kind, 10, 5, B=700, steps=12, autoreset=True, time_limit=time_limit, seed=17 + time_limit)
 
 
+def test_workspace_reused_across_generator_kinds(rbg, orc):
+    """One auto-reset workspace serving env batches of different generator kinds in turn: speculative
+    (next-episode cache, self-clearing counters) -> seed_extension (plain reset lists) -> speculative.
+    The library must re-adopt the workspace when the kind changes hands (regression: the
+    seed_extension path left its reset count behind and the next batch's lists started mid-buffer)."""
+    import torch
+
+    gens = {"parallel_random_walk": rbg.ParallelRandomWalkGenerator, "uniform": rbg.UniformRandomGenerator, "seed_extension": rbg.SeedExtensionGenerator}
+    B, G, N = 700, 10, 5
+    token = None
+    for i, (kind, tl) in enumerate((("uniform", 1), ("seed_extension", 1), ("uniform", 1), ("parallel_random_walk", 2), ("seed_extension", 2), ("parallel_random_walk", 1))):
+        env = rbg.Connector(generator=gens[kind](G, N), time_limit=tl)
+        if token is not None:
+            env._rbg_ws_token = token  # share the first env's workspace
+        keys, kref = _keys(rbg, orc, 40 + i, B)
+        st, ts = env.reset(keys)
+        rst, rts = orc.connector_reset_batch(kind, kref, G, N)
+        for t in range(4):
+            act = orc.random_actions_batch(rst)
+            st, ts = rbg.VmapAutoResetWrapper(env).step(st, torch.from_numpy(act).cuda())
+            rst, rts = orc.connector_step_batch(rst, act, time_limit=tl, autoreset_kind=kind)
+            _assert_state(st, rst, f"batch {i} ({kind}) step {t}")
+            _assert_timestep(ts, rts, f"batch {i} ({kind}) step {t}")
+        if token is None:
+            token = env._rbg_ws_token
+
+
 def test_connector_autoreset_two_batches_share_nothing(rbg, orc):
     """Two env batches stepped alternately (different workspaces by shape) stay independent."""
     import torch
