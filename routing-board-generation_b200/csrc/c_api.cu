@@ -209,6 +209,23 @@ struct AutoResetCtx {
 static std::mutex g_ar_mu;
 static std::unordered_map<void *, AutoResetCtx> g_ar;
 
+// The next speculative call on `workspace` must adopt it afresh (counters zeroed, cache warm-started):
+// its contents are no longer what the recorded context left there.  Pending refills are joined first.
+static void invalidate_workspace(void *workspace, cudaStream_t stream, bool block = false) {
+  std::lock_guard<std::mutex> lock(g_ar_mu);
+  auto it = g_ar.find(workspace);
+  if (it == g_ar.end()) return;
+  for (int i = 0; i < 2; ++i)
+    if (it->second.refill_pending[i]) {
+      if (block)
+        cudaEventSynchronize(it->second.refill_done[i]);
+      else
+        cudaStreamWaitEvent(stream, it->second.refill_done[i], 0);
+      it->second.refill_pending[i] = false;
+    }
+  it->second.B = 0;
+}
+
 static bool speculative_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -324,16 +341,7 @@ static int connector_step_impl(const rbg_state *in, const rbg_state *out, const 
     // This path leaves its reset count in the counter.  If the same workspace has served (or will
     // serve) a speculative batch, that batch must adopt it afresh: its kernels rely on counters
     // that are zero between steps.
-    std::lock_guard<std::mutex> lock(g_ar_mu);
-    auto it = g_ar.find(workspace);
-    if (it != g_ar.end()) {
-      for (int i = 0; i < 2; ++i)
-        if (it->second.refill_pending[i]) {
-          cudaStreamWaitEvent(stream, it->second.refill_done[i], 0);
-          it->second.refill_pending[i] = false;
-        }
-      it->second.B = 0;
-    }
+    invalidate_workspace(workspace, stream);
   }
   if ((rc = launch_env(p, stream))) return rc;
   // VmapAutoResetWrapper._auto_reset: key, _ = split(state.key); reset(key):
@@ -377,6 +385,17 @@ static std::mutex g_scratch_mu;
 static Scratch g_scratch;
 static cudaStream_t g_streams[3] = {nullptr, nullptr, nullptr};
 static cudaEvent_t g_stream_ev[3] = {nullptr, nullptr, nullptr};
+
+// Who laid the scratch out last (a step variant with auto-reset keeps its workspaces there between
+// calls): any other use, shape or base pointer means those workspaces have been overwritten.
+struct ScratchSig {
+  int fn = 0;
+  int64_t B = 0;
+  int G = 0, N = 0, kind = -1;
+  void *base = nullptr;
+  bool operator==(const ScratchSig &o) const { return fn == o.fn && B == o.B && G == o.G && N == o.N && kind == o.kind && base == o.base; }
+};
+static ScratchSig g_scratch_sig;
 
 static int scratch_get(size_t bytes, int device, void **out) {
   if (g_scratch.ptr && (g_scratch.bytes < bytes || g_scratch.device != device)) {
@@ -901,6 +920,15 @@ static int use_device(int device, int *cur) {
   return RBG_OK;
 }
 
+// A host-variant call is about to use the scratch as `sig` describes.  If that is not how it was
+// used last, the auto-reset workspaces a step variant keeps in it (`nws` of them, `stride` bytes
+// apart from `ws`) hold someone else's bytes: their contexts are invalidated.
+static void scratch_claim(const ScratchSig &sig, uint8_t *ws, size_t stride, int64_t nws) {
+  if (g_scratch_sig == sig) return;
+  g_scratch_sig = sig;
+  for (int64_t i = 0; i < nws; ++i) invalidate_workspace(ws + (size_t)i * stride, nullptr, true);
+}
+
 int rbg_prw_generate_host(const uint32_t *keys, int64_t B, int G, int N, int32_t *heads, int32_t *targets,
                           int32_t *solved, int device) {
   int rc, dev;
@@ -916,6 +944,7 @@ int rbg_prw_generate_host(const uint32_t *keys, int64_t B, int G, int N, int32_t
   size.take<int32_t>((size_t)B * G * G);
   void *base;
   if ((rc = scratch_get(size.off + 256, dev, &base))) return rc;
+  scratch_claim(ScratchSig{1, B, G, N, -1, base}, nullptr, 0, 0);
   Carver c{reinterpret_cast<uint8_t *>(base)};
   uint32_t *dk = c.take<uint32_t>((size_t)B * 2);
   int32_t *dh = c.take<int32_t>((size_t)B * 2 * N);
@@ -957,6 +986,7 @@ int rbg_connector_reset_host(int kind, const uint32_t *keys, int64_t B, int G, i
   carve_timestep(size, B, G, N, &dt);
   void *base;
   if ((rc = scratch_get(size.off + 256, dev, &base))) return rc;
+  scratch_claim(ScratchSig{2, B, G, N, kind, base}, nullptr, 0, 0);
   Carver c{reinterpret_cast<uint8_t *>(base)};
   uint32_t *dk = c.take<uint32_t>((size_t)B * 2);
   carve_state(c, B, G, N, &ds);
@@ -1007,6 +1037,7 @@ int rbg_connector_step_host(const rbg_state *in, const rbg_state *out, const int
   carve_timestep(c, B, G, N, &dt);
   int32_t *da = c.take<int32_t>((size_t)B * N);
   uint8_t *ws = c.take<uint8_t>((size_t)nslices * ws_bytes);
+  scratch_claim(ScratchSig{3, B, G, N, params->autoreset_kind, base}, ws, ws_bytes, nslices);
   int si = 0;
   for (int64_t off = 0; off < B; off += sl, ++si) {
     const int64_t n = (B - off) < sl ? (B - off) : sl;
@@ -1055,6 +1086,7 @@ int rbg_connector_step_host_io(const rbg_state *state, const int32_t *action, in
   carve_timestep(c, B, G, N, &dt);
   int32_t *da = c.take<int32_t>((size_t)B * N);
   uint8_t *ws = c.take<uint8_t>((size_t)nslices * ws_bytes);
+  scratch_claim(ScratchSig{4, B, G, N, params->autoreset_kind, base}, ws, ws_bytes, nslices);
   // One compute stream runs the slices' kernels back to back (the whole batch is ~0.1 ms of
   // kernels, the copies 2.4 ms); the two copy streams take the observation (96 % of the bytes)
   // of each slice as soon as its kernel is done, so the bus is busy from the first slice on.

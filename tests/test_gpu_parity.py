@@ -747,6 +747,37 @@ def test_step_host_io_matches_oracle(rbg, orc):
         _assert_state(st, rst, f"step {step}")
 
 
+def test_step_host_io_survives_other_host_calls(rbg, orc):
+    """The host-variant step keeps its auto-reset workspaces in the library's device scratch.  Another
+    host-variant call in between overwrites that scratch, and a new env batch of the same shape comes
+    next: the step must notice and start from a clean workspace (every env resets every step here)."""
+    L, lib = rbg._lib, rbg._lib.load()
+    G, N, B = 10, 5, 4500
+    params = L.rbg_env_params(1, -0.03, 0.1, 0)
+    h = dict(obs=np.empty((B, N, G, G), np.int32), mask=np.empty((B, N, 5), np.uint8), sc=np.empty(B, np.int32), reward=np.empty((B, N), np.float32), discount=np.empty((B, N), np.float32),
+             step_type=np.empty(B, np.int8), nc=np.empty(B, np.int32), rc=np.empty(B, np.float32), tpl=np.empty(B, np.int32))
+    t = L.rbg_timestep(*(h[k].ctypes.data for k in ("obs", "mask", "sc", "reward", "discount", "step_type", "nc", "rc", "tpl")))
+    for batch in range(3):
+        keys, kref = _keys(rbg, orc, 60 + batch, B)
+        env = rbg.VmapAutoResetWrapper(rbg.Connector(generator=rbg.ParallelRandomWalkGenerator(G, N), time_limit=1))
+        st, _ = env.reset(keys)
+        rst, _ = orc.connector_reset_batch("parallel_random_walk", kref, G, N)
+        a = st.agents
+        s = L.rbg_state(st.grid.data_ptr(), st.step_count.data_ptr(), a.id.data_ptr(), a.start.data_ptr(), a.target.data_ptr(), a.position.data_ptr(), st.key.data_ptr())
+        for step in range(3):
+            act = orc.random_actions_batch(rst)
+            L.check(lib.rbg_connector_step_host_io(C.byref(s), act.ctypes.data, B, G, N, C.byref(params), C.byref(t), -1))
+            rst, rts = orc.connector_step_batch(rst, act, time_limit=1, autoreset_kind="parallel_random_walk")
+            assert np.array_equal(h["obs"], rts["obs"]) and np.array_equal(h["step_type"], rts["step_type"]), (batch, step)
+            _assert_state(st, rst, f"batch {batch} step {step}")
+        # something else uses (and overwrites) the scratch
+        n2 = 6000 + 500 * batch
+        k2 = orc.split(orc.PRNGKey(9), n2)
+        heads, targets, solved = np.empty((n2, 2, N), np.int32), np.empty((n2, 2, N), np.int32), np.empty((n2, G, G), np.int32)
+        assert lib.rbg_prw_generate_host(k2.ctypes.data, n2, G, N, heads.ctypes.data, targets.ctypes.data, solved.ctypes.data, -1) == 0
+        assert np.array_equal(solved, orc.prw_generate_batch(k2, G, N)[2])
+
+
 def test_cabi_argument_errors(rbg):
     """Bad arguments come back as negative codes with a message, never as a crash or a silent fallback."""
     import torch
