@@ -159,7 +159,10 @@ int rbg_connector_reset(int kind, const uint32_t *keys, int64_t B, int G, int N,
  * the reset lists it caches, per env, the next episode's start / target pins, which
  * the library generates ahead of time on an internal side stream (the reset key of
  * an episode is known when the episode starts).  16-byte aligned, need not be
- * cleared.  Call rbg_workspace_release before freeing it. */
+ * cleared.  Call rbg_workspace_release before freeing it, and before handing it to
+ * another env batch (the library re-initialises it by itself when the shape or the
+ * generator kind changes, or after a SeedExtension batch has used it; a batch of the
+ * same shape and kind would merely start with cache misses). */
 int64_t rbg_step_workspace_bytes(int64_t B, int G, int N);
 /* waits for the side-stream work tied to `workspace` and forgets it */
 int rbg_workspace_release(void *workspace);
