@@ -246,7 +246,7 @@ def _workspace(B: int, G: int, N: int, owner=None) -> torch.Tensor:
         nbytes = int(_lib.load().rbg_step_workspace_bytes(B, G, N))
         _workspaces[k] = torch.empty((nbytes + 15) // 16 * 16, dtype=torch.uint8, device=dev)
         if owner is not None and not isinstance(token, tuple):
-            weakref.finalize(owner, _drop_workspace, k)
+            weakref.finalize(owner, _drop_workspace, k).atexit = False  # nothing to release once the process is exiting
     return _workspaces[k]
 
 
