@@ -778,6 +778,19 @@ def test_step_host_io_survives_other_host_calls(rbg, orc):
         assert np.array_equal(solved, orc.prw_generate_batch(k2, G, N)[2])
 
 
+def test_mixed_api_stress(rbg):
+    """tools/stress_mixed.py: env batches of all generator kinds created, stepped in random order through
+    step / step_random / rollout_random and dropped at random (workspaces change hands), every result
+    against the oracle."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "stress_mixed.py"), "160", "7"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and r.stdout.strip().startswith("ok"), (r.stdout[-800:], r.stderr[-2000:])
+
+
 def test_cabi_argument_errors(rbg):
     """Bad arguments come back as negative codes with a message, never as a crash or a silent fallback."""
     import torch
