@@ -21,10 +21,6 @@ struct SmemGrid {
   __device__ __forceinline__ uint32_t at(int r, int c) const {
     return base[(r + pad) * S + (c + pad)];
   }
-  __device__ __forceinline__ uint32_t at_checked(int r, int c) const {
-    const bool in = (unsigned)r < (unsigned)G && (unsigned)c < (unsigned)G;
-    return in ? at(r, c) : 0xFFu;
-  }
 };
 
 // is_valid_position for the four moves in action order UP, RIGHT, DOWN, LEFT.
