@@ -23,6 +23,15 @@ import sys
 import tempfile
 import time
 
+# torchrun exports OMP_NUM_THREADS=1 to its workers.  libgomp reads it when it is first loaded, and a
+# later num_threads(n) clause then runs the CPU arm 8x SLOWER than a single thread (measured), so the
+# value is replaced by the core count before anything that links OpenMP is imported.
+if os.environ.get("OMP_NUM_THREADS") == "1" and "RANK" in os.environ:
+    try:
+        os.environ["OMP_NUM_THREADS"] = str(max(1, len(os.sched_getaffinity(0))))
+    except AttributeError:
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -391,11 +400,21 @@ def _cpu_workload(orc, B, nthreads):
     return step
 
 
+def _host_threads() -> int:
+    """Every core this process may run on.  Not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1
+    to its workers, which would quietly turn the CPU arm into a single-thread run at --gpus > 1."""
+    try:
+        n = max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        n = max(1, os.cpu_count() or 1)
+    return n
+
+
 def _cpu_baseline(budget_s: float = 15.0):
+    cores = _host_threads()
     from oracle import oracle as orc
 
     orc.build()
-    cores = orc.max_threads()
     B = 16384
     step = _cpu_workload(orc, B, cores)
     for _ in range(2):
@@ -416,10 +435,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    cores = _host_threads()
     from oracle import oracle as orc
 
     orc.build()
-    cores = orc.max_threads()
     B = args.envs
     step = _cpu_workload(orc, B, cores)
     for _ in range(max(args.warmup, 1)):
