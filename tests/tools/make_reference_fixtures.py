@@ -12,6 +12,8 @@ What is pinned this way (none of it has a golden in the reference itself):
     default and the non-default options; extend_wires_jax and optimise_wire in isolation
   * BoardDatasetGeneratorJAX: the stored boards and the randint pick of __call__
     (`python tests/tools/make_reference_fixtures.py dataset` regenerates only this section)
+  * the BASELINE shapes: generate_board at 20x20/10, 24x24/12, 32x32/16, 40x40/32 (`... large`) and
+    SeedExtension at 14x14/7, 20x20/10 (`... seedext_large`), appended to the lists above
 The shim's jax.random is checked first against the reference-owned goldens by running the reference's
 own test file (test_parallel_random_walk_board.py, 35 tests) under it.
 """
@@ -69,9 +71,79 @@ def dataset_section():
     print("merged into", OUT)
 
 
+def large_section():
+    """ParallelRandomWalkBoard.generate_board at the BASELINE shapes 20x20/10 and 32x32/16 (slow under the
+    shim: minutes per board) -> appended to the prw_generate_board list of the existing JSON."""
+    sys.path.insert(0, SHIM)
+    sys.path.insert(0, REF)
+    import jax
+    import numpy as np
+    from routing_board_generation.board_generation_methods.jax_implementation.board_generation.parallel_random_walk import ParallelRandomWalkBoard
+
+    def L(x):
+        return np.asarray(x).astype(np.int64).tolist()
+
+    with open(OUT) as f:
+        data = json.load(f)
+    have = {(e["G"], e["N"], e["seed"]) for e in data["prw_generate_board"]}
+    t0 = time.time()
+    for (G, N, seed, n) in ((20, 10, 61, 3), (32, 16, 62, 2), (20, 10, 63, 12), (32, 16, 64, 6), (40, 32, 65, 2), (24, 12, 66, 4)):
+        if (G, N, seed) in have:
+            continue
+        board = ParallelRandomWalkBoard(G, G, N)
+        ks = np.asarray(jax.random.split(jax.random.PRNGKey(seed), n))
+        rows = []
+        for k in ks:
+            heads, targets, solved = board.generate_board(jax.numpy.array(k))
+            rows.append(dict(heads=L(heads), targets=L(targets), solved=L(solved)))
+            print(f"prw {G}x{G}/{N}: board {len(rows)}/{n}  [{time.time() - t0:.0f}s]", flush=True)
+        data["prw_generate_board"].append(dict(G=G, N=N, seed=seed, n=n, boards=rows))
+        with open(OUT, "w") as f:
+            json.dump(data, f, separators=(",", ":"))
+    print("merged into", OUT)
+
+
+def seedext_large_section():
+    """SeedExtensionBoard.return_solved_board / generate_starts_ends at 14x14/7 (BASELINE configs[3]) and
+    20x20/10 -> appended to the seedext_solved list of the existing JSON."""
+    sys.path.insert(0, SHIM)
+    sys.path.insert(0, REF)
+    import jax
+    import numpy as np
+    from routing_board_generation.board_generation_methods.jax_implementation.board_generation.seed_extension import SeedExtensionBoard
+
+    def L(x):
+        return np.asarray(x).astype(np.int64).tolist()
+
+    with open(OUT) as f:
+        data = json.load(f)
+    have = {(e["G"], e["N"], e["seed"]) for e in data["seedext_solved"]}
+    t0 = time.time()
+    for (G, N, seed, n) in ((14, 7, 71, 10), (20, 10, 72, 3)):
+        if (G, N, seed) in have:
+            continue
+        board = SeedExtensionBoard(G, G, N)
+        ks = np.asarray(jax.random.split(jax.random.PRNGKey(seed), n))
+        rows = []
+        for k in ks:
+            k = jax.numpy.array(k)
+            solved = board.return_solved_board(k)
+            (sr, sc), (er, ec) = board.generate_starts_ends(k)
+            rows.append(dict(solved=L(solved), starts=[L(sr), L(sc)], ends=[L(er), L(ec)]))
+            print(f"seed extension {G}x{G}/{N}: board {len(rows)}/{n}  [{time.time() - t0:.0f}s]", flush=True)
+        data["seedext_solved"].append(dict(G=G, N=N, seed=seed, n=n, options={}, boards=rows))
+        with open(OUT, "w") as f:
+            json.dump(data, f, separators=(",", ":"))
+    print("merged into", OUT)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "seedext_large":
+        return seedext_large_section()
     if len(sys.argv) > 1 and sys.argv[1] == "dataset":
         return dataset_section()
+    if len(sys.argv) > 1 and sys.argv[1] == "large":
+        return large_section()
     print("reference tests under the shim:", run_reference_tests())
     sys.path.insert(0, SHIM)
     sys.path.insert(0, REF)
