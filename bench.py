@@ -342,6 +342,25 @@ def _secondary_prw(args, rbg, peak):
         bytes_ = PRW_BOARD_BYTES[(g, n)] * b
         out.append({"metric": "prw_solved_boards_per_sec", "workload": f"ParallelRandomWalkBoard.generate_board {g}x{g}/{n} B={b}", "value": round(b / (ms / 1e3), 1), "unit": "boards/s", "ms_per_batch": round(ms, 4),
                     "output_gbs": round(bytes_ / (ms / 1e3) / 1e9, 2), "hbm_frac": round(bytes_ / (ms / 1e3) / 1e9 / peak, 5), "bound": "integer issue (threefry2x32), see DESIGN.md"})
+    # the same headline workload through the per-step API (one rbg_connector_step_random call per env step:
+    # env_warp_kernel + reset kernel + side-stream cache refill), for callers that cannot use the fused rollout
+    g, n, b = G, N, 65536
+    env = rbg.VmapAutoResetWrapper(rbg.Connector(generator=rbg.ParallelRandomWalkGenerator(g, n), time_limit=TIME_LIMIT))
+    st, _ = env.reset(rbg.split(rbg.PRNGKey(0), b))
+    ts1 = rbg.engine.alloc_timestep(b, g, n)
+    for _ in range(160):
+        st, _, _ = rbg.engine.connector_step(st, None, TIME_LIMIT, -0.03, 0.1, autoreset_kind="parallel_random_walk", inplace=True, random_policy=True, out=ts1, owner=env)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 200
+    e0.record()
+    for _ in range(reps):
+        st, _, _ = rbg.engine.connector_step(st, None, TIME_LIMIT, -0.03, 0.1, autoreset_kind="parallel_random_walk", inplace=True, random_policy=True, out=ts1, owner=env)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    out.append({"metric": "connector_env_steps_per_sec", "workload": f"per-step API (one Python call = one rbg_connector_step_random per env step) {g}x{g}/{n} B={b}", "value": round(b / (ms / 1e3), 1), "unit": "env-steps/s",
+                "ms_per_step": round(ms, 4), "output_gbs": round(STEP_BYTES * b / (ms / 1e3) / 1e9, 1), "hbm_frac": round(STEP_BYTES * b / (ms / 1e3) / 1e9 / peak, 4)})
     # fused generate + reset + rollout at the A2C rollout shape (BASELINE configs[4]): 32x32 / 16 agents, 20 steps
     g, n, b, T = 32, 16, 8192, 20
     env = rbg.VmapAutoResetWrapper(rbg.Connector(generator=rbg.ParallelRandomWalkGenerator(g, n), time_limit=TIME_LIMIT))
