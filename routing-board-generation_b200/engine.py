@@ -22,13 +22,24 @@ from .types import Agent, Observation, State, TimeStep
 GENERATOR_KINDS = {"parallel_random_walk": GEN_PRW, "uniform": GEN_UNIFORM, "seed_extension": GEN_SEEDEXT}
 
 
+_cuda_checked = False
+
+
 def _device() -> torch.device:
-    if not torch.cuda.is_available():
-        raise RuntimeError("routing-board-generation_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    global _cuda_checked
+    if not _cuda_checked:  # checked once: the per-step API is called tens of thousands of times per second
+        if not torch.cuda.is_available():
+            raise RuntimeError("routing-board-generation_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        _cuda_checked = True
     return torch.device("cuda", torch.cuda.current_device())
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream() -> int:
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -141,6 +152,10 @@ def _dims(st: State) -> Tuple[int, int, int]:
 
 
 def _contig_state(st: State) -> State:
+    a = st.agents
+    if (st.grid.is_contiguous() and st.step_count.is_contiguous() and st.key.is_contiguous() and a.id.is_contiguous() and a.start.is_contiguous()
+            and a.target.is_contiguous() and a.position.is_contiguous()):
+        return st
     return st.map(lambda t: t if t.is_contiguous() else t.contiguous())
 
 
