@@ -766,7 +766,21 @@ static int rollout_fused(const rbg_state *state, int32_t *action_out, int64_t T,
     q.cache_key = reinterpret_cast<uint2 *>(ws + wl.cache_key);
     q.cache_pins = reinterpret_cast<uint32_t *>(ws + wl.cache_pins);
   };
-  if (ctx->B != B || ctx->G != G || ctx->N != N || ctx->kind != kind) {
+  // Next-episode cache + refill kernel, or every reset generated inside the rollout kernel?  Inside,
+  // a whole warp generates one board (prw_kernel packs 32 / Np per warp), but the work hides in the
+  // kernel's idle issue slots and no refill kernel runs.  Measured: the cache wins while a step emits
+  // little per env (10x10/5: 2.10 vs 1.45 G env-steps/s, 16x16/8: 678 vs 636 M), in-kernel generation
+  // wins for large boards, where resets are rare per byte written (24x24/12: 214 vs 183 M, 32x32/16:
+  // 95 vs 84 M, 40x40/32: 26.8 vs 23.3 M); 20x20/10 (16 000 B per env-step) is the break-even.
+  static int no_cache_env = -2;
+  if (no_cache_env == -2) {
+    const char *ex = getenv("RBG_ROLLOUT_NO_CACHE");
+    no_cache_env = ex ? (atoi(ex) != 0 ? 1 : 0) : -1;
+  }
+  const bool no_cache = no_cache_env >= 0 ? no_cache_env == 1 : (size_t)N * G * G * 4 > 16384;
+  if (no_cache) {
+    ctx->B = 0;  // the cache is not maintained: a later step-wise call adopts the workspace afresh
+  } else if (ctx->B != B || ctx->G != G || ctx->N != N || ctx->kind != kind) {
     if ((e = cudaMemsetAsync(ws, 0, 256, stream)) != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(counters)");
     PrwParams q;  // warm start: the next episode of every env
     cache_params(q);
@@ -796,6 +810,7 @@ static int rollout_fused(const rbg_state *state, int32_t *action_out, int64_t T,
   p.cache_tag = reinterpret_cast<const unsigned long long *>(ws + wl.cache_tag);
   p.cache_key = reinterpret_cast<const uint2 *>(ws + wl.cache_key);
   p.cache_pins = reinterpret_cast<const uint32_t *>(ws + wl.cache_pins);
+  if (no_cache) p.cache_tag = nullptr;
   // Slices of the batch on their own streams: each slice alternates rollout chunk -> cache
   // refill, and while one slice's (memory-bound) rollout drains, another slice's (issue-bound)
   // refill and the ramp of its next chunk fill the SMs.  Slices never share an env, a list or
@@ -835,7 +850,9 @@ static int rollout_fused(const rbg_state *state, int32_t *action_out, int64_t T,
       p.refill_list = reinterpret_cast<int32_t *>(ws + wl.refill_list[0]) + p.env_lo;
       p.refill_keys = reinterpret_cast<uint32_t *>(ws + wl.refill_keys[0]) + 2 * p.env_lo;
       p.refill_count = reinterpret_cast<int32_t *>(ws + 64 + 16 * s);
+      if (no_cache) p.refill_list = nullptr;
       if ((rc = launch_rollout(p, kind, n, action_out ? action_out + t0 * B * N : nullptr, st))) return rc;
+      if (no_cache) continue;
       PrwParams q;  // refill the cache entries consumed in this chunk (the kernel clears the counter when done)
       cache_params(q);
       q.keys = p.refill_keys;

@@ -498,10 +498,8 @@ def test_rollout_matches_stepwise_oracle(rbg, orc, kind, G, N, B, T, time_limit)
     _assert_state(st, rst, "after the second rollout")
 
 
-@pytest.mark.parametrize("slices", [1, 3, 4])
-def test_rollout_slice_counts(rbg, slices):
-    """The fused rollout splits the batch into slices that run on separate streams (2 by default);
-    RBG_ROLLOUT_SLICES (read once per process, hence the subprocess) selects 1, 3 or 4: same results."""
+def _rollout_in_subprocess(env_vars, G, N, B, T, time_limit=6):
+    """A fused rollout against the oracle in a fresh process (the library reads its switches once)."""
     import os
     import subprocess
     import sys
@@ -511,9 +509,9 @@ def test_rollout_slice_counts(rbg, slices):
         "import sys, numpy as np; sys.path.insert(0, %r)\n"
         "import routing_board_generation_b200 as rbg\n"
         "from oracle import oracle as orc\n"
-        "G, N, B, T = 10, 5, 8200, 21\n"
+        "G, N, B, T, TL = %d, %d, %d, %d, %d\n"
         "k = rbg.split(rbg.PRNGKey(5), B); kr = orc.split(orc.PRNGKey(5), B)\n"
-        "env = rbg.VmapAutoResetWrapper(rbg.Connector(generator=rbg.ParallelRandomWalkGenerator(G, N), time_limit=6))\n"
+        "env = rbg.VmapAutoResetWrapper(rbg.Connector(generator=rbg.ParallelRandomWalkGenerator(G, N), time_limit=TL))\n"
         "st, _ = env.reset(k); rst, _ = orc.connector_reset_batch('parallel_random_walk', kr, G, N)\n"
         "for rep in range(2):\n"
         "    st, ts, act = env.rollout_random(st, T)\n"
@@ -521,13 +519,30 @@ def test_rollout_slice_counts(rbg, slices):
         "    for t in range(T):\n"
         "        a = orc.random_actions_batch(rst)\n"
         "        assert np.array_equal(act[t].cpu().numpy(), a), t\n"
-        "        rst, rts = orc.connector_step_batch(rst, a, time_limit=6, autoreset_kind='parallel_random_walk')\n"
+        "        rst, rts = orc.connector_step_batch(rst, a, time_limit=TL, autoreset_kind='parallel_random_walk')\n"
         "        assert np.array_equal(obs[t], rts['obs']) and np.array_equal(rew[t], rts['reward']) and np.array_equal(stype[t], rts['step_type']), t\n"
         "    assert np.array_equal(st.grid.cpu().numpy(), rst['grid']) and np.array_equal(st.key.cpu().numpy(), rst['key'])\n"
-        "print('slices ok')\n"
-    ) % root
-    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, RBG_ROLLOUT_SLICES=str(slices)), capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and "slices ok" in r.stdout, (r.stdout[-500:], r.stderr[-2000:])
+        "    st, ts1 = env.step(st, a)  # a step-wise call in between shares the workspace\n"
+        "    rst, rts = orc.connector_step_batch(rst, a, time_limit=TL, autoreset_kind='parallel_random_walk')\n"
+        "    assert np.array_equal(ts1.observation.grid.cpu().numpy(), rts['obs']) and np.array_equal(st.grid.cpu().numpy(), rst['grid'])\n"
+        "print('rollout ok')\n"
+    ) % (root, G, N, B, T, time_limit)
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env_vars), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "rollout ok" in r.stdout, (r.stdout[-500:], r.stderr[-2000:])
+
+
+@pytest.mark.parametrize("slices", [1, 3, 4])
+def test_rollout_slice_counts(rbg, slices):
+    """The fused rollout splits the batch into slices that run on separate streams (2 by default);
+    RBG_ROLLOUT_SLICES selects 1, 3 or 4: same results."""
+    _rollout_in_subprocess({"RBG_ROLLOUT_SLICES": str(slices)}, 10, 5, 8200, 21)
+
+
+@pytest.mark.parametrize("no_cache,G,N,B", [("1", 10, 5, 4300), ("0", 24, 12, 300), ("1", 7, 3, 900)])
+def test_rollout_generation_modes(rbg, no_cache, G, N, B):
+    """Resets served by the next-episode cache + refill kernel (default for small boards) or all generated
+    inside the rollout kernel (default for large boards): RBG_ROLLOUT_NO_CACHE forces the other one."""
+    _rollout_in_subprocess({"RBG_ROLLOUT_NO_CACHE": no_cache}, G, N, B, 21, time_limit=5)
 
 
 @pytest.mark.parametrize("G,N,B,T,time_limit", [(10, 5, 65536, 45, 50), (32, 16, 8192, 22, 9)])
