@@ -106,6 +106,14 @@ def test_bench_reference_arm_single_and_torchrun():
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1 and json.loads(lines[0])["n_gpus"] == 2
+    # torchrun hands its workers OMP_NUM_THREADS=1 when the variable is unset: the CPU arm must still use
+    # every core it may run on (it used to drop to one thread, and a slow one, at --gpus > 1)
+    env1 = {k: v for k, v in os.environ.items() if k != "OMP_NUM_THREADS"}
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", str(port + 1),
+                        os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1", "--envs", "128"], capture_output=True, text=True, env=env1, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
+    assert line["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
 
 
 def test_bench_product_arm_refuses_to_run_without_a_gpu():
