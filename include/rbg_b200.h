@@ -205,10 +205,21 @@ int rbg_connector_rollout_random(const rbg_state *state, int32_t *action_out,
                                  const rbg_timestep *ts, void *workspace,
                                  void *stream);
 
-/* Board validity (numpy_implementation/utils/post_processor_utils_numpy.py:34-155,
- * board_processor.py:111-162).  flags int32[B]: 0 valid; bit0 encoding out of
- * range, bit1 head/target count, bit2 neighbour-count rule, bit3 head and
- * target not connected, bit4 zero-length wire (lone TARGET, a PRW quirk). */
+/* Board validity: the reference's NumPy rules (numpy_implementation/utils/
+ * post_processor_utils_numpy.py:34-155 = UP, numpy_implementation/utils/board_processor.py:111-162,
+ * 391-487 = BP).  flags int32[B], 0 = valid by every rule:
+ *     1  EncodingOutOfRangeError: a code < 0 or > 3N (verify_encodings_range BP:406-416); as in
+ *        is_valid_board (BP:391-404) nothing else is evaluated then
+ *     2  MissingHeadTailError: some wire has no POSITION or no TARGET code (BP:419-431, UP:72-85)
+ *     4  InvalidWireStructureError: verify_wire_validity is False (UP:88-121, BP:433-454)
+ *     8  a wire's (first) head and target are not connected through the wire's own cells
+ *    16  zero-length wire: a lone TARGET (a ParallelRandomWalk quirk; the reference reports 2 | 4)
+ *    32  a wire has several heads or targets (the DuplicateHeadsTailsError the reference means to
+ *        raise but cannot: its counts run over np.setdiff1d = unique values)
+ *    64  PathNotFoundError: BoardProcessor.get_path_from_head_and_target (BP:111-162) finds no path
+ *        through the wire's own cells and EMPTY cells
+ *   128  rule 2 or 4 is broken by something other than a zero-length wire
+ * A generated board is sound when (flags & (1 | 8 | 32 | 64 | 128)) == 0. */
 int rbg_validate(const int32_t *boards, int64_t B, int G, int N, int32_t *flags,
                  void *stream);
 

@@ -926,73 +926,108 @@ void orc_connector_step(int G, int N, int32_t *grid, int32_t *step_count,
 }
 
 /* ======================================================================== */
-/* validity rules (numpy post_processor_utils_numpy.py:34-155,               */
-/* board_processor.py:111-162)                                               */
+/* validity rules: the reference's NumPy code, function by function           */
+/*   UP = numpy_implementation/utils/post_processor_utils_numpy.py            */
+/*   BP = numpy_implementation/utils/board_processor.py                       */
+/* Pinned by tests/golden/validity_reference.npz = verdicts of those very     */
+/* functions (imported unmodified) on 2 400 boards,                           */
+/* tests/tools/make_validity_fixtures.py.                                     */
 /* ======================================================================== */
+
+/* num_wire_neighbors (UP:124-155, BP:456-487): adjacent cells whose code lies in
+ * [3w+1, 3w+3], w = (label-1)//3, order up, left, down, right */
+static int val_wire_neighbours(int G, const int32_t *board, int k) {
+  const int w = (board[k] - 1) / 3, lo = 3 * w + PATH, hi = 3 * w + TARGET;
+  const int r = k / G, c = k % G;
+  int nb = 0;
+  if (r > 0 && board[k - G] >= lo && board[k - G] <= hi) nb++;
+  if (c > 0 && board[k - 1] >= lo && board[k - 1] <= hi) nb++;
+  if (r < G - 1 && board[k + G] >= lo && board[k + G] <= hi) nb++;
+  if (c < G - 1 && board[k + 1] >= lo && board[k + 1] <= hi) nb++;
+  return nb;
+}
+
+/* breadth-first search from `from` to `to` through cells whose code passes `ok`:
+ * with_empty = 0: the wire's own codes only (the invariant "a wire connects its own
+ * start and target"); with_empty = 1: own codes and EMPTY = the valid_cells list of
+ * BoardProcessor.get_path_from_head_and_target (BP:111-162), whose PathNotFoundError
+ * is raised exactly when this search fails (the shuffled move order picks among
+ * shortest paths, it cannot change whether one exists). */
+static int val_reachable(int G, const int32_t *board, int w, int from, int to, int with_empty,
+                         int32_t *queue, uint8_t *seen) {
+  const int cells = G * G, lo = 3 * w + PATH, hi = 3 * w + TARGET;
+  memset(seen, 0, (size_t)cells);
+  int qh = 0, qt = 0;
+  queue[qt++] = from;
+  seen[from] = 1;
+  while (qh < qt) {
+    const int k = queue[qh++];
+    if (k == to) return 1;
+    const int r = k / G, c = k % G;
+    const int nbk[4] = {c < G - 1 ? k + 1 : -1, c > 0 ? k - 1 : -1, r < G - 1 ? k + G : -1, r > 0 ? k - G : -1};
+    for (int j = 0; j < 4; ++j) {
+      const int p = nbk[j];
+      if (p < 0 || seen[p]) continue;
+      const int32_t v = board[p];
+      if ((v >= lo && v <= hi) || (with_empty && v == EMPTY)) {
+        seen[p] = 1;
+        queue[qt++] = p;
+      }
+    }
+  }
+  return 0;
+}
+
+/* Flags (0 = valid by every rule):
+ *   1   EncodingOutOfRangeError: a code < 0 or > 3N (verify_encodings_range BP:406-416); as in
+ *       is_valid_board (BP:391-404, UP:34-48) nothing else is evaluated then
+ *   2   MissingHeadTailError: some wire has no POSITION or no TARGET code
+ *       (verify_number_heads_tails BP:419-431, UP:72-85)
+ *   4   InvalidWireStructureError: verify_wire_validity (UP:88-121, BP:433-454) is False
+ *   8   a wire's first head and first target are not connected through its own cells
+ *  16   zero-length wire: a lone TARGET, no head, no path (ParallelRandomWalk quirk);
+ *       the reference reports it as 2 | 4
+ *  32   a wire has more than one head or target (the DuplicateHeadsTailsError the reference means to
+ *       raise; its counts run over np.setdiff1d(...) = unique values, so it never can)
+ *  64   PathNotFoundError: get_path_from_head_and_target (BP:111-162) finds no path for some wire
+ * 128   rule 2 or 4 is broken by something OTHER than a zero-length wire */
 int orc_validate_board(int G, int N, const int32_t *board) {
   const int cells = G * G;
   int flags = 0;
-  int heads[ORC_MAX_N] = {0}, targets[ORC_MAX_N] = {0}, hpos[ORC_MAX_N], tpos[ORC_MAX_N];
-  for (int k = 0; k < cells; ++k) {
-    int32_t v = board[k];
-    if (v < 0 || v > 3 * N) {
-      flags |= 1;
-      continue;
-    }
-    if (v == 0) continue;
-    int w = (v - 1) / 3, t = (v - 1) % 3 + 1;
-    if (t == POSITION) heads[w]++, hpos[w] = k;
-    if (t == TARGET) targets[w]++, tpos[w] = k;
-  }
+  for (int k = 0; k < cells; ++k)
+    if (board[k] < 0 || board[k] > 3 * N) flags |= 1;
   if (flags) return flags;
+  int heads[ORC_MAX_N] = {0}, targets[ORC_MAX_N] = {0}, paths[ORC_MAX_N] = {0}, hpos[ORC_MAX_N], tpos[ORC_MAX_N];
+  for (int k = 0; k < cells; ++k) { /* row-major: the first hit is np.argwhere(...)[0] (BP:79-82) */
+    const int32_t v = board[k];
+    if (v == 0) continue;
+    const int w = (v - 1) / 3, t = (v - 1) % 3 + 1;
+    if (t == PATH) paths[w]++;
+    if (t == POSITION && heads[w]++ == 0) hpos[w] = k;
+    if (t == TARGET && targets[w]++ == 0) tpos[w] = k;
+  }
+  int zero_len[ORC_MAX_N];
   for (int w = 0; w < N; ++w) {
-    if (heads[w] == 0 && targets[w] == 1) {
-      flags |= 16; /* zero-length wire: a lone TARGET (PRW quirk) */
-      continue;
-    }
-    if (heads[w] != 1 || targets[w] != 1) flags |= 2;
+    zero_len[w] = (heads[w] == 0 && targets[w] == 1 && paths[w] == 0);
+    if (zero_len[w]) flags |= 16;
+    if (heads[w] < 1 || targets[w] < 1) flags |= zero_len[w] ? 2 : (2 | 128);
+    if (heads[w] > 1 || targets[w] > 1) flags |= 32;
   }
   for (int k = 0; k < cells; ++k) {
-    int32_t v = board[k];
-    if (v == 0) continue;
-    int w = (v - 1) / 3, t = (v - 1) % 3 + 1;
-    if (heads[w] == 0) continue; /* zero-length wire */
-    int r = k / G, c = k % G, nb = 0;
-    nb += (r > 0 && board[k - G] > 0 && (board[k - G] - 1) / 3 == w);
-    nb += (r < G - 1 && board[k + G] > 0 && (board[k + G] - 1) / 3 == w);
-    nb += (c > 0 && board[k - 1] > 0 && (board[k - 1] - 1) / 3 == w);
-    nb += (c < G - 1 && board[k + 1] > 0 && (board[k + 1] - 1) / 3 == w);
-    if (t == PATH ? nb != 2 : nb != 1) flags |= 4;
+    const int32_t v = board[k];
+    if (v <= 0) continue;
+    const int t = (v - 1) % 3 + 1, nb = val_wire_neighbours(G, board, k);
+    if (t == PATH ? nb != 2 : nb != 1) flags |= zero_len[(v - 1) / 3] ? 4 : (4 | 128);
   }
-  /* connectivity head -> target through own cells */
-  int32_t *stack = (int32_t *)malloc(sizeof(int32_t) * (size_t)cells);
+  int32_t *queue = (int32_t *)malloc(sizeof(int32_t) * (size_t)cells);
   uint8_t *seen = (uint8_t *)malloc((size_t)cells);
   for (int w = 0; w < N; ++w) {
-    if (heads[w] != 1 || targets[w] != 1) continue;
-    memset(seen, 0, (size_t)cells);
-    int sp = 0, found = 0;
-    stack[sp++] = hpos[w];
-    seen[hpos[w]] = 1;
-    while (sp) {
-      int k = stack[--sp];
-      if (k == tpos[w]) {
-        found = 1;
-        break;
-      }
-      int r = k / G, c = k % G;
-      const int nbk[4] = {r > 0 ? k - G : -1, r < G - 1 ? k + G : -1, c > 0 ? k - 1 : -1, c < G - 1 ? k + 1 : -1};
-      for (int j = 0; j < 4; ++j) {
-        int p = nbk[j];
-        if (p < 0 || seen[p]) continue;
-        if (board[p] > 0 && (board[p] - 1) / 3 == w) {
-          seen[p] = 1;
-          stack[sp++] = p;
-        }
-      }
-    }
-    if (!found) flags |= 8;
+    if (heads[w] < 1 || targets[w] < 1) continue;
+    if (val_reachable(G, board, w, hpos[w], tpos[w], 0, queue, seen)) continue; /* then a path through own + EMPTY cells exists too */
+    flags |= 8;
+    if (!val_reachable(G, board, w, hpos[w], tpos[w], 1, queue, seen)) flags |= 64;
   }
-  free(stack);
+  free(queue);
   free(seen);
   return flags;
 }

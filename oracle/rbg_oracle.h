@@ -126,10 +126,13 @@ void orc_connector_step(int G, int N, int32_t *grid, int32_t *step_count,
                         int32_t *num_connections, float *ratio_connections,
                         int32_t *total_path_length);
 
-/* ---- validity (numpy_implementation/utils/post_processor_utils_numpy.py:34-155,
- *      board_processor.py:111-162) -------------------------------------- */
-/* returns bitmask: 0 = valid. bit0 bad encoding, bit1 head/target count,
- * bit2 neighbour-count rule, bit3 not connected, bit4 zero-length wire */
+/* ---- validity: numpy_implementation/utils/post_processor_utils_numpy.py:34-155 (UP),
+ *      numpy_implementation/utils/board_processor.py:111-162,391-487 (BP); pinned by
+ *      tests/golden/validity_reference.npz (the reference's own verdicts) ---- */
+/* returns a bitmask, 0 = valid.  1 EncodingOutOfRangeError (nothing else evaluated), 2 MissingHeadTailError,
+ * 4 InvalidWireStructureError (verify_wire_validity False), 8 head / target not connected through own cells,
+ * 16 zero-length wire (lone TARGET), 32 duplicated head / target, 64 PathNotFoundError (no path through
+ * own + EMPTY cells), 128 rule 2 or 4 broken by something other than a zero-length wire */
 int orc_validate_board(int G, int N, const int32_t *board);
 
 /* ---- batched (OpenMP over boards/envs) ---------------------------------- */

@@ -91,12 +91,50 @@ int launch_dataset_state(const uint32_t *keys, int64_t B, int G, int N, const in
   return check_launch("dataset_state_kernel");
 }
 
-// Board validity, one warp per board (rules: reference
-// numpy_implementation/utils/post_processor_utils_numpy.py:34-155 and the
-// head->target connectivity of board_processor.py:111-162).
-// flags: bit0 encoding range, bit1 head/target count, bit2 neighbour-count
-// rule, bit3 head and target not connected, bit4 zero-length wire.
+// Board validity, one warp per board.  The rules are the reference's NumPy functions
+// (numpy_implementation/utils/post_processor_utils_numpy.py:34-155 = UP,
+// numpy_implementation/utils/board_processor.py:111-162,391-487 = BP); flag bits as in
+// include/rbg_b200.h rbg_validate.  tests/golden/validity_reference.npz holds the reference's own
+// verdicts on 2 400 boards.
 constexpr int VAL_WARPS = 4;
+
+struct ValSmem {
+  uint8_t *grid, *reached;
+  int *heads, *targets, *paths, *hpos, *tpos;
+};
+
+// flood `reached` from the cells already marked, through cells whose wire id matches their own
+// (strict = wire cells only, every wire at once) or, for one wire `w`, through its cells and EMPTY
+__device__ __forceinline__ void val_flood(const ValSmem &s, int G, int cells, int lane, int w, int stop_at) {
+  for (int it = 0; it < cells; ++it) {
+    bool changed = false;
+    for (int i = lane; i < cells; i += 32) {
+      const int v = s.grid[i];
+      if (s.reached[i]) continue;
+      int cw;  // the wire whose flood may enter this cell
+      if (w < 0) {
+        if (v == 0) continue;
+        cw = (v - 1) / 3;
+      } else {
+        if (v != 0 && (v - 1) / 3 != w) continue;
+        cw = w;
+      }
+      const int r = i / G, c = i - r * G;
+      auto from = [&](int k) {
+        if (!s.reached[k]) return false;
+        const int u = s.grid[k];
+        return w < 0 ? (u > 0 && (u - 1) / 3 == cw) : true;  // (with w >= 0 only passable cells are ever marked)
+      };
+      if ((r > 0 && from(i - G)) || (r < G - 1 && from(i + G)) || (c > 0 && from(i - 1)) || (c < G - 1 && from(i + 1))) {
+        s.reached[i] = 1;
+        changed = true;
+      }
+    }
+    __syncwarp();
+    if (!__any_sync(FULL, changed)) break;
+    if (stop_at >= 0 && s.reached[stop_at]) break;
+  }
+}
 
 __global__ void __launch_bounds__(VAL_WARPS * 32) validate_kernel(const int32_t *__restrict__ boards, long long B,
                                                                   int G, int N, int32_t *__restrict__ flags) {
@@ -104,71 +142,91 @@ __global__ void __launch_bounds__(VAL_WARPS * 32) validate_kernel(const int32_t 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cells = G * G;
   const int cp = (cells + 15) & ~15;
-  uint8_t *grid = smem_raw + (size_t)warp * (2 * cp + 4 * 4 * RBG_MAX_N);
-  uint8_t *reached = grid + cp;
-  int *heads = reinterpret_cast<int *>(reached + cp);
-  int *targets = heads + RBG_MAX_N, *hpos = targets + RBG_MAX_N, *tpos = hpos + RBG_MAX_N;
+  ValSmem s;
+  s.grid = smem_raw + (size_t)warp * (2 * cp + 5 * 4 * RBG_MAX_N);
+  s.reached = s.grid + cp;
+  s.heads = reinterpret_cast<int *>(s.reached + cp);
+  s.targets = s.heads + RBG_MAX_N;
+  s.paths = s.targets + RBG_MAX_N;
+  s.hpos = s.paths + RBG_MAX_N;
+  s.tpos = s.hpos + RBG_MAX_N;
   for (long long b = (long long)blockIdx.x * VAL_WARPS + warp; b < B; b += (long long)gridDim.x * VAL_WARPS) {
     const int32_t *src = boards + b * cells;
     int fl = 0;
-    if (lane < N) heads[lane] = targets[lane] = 0;
+    if (lane < N) {
+      s.heads[lane] = s.targets[lane] = s.paths[lane] = 0;
+      s.hpos[lane] = s.tpos[lane] = cells;
+    }
     __syncwarp();
+    // verify_encodings_range (BP:406-416); is_valid_board raises there, so nothing else is evaluated
     for (int i = lane; i < cells; i += 32) {
       const int v = __ldg(src + i);
       if (v < 0 || v > 3 * N) fl |= 1;
-      grid[i] = (uint8_t)v;
-      reached[i] = 0;
+      s.grid[i] = (uint8_t)v;
+      s.reached[i] = 0;
     }
     fl = __reduce_or_sync(FULL, fl);
-    if (fl) {  // the oracle stops at the first rule, so do we
+    if (fl) {
       if (lane == 0) flags[b] = fl;
       __syncwarp();
       continue;
     }
     __syncwarp();
+    // per wire: code counts, FIRST head / target in row-major order (np.argwhere(...)[0], BP:79-82)
     for (int i = lane; i < cells; i += 32) {
-      const int v = grid[i];
+      const int v = s.grid[i];
       if (v == 0) continue;
       const int w = (v - 1) / 3, t = (v - 1) % 3 + 1;
+      if (t == PATH) atomicAdd(&s.paths[w], 1);
       if (t == POSITION) {
-        atomicAdd(&heads[w], 1);
-        hpos[w] = i;
+        atomicAdd(&s.heads[w], 1);
+        atomicMin(&s.hpos[w], i);
       }
       if (t == TARGET) {
-        atomicAdd(&targets[w], 1);
-        tpos[w] = i;
+        atomicAdd(&s.targets[w], 1);
+        atomicMin(&s.tpos[w], i);
       }
     }
     __syncwarp();
-    bool eligible = false;
+    // verify_number_heads_tails (BP:419-431): absence only (its counts run over unique values)
+    bool eligible = false, zl = false;
     if (lane < N) {
-      if (heads[lane] == 0 && targets[lane] == 1) fl |= 16;
-      else if (heads[lane] != 1 || targets[lane] != 1) fl |= 2;
-      else eligible = true;
+      const int nh = s.heads[lane], nt = s.targets[lane];
+      zl = nh == 0 && nt == 1 && s.paths[lane] == 0;  // zero-length wire: a lone TARGET
+      if (zl) fl |= 16;
+      if (nh < 1 || nt < 1) fl |= zl ? 2 : (2 | 128);
+      if (nh > 1 || nt > 1) fl |= 32;
+      eligible = nh >= 1 && nt >= 1;
     }
-    auto same = [&](int i, int w) { const int v = grid[i]; return v > 0 && (v - 1) / 3 == w; };
+    const uint32_t zmask = __ballot_sync(FULL, zl);
+    // verify_wire_validity (UP:88-121) with num_wire_neighbors (UP:124-155)
+    auto same = [&](int i, int w) { const int v = s.grid[i]; return v > 0 && (v - 1) / 3 == w; };
+    bool struct_bad = false;  // ... at a cell that does not belong to a zero-length wire
     for (int i = lane; i < cells; i += 32) {
-      const int v = grid[i];
+      const int v = s.grid[i];
       if (v == 0) continue;
       const int w = (v - 1) / 3, t = (v - 1) % 3 + 1;
-      if (heads[w] == 0) continue;
       const int r = i / G, c = i - r * G;
       int nb = 0;
       nb += (r > 0 && same(i - G, w));
       nb += (r < G - 1 && same(i + G, w));
       nb += (c > 0 && same(i - 1, w));
       nb += (c < G - 1 && same(i + 1, w));
-      if (t == PATH ? nb != 2 : nb != 1) fl |= 4;
+      if (t == PATH ? nb != 2 : nb != 1) {
+        const bool excused = (zmask >> w) & 1u;
+        fl |= excused ? 4 : (4 | 128);
+        struct_bad |= !excused;
+      }
     }
-    // connectivity head -> target through own-wire cells.  When the neighbour-count rule holds
-    // (warp-uniform test) every wire cell has at most two same-wire neighbours, so a wire is a simple
-    // chain and lane w can just walk it from its head; otherwise flood from every head.
-    const bool chains = __reduce_or_sync(FULL, fl & 4) == 0;
-    if (chains) {
+    // first head -> first target through the wire's own cells.  When the neighbour rule holds for every
+    // cell of the wires that have a head (warp-uniform test), such a wire is a set of simple chains and
+    // lane w just walks the one that starts at its head; otherwise flood from every first head at once.
+    bool connected = false;
+    if (!__any_sync(FULL, struct_bad)) {
       if (eligible) {
-        int cur = hpos[lane], prev = -1;
-        reached[cur] = 1;
-        for (int step = 0; step < cells && cur != tpos[lane]; ++step) {
+        int cur = s.hpos[lane], prev = -1;
+        const int goal = s.tpos[lane];
+        for (int step = 0; step < cells && cur != goal; ++step) {
           const int r = cur / G, c = cur - r * G;
           int nxt = -1;
           if (r > 0 && cur - G != prev && same(cur - G, lane)) nxt = cur - G;
@@ -178,32 +236,31 @@ __global__ void __launch_bounds__(VAL_WARPS * 32) validate_kernel(const int32_t 
           if (nxt < 0) break;
           prev = cur;
           cur = nxt;
-          reached[cur] = 1;
         }
+        connected = cur == goal;
       }
-      __syncwarp();
     } else {
-      if (eligible) reached[hpos[lane]] = 1;
+      if (eligible) s.reached[s.hpos[lane]] = 1;
       __syncwarp();
-      for (int it = 0; it < cells; ++it) {
-        bool changed = false;
-        for (int i = lane; i < cells; i += 32) {
-          const int v = grid[i];
-          if (v == 0 || reached[i]) continue;
-          const int w = (v - 1) / 3;
-          const int r = i / G, c = i - r * G;
-          const bool hit = (r > 0 && reached[i - G] && same(i - G, w)) || (r < G - 1 && reached[i + G] && same(i + G, w)) ||
-                           (c > 0 && reached[i - 1] && same(i - 1, w)) || (c < G - 1 && reached[i + 1] && same(i + 1, w));
-          if (hit) {
-            reached[i] = 1;
-            changed = true;
-          }
-        }
-        __syncwarp();
-        if (!__any_sync(FULL, changed)) break;
-      }
+      val_flood(s, G, cells, lane, -1, -1);
+      if (eligible) connected = s.reached[s.tpos[lane]] != 0;
     }
-    if (eligible && !reached[tpos[lane]]) fl |= 8;
+    if (eligible && !connected) fl |= 8;
+    // get_path_from_head_and_target (BP:111-162) for the wires that are not connected through their own
+    // cells: the same search through own cells AND EMPTY ones; PathNotFoundError when it fails
+    uint32_t todo = __ballot_sync(FULL, eligible && !connected);
+    while (todo) {
+      const int w = __ffs(todo) - 1;
+      todo &= todo - 1;
+      for (int i = lane; i < cells; i += 32) s.reached[i] = 0;
+      __syncwarp();
+      const int goal = s.tpos[w];
+      if (lane == 0) s.reached[s.hpos[w]] = 1;
+      __syncwarp();
+      val_flood(s, G, cells, lane, w, goal);
+      if (!s.reached[goal]) fl |= 64;
+      __syncwarp();
+    }
     fl = __reduce_or_sync(FULL, fl);
     if (lane == 0) flags[b] = fl;
     __syncwarp();
@@ -213,7 +270,7 @@ __global__ void __launch_bounds__(VAL_WARPS * 32) validate_kernel(const int32_t 
 int launch_validate(const int32_t *boards, int64_t B, int G, int N, int32_t *flags, cudaStream_t stream) {
   if (B <= 0) return RBG_OK;
   const int cells = G * G, cp = (cells + 15) & ~15;
-  const size_t smem = (size_t)VAL_WARPS * (2 * cp + 4 * 4 * RBG_MAX_N);
+  const size_t smem = (size_t)VAL_WARPS * (2 * cp + 5 * 4 * RBG_MAX_N);
   int64_t ctas = (B + VAL_WARPS - 1) / VAL_WARPS;
   if (ctas > 148 * 64) ctas = 148 * 64;
   {

@@ -198,7 +198,8 @@ def test_prw_full_size_invariants(rbg, G, N, B):
     keys = rbg.split(rbg.PRNGKey(0), 1048576 if G == 20 else B, 0, B)
     heads, targets, solved = rbg.ParallelRandomWalkBoard(G, G, N).generate_board(keys)
     flags = rbg.engine.validate(solved, N)
-    assert int((flags & ~16).abs().max()) == 0
+    # sound: own-cell connectivity, no duplicates, nothing but zero-length wires (lone TARGETs) breaks rules 2 / 4
+    assert int((flags & (1 | 8 | 32 | 64 | 128)).abs().max()) == 0
     # heads / targets agree with the codes on the board
     import torch
 
@@ -644,6 +645,17 @@ def test_multi_to_single_wrapper(rbg, orc):
 
 
 # -------------------------------------------------------------- board validity
+def test_validate_matches_reference_verdicts(rbg):
+    """rbg_validate against what the reference's own NumPy validity code says about 2 400 generated and corrupted
+    boards (tests/golden/validity_reference.npz, made by tests/tools/make_validity_fixtures.py)."""
+    import torch
+    from test_validity_reference import check_flags_against_reference, load_validity_fixture
+
+    fx = load_validity_fixture()
+    n = check_flags_against_reference(fx, lambda boards, N: _np(rbg.engine.validate(torch.from_numpy(boards).cuda(), N)))
+    assert n == len(fx["outcome"]) >= 2000
+
+
 def test_validate_matches_oracle_on_corrupted_boards(rbg, orc):
     import torch
 
@@ -657,7 +669,15 @@ def test_validate_matches_oracle_on_corrupted_boards(rbg, orc):
     ref = orc.validate_batch(boards, N)
     got = _np(rbg.engine.validate(torch.from_numpy(boards).cuda(), N))
     assert np.array_equal(got, ref)
-    assert (ref != 0).sum() > B // 8 and (ref == 0).sum() >= B // 2
+    assert (ref != 0).sum() > B // 8 and (ref == 0).sum() >= B // 2 - 64
+    for (G, N, B) in ((7, 12, 512), (32, 16, 256), (5, 3, 512)):  # dense boards (zero-length wires), big boards, heavier damage
+        boards = orc.prw_generate_batch(orc.split(orc.PRNGKey(5), B), G, N)[2]
+        for b in range(0, B, 2):
+            for _ in range(rng.integers(1, 8)):
+                boards[b, rng.integers(G), rng.integers(G)] = rng.integers(0, 3 * N + 1)
+        ref = orc.validate_batch(boards, N)
+        got = _np(rbg.engine.validate(torch.from_numpy(boards).cuda(), N))
+        assert np.array_equal(got, ref), (G, N)
 
 
 # --------------------------------------------------------------- host variants
