@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define RBG_VERSION 100
+#define RBG_VERSION 200
 
 #define RBG_OK 0
 #define RBG_EINVAL (-1)   /* bad size / null pointer / unsupported config */
@@ -64,6 +64,8 @@ extern "C" {
 #define RBG_GEN_PRW 0     /* ParallelRandomWalkGenerator  PRWG:46-77 */
 #define RBG_GEN_UNIFORM 1 /* UniformRandomGenerator       UG:70-109  */
 #define RBG_GEN_SEEDEXT 2 /* SeedExtensionGenerator       RSG:28-57  */
+#define RBG_GEN_DATASET 3 /* BoardDatasetGeneratorJAX     rl_training/offline_generation/dataset_generator_jax.py:112-141
+                             (needs rbg_env_params.dataset_* / the *_dataset entry points) */
 
 /* jumanji Connector `State` pytree (JUM types.py; field order as printed in
  * package_evaluation/profiling_generators.ipynb cell 4), struct-of-arrays with
@@ -98,6 +100,11 @@ typedef struct rbg_env_params {
   float connected_reward; /* 0.1  */
   int32_t autoreset_kind; /* <0: plain Connector.step; else VmapAutoResetWrapper
                              (ST:166) resetting with that RBG_GEN_* generator */
+  /* RBG_GEN_DATASET only (ST:119-133,158: Connector(generator=BoardDatasetGeneratorJAX(...))):
+   * the K pre-generated boards' pins as generate_n_boards stores them, DEVICE int32[K,2,N] */
+  const int32_t *dataset_heads;
+  const int32_t *dataset_targets;
+  int64_t dataset_K;
 } rbg_env_params;
 
 int rbg_version(void);
@@ -130,6 +137,17 @@ int rbg_generator_state(int kind, const uint32_t *keys, int64_t B, int G, int N,
 int rbg_dataset_state(const uint32_t *keys, int64_t B, int G, int N,
                       const int32_t *heads, const int32_t *targets, int64_t K,
                       const rbg_state *out, void *stream);
+
+/* Connector(generator=BoardDatasetGeneratorJAX(...)).reset(key)  (ST:119-133,158,400) =
+ * rbg_dataset_state + rbg_connector_observe */
+int rbg_connector_reset_dataset(const uint32_t *keys, int64_t B, int G, int N,
+                                const int32_t *heads, const int32_t *targets, int64_t K,
+                                const rbg_state *state, const rbg_timestep *ts, void *stream);
+
+/* jax.vmap(lambda k: jax.random.split(k, num))(keys): keys[B,2] -> out[B,num,2].  The per-env key
+ * derivations around the env (`key, _ = split(state.key)` of VmapAutoResetWrapper._auto_reset;
+ * load_and_test_agents.ipynb cell 10) for callers that reset with their own Generator. */
+int rbg_split_each(const uint32_t *keys, int64_t B, int num, uint32_t *out, void *stream);
 
 /* SeedExtensionBoard(G,G,N).return_solved_board(key, randomness, two_sided,
  * extension_iterations, extension_steps)   SE:149-227.

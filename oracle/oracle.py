@@ -19,8 +19,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "librbg_oracle.so")
 
-GEN_PRW, GEN_UNIFORM, GEN_SEEDEXT = 0, 1, 2
-GEN_KINDS = {"parallel_random_walk": GEN_PRW, "uniform": GEN_UNIFORM, "seed_extension": GEN_SEEDEXT}
+GEN_PRW, GEN_UNIFORM, GEN_SEEDEXT, GEN_DATASET = 0, 1, 2, 3
+GEN_KINDS = {"parallel_random_walk": GEN_PRW, "uniform": GEN_UNIFORM, "seed_extension": GEN_SEEDEXT, "dataset": GEN_DATASET}
 
 u32p = C.POINTER(C.c_uint32)
 i32p = C.POINTER(C.c_int32)
@@ -310,9 +310,10 @@ def connector_reset_batch(kind, keys, G: int, N: int, nthreads: int = 0):
     return st, connector_observe_batch(st, nthreads)
 
 
-def connector_step_batch(state: Dict[str, np.ndarray], action, time_limit: int = 50, timestep_reward: float = -0.03, connected_reward: float = 0.1, autoreset_kind=-1, nthreads: int = 0, inplace: bool = False, out: Optional[Dict[str, np.ndarray]] = None):
+def connector_step_batch(state: Dict[str, np.ndarray], action, time_limit: int = 50, timestep_reward: float = -0.03, connected_reward: float = 0.1, autoreset_kind=-1, nthreads: int = 0, inplace: bool = False, out: Optional[Dict[str, np.ndarray]] = None, dataset=None):
     """Connector.step (autoreset_kind < 0) or VmapAutoResetWrapper(Connector).step.
-    `out`: a timestep dict from a previous call to write into (no fresh allocation / page faults)."""
+    `out`: a timestep dict from a previous call to write into (no fresh allocation / page faults).
+    `dataset` = (heads[K,2,N], targets[K,2,N]) with autoreset_kind "dataset" (BoardDatasetGeneratorJAX)."""
     if isinstance(autoreset_kind, str):
         autoreset_kind = GEN_KINDS[autoreset_kind]
     if not inplace:
@@ -321,9 +322,14 @@ def connector_step_batch(state: Dict[str, np.ndarray], action, time_limit: int =
     N = state["target"].shape[1]
     action = _i32(action).reshape(B, N)
     ts = _alloc_timestep(B, G, N) if out is None else out
-    lib().orc_connector_step_batch(
+    if autoreset_kind == GEN_DATASET:
+        dh, dt = _i32(dataset[0]), _i32(dataset[1])
+        ds_args = (_p(dh, i32p), _p(dt, i32p), C.c_int64(dh.shape[0]))
+    else:
+        ds_args = (None, None, C.c_int64(0))
+    lib().orc_connector_step_batch_ds(
         C.c_int64(B), C.c_int(G), C.c_int(N), _p(state["grid"], i32p), _p(state["step_count"], i32p), _p(state["start"], i32p), _p(state["target"], i32p), _p(state["position"], i32p), _p(state["key"], u32p), _p(action, i32p),
-        C.c_int(time_limit), C.c_float(timestep_reward), C.c_float(connected_reward), C.c_int(autoreset_kind),
+        C.c_int(time_limit), C.c_float(timestep_reward), C.c_float(connected_reward), C.c_int(autoreset_kind), *ds_args,
         _p(ts["obs"], i32p), _p(ts["action_mask"], u8p), _p(ts["reward"], f32p), _p(ts["discount"], f32p), _p(ts["step_type"], i8p), _p(ts["num_connections"], i32p), _p(ts["ratio_connections"], f32p), _p(ts["total_path_length"], i32p), _p(ts["obs_step_count"], i32p), C.c_int(nthreads))
     return state, ts
 

@@ -1131,18 +1131,21 @@ void orc_connector_observe_batch(int64_t B, int G, int N, const int32_t *grid,
   }
 }
 
-void orc_connector_step_batch(int64_t B, int G, int N, int32_t *grid,
-                              int32_t *step_count, int32_t *start,
-                              int32_t *target, int32_t *position,
-                              uint32_t *key, const int32_t *action,
-                              int time_limit, float timestep_reward,
-                              float connected_reward, int autoreset_kind,
-                              int32_t *obs, uint8_t *mask, float *reward,
-                              float *discount, int8_t *step_type,
-                              int32_t *num_connections,
-                              float *ratio_connections,
-                              int32_t *total_path_length,
-                              int32_t *obs_step_count, int nthreads) {
+/* autoreset_kind 3 = BoardDatasetGeneratorJAX over ds_heads / ds_targets [ds_K,2,N]
+ * (rl_training/setup_train.py:119-133,158: Connector(generator=BoardDatasetGeneratorJAX(...))) */
+void orc_connector_step_batch_ds(int64_t B, int G, int N, int32_t *grid,
+                                 int32_t *step_count, int32_t *start,
+                                 int32_t *target, int32_t *position,
+                                 uint32_t *key, const int32_t *action,
+                                 int time_limit, float timestep_reward,
+                                 float connected_reward, int autoreset_kind,
+                                 const int32_t *ds_heads, const int32_t *ds_targets, int64_t ds_K,
+                                 int32_t *obs, uint8_t *mask, float *reward,
+                                 float *discount, int8_t *step_type,
+                                 int32_t *num_connections,
+                                 float *ratio_connections,
+                                 int32_t *total_path_length,
+                                 int32_t *obs_step_count, int nthreads) {
   int nt = pick_threads(nthreads);
   (void)nt;
 #pragma omp parallel for num_threads(nt) schedule(dynamic, 64)
@@ -1160,13 +1163,35 @@ void orc_connector_step_batch(int64_t B, int G, int N, int32_t *grid,
       uint32_t ks[4];
       int32_t ids[ORC_MAX_N];
       orc_split(&key[2 * b], 2, ks);
-      orc_state(autoreset_kind, &ks[0], G, N, g, &step_count[b], ids, &start[b * 2 * N],
-                &target[b * 2 * N], &position[b * 2 * N], &key[2 * b]);
+      if (autoreset_kind == 3)
+        orc_dataset_state(&ks[0], G, N, ds_heads, ds_targets, ds_K, g, &step_count[b], ids, &start[b * 2 * N],
+                          &target[b * 2 * N], &position[b * 2 * N], &key[2 * b]);
+      else
+        orc_state(autoreset_kind, &ks[0], G, N, g, &step_count[b], ids, &start[b * 2 * N],
+                  &target[b * 2 * N], &position[b * 2 * N], &key[2 * b]);
       orc_connector_action_mask(G, N, g, &target[b * 2 * N], &position[b * 2 * N], &mask[b * 5 * N]);
       orc_connector_obs(G, N, g, ob);
     }
     if (obs_step_count) obs_step_count[b] = step_count[b];
   }
+}
+
+void orc_connector_step_batch(int64_t B, int G, int N, int32_t *grid,
+                              int32_t *step_count, int32_t *start,
+                              int32_t *target, int32_t *position,
+                              uint32_t *key, const int32_t *action,
+                              int time_limit, float timestep_reward,
+                              float connected_reward, int autoreset_kind,
+                              int32_t *obs, uint8_t *mask, float *reward,
+                              float *discount, int8_t *step_type,
+                              int32_t *num_connections,
+                              float *ratio_connections,
+                              int32_t *total_path_length,
+                              int32_t *obs_step_count, int nthreads) {
+  orc_connector_step_batch_ds(B, G, N, grid, step_count, start, target, position, key, action, time_limit,
+                              timestep_reward, connected_reward, autoreset_kind, NULL, NULL, 0, obs, mask, reward,
+                              discount, step_type, num_connections, ratio_connections, total_path_length,
+                              obs_step_count, nthreads);
 }
 
 void orc_validate_batch(int64_t B, int G, int N, const int32_t *boards,

@@ -169,6 +169,19 @@ void orc_connector_step_batch(int64_t B, int G, int N, int32_t *grid,
                               float *ratio_connections,
                               int32_t *total_path_length,
                               int32_t *obs_step_count, int nthreads);
+void orc_connector_step_batch_ds(int64_t B, int G, int N, int32_t *grid,
+                                 int32_t *step_count, int32_t *start,
+                                 int32_t *target, int32_t *position,
+                                 uint32_t *key, const int32_t *action,
+                                 int time_limit, float timestep_reward,
+                                 float connected_reward, int autoreset_kind /* 3 = dataset */,
+                                 const int32_t *ds_heads, const int32_t *ds_targets, int64_t ds_K,
+                                 int32_t *obs, uint8_t *mask, float *reward,
+                                 float *discount, int8_t *step_type,
+                                 int32_t *num_connections,
+                                 float *ratio_connections,
+                                 int32_t *total_path_length,
+                                 int32_t *obs_step_count, int nthreads);
 void orc_validate_batch(int64_t B, int G, int N, const int32_t *boards,
                         int32_t *flags, int nthreads);
 /* the bench's random policy (OUR convention, not a parity surface):

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("RBG_B200_LIB") or os.path.join(_HERE, "lib", "librbg_b200.so")  # override: A/B builds of the same CUDA library
 
-GEN_PRW, GEN_UNIFORM, GEN_SEEDEXT = 0, 1, 2
+GEN_PRW, GEN_UNIFORM, GEN_SEEDEXT, GEN_DATASET = 0, 1, 2, 3
 MAX_G, MAX_N = 40, 32
 
 
@@ -32,7 +32,8 @@ class rbg_timestep(C.Structure):
 
 
 class rbg_env_params(C.Structure):
-    _fields_ = [("time_limit", C.c_int32), ("timestep_reward", C.c_float), ("connected_reward", C.c_float), ("autoreset_kind", C.c_int32)]
+    _fields_ = [("time_limit", C.c_int32), ("timestep_reward", C.c_float), ("connected_reward", C.c_float), ("autoreset_kind", C.c_int32),
+                ("dataset_heads", C.c_void_p), ("dataset_targets", C.c_void_p), ("dataset_K", C.c_int64)]
 
 
 # every symbol include/rbg_b200.h declares: (restype, argtypes)
@@ -46,6 +47,8 @@ SYMBOLS = {
     "rbg_prw_generate": (_int, [_vp, _i64, _int, _int, _vp, _vp, _vp, _vp, _vp]),
     "rbg_generator_state": (_int, [_int, _vp, _i64, _int, _int, _SP, _vp]),
     "rbg_dataset_state": (_int, [_vp, _i64, _int, _int, _vp, _vp, _i64, _SP, _vp]),
+    "rbg_connector_reset_dataset": (_int, [_vp, _i64, _int, _int, _vp, _vp, _i64, _SP, _TP, _vp]),
+    "rbg_split_each": (_int, [_vp, _i64, _int, _vp, _vp]),
     "rbg_seedext_solved": (_int, [_vp, _i64, _int, _int, _f, _int, _int, _i64, _vp, _vp]),
     "rbg_seedext_starts_ends": (_int, [_vp, _i64, _int, _int, _f, _int, _int, _i64, _vp, _vp, _vp]),
     "rbg_connector_observe": (_int, [_SP, _i64, _int, _int, _TP, _vp]),

@@ -78,22 +78,32 @@ static int check_dims(int64_t B, int G, int N, int need_cells_per_agent) {
 static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static bool aligned8(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }
 
-static int check_state(const rbg_state *s, const char *name) {
+// 16-byte alignment of the bulk arrays is needed by the 128-bit path only, i.e. when G*G % 4 == 0 (otherwise the
+// kernels use scalar accesses, and e.g. the step slices of a stacked rollout are legitimately unaligned)
+static int check_state(const rbg_state *s, const char *name, int G) {
   if (!s) return set_error(RBG_EINVAL, "%s is NULL", name);
   if (!s->grid || !s->step_count || !s->agent_id || !s->start || !s->target || !s->position || !s->key)
     return set_error(RBG_EINVAL, "%s has a NULL field", name);
-  if (!aligned16(s->grid)) return set_error(RBG_EALIGN, "%s.grid not 16-byte aligned", name);
+  if ((G * G) % 4 == 0 && !aligned16(s->grid)) return set_error(RBG_EALIGN, "%s.grid not 16-byte aligned", name);
   if (!aligned8(s->start) || !aligned8(s->target) || !aligned8(s->position))
     return set_error(RBG_EALIGN, "%s.start/target/position not 8-byte aligned", name);
   return RBG_OK;
 }
 
-static int check_timestep(const rbg_timestep *t) {
+static int check_timestep(const rbg_timestep *t, int G) {
   if (!t) return set_error(RBG_EINVAL, "timestep is NULL");
   if (!t->obs_grid || !t->action_mask || !t->obs_step_count || !t->reward || !t->discount || !t->step_type ||
       !t->num_connections || !t->ratio_connections || !t->total_path_length)
     return set_error(RBG_EINVAL, "timestep has a NULL field");
-  if (!aligned16(t->obs_grid)) return set_error(RBG_EALIGN, "timestep.obs_grid not 16-byte aligned");
+  if ((G * G) % 4 == 0 && !aligned16(t->obs_grid)) return set_error(RBG_EALIGN, "timestep.obs_grid not 16-byte aligned");
+  return RBG_OK;
+}
+
+static int check_dataset(const rbg_env_params *params) {
+  if (!params->dataset_heads || !params->dataset_targets)
+    return set_error(RBG_EINVAL, "autoreset_kind RBG_GEN_DATASET needs params->dataset_heads / dataset_targets (device int32[K,2,N])");
+  if (params->dataset_K < 1 || params->dataset_K > 0x7fffffffLL)
+    return set_error(RBG_EINVAL, "autoreset_kind RBG_GEN_DATASET: number of boards dataset_K=%lld", (long long)params->dataset_K);
   return RBG_OK;
 }
 
@@ -240,15 +250,17 @@ static int connector_step_impl(const rbg_state *in, const rbg_state *out, const 
                                const rbg_timestep *ts, void *workspace, cudaStream_t stream) {
   int rc;
   if ((rc = check_dims(B, G, N, 1))) return rc;
-  if ((rc = check_state(in, "state_in"))) return rc;
-  if ((rc = check_state(out, "state_out"))) return rc;
-  if ((rc = check_timestep(ts))) return rc;
+  if ((rc = check_state(in, "state_in", G))) return rc;
+  if ((rc = check_state(out, "state_out", G))) return rc;
+  if ((rc = check_timestep(ts, G))) return rc;
   if (!params) return set_error(RBG_EINVAL, "params is NULL");
   if (!random_policy && !action) return set_error(RBG_EINVAL, "action is NULL");
   const bool autoreset = params->autoreset_kind >= 0;
-  if (autoreset && !workspace) return set_error(RBG_EINVAL, "auto-reset needs a workspace (rbg_step_workspace_bytes)");
-  if (autoreset && params->autoreset_kind > RBG_GEN_SEEDEXT)
+  const bool dataset = params->autoreset_kind == RBG_GEN_DATASET;
+  if (autoreset && !dataset && !workspace) return set_error(RBG_EINVAL, "auto-reset needs a workspace (rbg_step_workspace_bytes)");
+  if (autoreset && params->autoreset_kind > RBG_GEN_DATASET)
     return set_error(RBG_EINVAL, "unknown autoreset generator kind %d", params->autoreset_kind);
+  if (dataset && (rc = check_dataset(params))) return rc;
   if (B == 0) return RBG_OK;
   EnvParams p;
   memset(&p, 0, sizeof(p));
@@ -263,7 +275,7 @@ static int connector_step_impl(const rbg_state *in, const rbg_state *out, const 
   p.N = N;
   p.mode = ENV_MODE_STEP;
   p.env = *params;
-  if (!autoreset) return launch_env(p, stream);
+  if (!autoreset || dataset) return launch_env(p, stream);  // dataset resets are a lookup inside the kernel
 
   uint8_t *ws = reinterpret_cast<uint8_t *>(workspace);
   if (!aligned16(ws)) return set_error(RBG_EALIGN, "workspace not 16-byte aligned");
@@ -609,7 +621,7 @@ int rbg_generator_state(int kind, const uint32_t *keys, int64_t B, int G, int N,
   int rc;
   if ((rc = check_dims(B, G, N, kind == RBG_GEN_UNIFORM ? 2 : 1))) return rc;
   if (!keys) return set_error(RBG_EINVAL, "keys is NULL");
-  if ((rc = check_state(out, "state"))) return rc;
+  if ((rc = check_state(out, "state", G))) return rc;
   if (B == 0) return RBG_OK;
   return generator_state_impl(kind, keys, B, G, N, out, nullptr, 0, nullptr, nullptr, (cudaStream_t)stream);
 }
@@ -621,7 +633,7 @@ int rbg_dataset_state(const uint32_t *keys, int64_t B, int G, int N, const int32
   if (B == 0) return RBG_OK;
   if (!keys || !heads || !targets) return set_error(RBG_EINVAL, "rbg_dataset_state: NULL pointer");
   if (K < 1 || K > 0x7fffffffLL) return set_error(RBG_EINVAL, "rbg_dataset_state: number of boards K=%lld", (long long)K);
-  if ((rc = check_state(out, "state"))) return rc;
+  if ((rc = check_state(out, "state", G))) return rc;
   return launch_dataset_state(keys, B, G, N, heads, targets, K, *out, (cudaStream_t)stream);
 }
 
@@ -672,8 +684,8 @@ int rbg_seedext_starts_ends(const uint32_t *keys, int64_t B, int G, int N, float
 int rbg_connector_observe(const rbg_state *state, int64_t B, int G, int N, const rbg_timestep *ts, void *stream) {
   int rc;
   if ((rc = check_dims(B, G, N, 1))) return rc;
-  if ((rc = check_state(state, "state"))) return rc;
-  if ((rc = check_timestep(ts))) return rc;
+  if ((rc = check_state(state, "state", G))) return rc;
+  if ((rc = check_timestep(ts, G))) return rc;
   if (B == 0) return RBG_OK;
   EnvParams p;
   memset(&p, 0, sizeof(p));
@@ -693,6 +705,21 @@ int rbg_connector_reset(int kind, const uint32_t *keys, int64_t B, int G, int N,
   int rc = rbg_generator_state(kind, keys, B, G, N, state, stream);
   if (rc) return rc;
   return rbg_connector_observe(state, B, G, N, ts, stream);
+}
+
+int rbg_connector_reset_dataset(const uint32_t *keys, int64_t B, int G, int N, const int32_t *heads, const int32_t *targets,
+                                int64_t K, const rbg_state *state, const rbg_timestep *ts, void *stream) {
+  int rc = rbg_dataset_state(keys, B, G, N, heads, targets, K, state, stream);
+  if (rc) return rc;
+  return rbg_connector_observe(state, B, G, N, ts, stream);
+}
+
+int rbg_split_each(const uint32_t *keys, int64_t B, int num, uint32_t *out, void *stream) {
+  if (B < 0 || B > 0x3fffffffLL) return set_error(RBG_EINVAL, "rbg_split_each: B=%lld", (long long)B);
+  if (num < 1 || num > 65536) return set_error(RBG_EINVAL, "rbg_split_each: num=%d outside [1,65536]", num);
+  if (B == 0) return RBG_OK;
+  if (!keys || !out) return set_error(RBG_EINVAL, "rbg_split_each: NULL pointer");
+  return launch_split_each(keys, B, num, out, (cudaStream_t)stream);
 }
 
 int64_t rbg_step_workspace_bytes(int64_t B, int G, int N) {
@@ -876,8 +903,8 @@ int rbg_connector_rollout_random(const rbg_state *state, int32_t *action_out, in
   int rc;
   if (T < 0) return set_error(RBG_EINVAL, "rollout length T=%lld", (long long)T);
   if ((rc = check_dims(B, G, N, 1))) return rc;
-  if ((rc = check_state(state, "state"))) return rc;
-  if ((rc = check_timestep(ts))) return rc;
+  if ((rc = check_state(state, "state", G))) return rc;
+  if ((rc = check_timestep(ts, G))) return rc;
   if (!params) return set_error(RBG_EINVAL, "params is NULL");
   // (when G*G % 4 == 0 every step slice of the stacked arrays keeps the 16-byte alignment the
   // vector path needs; otherwise the kernels use scalar accesses)
@@ -885,6 +912,30 @@ int rbg_connector_rollout_random(const rbg_state *state, int32_t *action_out, in
   const int kind = params->autoreset_kind;
   static int fused = -1;
   if (fused < 0) fused = env_int("RBG_NO_FUSED_ROLLOUT") ? 0 : 1;
+  if (kind > RBG_GEN_DATASET) return set_error(RBG_EINVAL, "unknown autoreset generator kind %d", kind);
+  if (kind < 0) return set_error(RBG_EINVAL, "rollout needs an auto-reset generator kind (params->autoreset_kind >= 0)");
+  if (kind == RBG_GEN_DATASET && (rc = check_dataset(params))) return rc;
+  if (fused && kind == RBG_GEN_DATASET) {
+    // resets are a table lookup inside the kernel: no cache, no refill, no workspace
+    int chunk = env_int("RBG_ROLLOUT_CHUNK");
+    if (chunk <= 0) chunk = 20;
+    EnvParams p;
+    memset(&p, 0, sizeof(p));
+    p.in = *state;
+    p.out = *state;
+    p.B = B;
+    p.G = G;
+    p.N = N;
+    p.mode = ENV_MODE_STEP;
+    p.random_policy = 1;
+    p.env = *params;
+    for (int64_t t0 = 0; t0 < T; t0 += chunk) {
+      const int n = (int)((T - t0) < chunk ? (T - t0) : chunk);
+      p.ts = timestep_at(*ts, t0 * B, G, N);
+      if ((rc = launch_rollout(p, kind, n, action_out ? action_out + t0 * B * N : nullptr, (cudaStream_t)stream))) return rc;
+    }
+    return RBG_OK;
+  }
   if (fused && speculative_enabled() && workspace && (kind == RBG_GEN_PRW || kind == RBG_GEN_UNIFORM)) {
     if (!aligned16(workspace)) return set_error(RBG_EALIGN, "workspace not 16-byte aligned");
     return rollout_fused(state, action_out, T, B, G, N, params, ts, workspace, (cudaStream_t)stream);
@@ -901,7 +952,7 @@ int rbg_connector_rollout_random(const rbg_state *state, int32_t *action_out, in
 int rbg_random_actions(const rbg_state *state, int64_t B, int G, int N, int32_t *action, void *stream) {
   int rc;
   if ((rc = check_dims(B, G, N, 1))) return rc;
-  if ((rc = check_state(state, "state"))) return rc;
+  if ((rc = check_state(state, "state", G))) return rc;
   if (!action) return set_error(RBG_EINVAL, "action is NULL");
   return launch_random_actions(*state, B, G, N, action, (cudaStream_t)stream);
 }
@@ -1082,7 +1133,7 @@ int rbg_connector_step_host_io(const rbg_state *state, const int32_t *action, in
   int rc, dev;
   if ((rc = check_dims(B, G, N, 1))) return rc;
   if (!action || !params || !ts) return set_error(RBG_EINVAL, "rbg_connector_step_host_io: NULL pointer");
-  if ((rc = check_state(state, "state"))) return rc;
+  if ((rc = check_state(state, "state", G))) return rc;
   if (B == 0) return RBG_OK;
   if ((rc = use_device(device, &dev))) return rc;
   cudaError_t e = cudaDeviceSynchronize();  // the State may have been produced on any stream of the caller

@@ -82,7 +82,9 @@ __global__ void __launch_bounds__(EW_WARPS * 32, RBG_ENV_MIN_CTAS) env_warp_kern
   if (e0 >= p.B) return;
   const int kc = (int)((p.B - e0) < (long long)K ? (p.B - e0) : (long long)K);
   const bool is_step = (p.mode == ENV_MODE_STEP);
-  const bool autoreset = is_step && p.env.autoreset_kind >= 0 && p.list != nullptr;
+  // BoardDatasetGeneratorJAX resets are a table lookup (a few threefry blocks + N pins): done right here
+  const bool ds = is_step && p.env.autoreset_kind == RBG_GEN_DATASET;
+  const bool autoreset = is_step && p.env.autoreset_kind >= 0 && (p.list != nullptr || ds);
   const bool inplace_grid = is_step && p.out.grid == p.in.grid;
   uint8_t *wg = smem_raw + p.so[0] + (size_t)warp * p.so[1];
   uint32_t *wg32 = reinterpret_cast<uint32_t *>(wg);
@@ -191,24 +193,44 @@ __global__ void __launch_bounds__(EW_WARPS * 32, RBG_ENV_MIN_CTAS) env_warp_kern
   const int sc = sc0 + (is_step ? 1 : 0);
   const bool terminal = is_step && env_ok && (ndone == N || sc >= p.env.time_limit);
   int tflag = terminal ? 1 : 0;
-  // The cache entry may be published by the refill kernel (side stream) while this kernel runs:
-  // ONE lane per env reads the tag and decides, the others take its verdict (lanes that each read
-  // the tag themselves could disagree on hit / miss if the tag lands between their loads).
+  // The cache entry may be REPLACED by the refill kernel (side stream) while this kernel runs, e.g. when a
+  // State is stepped twice (functional use, inplace=False) or two batches share a workspace.  The entry is
+  // a seqlock whose version is its tag: the writer (prw_kernel, to_cache) invalidates the tag, fences,
+  // writes key and pins, fences, publishes the new tag; a reader takes the entry only if the tag reads as
+  // expected BEFORE and AFTER its own loads of key / pin, and every lane of the env must agree (ballot),
+  // otherwise the env goes down the synchronous reset path like any other miss.
   int hit_i = 0;
-  uint32_t ck0 = 0, ck1 = 0;
-  if (terminal && autoreset && a == 0 && p.cache_tag) {
-    const unsigned long long tag = __ldcg(p.cache_tag + e);
-    if (tag == (((unsigned long long)k1 << 32) | k0)) {
+  uint32_t ck0 = 0, ck1 = 0, cpin = 0;
+  if (terminal && autoreset && !ds && p.cache_tag) {
+    const unsigned long long want = ((unsigned long long)k1 << 32) | k0;
+    if (__ldcg(p.cache_tag + e) == want) {
       __threadfence();
       const uint2 nk = __ldcg(p.cache_key + e);
       ck0 = nk.x;
       ck1 = nk.y;
-      hit_i = 1;
+      if (a < N) cpin = __ldcg(p.cache_pins + e * N + a);
+      __threadfence();
+      hit_i = __ldcg(p.cache_tag + e) == want ? 1 : 0;
     }
   }
-  hit_i = __shfl_sync(FULL, hit_i, j * Np);
-  ck0 = __shfl_sync(FULL, ck0, j * Np);
-  ck1 = __shfl_sync(FULL, ck1, j * Np);
+  {
+    const uint32_t okm = __ballot_sync(FULL, hit_i != 0) & gmask;
+    hit_i = (okm == gmask) ? 1 : 0;
+  }
+  if (terminal && ds) {
+    // VmapAutoResetWrapper._auto_reset: key, _ = split(state.key); then BoardDatasetGeneratorJAX.__call__
+    uint32_t a0, a1, b0, b1;
+    split2(k0, k1, a0, a1, b0, b1);
+    const uint32_t which = dataset_pick(a0, a1, (uint32_t)p.env.dataset_K, ck0, ck1);
+    if (a < N) {
+      const int32_t *h = p.env.dataset_heads + (size_t)which * 2 * N, *t = p.env.dataset_targets + (size_t)which * 2 * N;
+      const int hi = G - 1;
+      const int sr = min(max(__ldg(h + a), 0), hi), sc_ = min(max(__ldg(h + N + a), 0), hi);
+      const int tr = min(max(__ldg(t + a), 0), hi), tc = min(max(__ldg(t + N + a), 0), hi);
+      cpin = ((uint32_t)sr << 24) | ((uint32_t)sc_ << 16) | ((uint32_t)tr << 8) | (uint32_t)tc;
+    }
+    hit_i = 1;
+  }
   if (terminal && autoreset) {
     const bool hit = hit_i != 0;
     uint32_t nk0 = ck0, nk1 = ck1;
@@ -217,7 +239,7 @@ __global__ void __launch_bounds__(EW_WARPS * 32, RBG_ENV_MIN_CTAS) env_warp_kern
       split2(k0, k1, a0, a1, b0, b1);
       split2(a0, a1, nk0, nk1, b0, b1);
     }
-    if (a == 0) {
+    if (a == 0 && !ds) {
       if (!hit) p.list[atomicAdd(p.list_count, 1)] = (int32_t)e;
       if (p.refill_list) {
         const int slot = atomicAdd(p.refill_count, 1);
@@ -238,9 +260,8 @@ __global__ void __launch_bounds__(EW_WARPS * 32, RBG_ENV_MIN_CTAS) env_warp_kern
     // those of the terminal step
     for (int i = a; i < cells; i += Np) g[i] = 0;
     if (a < N) {
-      const uint32_t pin = __ldcg(p.cache_pins + e * N + a);
-      pos = (int)(pin >> 16);
-      tgt = (int)(pin & 0xffffu);
+      pos = (int)(cpin >> 16);
+      tgt = (int)(cpin & 0xffffu);
     }
     __syncwarp(gmask);
     if (a < N) g[(pos >> 8) * G + (pos & 255)] = (uint8_t)(3 * a + POSITION);
@@ -493,7 +514,19 @@ __global__ void __launch_bounds__(EW_WARPS * 32, RBG_ROLLOUT_MIN_CTAS) rollout_w
     bool hit = false;
     uint32_t nk0 = 0, nk1 = 0;
     int npos = pos, ntgt = tgt;
-    if (terminal && p.cache_tag) {
+    if (terminal && rp.kind == RBG_GEN_DATASET) {
+      // VmapAutoResetWrapper._auto_reset: key, _ = split(state.key); then BoardDatasetGeneratorJAX.__call__
+      uint32_t a0, a1, b0, b1;
+      split2(k0, k1, a0, a1, b0, b1);
+      const uint32_t which = dataset_pick(a0, a1, (uint32_t)p.env.dataset_K, nk0, nk1);
+      if (a < N) {
+        const int32_t *h = p.env.dataset_heads + (size_t)which * 2 * N, *tt = p.env.dataset_targets + (size_t)which * 2 * N;
+        const int hi = G - 1;
+        npos = (min(max(__ldg(h + a), 0), hi) << 8) | min(max(__ldg(h + N + a), 0), hi);
+        ntgt = (min(max(__ldg(tt + a), 0), hi) << 8) | min(max(__ldg(tt + N + a), 0), hi);
+      }
+      hit = true;
+    } else if (terminal && p.cache_tag) {
       const unsigned long long tag = __ldcg(p.cache_tag + e);
       const uint2 nk = __ldcg(p.cache_key + e);
       const uint32_t pin = a < N ? __ldcg(p.cache_pins + e * N + a) : 0u;

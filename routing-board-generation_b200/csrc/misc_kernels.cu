@@ -35,6 +35,34 @@ int launch_split_keys(uint32_t k0, uint32_t k1, int64_t B, int64_t offset, int64
   return check_launch("split_keys_kernel");
 }
 
+// jax.vmap(lambda k: jax.random.split(k, num))(keys): out[b, i] = (flat[2i], flat[2i+1]) of
+// threefry_2x32(keys[b], iota(2 * num)); one thread per output word.
+__global__ void __launch_bounds__(256) split_each_kernel(const uint32_t *__restrict__ keys, long long B, int num,
+                                                         uint32_t *__restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * 2 * num) return;
+  const long long b = i / (2 * num);
+  const uint32_t f = (uint32_t)(i - b * 2 * num);
+  uint32_t o0, o1;
+  if (f < (uint32_t)num) {
+    tf_block(keys[2 * b], keys[2 * b + 1], f, f + (uint32_t)num, o0, o1);
+    out[i] = o0;
+  } else {
+    tf_block(keys[2 * b], keys[2 * b + 1], f - (uint32_t)num, f, o0, o1);
+    out[i] = o1;
+  }
+}
+
+int launch_split_each(const uint32_t *keys, int64_t B, int num, uint32_t *out, cudaStream_t stream) {
+  const int64_t n = B * 2 * num;
+  if (n <= 0) return RBG_OK;
+  {
+    LaunchScope scope(RBG_K_SPLIT, stream);
+    split_each_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(keys, B, num, out);
+  }
+  return check_launch("split_each_kernel");
+}
+
 // BoardDatasetGeneratorJAX.__call__ (dataset_generator_jax.py:112-141), one warp per env:
 // key, _ = split(key); which = randint(key, (), 0, K) with jax's two-draw formula
 // (SURVEY A.9); pins-only grid from heads[which] / targets[which] (heads first, then targets).
@@ -47,13 +75,8 @@ __global__ void __launch_bounds__(DS_WARPS * 32) dataset_state_kernel(const uint
   const long long e = (long long)blockIdx.x * DS_WARPS + (threadIdx.x >> 5);
   if (e >= B) return;
   const int cells = G * G;
-  uint32_t k0, k1, b0, b1, h0, h1, l0, l1;
-  split2(keys[2 * e], keys[2 * e + 1], k0, k1, b0, b1);  // State.key = split(key)[0]
-  split2(k0, k1, h0, h1, l0, l1);                        // randint: k1, k2 = split(key)
-  const uint32_t hi = bits_scalar(h0, h1), lo = bits_scalar(l0, l1);
-  uint32_t mult = 65536u % K;
-  mult = (uint32_t)(((unsigned long long)mult * mult) % K);
-  const uint32_t which = ((hi % K) * mult + (lo % K)) % K;  // uint32 wrap-around as in jax
+  uint32_t k0, k1;
+  const uint32_t which = dataset_pick(keys[2 * e], keys[2 * e + 1], K, k0, k1);
   int32_t *grid = st.grid + e * cells;
   for (int i = lane; i < cells; i += 32) grid[i] = 0;
   int sr = 0, sc = 0, tr = 0, tc = 0;

@@ -323,8 +323,12 @@ __global__ void __launch_bounds__(256) prw_kernel(const PrwParams p) {
     const long long e = p.list ? (long long)p.list[base + m] : base + m;
     const uint8_t *g = s.grid + (size_t)m * SBp;
     if (p.to_cache) {
-      // auto-reset cache entry: (start, target) pins + State.key of this episode,
-      // published under the key of the episode it succeeds (tag written last)
+      // auto-reset cache entry: (start, target) pins + State.key of this episode, published under the key
+      // of the episode it succeeds.  Seqlock with the tag as version: invalidate, fence, write, fence,
+      // publish (readers re-check the tag after their loads: connector_kernel.cu env_warp_kernel)
+      if (lane == 0) *reinterpret_cast<volatile unsigned long long *>(p.cache_tag + e) = 0ull;
+      __threadfence();
+      __syncwarp();
       if (lane < N) {
         const uint32_t st_ = s.start[m * Np + lane], fi = s.fin[m * Np + lane];
         p.cache_pins[e * N + lane] = (st_ << 16) | fi;

@@ -106,6 +106,21 @@ __device__ __forceinline__ uint32_t randint_pow2(uint32_t k0, uint32_t k1,
   return bits_scalar(b0, b1) & (span - 1u);
 }
 
+// BoardDatasetGeneratorJAX.__call__ (rl_training/offline_generation/dataset_generator_jax.py:112-141):
+// `key, _ = split(key)` -> State.key (nk0, nk1); `which = randint(key, (), 0, K)` with jax's two-draw
+// formula: k1, k2 = split(key); ((bits(k1) % K) * ((2^16 % K)^2 % K) + bits(k2) % K) % K
+// in uint32 wrap-around arithmetic.
+__device__ __forceinline__ uint32_t dataset_pick(uint32_t k0, uint32_t k1, uint32_t K,
+                                                 uint32_t &nk0, uint32_t &nk1) {
+  uint32_t b0, b1, h0, h1, l0, l1;
+  split2(k0, k1, nk0, nk1, b0, b1);
+  split2(nk0, nk1, h0, h1, l0, l1);
+  const uint32_t hi = bits_scalar(h0, h1), lo = bits_scalar(l0, l1);
+  uint32_t mult = 65536u % K;
+  mult = (uint32_t)(((unsigned long long)mult * mult) % K);
+  return ((hi % K) * mult + (lo % K)) % K;
+}
+
 // exact n / d for n*d < 2^32 (host checks the range), d >= 1
 struct FastDiv {
   uint32_t mul;

@@ -96,6 +96,7 @@ int launch_random_actions(const rbg_state &st, int64_t B, int G, int N,
 // ---- misc kernels (misc_kernels.cu) --------------------------------------
 int launch_split_keys(uint32_t k0, uint32_t k1, int64_t B, int64_t offset,
                       int64_t count, uint32_t *out, cudaStream_t stream);
+int launch_split_each(const uint32_t *keys, int64_t B, int num, uint32_t *out, cudaStream_t stream);
 int launch_dataset_state(const uint32_t *keys, int64_t B, int G, int N, const int32_t *heads, const int32_t *targets, int64_t K,
                          const rbg_state &st, cudaStream_t stream);
 int launch_validate(const int32_t *boards, int64_t B, int G, int N,

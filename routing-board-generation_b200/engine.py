@@ -16,10 +16,10 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import GEN_PRW, GEN_SEEDEXT, GEN_UNIFORM, rbg_env_params, rbg_state, rbg_timestep
+from ._lib import GEN_DATASET, GEN_PRW, GEN_SEEDEXT, GEN_UNIFORM, rbg_env_params, rbg_state, rbg_timestep
 from .types import Agent, Observation, State, TimeStep
 
-GENERATOR_KINDS = {"parallel_random_walk": GEN_PRW, "uniform": GEN_UNIFORM, "seed_extension": GEN_SEEDEXT}
+GENERATOR_KINDS = {"parallel_random_walk": GEN_PRW, "uniform": GEN_UNIFORM, "seed_extension": GEN_SEEDEXT, "dataset": GEN_DATASET}
 
 
 _cuda_checked = False
@@ -101,6 +101,32 @@ def split(key, num: int = 2, offset: int = 0, count: Optional[int] = None) -> to
     karr = (C.c_uint32 * 2)(int(k[0]), int(k[1]))
     _lib.check(_lib.load().rbg_split_keys(karr, num, offset, count, out.data_ptr(), _stream()))
     return out
+
+
+def split_each(keys: torch.Tensor, num: int = 2) -> torch.Tensor:
+    """jax.vmap(lambda k: jax.random.split(k, num))(keys): uint32[B,2] -> uint32[B,num,2]."""
+    keys, _ = as_keys(keys)
+    out = torch.empty((keys.shape[0], num, 2), dtype=torch.uint32, device=_device())
+    _lib.check(_lib.load().rbg_split_each(keys.data_ptr(), keys.shape[0], num, out.data_ptr(), _stream()))
+    return out
+
+
+def _env_params(time_limit, timestep_reward, connected_reward, autoreset_kind, dataset=None):
+    """rbg_env_params; `dataset` = (heads int32[K,2,N], targets int32[K,2,N]) device tensors for kind "dataset".
+    Returns (params, keepalive)."""
+    if isinstance(autoreset_kind, str):
+        autoreset_kind = GENERATOR_KINDS[autoreset_kind]
+    p = rbg_env_params(int(time_limit), float(timestep_reward), float(connected_reward), int(autoreset_kind), None, None, 0)
+    keep = None
+    if autoreset_kind == GEN_DATASET:
+        if dataset is None:
+            raise ValueError("auto-reset with the dataset generator needs dataset=(heads, targets)")
+        heads, targets = (as_tensor(t, torch.int32) for t in dataset)
+        if heads.dim() != 3 or heads.shape[1] != 2 or heads.shape != targets.shape:
+            raise ValueError(f"dataset heads / targets must be int32[K,2,N], got {tuple(heads.shape)} / {tuple(targets.shape)}")
+        p.dataset_heads, p.dataset_targets, p.dataset_K = heads.data_ptr(), targets.data_ptr(), heads.shape[0]
+        keep = (heads, targets)
+    return p, keep
 
 
 # ------------------------------------------------------------------ structs
@@ -228,12 +254,16 @@ def connector_observe(st: State, out: Optional[TimeStep] = None) -> TimeStep:
     return ts
 
 
-def connector_reset(kind, keys: torch.Tensor, G: int, N: int) -> Tuple[State, TimeStep]:
+def connector_reset(kind, keys: torch.Tensor, G: int, N: int, dataset=None) -> Tuple[State, TimeStep]:
     kind = GENERATOR_KINDS[kind] if isinstance(kind, str) else kind
     B = keys.shape[0]
     st, ts = alloc_state(B, G, N), alloc_timestep(B, G, N)
     s, t = _state_struct(st), _timestep_struct(ts)
-    _lib.check(_lib.load().rbg_connector_reset(kind, keys.data_ptr(), B, G, N, C.byref(s), C.byref(t), _stream()))
+    if kind == GEN_DATASET:
+        heads, targets = (as_tensor(x, torch.int32) for x in dataset)
+        _lib.check(_lib.load().rbg_connector_reset_dataset(keys.data_ptr(), B, G, N, heads.data_ptr(), targets.data_ptr(), heads.shape[0], C.byref(s), C.byref(t), _stream()))
+    else:
+        _lib.check(_lib.load().rbg_connector_reset(kind, keys.data_ptr(), B, G, N, C.byref(s), C.byref(t), _stream()))
     return st, ts
 
 
@@ -275,7 +305,7 @@ def _drop_workspace(k) -> None:
             pass
 
 
-def connector_step(st: State, action, time_limit: int = 50, timestep_reward: float = -0.03, connected_reward: float = 0.1, autoreset_kind=-1, inplace: bool = False, random_policy: bool = False, out: Optional[TimeStep] = None, owner=None):
+def connector_step(st: State, action, time_limit: int = 50, timestep_reward: float = -0.03, connected_reward: float = 0.1, autoreset_kind=-1, inplace: bool = False, random_policy: bool = False, out: Optional[TimeStep] = None, owner=None, dataset=None):
     """Connector.step (autoreset_kind < 0) or VmapAutoResetWrapper(Connector).step over a batch.
 
     random_policy=True ignores `action`, samples the uniform-over-legal-actions policy in the
@@ -287,8 +317,8 @@ def connector_step(st: State, action, time_limit: int = 50, timestep_reward: flo
     B, G, N = _dims(st)
     new = st if inplace else alloc_state(B, G, N)
     ts = alloc_timestep(B, G, N) if out is None else out
-    params = rbg_env_params(int(time_limit), float(timestep_reward), float(connected_reward), int(autoreset_kind))
-    ws = _workspace(B, G, N, owner) if autoreset_kind >= 0 else None
+    params, _keep = _env_params(time_limit, timestep_reward, connected_reward, autoreset_kind, dataset)
+    ws = _workspace(B, G, N, owner) if 0 <= autoreset_kind != GEN_DATASET else None
     s_in, s_out, t = _state_struct(st), _state_struct(new), _timestep_struct(ts)
     lib = _lib.load()
     if random_policy:
@@ -300,7 +330,7 @@ def connector_step(st: State, action, time_limit: int = 50, timestep_reward: flo
     return new, ts
 
 
-def connector_rollout_random(st: State, n_steps: int, time_limit: int = 50, timestep_reward: float = -0.03, connected_reward: float = 0.1, autoreset_kind="parallel_random_walk", out: Optional[TimeStep] = None, actions: Optional[torch.Tensor] = None, owner=None):
+def connector_rollout_random(st: State, n_steps: int, time_limit: int = 50, timestep_reward: float = -0.03, connected_reward: float = 0.1, autoreset_kind="parallel_random_walk", out: Optional[TimeStep] = None, actions: Optional[torch.Tensor] = None, owner=None, dataset=None):
     """n_steps auto-reset random-policy steps in ONE library call (the reference's `n_steps` scan).
     `st` is updated in place; returns (st, TimeStep stacked [n_steps, B, ...], actions[n_steps, B, N])."""
     if isinstance(autoreset_kind, str):
@@ -311,10 +341,10 @@ def connector_rollout_random(st: State, n_steps: int, time_limit: int = 50, time
             raise ValueError("rollout updates the State in place: its leaves must be contiguous")
     ts = alloc_timestep(B, G, N, n_steps) if out is None else out
     act = torch.empty((n_steps, B, N), dtype=torch.int32, device=_device()) if actions is None else actions
-    params = rbg_env_params(int(time_limit), float(timestep_reward), float(connected_reward), int(autoreset_kind))
-    ws = _workspace(B, G, N, owner)
+    params, _keep = _env_params(time_limit, timestep_reward, connected_reward, autoreset_kind, dataset)
+    ws = _workspace(B, G, N, owner) if autoreset_kind != GEN_DATASET else None
     s, t = _state_struct(st), _timestep_struct(ts)
-    _lib.check(_lib.load().rbg_connector_rollout_random(C.byref(s), act.data_ptr(), n_steps, B, G, N, C.byref(params), C.byref(t), ws.data_ptr(), _stream()))
+    _lib.check(_lib.load().rbg_connector_rollout_random(C.byref(s), act.data_ptr(), n_steps, B, G, N, C.byref(params), C.byref(t), ws.data_ptr() if ws is not None else None, _stream()))
     return st, ts, act
 
 

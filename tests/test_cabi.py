@@ -40,7 +40,7 @@ def test_header_symbols_are_exported(lib):
 
 
 def test_version_and_error_string(lib):
-    assert lib.rbg_version() == 100
+    assert lib.rbg_version() == 200
     rc = lib.rbg_prw_generate(None, 4, 10, 5, None, None, None, None, None)
     assert rc == -1 and b"NULL" in lib.rbg_last_error()
     rc = lib.rbg_prw_generate(None, 4, 99, 5, None, None, None, None, None)
@@ -55,7 +55,7 @@ def test_struct_layouts_match_header():
     L = pkg._lib
     assert C.sizeof(L.rbg_state) == 7 * C.sizeof(C.c_void_p)
     assert C.sizeof(L.rbg_timestep) == 9 * C.sizeof(C.c_void_p)
-    assert C.sizeof(L.rbg_env_params) == 16
+    assert C.sizeof(L.rbg_env_params) == 40
     assert [f[0] for f in L.rbg_state._fields_] == ["grid", "step_count", "agent_id", "start", "target", "position", "key"]
 
 

@@ -547,44 +547,43 @@ def test_rollout_generation_modes(rbg, no_cache, G, N, B):
 
 
 @pytest.mark.parametrize("G,N,B,T,time_limit", [(10, 5, 65536, 45, 50), (32, 16, 8192, 22, 9)])
-def test_rollout_full_size_two_paths_agree(rbg, G, N, B, T, time_limit):
-    """BASELINE configs[1] and [4] at full size, where the oracle would take minutes: the fused rollout
-    (rollout_warp_kernel, bulk refill, two batch slices on two streams) and the step-by-step path
-    (env_warp_kernel, speculative + synchronous reset kernels) are independent implementations and must
-    produce the same State and the same TimeStep leaves at every step; plus invariants of the stream."""
+def test_rollout_full_size_matches_oracle(rbg, orc, G, N, B, T, time_limit):
+    """BASELINE configs[1] (65 536 envs, 10x10/5) and configs[4] (32x32/16, 8 192 envs) at FULL size against the
+    oracle: every leaf of every TimeStep of the fused rollout (rollout_warp_kernel, bulk refill, two batch slices
+    on two streams) and the final State; then the step-by-step path (env_warp_kernel, speculative + synchronous
+    reset kernels) continues from that State for a few steps, also against the oracle."""
     import torch
 
-    keys = rbg.split(rbg.PRNGKey(0), B)
+    keys, kref = _keys(rbg, orc, 0, B)
     gen = rbg.ParallelRandomWalkGenerator(G, N)
-    env_a = rbg.VmapAutoResetWrapper(rbg.Connector(generator=gen, time_limit=time_limit))
-    env_b = rbg.VmapAutoResetWrapper(rbg.Connector(generator=gen, time_limit=time_limit))
-    sa, _ = env_a.reset(keys)
-    sb, _ = env_b.reset(keys)
-    sa, ts, act = env_a.rollout_random(sa, T)
-    resets = 0
-    for t in range(T):
-        sb, tb, ab = env_b.step_random(sb, inplace=True)
-        assert torch.equal(act[t], ab), f"actions differ at step {t}"
-        for name, x, y in (("obs", ts.observation.grid[t], tb.observation.grid), ("mask", ts.observation.action_mask[t], tb.observation.action_mask),
-                           ("step_count", ts.observation.step_count[t], tb.observation.step_count), ("reward", ts.reward[t], tb.reward),
-                           ("discount", ts.discount[t], tb.discount), ("step_type", ts.step_type[t], tb.step_type),
-                           ("num_connections", ts.extras["num_connections"][t], tb.extras["num_connections"]),
-                           ("ratio_connections", ts.extras["ratio_connections"][t], tb.extras["ratio_connections"]),
-                           ("total_path_length", ts.extras["total_path_length"][t], tb.extras["total_path_length"])):
-            assert torch.equal(x, y), f"{name} differs at step {t}"
-        last = ts.step_type[t] == 2
-        resets += int(last.sum())
-        # a terminal step restarts the episode: step_count 0 and every agent free to NOOP
-        assert int(ts.observation.step_count[t][last].abs().sum()) == 0
-        assert bool((ts.observation.action_mask[t][..., 0] == 1).all())
-        # each agent sees itself as wire 0: exactly one POSITION (2) per view unless it sits on its target
-        heads = (ts.observation.grid[t] == 2).sum(dim=(2, 3))
-        assert int(heads.max()) <= 1
+    env = rbg.VmapAutoResetWrapper(rbg.Connector(generator=gen, time_limit=time_limit))
+    st, ts0 = env.reset(keys)
+    rst, rts = orc.connector_reset_batch("parallel_random_walk", kref, G, N)
+    _assert_state(st, rst, "after reset")
+    _assert_timestep(ts0, rts, "after reset")
+    chunk = 9 if G == 10 else 11  # an odd chunking of T: the TimeStep stack of a chunk must fit beside the oracle's copy
+    resets, t = 0, 0
+    out = {k: v.copy() for k, v in rts.items()}
+    while t < T:
+        n = min(chunk, T - t)
+        st, ts, act = env.rollout_random(st, n)
+        acts = _np(act)
+        for i in range(n):
+            a = orc.random_actions_batch(rst)
+            assert np.array_equal(acts[i], a), f"actions differ at step {t + i}"
+            rst, rts = orc.connector_step_batch(rst, a, time_limit=time_limit, autoreset_kind="parallel_random_walk", inplace=True, out=out)
+            _assert_timestep(ts[i], rts, f"at step {t + i}")
+            resets += int((rts["step_type"] == 2).sum())
+        _assert_state(st, rst, f"after step {t + n}")
+        t += n
     assert resets > B // 2, "the run must exercise the auto-reset"
-    for name in ("grid", "step_count", "key"):
-        assert torch.equal(getattr(sa, name), getattr(sb, name)), name
-    for name in ("id", "start", "target", "position"):
-        assert torch.equal(getattr(sa.agents, name), getattr(sb.agents, name)), name
+    for i in range(3):
+        a = orc.random_actions_batch(rst)
+        st, ts1, got = env.step_random(st, inplace=True)
+        assert np.array_equal(_np(got), a)
+        rst, rts = orc.connector_step_batch(rst, a, time_limit=time_limit, autoreset_kind="parallel_random_walk", inplace=True, out=out)
+        _assert_timestep(ts1, rts, f"step-wise step {i} after the rollout")
+        _assert_state(st, rst, f"step-wise step {i} after the rollout")
 
 
 def test_rollout_long_horizon(rbg, orc):
@@ -642,6 +641,292 @@ def test_multi_to_single_wrapper(rbg, orc):
     st, ts = env.reset(keys)
     assert ts.reward.shape == (64,) and ts.discount.shape == (64,)
     assert float(ts.discount.min()) == 1.0
+
+
+def test_reference_env_composition_values(rbg, orc):
+    """The composition the reference builds (rl_training/setup_train.py:158-166):
+    VmapAutoResetWrapper(MultiToSingleWrapper(Connector(generator))).  reset, step, step_random and
+    rollout_random all return the AGGREGATED reward (sum over agents) and discount (max over agents)."""
+    import torch
+
+    G, N, B, TL = 8, 4, 700, 6
+    keys, kref = _keys(rbg, orc, 15, B)
+    env = rbg.VmapAutoResetWrapper(rbg.MultiToSingleWrapper(rbg.Connector(generator=rbg.ParallelRandomWalkGenerator(G, N), time_limit=TL)))
+    st, ts = env.reset(keys)
+    rst, rts = orc.connector_reset_batch("parallel_random_walk", kref, G, N)
+    assert ts.reward.shape == (B,) and float(ts.reward.abs().max()) == 0.0 and float(ts.discount.min()) == 1.0
+
+    def check(ts, rts, where):
+        assert ts.reward.shape == (B,) and ts.discount.shape == (B,), where
+        np.testing.assert_allclose(_np(ts.reward), rts["reward"].sum(axis=1, dtype=np.float32), rtol=0, atol=2e-7, err_msg=where)  # float32 sum: order of the N addends is free
+        assert np.array_equal(_np(ts.discount), rts["discount"].max(axis=1)), where
+        assert np.array_equal(_np(ts.step_type), rts["step_type"]) and np.array_equal(_np(ts.observation.grid), rts["obs"]), where
+
+    seen_mixed = False
+    for t in range(14):
+        a = orc.random_actions_batch(rst)
+        if t % 2:
+            st, ts = env.step(st, torch.from_numpy(a).cuda())
+        else:
+            st, ts, got = env.step_random(st)
+            assert np.array_equal(_np(got), a)
+        rst, rts = orc.connector_step_batch(rst, a, time_limit=TL, autoreset_kind="parallel_random_walk")
+        check(ts, rts, f"step {t}")
+        d = rts["discount"]
+        seen_mixed |= bool(((d.max(axis=1) == 1) & (d.min(axis=1) == 0)).any())  # max, not min / mean
+    assert seen_mixed
+    st, ts, act = env.rollout_random(st, 9)
+    assert ts.reward.shape == (9, B) and ts.discount.shape == (9, B)
+    for t in range(9):
+        a = orc.random_actions_batch(rst)
+        rst, rts = orc.connector_step_batch(rst, a, time_limit=TL, autoreset_kind="parallel_random_walk")
+        check(ts[t], rts, f"rollout step {t}")
+    _assert_state(st, rst)
+
+
+class _CudaFixtureEnv:
+    """reset / step of the product package in the terms of tests/test_connector_reference.py."""
+
+    def __init__(self, rbg, m, z):
+        self.rbg, self.m = rbg, m
+        G, N = m["G"], m["N"]
+        g = m["generator"]
+        if g.startswith("offline_"):
+            gen = rbg.BoardDatasetGeneratorJAX.__new__(rbg.BoardDatasetGeneratorJAX)  # the fixture's own stored boards (the reference's K = 7)
+            rbg.Generator.__init__(gen, G, N)
+            gen.heads = rbg.engine.as_tensor(z[f"{m['tag']}/dataset_heads"])
+            gen.targets = rbg.engine.as_tensor(z[f"{m['tag']}/dataset_targets"])
+        else:
+            gen = {"parallel_random_walk": rbg.ParallelRandomWalkGenerator, "uniform": rbg.UniformRandomGenerator, "seed_extension": rbg.SeedExtensionGenerator}[g](G, N)
+        self.env = rbg.Connector(generator=gen, time_limit=m["time_limit"])
+        self.vec = rbg.VmapAutoResetWrapper(rbg.MultiToSingleWrapper(self.env) if m.get("aggregate") else self.env)
+
+    @staticmethod
+    def _dicts(st, ts):
+        d = _state_np(st)
+        t = dict(obs=_np(ts.observation.grid), action_mask=_np(ts.observation.action_mask), obs_step_count=_np(ts.observation.step_count), reward=_np(ts.reward),
+                 discount=_np(ts.discount), step_type=_np(ts.step_type), num_connections=_np(ts.extras["num_connections"]),
+                 ratio_connections=_np(ts.extras["ratio_connections"]), total_path_length=_np(ts.extras["total_path_length"]))
+        return d, t
+
+    def reset(self, keys):
+        env = self.vec if self.m["kind"] == "vmapped" else self.env
+        self.st, ts = env.reset(np.ascontiguousarray(keys))
+        return self._dicts(self.st, ts)
+
+    def step(self, _st, action, autoreset):
+        import torch
+
+        act = torch.from_numpy(np.ascontiguousarray(action)).cuda()
+        self.st, ts = (self.vec if autoreset else self.env).step(self.st, act)
+        return self._dicts(self.st, ts)
+
+
+def test_connector_reference_fixtures_on_gpu(rbg):
+    """The CUDA path through the package's public API against tests/golden/connector_reference.npz: TimeSteps of an
+    independent second restatement of jumanji's Connector + wrappers driven like the reference drives them
+    (tests/tools/make_connector_fixtures.py; N-version agreement, see tests/test_connector_reference.py)."""
+    import test_connector_reference as tcr
+
+    z, meta = tcr.load_connector_fixture()
+    term = early = 0
+    for m in meta:
+        if m["kind"] == "vmapped":
+            a, b, _ = tcr.run_vmapped(z, m, _CudaFixtureEnv(rbg, m, z))
+            term, early = term + a, early + b
+        elif m["kind"] == "episodes":
+            assert tcr.run_episodes(z, m, _CudaFixtureEnv(rbg, m, z)) > 50
+        else:  # demos/board_generator_demo.py:29-97, the private trio
+            import torch
+
+            env = rbg.Connector()
+            tag = m["tag"]
+            for i in range(m["n"]):
+                ag = rbg.Agent(id=torch.arange(5, dtype=torch.int32).cuda(), start=torch.from_numpy(z[f"{tag}/s_start"][i].astype(np.int32)).cuda(),
+                               target=torch.from_numpy(z[f"{tag}/s_target"][i].astype(np.int32)).cuda(), position=torch.from_numpy(z[f"{tag}/s_position"][i].astype(np.int32)).cuda())
+                grid = torch.from_numpy(z[f"{tag}/s_grid"][i].astype(np.int32)).cuda()
+                assert np.array_equal(_np(env._obs_from_grid(grid)), z[f"{tag}/t_obs"][i])
+                assert np.array_equal(_np(env._get_action_mask_all(ag, grid)), z[f"{tag}/t_action_mask"][i])
+                one = rbg.Agent(id=ag.id[2], start=ag.start[2], target=ag.target[2], position=ag.position[2])
+                assert np.array_equal(_np(env._get_action_mask(one, grid)), z[f"{tag}/t_action_mask"][i][2])
+                ex = env._get_extras(rbg.State(key=torch.zeros(2, dtype=torch.int32).cuda().view(torch.uint32), grid=grid, step_count=torch.zeros((), dtype=torch.int32).cuda(), agents=ag))
+                assert int(ex["num_connections"]) == int(z[f"{tag}/t_num_connections"][i]) and int(ex["total_path_length"]) == int(z[f"{tag}/t_total_path_length"][i])
+    assert term > 150 and early > 20
+
+
+@pytest.mark.parametrize("board_name,G,N,K,time_limit", [("offline_parallel_rw", 10, 5, 200, 7), ("offline_seed_extension", 8, 4, 37, 5), ("offline_parallel_rw", 5, 3, 3, 2)])
+def test_connector_with_dataset_generator(rbg, orc, board_name, G, N, K, time_limit):
+    """Connector(generator=BoardDatasetGeneratorJAX(...)) as rl_training/setup_train.py:119-133,158 builds it:
+    reset, 60 auto-reset steps and a fused rollout against the oracle (the in-kernel reset is a table lookup)."""
+    import torch
+
+    B = 900
+    gen = rbg.BoardDatasetGeneratorJAX(G, N, board_name=board_name, number_of_boards=K)
+    heads, targets = _np(gen.heads), _np(gen.targets)
+    env = rbg.VmapAutoResetWrapper(rbg.Connector(generator=gen, time_limit=time_limit))
+    keys, kref = _keys(rbg, orc, 41, B)
+    st, ts = env.reset(keys)
+    rst = orc.dataset_state_batch(kref, G, N, heads, targets)
+    rts = orc.connector_observe_batch(rst)
+    _assert_state(st, rst, "after reset")
+    _assert_timestep(ts, rts, "after reset")
+    rng = np.random.default_rng(1)
+    resets = 0
+    for t in range(60):
+        a = rng.integers(0, 5, size=(B, N)).astype(np.int32) if t % 3 == 2 else orc.random_actions_batch(rst)
+        st, ts = env.step(st, torch.from_numpy(a).cuda(), inplace=bool(t % 2))
+        rst, rts = orc.connector_step_batch(rst, a, time_limit=time_limit, autoreset_kind="dataset", dataset=(heads, targets))
+        _assert_state(st, rst, f"at step {t}")
+        _assert_timestep(ts, rts, f"at step {t}")
+        resets += int((rts["step_type"] == 2).sum())
+    assert resets > 4 * B
+    st, ts, act = env.rollout_random(st, 23)
+    for t in range(23):
+        a = orc.random_actions_batch(rst)
+        assert np.array_equal(_np(act[t]), a), f"actions differ at rollout step {t}"
+        rst, rts = orc.connector_step_batch(rst, a, time_limit=time_limit, autoreset_kind="dataset", dataset=(heads, targets))
+        _assert_timestep(ts[t], rts, f"at rollout step {t}")
+    _assert_state(st, rst, "after the rollout")
+
+
+def test_connector_with_user_defined_generator(rbg, orc):
+    """`Generator` is an open ABC in the reference (uniform_generator.py:26-53): any subclass works in Connector.
+    This one builds its State with torch ops from the key (two wires on fixed rows, columns from the key bits)."""
+    import torch
+
+    G, N, B, TL = 6, 2, 300, 4
+
+    class RowsGenerator(rbg.Generator):
+        def __call__(self, key):
+            k = rbg.engine.as_keys(key)[0].view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+            Bk = k.shape[0]
+            c0, c1 = (k[:, 0] % G).int(), (k[:, 1] % G).int()
+            start = torch.stack([torch.stack([torch.zeros_like(c0), c0], -1), torch.stack([torch.full_like(c1, 2), c1], -1)], 1)
+            target = torch.stack([torch.stack([torch.ones_like(c0) * (G - 1), c1], -1), torch.stack([torch.full_like(c1, 4), c0], -1)], 1)
+            grid = torch.zeros((Bk, G, G), dtype=torch.int32, device=k.device)
+            b = torch.arange(Bk, device=k.device)
+            for i in range(N):
+                grid[b, start[:, i, 0].long(), start[:, i, 1].long()] = 2 + 3 * i
+                grid[b, target[:, i, 0].long(), target[:, i, 1].long()] = 3 + 3 * i
+            newkey = rbg.engine.split_each(rbg.engine.as_keys(key)[0], 2)[:, 0].contiguous()
+            return rbg.State(key=newkey, grid=grid, step_count=torch.zeros(Bk, dtype=torch.int32, device=k.device),
+                             agents=rbg.Agent(id=torch.arange(N, dtype=torch.int32, device=k.device).expand(Bk, N).contiguous(), start=start.int().contiguous(),
+                                              target=target.int().contiguous(), position=start.int().contiguous()))
+
+    gen = RowsGenerator(G, N)
+    env = rbg.VmapAutoResetWrapper(rbg.Connector(generator=gen, time_limit=TL))
+    keys, kref = _keys(rbg, orc, 43, B)
+    st, ts = env.reset(keys)
+    rst = {k: v for k, v in _state_np(st).items()}
+    rts = orc.connector_observe_batch(rst)
+    _assert_timestep(ts, rts, "after reset")
+    assert np.array_equal(_np(st.key), np.stack([orc.split(k)[0] for k in kref]))
+    resets = 0
+    for t in range(13):
+        a = orc.random_actions_batch(rst)
+        st, ts, got = env.step_random(st)
+        assert np.array_equal(_np(got), a)
+        prev_key = rst["key"].copy()
+        rst, rts = orc.connector_step_batch(rst, a, time_limit=TL)  # plain step, then the wrapper's auto-reset by hand
+        last = rts["step_type"] == 2
+        if last.any():
+            nk = np.stack([orc.split(k)[0] for k in prev_key[last]])
+            fresh = _state_np(gen(nk))
+            fts = orc.connector_observe_batch(fresh)
+            for f in ("grid", "step_count", "agent_id", "start", "target", "position", "key"):
+                rst[f][last] = fresh[f]
+            for f in ("obs", "action_mask", "obs_step_count"):
+                rts[f][last] = fts[f]
+        _assert_state(st, rst, f"at step {t}")
+        _assert_timestep(ts, rts, f"at step {t}")
+        resets += int(last.sum())
+    assert resets >= 2 * B
+
+
+def test_random_policy_is_uniform_over_legal_actions(rbg, orc):
+    """make_random_policy_connector (setup_train.py:246) is "distribution-equal", not bit-equal, to upstream's
+    masked categorical: chi-square of the sampled actions against the uniform law over each agent's legal
+    actions (NOOP included), pooled by number of legal actions; and no illegal action is ever drawn."""
+    import torch
+
+    G, N, B = 10, 5, 65536
+    keys = rbg.split(rbg.PRNGKey(123), B)
+    env = rbg.VmapAutoResetWrapper(rbg.Connector(generator=rbg.ParallelRandomWalkGenerator(G, N), time_limit=50))
+    st, ts = env.reset(keys)
+    for _ in range(6):  # a few steps in, so that masks are diverse
+        st, ts, _a = env.step_random(st, inplace=True)
+    mask = ts.observation.action_mask  # the mask the policy samples from at the next step
+    act = rbg.make_random_policy_connector()(st).long()
+    assert bool(mask.gather(2, act[..., None]).all()), "an illegal action was sampled"
+    m = mask.reshape(-1, 5).cpu().numpy().astype(bool)
+    a = act.reshape(-1).cpu().numpy()
+    nlegal = m.sum(axis=1)
+    for k in (2, 3, 4, 5):
+        sel = nlegal == k
+        n = int(sel.sum())
+        if n < 5000:
+            continue
+        # rank of the chosen action among the legal ones must be uniform on {0..k-1}
+        rank = (np.cumsum(m[sel], axis=1) - 1)[np.arange(n), a[sel]]
+        obs = np.bincount(rank, minlength=k).astype(float)
+        chi2 = float(((obs - n / k) ** 2 / (n / k)).sum())
+        # 99.99 % quantiles of chi-square with k-1 degrees of freedom: 15.1, 18.4, 21.1, 23.5
+        assert chi2 < {2: 15.1, 3: 18.4, 4: 21.1, 5: 23.5}[k], (k, n, obs.tolist(), chi2)
+    # different agents / envs / steps draw independently: the action of agent 0 says nothing about agent 1
+    both = (nlegal.reshape(B, N)[:, 0] == 5) & (nlegal.reshape(B, N)[:, 1] == 5)
+    if both.sum() > 10000:
+        tab = np.zeros((5, 5))
+        aa = a.reshape(B, N)[both]
+        np.add.at(tab, (aa[:, 0], aa[:, 1]), 1)
+        exp = tab.sum(1, keepdims=True) * tab.sum(0, keepdims=True) / tab.sum()
+        assert float(((tab - exp) ** 2 / exp).sum()) < 45.0  # 16 degrees of freedom, 99.99 % quantile 44.3
+
+
+def test_state_stepped_twice_keeps_its_boards_pure(rbg, orc):
+    """Functional use (inplace=False): the same State stepped again and again while the side stream refills the
+    next-episode cache.  A reader must never take a half-rewritten cache entry (seqlock on the tag): every reset
+    board is still a pure function of its key."""
+    import torch
+
+    G, N, B, TL = 10, 5, 8192, 2
+    keys, kref = _keys(rbg, orc, 61, B)
+    env = rbg.VmapAutoResetWrapper(rbg.Connector(generator=rbg.ParallelRandomWalkGenerator(G, N), time_limit=TL))
+    st0, _ = env.reset(keys)
+    rst0, _ = orc.connector_reset_batch("parallel_random_walk", kref, G, N)
+    a = orc.random_actions_batch(rst0)
+    act = torch.from_numpy(a).cuda()
+    st1, _ = env.step(st0, act)
+    rst1, _ = orc.connector_step_batch(rst0, a, time_limit=TL, autoreset_kind="parallel_random_walk")
+    a1 = orc.random_actions_batch(rst1)
+    act1 = torch.from_numpy(a1).cuda()
+    rst2, rts2 = orc.connector_step_batch(rst1, a1, time_limit=TL, autoreset_kind="parallel_random_walk")  # every env resets here
+    assert (rts2["step_type"] == 2).all()
+    for rep in range(30):  # st1 over and over, interleaved with steps of its successor that trigger refills of the same entries
+        st2, ts2 = env.step(st1, act1)
+        _assert_state(st2, rst2, f"rep {rep}")
+        _assert_timestep(ts2, rts2, f"rep {rep}")
+        a2 = orc.random_actions_batch(rst2)
+        st3, _ = env.step(st2, torch.from_numpy(a2).cuda())
+        rst3, _ = orc.connector_step_batch(rst2, a2, time_limit=TL, autoreset_kind="parallel_random_walk")
+        _assert_state(st3, rst3, f"rep {rep} successor")
+
+
+def test_unaligned_step_slices_of_a_stacked_rollout(rbg, orc):
+    """G*G % 4 != 0: the kernels use scalar accesses and the per-step slices of a stacked rollout are not
+    16-byte aligned (5x5/3, B = 1: 75 int32 per step).  The step-wise rollout path (SeedExtension resets) must
+    accept them."""
+    G, N, B, T, TL = 5, 3, 1, 6, 3
+    keys, kref = _keys(rbg, orc, 5, B)
+    env = rbg.VmapAutoResetWrapper(rbg.Connector(generator=rbg.SeedExtensionGenerator(G, N), time_limit=TL))
+    st, _ = env.reset(keys)
+    rst, _ = orc.connector_reset_batch("seed_extension", kref, G, N)
+    st, ts, act = env.rollout_random(st, T)
+    for t in range(T):
+        a = orc.random_actions_batch(rst)
+        assert np.array_equal(_np(act[t]), a)
+        rst, rts = orc.connector_step_batch(rst, a, time_limit=TL, autoreset_kind="seed_extension")
+        _assert_timestep(ts[t], rts, f"at step {t}")
+    _assert_state(st, rst)
 
 
 # -------------------------------------------------------------- board validity

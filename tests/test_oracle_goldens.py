@@ -142,13 +142,15 @@ def test_seedext_seed_cells(orc, goldens):  # SURVEY Appendix C (derived; shares
 
 @pytest.mark.parametrize("G,N", [(5, 3), (10, 5), (14, 7), (20, 10), (32, 16)])
 def test_prw_boards_are_valid(orc, G, N):
-    """Every generated board passes the reference's validity rules
-    (post_processor_utils_numpy.py:34-155, board_processor.py:111-162); bit4 marks the
-    zero-length-wire quirk the reference can emit."""
+    """Every generated board is sound by the reference's validity rules
+    (post_processor_utils_numpy.py:34-155, board_processor.py:111-162); the only defect is the
+    zero-length-wire quirk the reference can emit (a lone TARGET, flagged 16, which the
+    reference's own checker rejects as 2 | 4)."""
     keys = orc.split(orc.PRNGKey(1), 256)
     _, _, solved, stats = orc.prw_generate_batch(keys, G, N)
     flags = orc.validate_batch(solved, N)
-    assert ((flags & ~16) == 0).all()
+    assert ((flags & (1 | 8 | 32 | 64 | 128)) == 0).all()
+    assert (((flags & 16) != 0) == ((flags & 6) != 0)).all()
     assert stats[:, 0].min() >= 0
 
 

@@ -57,5 +57,10 @@ def scan(f, init, xs, length=None):
     return carry, _tu.tree_stack(ys)
 
 
+def map(f, xs):  # noqa: A001
+    n = _tu.tree_leaves(xs)[0].shape[0]
+    return _tu.tree_stack([f(_tu.tree_map(lambda a: a[i], xs)) for i in range(n)])
+
+
 def convert_element_type(x, dtype):
     return asarr(x, dtype)

@@ -100,6 +100,10 @@ def sum(a, axis=None):  # noqa: A001
     return asarr(r, _np.int32 if a.dtype.kind in "biu" else None)
 
 
+def mean(a, axis=None):
+    return asarr(_np.mean(_np.asarray(a), axis=axis, dtype=_np.float32), _np.float32)
+
+
 def cumsum(a, axis=None):
     return _w(_np.cumsum(_np.asarray(a), axis=axis, dtype=_np.asarray(a).dtype))
 

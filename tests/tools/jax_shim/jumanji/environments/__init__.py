@@ -1,1 +1,1 @@
-
+from jumanji.environments.routing.connector.env import Connector  # noqa: F401

@@ -4,7 +4,7 @@ mirrors is_valid_position at :401-429)."""
 import jax
 import jax.numpy as jnp
 
-from .constants import DOWN, EMPTY, LEFT, NOOP, PATH, POSITION, RIGHT, TARGET, UP  # noqa: F401
+from .constants import AGENT_INITIAL_VALUE, DOWN, EMPTY, LEFT, NOOP, PATH, POSITION, RIGHT, TARGET, UP  # noqa: F401
 from .types import Agent
 
 
@@ -83,3 +83,14 @@ def get_correction_mask(old_grid, joined_grid, agent_id):
     agent_collided = ~jnp.any(joined_grid == position)
     correction_mask = jnp.where(agent_collided, (old_grid == position) * 1, jnp.zeros_like(old_grid))
     return correction_mask, agent_collided
+
+
+def switch_perspective(grid, agent_id, num_agents):
+    """Encodes the observation with respect to the current agent defined by `agent_id`: in each agent's
+    observation its own path / position / target are 1, 2, 3 and the other agents follow cyclically."""
+    new_grid = grid - AGENT_INITIAL_VALUE  # Center on first agent
+    new_grid -= 3 * agent_id  # Center on current agent
+    new_grid %= 3 * num_agents  # Values of other agents wrap around
+    new_grid += AGENT_INITIAL_VALUE
+    # Take care of zeros: empty cells stay empty
+    return jnp.where(grid == EMPTY, EMPTY, new_grid)
