@@ -64,7 +64,7 @@ def test_library_is_the_cuda_one(rbg):
     arch, sms = C.c_int(), C.c_int()
     assert lib.rbg_device_info(C.byref(arch), C.byref(sms)) == 0
     assert arch.value >= 100 and sms.value > 0
-    assert lib.rbg_version() == 100
+    assert lib.rbg_version() == 200
 
 
 def test_split_keys(rbg, orc):
