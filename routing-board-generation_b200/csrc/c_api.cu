@@ -179,12 +179,12 @@ static int generator_state_impl(int kind, const uint32_t *keys, int64_t B, int G
 // terminations in consecutive steps) take the synchronous reset kernel.  Results are
 // identical either way: a board is a pure function of its key.
 struct WsLayout {
-  size_t sync_list, refill_list[2], refill_keys[2], cache_tag, cache_key, cache_pins, total;
+  size_t sync_list, refill_list[2], refill_keys[2], cache_tag, cache_key, cache_pins, group_done, group_pending, total;
 };
 static WsLayout ws_layout(int64_t B, int N) {
   auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
   WsLayout w;
-  size_t off = 256;  // counters: sync @0, refill[0] @64, refill[1] @128
+  size_t off = 512;  // counters: sync @0, refill[0] @64, refill[1] @128; persistent rollout: 16 sets of 4 ints @256
   const size_t b = (size_t)(B > 0 ? B : 0);
   w.sync_list = off;
   off = up(off + 4 * b);
@@ -200,6 +200,10 @@ static WsLayout ws_layout(int64_t B, int N) {
   off = up(off + 8 * b);
   w.cache_pins = off;
   off = up(off + 4 * b * (size_t)N);
+  w.group_done = off;  // persistent rollout: per env group, the last launch that wrote it / its requests in flight
+  off = up(off + 4 * b);
+  w.group_pending = off;
+  off = up(off + 4 * b);
   w.total = off;
   return w;
 }
@@ -208,6 +212,8 @@ struct AutoResetCtx {
   int64_t B = 0;
   int G = 0, N = 0, kind = -1;
   uint64_t step = 0;
+  int persist_epoch = 0;  // launches of the persistent rollout on this workspace
+  int persist_groups = 0; // group size the flags were laid out for
   cudaStream_t side = nullptr;
   cudaEvent_t env_done = nullptr;
   cudaEvent_t refill_done[2] = {nullptr, nullptr};
@@ -332,6 +338,7 @@ static int connector_step_impl(const rbg_state *in, const rbg_state *out, const 
       ctx->N = N;
       ctx->kind = kind;
       ctx->step = 0;
+      ctx->persist_epoch = 0;
     }
     par = (int)(ctx->step & 1);
     // the refill launched two steps ago used this parity's list buffers
@@ -804,7 +811,14 @@ static int rollout_fused(const rbg_state *state, int32_t *action_out, int64_t T,
     const char *ex = getenv("RBG_ROLLOUT_NO_CACHE");
     no_cache_env = ex ? (atoi(ex) != 0 ? 1 : 0) : -1;
   }
-  const bool no_cache = no_cache_env >= 0 ? no_cache_env == 1 : (size_t)N * G * G * 4 > 16384;
+  // RBG_ROLLOUT_IMPL=legacy: rollout_warp_kernel + refill kernel (round 1); default: the persistent kernel whose
+  // CTAs carry their own generator warps (rollout_persist_kernel), which always works from the cache
+  static int persist = -1;
+  if (persist < 0) {
+    const char *ex = getenv("RBG_ROLLOUT_IMPL");
+    persist = (ex && strcmp(ex, "legacy") == 0) ? 0 : 1;
+  }
+  const bool no_cache = persist ? false : (no_cache_env >= 0 ? no_cache_env == 1 : (size_t)N * G * G * 4 > 16384);
   if (no_cache) {
     ctx->B = 0;  // the cache is not maintained: a later step-wise call adopts the workspace afresh
   } else if (ctx->B != B || ctx->G != G || ctx->N != N || ctx->kind != kind) {
@@ -818,6 +832,7 @@ static int rollout_fused(const rbg_state *state, int32_t *action_out, int64_t T,
     ctx->N = N;
     ctx->kind = kind;
     ctx->step = 0;
+    ctx->persist_epoch = 0;
   }
   static int chunk_env = -1;
   if (chunk_env < 0) {
@@ -848,7 +863,7 @@ static int rollout_fused(const rbg_state *state, int32_t *action_out, int64_t T,
     if (slices_env <= 0) slices_env = 2;
     if (slices_env > 4) slices_env = 4;
   }
-  int nsl = slices_env;
+  int nsl = persist ? 1 : slices_env;  // a persistent grid fills the machine by itself; its launches overlap head to tail instead
   while (nsl > 1 && B < (int64_t)nsl * 2048) --nsl;
   if (g_timing.load(std::memory_order_relaxed)) nsl = 1;  // event pairs must time one kernel at a time
   int64_t cuts[5];
@@ -877,6 +892,26 @@ static int rollout_fused(const rbg_state *state, int32_t *action_out, int64_t T,
       p.refill_list = reinterpret_cast<int32_t *>(ws + wl.refill_list[0]) + p.env_lo;
       p.refill_keys = reinterpret_cast<uint32_t *>(ws + wl.refill_keys[0]) + 2 * p.env_lo;
       p.refill_count = reinterpret_cast<int32_t *>(ws + 64 + 16 * s);
+      if (persist) {
+        static int overlap_env = -1;  // RBG_ROLLOUT_OVERLAP=0: plain stream order between launches
+        if (overlap_env < 0) {
+          const char *ex = getenv("RBG_ROLLOUT_OVERLAP");
+          overlap_env = (ex && atoi(ex) == 0) ? 0 : 1;
+        }
+        if (ctx->persist_epoch == 0 || ctx->persist_epoch > 0x3fffffff) {  // flags start at 0 = "written by launch 0"
+          if ((e = cudaMemsetAsync(ws + wl.group_done, 0, (wl.group_pending - wl.group_done) + 4 * (size_t)B, st)) != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(group flags)");
+          if ((e = cudaMemsetAsync(ws + 256, 0, 256, st)) != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(persist counters)");
+          ctx->persist_epoch = 0;
+        }
+        const int epoch = ++ctx->persist_epoch;
+        const bool overlap = overlap_env == 1 && epoch > 1 && !g_timing.load(std::memory_order_relaxed);
+        if ((rc = launch_rollout_persist(p, kind, n, action_out ? action_out + t0 * B * N : nullptr, reinterpret_cast<int32_t *>(ws + 256),
+                                         reinterpret_cast<int32_t *>(ws + wl.group_done), reinterpret_cast<int32_t *>(ws + wl.group_pending), epoch, overlap,
+                                         reinterpret_cast<uint64_t *>(ws + wl.cache_tag), reinterpret_cast<uint2 *>(ws + wl.cache_key),
+                                         reinterpret_cast<uint32_t *>(ws + wl.cache_pins), st)))
+          return rc;
+        continue;
+      }
       if (no_cache) p.refill_list = nullptr;
       if ((rc = launch_rollout(p, kind, n, action_out ? action_out + t0 * B * N : nullptr, st))) return rc;
       if (no_cache) continue;

@@ -18,6 +18,7 @@
 #include <stdlib.h>
 
 #include "connector_device.cuh"
+#include "gen_warp.cuh"
 #include "obs_stage.cuh"
 #include "prw_warp.cuh"
 #include "rbg_host.h"
@@ -639,6 +640,370 @@ __global__ void __launch_bounds__(EW_WARPS * 32, RBG_ROLLOUT_MIN_CTAS) rollout_w
   }
 }
 
+// ---------------------------------------------------------------------------
+// rollout_persist_kernel: the fused rollout as a PERSISTENT kernel with generator warps.
+//
+// Same step logic and lane layout as rollout_warp_kernel.  What changes is who does what, when:
+//  * the grid is sized to the machine (resident CTAs x SM count); an env warp pulls groups of K envs from a
+//    global counter until none are left, so there are no CTA waves and the DRAM write rate does not dip at
+//    wave boundaries;
+//  * every CTA carries GEN_WARPS generator warps (gen_warp.cuh).  When an env finishes, its warp swaps in the
+//    env's cached next episode and posts a request for the episode AFTER that one; a generator warp of the
+//    same CTA produces it (ParallelRandomWalk walk / Uniform selection, W lanes per board) into the env's
+//    cache entry while the env warps keep streaming observations.  Generation is integer-issue bound, the
+//    rollout HBM-write bound with half of the issue slots idle: inside one CTA the two share an SM, which a
+//    separate refill kernel could not (the rollout CTAs' shared memory fills the SM);
+//  * an env that needs an episode which is not there yet (a second termination within a few steps of the
+//    first) waits for its generator warp; nothing is generated by env warps, no refill kernel, no lists;
+//  * launch overlap: a persistent grid ends raggedly (env warps finish within one group time of each other,
+//    the generator warps drain their rings after that: together 12-16 % of a 20-step launch with nothing
+//    to do).  Consecutive rollout launches on a stream are therefore chained by programmatic dependent
+//    launch: the next launch's CTAs take the SM slots as this launch's CTAs leave.  What orders the two
+//    launches is per GROUP, not per grid: group g of launch e+1 is loaded only when launch e has written
+//    group g's State (group_done[g] >= e) AND every episode it requested for those envs has been published
+//    (group_pending[g] == 0), both with release / acquire semantics at GPU scope.
+//    The group counter of a launch is one of kPersistSets sets {next group, env warps done, owner}; a launch may
+//    use set (epoch % kPersistSets) only once the launch that used it last has recycled it (owner == epoch), so
+//    however many small launches are in flight at once they never share a counter.
+constexpr int kPersistSets = 16;
+constexpr int kPersistSetInts = 4;
+constexpr int GEN_WARPS_MAX = 4;
+#ifndef RBG_PERSIST_MIN_CTAS
+#define RBG_PERSIST_MIN_CTAS 4
+#endif
+
+struct PersistParams {
+  int *counter;   // [0] next env group, [1] env warps that have finished (the last one clears both), [2] epoch that may use the set next (0: any of the first kPersistSets)
+  int *group_done;     // [ngroups] last launch epoch that has written the group's State
+  int *group_pending;  // [ngroups] episode requests in flight
+  int epoch;           // this launch (> 0, +1 per launch on the workspace)
+  int ngroups;    // groups of K envs in [env_lo, env_hi)
+  int gen_warps;  // generator warps per CTA (1..GEN_WARPS_MAX)
+  int tmpl_off;   // smem byte offsets: empty padded board, queues, done flag, generator scratch
+  int q_off, done_off, gscr_off, gscr_stride;
+  int gcand_bytes, gsel_bytes;
+};
+
+template <int OBS>
+__global__ void __launch_bounds__((EW_WARPS + 2) * 32, RBG_PERSIST_MIN_CTAS)
+    rollout_persist_kernel(const EnvParams p, const RolloutParams rp, const PersistParams pp, const GenWarpCfg gc) {
+  constexpr bool VEC = OBS != 0;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int G = p.G, N = p.N, cells = p.cells;
+  const int Np = p.Np, K = 32 / Np, c4 = cells >> 2;
+  constexpr int RS = OBS_RS;
+  uint8_t *lut = smem_raw;
+  const int nthreads = blockDim.x, nwarps = nthreads >> 5;
+  for (int a = warp; a < N; a += nwarps)
+    for (int v = lane; v < RS; v += 32) lut[a * RS + v] = v <= 3 * N ? (uint8_t)obs_value(v, 3 * a, 3 * N) : (uint8_t)0;
+  float *ratio_lut = reinterpret_cast<float *>(smem_raw + rp.ratio_off);  // n / N for n = 0..N (extras: ratio_connections)
+  if (tid <= N) ratio_lut[tid] = __fdiv_rn((float)tid, (float)N);
+  uint8_t *tmpl = smem_raw + pp.tmpl_off;
+  for (int i = tid; i < gc.SBp; i += nthreads) {
+    const int r = i / gc.S, c = i - r * gc.S;
+    tmpl[i] = (r >= 2 && r < G + 2 && c >= 2 && c < G + 2) ? 0 : 0xFF;
+  }
+  GenQueue *queues = reinterpret_cast<GenQueue *>(smem_raw + pp.q_off);
+  volatile int *env_done = reinterpret_cast<volatile int *>(smem_raw + pp.done_off);
+  if (warp < pp.gen_warps) genq_init(queues + warp, lane);
+  if (tid == 0) *env_done = 0;
+  // the next launch on the stream may start as soon as SM slots free up (it orders itself per group, see above)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  __syncthreads();  // the only CTA-wide barrier
+
+  if (warp >= EW_WARPS) {  // ---- generator warp
+    const int gw = warp - EW_WARPS;
+    if (gw >= pp.gen_warps) return;
+#ifdef RBG_PERSIST_STATS
+    if (lane == 0) {
+      RBG_STAT(8, 1);  // generator warps
+    }
+#endif
+    uint8_t *gb = smem_raw + pp.gscr_off + (size_t)gw * pp.gscr_stride;
+    GenWarpScratch gs;
+    gs.cand = reinterpret_cast<uint64_t *>(gb);
+    gs.sel = reinterpret_cast<uint16_t *>(gb + pp.gcand_bytes);
+    gs.board = gb + pp.gcand_bytes + pp.gsel_bytes;
+    gs.tmpl = tmpl;
+#ifdef RBG_PERSIST_TRACE
+    const unsigned long long tr0 = rbg_gtime();
+#endif
+    gen_warp_loop(gc, gs, queues + gw, env_done, EW_WARPS, lane);
+#ifdef RBG_PERSIST_TRACE
+    if (lane == 0) {
+      const int wi = blockIdx.x * (EW_WARPS + 2) + warp;
+      g_persist_trace[3 * wi] = tr0;
+      g_persist_trace[3 * wi + 1] = rbg_gtime();
+      g_persist_trace[3 * wi + 2] = 1000000;
+    }
+#endif
+    return;
+  }
+
+  // ---- env warp
+#ifdef RBG_PERSIST_STATS
+  if (lane == 0) {
+    RBG_STAT(12, 1);  // env warps
+    RBG_STAT(13, clock64());  // (start stamps; the exit stamps are added below: sum(exit) - sum(start) = total env-warp time)
+  }
+#endif
+  uint8_t *wg = smem_raw + p.so[0] + (size_t)warp * p.so[1];
+  uint32_t *wg32 = reinterpret_cast<uint32_t *>(wg);
+  const int j = lane / Np, a = lane & (Np - 1);
+  const uint32_t gmask = Np == 32 ? FULL : (((1u << Np) - 1u) << (j * Np));
+  uint8_t *g = wg + (size_t)j * cells;
+  const SmemGrid sg{g, G, 0, G};
+  ObsStager os;
+  if (VEC) os.init(smem_raw + rp.stage_off + (size_t)warp * rp.stage_warp, lut, wg32, N, c4, p.divC4, lane, rp.stage_bytes, rp.stage_nbuf, rp.ce, rp.cv);
+#ifdef RBG_PERSIST_TRACE
+  const unsigned long long tr0 = rbg_gtime();
+  int tr_groups = 0;
+#endif
+
+  if (lane == 0) {  // the launch that used this counter set last (kPersistSets launches ago) must have recycled it
+    for (;;) {
+      const int owner = ld_acquire_s32(pp.counter + 2);
+      if (owner == pp.epoch || (owner == 0 && pp.epoch <= kPersistSets)) break;
+      __nanosleep(500);
+    }
+  }
+  __syncwarp();
+  for (;;) {
+    int grp = 0;
+    if (lane == 0) grp = atomicAdd(pp.counter, 1);
+    grp = __shfl_sync(FULL, grp, 0);
+    if (grp >= pp.ngroups) break;
+#ifdef RBG_PERSIST_TRACE
+    ++tr_groups;
+#endif
+    const long long e0 = p.env_lo + (long long)grp * K;
+    const int kc = (int)((p.env_hi - e0) < (long long)K ? (p.env_hi - e0) : (long long)K);
+    const bool env_ok = j < kc, agent = env_ok && a < N;
+    const long long e = e0 + (env_ok ? j : 0);
+    GenQueue *myq = queues + (int)(e % pp.gen_warps);
+    // the previous launch may still be running: its State of this group, and the episodes it asked for
+    if (lane == 0) {
+      while (ld_acquire_s32(pp.group_done + grp) < pp.epoch - 1 || ld_acquire_s32(pp.group_pending + grp) != 0) __nanosleep(200);
+    }
+    __syncwarp();
+
+    // ---- load the State once
+    if (VEC) {
+      const int4 *src = reinterpret_cast<const int4 *>(p.in.grid) + e0 * c4;
+      const int nq = kc * c4;
+      for (int q0 = lane; q0 < nq; q0 += 128) {
+        int4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = (q0 + 32 * u < nq) ? __ldg(src + q0 + 32 * u) : make_int4(0, 0, 0, 0);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (q0 + 32 * u < nq)
+            wg32[q0 + 32 * u] = (uint32_t)(v[u].x & 0xff) | ((uint32_t)(v[u].y & 0xff) << 8) | ((uint32_t)(v[u].z & 0xff) << 16) | ((uint32_t)(v[u].w & 0xff) << 24);
+      }
+    } else {
+      const int32_t *src = p.in.grid + e0 * cells;
+      for (int i = lane; i < kc * cells; i += 32) wg[i] = (uint8_t)__ldg(src + i);
+    }
+    int pos = 0, tgt = 0, start = 0, sc = 0;
+    uint32_t k0 = 0, k1 = 0;
+    if (agent) {
+      const int2 ps = __ldg(reinterpret_cast<const int2 *>(p.in.position) + e * N + a);
+      const int2 tg = __ldg(reinterpret_cast<const int2 *>(p.in.target) + e * N + a);
+      const int2 st = __ldg(reinterpret_cast<const int2 *>(p.in.start) + e * N + a);
+      pos = (ps.x << 8) | ps.y;
+      tgt = (tg.x << 8) | tg.y;
+      start = (st.x << 8) | st.y;
+    }
+    if (env_ok) {
+      sc = p.in.step_count[e];
+      k0 = p.in.key[2 * e];
+      k1 = p.in.key[2 * e + 1];
+      // an env whose next episode is not in the cache (first use of the workspace): ask for it right away
+      if (a == 0 && ld_acquire_u64(p.cache_tag + e) != (((unsigned long long)k1 << 32) | k0)) {
+        atomicAdd(pp.group_pending + grp, 1);
+        genq_post(myq, (int)e, k0, k1);
+      }
+    }
+    __syncwarp();
+    int paths = 0;  // PATH cells of the env (extras: total_path_length), carried across steps
+    if (env_ok) {
+      if (VEC) {
+        for (int q = a; q < c4; q += Np) paths += count_path_codes(wg32[j * c4 + q]);
+      } else {
+        for (int i = a; i < cells; i += Np) paths += (g[i] % 3u == 1u) ? 1 : 0;
+      }
+    }
+    for (int off = Np >> 1; off; off >>= 1) paths += __shfl_xor_sync(FULL, paths, off);
+    uint32_t mk3 = 0;  // the action mask of the state an env is in: what step t emits is what step t+1's policy samples from
+    if (agent) mk3 = move_mask(sg, pos >> 8, pos & 255, a, pos == tgt);
+    int4 *obs_t = nullptr;
+    long long obs_step = 0;
+    if (VEC) {
+      obs_t = reinterpret_cast<int4 *>(p.ts.obs_grid) + e0 * N * c4;
+      obs_step = p.B * N * c4;
+    }
+
+    for (int t = 0; t < rp.T; ++t) {
+      const long long tb = (long long)t * p.B;
+      // ---- agents: sample action, move_position, is_valid_position, collisions
+      const bool was = agent && pos == tgt;
+      const int r = pos >> 8, c = pos & 255;
+      const long long row_e = tb + e, row_a = row_e * N + a;
+      int dest = -1;
+      if (agent) {
+        const int action = random_action(k0, k1, (uint32_t)sc, (uint32_t)a, mk3);
+        if (rp.action_out) rp.action_out[row_a] = action;
+        if (action != NOOP) dest = r * G + c + (action == UP ? -G : (action == DOWN ? G : (action == RIGHT ? 1 : -1)));
+      }
+      const uint32_t mval = dest >= 0 ? (((uint32_t)j << 16) | (uint32_t)dest) : (0x80000000u | (uint32_t)lane);
+#ifdef RBG_ENV_SHFL_COLLISION
+      const bool win = wins_collision(mval, dest >= 0, a, j * Np, N);
+#else
+      const uint32_t mm = __match_any_sync(FULL, mval);
+      const bool win = dest >= 0 && lane == 31 - __clz(mm);
+#endif
+      __syncwarp();
+      if (win) {
+        g[r * G + c] = (uint8_t)(3 * a + PATH);
+        g[dest] = (uint8_t)(3 * a + POSITION);
+        uint32_t nr, nc;
+        p.divG.divmod((uint32_t)dest, nr, nc);
+        pos = (int)((nr << 8) | nc);
+      }
+      __syncwarp();
+      // ---- action mask, connected / done, reward on the new grid
+      const bool now = agent && pos == tgt;
+      mk3 = 0;
+      if (agent) mk3 = move_mask(sg, pos >> 8, pos & 255, a, now);
+      const bool done = now || mk3 == 0u;
+      const float rew = __fadd_rn(__fmul_rn(p.env.connected_reward, (!was && now) ? 1.0f : 0.0f), __fmul_rn(p.env.timestep_reward, was ? 0.0f : 1.0f));
+      const int ndone = __popc(__ballot_sync(FULL, agent && done) & gmask);
+      const int nconn = __popc(__ballot_sync(FULL, now) & gmask);
+      paths += __popc(__ballot_sync(FULL, win) & gmask);
+      sc += 1;
+      const bool terminal = env_ok && (ndone == N || sc >= p.env.time_limit);
+      const int tpl = paths + N;
+      // ---- small outputs of step t (the terminal step keeps its reward / discount / step_type / extras)
+      if (env_ok && a == 0) {
+        p.ts.step_type[row_e] = (int8_t)(terminal ? 2 : 1);
+        p.ts.num_connections[row_e] = nconn;
+        p.ts.ratio_connections[row_e] = ratio_lut[nconn];
+        p.ts.total_path_length[row_e] = tpl;
+        p.ts.obs_step_count[row_e] = terminal ? 0 : sc;
+      }
+      if (agent) {
+        p.ts.reward[row_a] = rew;
+        p.ts.discount[row_a] = (terminal || done) ? 0.0f : 1.0f;
+      }
+      // ---- auto-reset: the env's cached next episode; its generator warp may still be working on it
+      if (terminal) {  // group-uniform
+        if (a == 0) RBG_STAT(7, 1);  // resets
+        const unsigned long long want = ((unsigned long long)k1 << 32) | k0;
+        if (a == 0)
+          while (ld_acquire_u64(p.cache_tag + e) != want) {
+            myq->urgent = 1;
+            RBG_STAT(6, 1);  // env-warp wait polls (0.1 us)
+            __nanosleep(100);
+          }
+        __syncwarp(gmask);
+        if (a != 0) (void)ld_acquire_u64(p.cache_tag + e);  // every lane orders its own reads behind the published tag
+        const uint2 nk = __ldcg(p.cache_key + e);
+        const uint32_t pin = a < N ? __ldcg(p.cache_pins + e * N + a) : 0u;
+        for (int i = a; i < cells; i += Np) g[i] = 0;
+        pos = (int)(pin >> 16);
+        tgt = (int)(pin & 0xffffu);
+        start = pos;
+        k0 = nk.x;
+        k1 = nk.y;
+        sc = 0;
+        paths = 0;
+        if (a == 0) {  // the episode after this one
+          atomicAdd(pp.group_pending + grp, 1);
+          genq_post(myq, (int)e, k0, k1);
+        }
+        __syncwarp(gmask);
+        if (a < N) g[(pos >> 8) * G + (pos & 255)] = (uint8_t)(3 * a + POSITION);
+        __syncwarp(gmask);
+        if (a < N) g[(tgt >> 8) * G + (tgt & 255)] = (uint8_t)(3 * a + TARGET);
+        __syncwarp(gmask);
+        if (a < N) mk3 = move_mask(sg, pos >> 8, pos & 255, a, pos == tgt);
+      }
+      __syncwarp();
+      if (agent) store_mask5(p.ts.action_mask + row_a * 5, mk3);
+      // ---- observation of step t
+      if (VEC) {
+        int4 *odst = obs_t;
+        obs_t += obs_step;
+        if (OBS == 2)
+          os.emit(kc, N, c4, lane, odst);
+        else
+          os.emit_direct(lut, wg32, kc, N, c4, lane, odst);
+      } else {
+        int32_t *odst = p.ts.obs_grid + (tb + e0) * N * cells;
+        for (int i = lane; i < kc * cells; i += 32) {
+          const int m = (int)p.divCells.div((uint32_t)i);
+          const uint32_t v = wg[i];
+          int32_t *o = odst + (size_t)m * N * cells + (i - m * cells);
+          for (int x = 0; x < N; ++x, o += cells) *o = lut[x * RS + v];
+        }
+      }
+      __syncwarp();  // the next step's writes must not overtake these reads
+    }
+
+    // ---- write the State once
+    if (VEC) {
+      int4 *gdst = reinterpret_cast<int4 *>(p.out.grid) + e0 * c4;
+      for (int q = lane; q < kc * c4; q += 32) gdst[q] = bytes_to_int4(wg32[q]);
+    } else {
+      int32_t *gdst = p.out.grid + e0 * cells;
+      for (int i = lane; i < kc * cells; i += 32) gdst[i] = wg[i];
+    }
+    if (env_ok && a == 0) {
+      p.out.step_count[e] = sc;
+      p.out.key[2 * e] = k0;
+      p.out.key[2 * e + 1] = k1;
+    }
+    if (agent) {
+      const long long ga = e * N + a;
+      reinterpret_cast<int2 *>(p.out.position)[ga] = make_int2(pos >> 8, pos & 255);
+      reinterpret_cast<int2 *>(p.out.target)[ga] = make_int2(tgt >> 8, tgt & 255);
+      reinterpret_cast<int2 *>(p.out.start)[ga] = make_int2(start >> 8, start & 255);
+      p.out.agent_id[ga] = a;
+    }
+    // the group's State is written (the observation copies of its last steps may still be in flight: nothing
+    // of a later launch depends on them); requests posted above were counted before this store
+    __threadfence();
+    __syncwarp();  // the next group's load overwrites the warp's grid slice
+    if (lane == 0) st_release_s32(pp.group_done + grp, pp.epoch);
+  }
+  if (OBS == 2) os.drain(lane);  // shared memory must outlive the bulk copies
+#ifdef RBG_PERSIST_STATS
+  if (lane == 0) RBG_STAT(14, clock64());
+#endif
+#ifdef RBG_PERSIST_TRACE
+  if (lane == 0) {
+    const int wi = blockIdx.x * (EW_WARPS + 2) + warp;
+    g_persist_trace[3 * wi] = tr0;
+    g_persist_trace[3 * wi + 1] = rbg_gtime();
+    g_persist_trace[3 * wi + 2] = tr_groups;
+  }
+#endif
+  // this env warp is done: tell the CTA's generator warps, and the grid (the last warp recycles the counters)
+  __syncwarp();
+  if (lane == 0) {
+    __threadfence_block();
+    atomicAdd(const_cast<int *>(env_done), 1);
+    __threadfence();
+    if (atomicAdd(pp.counter + 1, 1) == (int)gridDim.x * EW_WARPS - 1) {
+      pp.counter[0] = 0;
+      pp.counter[1] = 0;
+      __threadfence();
+      st_release_s32(pp.counter + 2, pp.epoch + kPersistSets);
+    }
+  }
+}
+
 // standalone random policy: one thread per (env, agent), grid read from global
 __global__ void __launch_bounds__(256) random_actions_kernel(rbg_state st, long long B, int G, int N,
                                                              FastDiv divN, int32_t *action) {
@@ -800,6 +1165,191 @@ int launch_rollout(EnvParams p, int kind, int T, int32_t *action_out, cudaStream
   }
   return check_launch("rollout_warp_kernel");
 }
+
+static int device_sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+// The persistent rollout with in-CTA generator warps (rollout_persist_kernel).  `cache_*` of `p` must be set;
+// `counter` points at two zeroed ints that the kernel recycles by itself.
+int launch_rollout_persist(EnvParams p, int kind, int T, int32_t *action_out, int32_t *counter, int32_t *group_done, int32_t *group_pending,
+                           int epoch, bool overlap, uint64_t *cache_tag_w, uint2 *cache_key_w, uint32_t *cache_pins_w, cudaStream_t stream) {
+  const int G = p.G, N = p.N;
+  p.cells = G * G;
+  const bool vec = (p.cells & 3) == 0;
+  p.divN = FastDiv::make((uint32_t)N);
+  p.divG = FastDiv::make((uint32_t)G);
+  p.divC4 = FastDiv::make((uint32_t)(vec ? p.cells >> 2 : 1));
+  p.divCells = FastDiv::make((uint32_t)p.cells);
+  if (p.B <= 0 || T <= 0) return RBG_OK;
+  if (p.env_hi <= p.env_lo) {
+    p.env_lo = 0;
+    p.env_hi = p.B;
+  }
+  int Np = 1;
+  while (Np < N) Np <<= 1;
+  p.Np = Np;
+  const int K = 32 / Np;
+  p.E = EW_WARPS * K;
+  auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  const size_t lutB = up16((size_t)N * OBS_RS + 256);
+  const size_t wgrid = up16((size_t)K * p.cells);
+  p.so[0] = (int)lutB;
+  p.so[1] = (int)wgrid;
+  RolloutParams rp;
+  memset(&rp, 0, sizeof(rp));
+  rp.T = T;
+  rp.kind = kind;
+  rp.action_out = action_out;
+  size_t off = lutB + EW_WARPS * wgrid;
+  rp.ratio_off = (int)off;
+  off = up16(off + 4 * (RBG_MAX_N + 4));
+  // generator configuration: W lanes per board, N + 2 of them busy when that fits (agents + the two key-advance lanes)
+  GenWarpCfg gc;
+  memset(&gc, 0, sizeof(gc));
+  gc.kind = kind;
+  gc.G = G;
+  gc.N = N;
+  int W = 1;
+  while (W < N + 2 && W < 32) W <<= 1;
+  gc.W = W;
+  gc.S = G + 4;
+  gc.SBp = (int)up16((size_t)gc.S * gc.S);
+  gc.cells = p.cells;
+  gc.nsel = kind == RBG_GEN_PRW ? N : 2 * N;
+  gc.nselp = (gc.nsel + 1) & ~1;
+  gc.cap = 4 * gc.nsel + 32;
+  {
+    const double frac = (2.0 * gc.nsel + 16.0) / (double)p.cells;
+    gc.thresh = frac >= 1.0 ? 0xffffffffu : (uint32_t)(frac * 4294967296.0);
+  }
+  gc.divG = p.divG;
+  {
+    static int patience_env = -2;
+    if (patience_env == -2) {
+      const char *ex = getenv("RBG_GEN_PATIENCE");
+      patience_env = ex ? atoi(ex) : -1;
+    }
+    gc.patience = patience_env >= 0 ? patience_env : 20;
+  }
+  gc.cache_tag = reinterpret_cast<unsigned long long *>(cache_tag_w);
+  gc.cache_key = cache_key_w;
+  gc.cache_pins = cache_pins_w;
+  PersistParams pp;
+  memset(&pp, 0, sizeof(pp));
+  pp.counter = counter + (epoch % kPersistSets) * kPersistSetInts;
+  pp.group_done = group_done;
+  pp.group_pending = group_pending;
+  pp.epoch = epoch;
+  pp.ngroups = (int)((p.env_hi - p.env_lo + K - 1) / K);
+  gc.group_pending = group_pending;
+  gc.env_lo = p.env_lo;
+  gc.kshift = 0;
+  while ((1 << gc.kshift) < K) ++gc.kshift;
+  static int gen_warps_env = -1;
+  if (gen_warps_env < 0) {
+    const char *ex = getenv("RBG_GEN_WARPS");
+    gen_warps_env = ex ? atoi(ex) : 0;
+  }
+  pp.gen_warps = gen_warps_env > 0 ? (gen_warps_env > 2 ? 2 : gen_warps_env) : 2;
+  pp.tmpl_off = (int)off;
+  off = up16(off + gc.SBp);
+  pp.q_off = (int)off;
+  off = up16(off + pp.gen_warps * sizeof(GenQueue));
+  pp.done_off = (int)off;
+  off += 16;
+  const int gpw = 32 / W;
+  pp.gcand_bytes = (int)up16((size_t)gc.cap * 8);
+  pp.gsel_bytes = (int)up16((size_t)gpw * gc.nselp * 2);
+  pp.gscr_stride = (int)up16((size_t)pp.gcand_bytes + pp.gsel_bytes + (size_t)gpw * gc.SBp);
+  pp.gscr_off = (int)off;
+  off += (size_t)pp.gen_warps * pp.gscr_stride;
+  rp.stage_off = (int)off;
+  rp.stage_nbuf = 1;
+  rp.ce = 1;
+  rp.cv = N;
+  if (vec) {
+    const ObsStagePlan pl = obs_stage_plan(K, N, p.cells, 4096, 8192);
+    rp.stage_bytes = pl.bytes;
+    rp.stage_nbuf = pl.nbuf;
+    rp.ce = pl.ce;
+    rp.cv = pl.cv;
+    rp.stage_warp = (int)up16((size_t)rp.stage_nbuf * rp.stage_bytes);
+    off += (size_t)EW_WARPS * rp.stage_warp;
+  }
+  const size_t smem = up16(off);
+  if (smem > 200 * 1024) return set_error(RBG_EINVAL, "rollout: shared memory %zu too large", smem);
+#ifdef RBG_OBS_DIRECT
+  const bool staged = false;
+#else
+  const bool staged = vec && rp.stage_nbuf != 0;
+#endif
+  const int threads = (EW_WARPS + pp.gen_warps) * 32;
+  const void *fn = staged ? (const void *)rollout_persist_kernel<2> : (vec ? (const void *)rollout_persist_kernel<1> : (const void *)rollout_persist_kernel<0>);
+  cudaError_t ce;
+  if (smem > 48 * 1024 && (ce = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+    return set_cuda_error(ce, "cudaFuncSetAttribute(rollout_persist_kernel)");
+  int resident = 0;
+  if ((ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, fn, threads, smem)) != cudaSuccess) return set_cuda_error(ce, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+  if (resident < 1) return set_error(RBG_EINVAL, "rollout_persist_kernel does not fit an SM (%zu bytes of shared memory)", smem);
+  static int force = -1;  // RBG_ROLLOUT_CTAS=n: at most n CTAs per SM (experiments)
+  if (force < 0) {
+    const char *ex = getenv("RBG_ROLLOUT_CTAS");
+    force = ex ? atoi(ex) : 0;
+  }
+  if (force > 0 && force < resident) resident = force;
+  int64_t ctas = (int64_t)resident * device_sm_count();
+  const int64_t need = (pp.ngroups + EW_WARPS - 1) / EW_WARPS;
+  if (ctas > need) ctas = need;
+  LaunchScope scope(RBG_K_ROLLOUT, stream);
+  // programmatic dependent launch: this grid may begin while the previous kernel of the stream is still
+  // running, if that kernel said so (rollout_persist_kernel does; anything else completes first)
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)ctas);
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = overlap ? 1 : 0;
+  if (staged)
+    ce = cudaLaunchKernelEx(&cfg, rollout_persist_kernel<2>, p, rp, pp, gc);
+  else if (vec)
+    ce = cudaLaunchKernelEx(&cfg, rollout_persist_kernel<1>, p, rp, pp, gc);
+  else
+    ce = cudaLaunchKernelEx(&cfg, rollout_persist_kernel<0>, p, rp, pp, gc);
+  if (ce != cudaSuccess) return set_cuda_error(ce, "cudaLaunchKernelEx(rollout_persist_kernel)");
+  return check_launch("rollout_persist_kernel");
+}
+
+#ifdef RBG_PERSIST_TRACE
+extern "C" int rbg_debug_persist_trace(unsigned long long *out, int n) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_persist_trace, sizeof(unsigned long long) * n);
+  return 0;
+}
+#endif
+
+#ifdef RBG_PERSIST_STATS
+extern "C" int rbg_debug_persist_stats(unsigned long long *out16, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out16, g_persist_stats, sizeof(unsigned long long) * 16);
+  if (reset) {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(g_persist_stats, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
 
 int launch_random_actions(const rbg_state &st, int64_t B, int G, int N, int32_t *action, cudaStream_t stream) {
   const int64_t n = B * N;

@@ -121,6 +121,40 @@ __device__ __forceinline__ uint32_t dataset_pick(uint32_t k0, uint32_t k1, uint3
   return ((hi % K) * mult + (lo % K)) % K;
 }
 
+// "Same destination -> only the highest agent id moves" (parallel_random_walk.py:104-145, jumanji
+// Connector._step_agents) inside a group of W lanes that starts at lane `base`, lane = agent: a mover
+// loses iff a HIGHER agent of its group moves to the same cell.  N shuffles; __match_any_sync, which
+// this replaces, serialises over the distinct values of the warp (one per non-moving lane as well) and was
+// the largest single stall of the latency-bound walk (profiles/r01d_prw_bulk_source_top.txt,
+// profiles/r02a_persist_source_top.txt).  `val` must be unique per lane for non-movers.
+__device__ __forceinline__ bool wins_collision(uint32_t val, bool moves, int a, int base, int N) {
+  bool lose = false;
+  for (int i = 1; i < N; ++i) {  // agent 0 never beats anyone
+    const uint32_t o = __shfl_sync(FULL, val, base + i);
+    lose |= (i > a) && (o == val);
+  }
+  return moves && !lose;
+}
+
+// global-memory flag with release / acquire semantics at GPU scope (cheaper than __threadfence pairs)
+__device__ __forceinline__ void st_release_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void st_release_s32(int *p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_s32(const int *p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // exact n / d for n*d < 2^32 (host checks the range), d >= 1
 struct FastDiv {
   uint32_t mul;

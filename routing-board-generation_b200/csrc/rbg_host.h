@@ -90,6 +90,11 @@ struct EnvParams {
 int launch_env(EnvParams p, cudaStream_t stream);
 // T random-policy auto-reset steps in one launch (kind: RBG_GEN_PRW / RBG_GEN_UNIFORM); ts fields stacked [T,B,...]
 int launch_rollout(EnvParams p, int kind, int T, int32_t *action_out, cudaStream_t stream);
+// the same as a persistent kernel whose CTAs carry their own generator warps (no refill kernel); needs the cache
+// `counter`: 8 zeroed ints (two sets, recycled by the kernel); group_done / group_pending: zeroed int[groups];
+// epoch: 1, 2, ... per launch on those arrays; overlap: chain to the previous launch of the stream (PDL)
+int launch_rollout_persist(EnvParams p, int kind, int T, int32_t *action_out, int32_t *counter, int32_t *group_done, int32_t *group_pending,
+                           int epoch, bool overlap, uint64_t *cache_tag_w, uint2 *cache_key_w, uint32_t *cache_pins_w, cudaStream_t stream);
 int launch_random_actions(const rbg_state &st, int64_t B, int G, int N,
                           int32_t *action, cudaStream_t stream);
 

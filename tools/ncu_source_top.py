@@ -58,3 +58,11 @@ print("# by file:", ", ".join(f"{k} {100 * v / tot:.1f}%" for k, v in byfile.mos
 print("# inst%  stall-sample%  avg active lanes  file:line  source")
 for k, v in inst.most_common(top):
     print(f"{100 * v / tot:5.1f}  {100 * samp[k] / ts:5.1f}  {thr[k] / max(v, 1):5.1f}  {k[0]}:{k[1]}  {srcs[k]}")
+
+bys = collections.Counter()
+for k, v in samp.items():
+    bys[k[0]] += v
+print("# stall samples by file:", ", ".join(f"{k} {100 * v / ts:.1f}%" for k, v in bys.most_common()))
+print("# top lines by stall samples")
+for k, v in samp.most_common(top // 2):
+    print(f"{100 * inst[k] / tot:5.1f}  {100 * v / ts:5.1f}  {thr[k] / max(inst[k], 1):5.1f}  {k[0]}:{k[1]}  {srcs[k]}")

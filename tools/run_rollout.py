@@ -9,8 +9,8 @@ import routing_board_generation_b200 as rbg
 
 a = [int(x) for x in sys.argv[1:]]
 G, N, B, T, calls, burn = (a + [10, 5, 65536, 20, 25, 8][len(a):])[:6]
-gen = rbg.ParallelRandomWalkGenerator(grid_size=G, num_agents=N)
-env = rbg.VmapAutoResetWrapper(rbg.Connector(generator=gen, time_limit=50))
+gen = (rbg.UniformRandomGenerator if os.environ.get('KIND') == 'uniform' else rbg.ParallelRandomWalkGenerator)(grid_size=G, num_agents=N)
+env = rbg.VmapAutoResetWrapper(rbg.Connector(generator=gen, time_limit=int(os.environ.get('TL', '50'))))
 keys = rbg.split(rbg.PRNGKey(0), B)
 st, _ = env.reset(keys)
 out = None
