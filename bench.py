@@ -107,6 +107,81 @@ class ClockSampler:
         return out
 
 
+# issue roofline of the generator kernels: one warp-instruction per clock per SM sub-partition
+SMSP_PER_SM = 4
+
+
+def _issue_peak(sm_count: int, sm_mhz: float) -> float:
+    return sm_count * SMSP_PER_SM * sm_mhz * 1e6  # warp-instructions / s
+
+
+def _profile_number(key: str):
+    """A per-launch / per-board figure from the committed ncu captures (profiles/traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(key)
+    except Exception:
+        return None
+
+
+class Dist:
+    """The multi-GPU plumbing of the bench: barrier, max over ranks (NCCL); no-ops at N = 1."""
+
+    def __init__(self, world, dev):
+        self.world, self.dev = world, dev
+
+    def sync(self):
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max(self, x: float) -> float:
+        import torch
+        import torch.distributed as dist
+
+        if self.world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def timed_samples(dd: Dist, enqueue, steps: int, min_ms: float = 60.0, samples: int = 5, probe_blocks: int = 2):
+    """Device time of `steps`-step blocks.  One SAMPLE = R blocks of exactly `steps` steps enqueued back to back
+    between two CUDA events (R chosen so that a sample lasts >= min_ms; a single 20-step block is 0.6 ms, far
+    too short to time alone, and events between the blocks would serialise launches that are chained head to
+    tail); bracketed by barrier + synchronize, max over ranks.  Returns (R, [ms per block for each sample])."""
+    import torch
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dd.sync()
+    e0.record()
+    for _ in range(probe_blocks):
+        enqueue(steps)
+    e1.record()
+    dd.sync()
+    est = dd.max(e0.elapsed_time(e1) / probe_blocks)
+    R = int(min(2000, max(1, -(-min_ms // max(est, 1e-3)))))
+    out = []
+    for _ in range(samples):
+        dd.sync()
+        e0.record()
+        for _ in range(R):
+            enqueue(steps)
+        e1.record()
+        dd.sync()
+        out.append(dd.max(e0.elapsed_time(e1)) / R)
+    return R, out
+
+
+def _stats(xs):
+    return {"median": round(statistics.median(xs), 6), "min": round(min(xs), 6), "max": round(max(xs), 6)}
+
+
 # ------------------------------------------------------------------ our arm
 def run_ours(args):
     import numpy as np
@@ -133,17 +208,12 @@ def run_ours(args):
 
     lib = rbg._lib.load()
     dev = torch.device("cuda", local)
+    dd = Dist(world, dev)
     B = args.envs
     total = B * world  # weak scaling: 65 536 envs per GPU
     keys = sharding.shard_keys(rbg.PRNGKey(0), total, rank, world)
     env = rbg.VmapAutoResetWrapper(rbg.Connector(generator=rbg.ParallelRandomWalkGenerator(G, N), time_limit=TIME_LIMIT))
     state, ts = env.reset(keys)
-
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
 
     # The timed loop drives the engine the way the reference's training / benchmark loop does: a
     # scan of `n_steps` = 20 env steps per call (configs/env/connector.yaml:27), here one
@@ -153,10 +223,9 @@ def run_ours(args):
     act = torch.empty((chunk, B, N), dtype=torch.int32, device=dev)
 
     def run_steps(k):
-        nonlocal state
         while k > 0:
             n = min(k, chunk)
-            engine.connector_rollout_random(state, n, TIME_LIMIT, -0.03, 0.1, autoreset_kind="parallel_random_walk", out=ts, actions=act)
+            engine.connector_rollout_random(state, n, TIME_LIMIT, -0.03, 0.1, autoreset_kind="parallel_random_walk", out=ts, actions=act, owner=env)
             k -= n
 
     # Burn-in to the stationary regime: right after reset() every env is at step 0, so the
@@ -164,99 +233,79 @@ def run_ours(args):
     # lengths later terminations are spread evenly (about 4 % of the envs per step).
     run_steps(args.burnin)
     run_steps(max(args.warmup, 3))
-    sync_all()
+    dd.sync()
 
-    # ---- timed region: exactly K steps, device-timed, max over ranks
+    # ---- timed region: blocks of exactly K steps, device-timed, max over ranks
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     rbg.launch_count(reset=True)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync_all()
-    e0.record()
-    run_steps(args.steps)
-    e1.record()
-    sync_all()
+    R, block_ms = timed_samples(dd, run_steps, args.steps, min_ms=args.min_ms, samples=args.samples)
     launches = rbg.launch_count()
-    ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = total * args.steps / (ms_max / 1e3)
+    ms_block = statistics.median(block_ms)
+    value = total * args.steps / (ms_block / 1e3)
 
-    # ---- the dominant kernel alone: event pairs recorded inside the library around every launch,
-    # over a second pass of the same K steps
+    # ---- the dominant kernel alone: event pairs recorded inside the library around every launch
+    # (which also switches the head-to-tail chaining of consecutive launches off), over a second pass
     rbg._lib.kernel_timing(True)
     for k in ("env", "prw", "rollout"):
         rbg._lib.kernel_time(k)
-    run_steps(args.steps)
+    n_pass = max(args.steps, 10 * chunk)
+    run_steps(n_pass)
     torch.cuda.synchronize()
     n_env, ms_env = rbg._lib.kernel_time("env")
     n_prw, ms_prw = rbg._lib.kernel_time("prw")
     n_ro, ms_ro = rbg._lib.kernel_time("rollout")
     rbg._lib.kernel_timing(False)
-    clocks = sampler.stop() if rank == 0 else None  # sampled over the timed region and this identical second pass
+    clocks = sampler.stop() if rank == 0 else None  # sampled over the timed region and the kernel-timing pass
     peak, peak_src = _peaks()
-    if n_ro:  # fused path: rollout_warp_kernel covers `lib_chunk` steps per launch
-        # (with kernel timing on the library launches the whole batch per kernel, one kernel at a time;
-        # the timed region above runs two half-batch slices on two streams so that they overlap)
-        steps_per_launch = args.steps / n_ro
-        # State read once + written once per launch; per step only the emitted TimeStep and the actions
-        alg = B * (2 * STATE_BYTES + steps_per_launch * (TS_BYTES + 4 * N))
-        k_ms = ms_ro / n_ro
-        achieved = alg / (k_ms / 1e3) / 1e9
-        step_alg = B * (TS_BYTES + 4 * N + 2 * STATE_BYTES / steps_per_launch)  # algorithmic bytes of one whole step
-        step_gbs = step_alg / (ms_max / args.steps / 1e3) / 1e9
-        roofline = {"kernel": "rollout_warp_kernel", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                    "traffic": _traffic_from_profile("rollout_warp_kernel"), "algorithmic_bytes_per_launch": int(alg), "steps_per_launch": steps_per_launch,
-                    "avg_launch_ms": round(k_ms, 5), "peak_source": peak_src, "kernel_share_of_step": round(ms_ro / max(ms_ro + ms_prw + ms_env, 1e-9), 4),
-                    "refill_kernel_avg_ms": round(ms_prw / max(n_prw, 1), 5),
-                    "whole_step": {"achieved": round(step_gbs, 1), "frac": round(step_gbs / peak, 4),
-                                   "note": "algorithmic bytes of a step / the timed region's ms_per_step: rollout and cache-refill kernels of two half-batch slices overlapping on two streams"}}
-    else:
-        env_ms = ms_env / max(n_env, 1)
-        achieved = STEP_BYTES * B / (env_ms / 1e3) / 1e9
-        roofline = {"kernel": "env_warp_kernel", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": _traffic_from_profile("env_kernel"),
-                    "algorithmic_bytes_per_launch": STEP_BYTES * B, "avg_launch_ms": round(env_ms, 5), "peak_source": peak_src,
-                    "kernel_share_of_step": round(ms_env / max(ms_env + ms_prw, 1e-9), 4), "prw_reset_kernel_avg_ms": round(ms_prw / max(n_prw, 1), 5)}
+    steps_per_launch = n_pass / max(n_ro, 1)
+    # State read once + written once per launch; per step only the emitted TimeStep and the actions
+    alg = B * (2 * STATE_BYTES + steps_per_launch * (TS_BYTES + 4 * N))
+    k_ms = ms_ro / max(n_ro, 1)
+    achieved = alg / (k_ms / 1e3) / 1e9
+    step_alg = B * (TS_BYTES + 4 * N + 2 * STATE_BYTES / steps_per_launch)  # algorithmic bytes of one whole step
+    step_gbs = step_alg / (ms_block / args.steps / 1e3) / 1e9
+    roofline = {"kernel": "rollout_persist_kernel", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "traffic": _profile_number("rollout_persist_kernel"), "algorithmic_bytes_per_launch": int(alg), "steps_per_launch": steps_per_launch,
+                "avg_launch_ms": round(k_ms, 5), "peak_source": peak_src, "kernel_share_of_step": round(ms_ro / max(ms_ro + ms_prw + ms_env, 1e-9), 4),
+                "other_kernels_in_the_step": {"prw_kernel_launches": n_prw, "env_kernel_launches": n_env},
+                "note": "one launch = 20 steps over the whole batch INCLUDING the regeneration of finished envs (generator warps inside the rollout CTAs); timed alone, launches not chained",
+                "whole_step": {"achieved": round(step_gbs, 1), "frac": round(step_gbs / peak, 4),
+                               "note": "algorithmic bytes of a step / the timed region's ms_per_step (launches chained head to tail by programmatic dependent launch)"}}
 
     # ---- e2e: the env-step call with HOST buffers through the C-ABI (rbg_connector_step_host_io):
     # actions H2D from pinned memory, step, whole TimeStep D2H, every step.
     e2e = None
-    secondary = []
     cpu_baseline = None
     if not args.skip_e2e:
         e2e = _e2e_host(args, rbg, lib, state, B, world, rank, dev)
-    if rank == 0 and world == 1 and not args.skip_secondary:
-        secondary = _secondary_prw(args, rbg, peak)
+    del ts, act
+    torch.cuda.empty_cache()
+    sm_mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
+    secondary = [] if args.skip_secondary else _secondary(args, rbg, dd, peak, rank, world, sm_mhz)
     if rank == 0 and world == 1 and not args.skip_cpu:
-        cpu_baseline = _cpu_baseline(budget_s=args.cpu_seconds)
+        cpu_baseline = _cpu_baseline(budget_s=args.cpu_seconds, burnin=args.burnin, envs=B)
+        if not args.skip_secondary:
+            _cpu_secondary(secondary, budget_s=max(2.0, args.cpu_seconds / 3))
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": round(ms_max / args.steps, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+            "ms_per_step": round(ms_block / args.steps, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
             "data": "synthetic (keys = split(PRNGKey(0), B), random-policy actions)",
             "config": {"workload": "connector_step_random_agent_autoreset_prw", "grid": G, "agents": N, "envs_per_gpu": B, "envs_total": total, "time_limit": TIME_LIMIT,
                        "generator": "ParallelRandomWalkGenerator", "parallelism": f"env-sharded x{world}", "burnin_steps": args.burnin,
                        "api": f"rbg_connector_rollout_random, {chunk} steps per call (the reference's n_steps scan), State in place, stacked TimeSteps and actions written every step",
                        "l2": f"no flush: every step writes {(TS_BYTES + 4 * N) * B / 1e6:.0f} MB per GPU into a fresh slice of the stacked [{chunk}, B, ...] outputs ({(TS_BYTES + 4 * N) * B * chunk / 1e9:.1f} GB per call), far beyond the 126 MB L2"},
+            "timing": {"what": f"a sample = {R} blocks of exactly {args.steps} steps enqueued back to back between two CUDA events (barrier + synchronize on both sides, max over ranks); value / ms_per_step from the median sample",
+                       "blocks_per_sample": R, "samples": len(block_ms), "ms_per_block": _stats(block_ms), "sample_ms": round(R * ms_block, 3)},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "secondary": secondary,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-
-
-def _traffic_from_profile(kernel: str):
-    """dram bytes per launch from the committed ncu --set full capture, if one exists (profiles/*.json)."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get(kernel)
-    except Exception:
-        return None
 
 
 def _e2e_host(args, rbg, lib, state, B, world, rank, dev):
@@ -320,92 +369,100 @@ def _e2e_host(args, rbg, lib, state, B, world, rank, dev):
             "d2h_gbs": round(mine, 1), "pinned_d2h_copy_gbs": round(bus, 1), "frac_of_bus": round(mine / bus, 3)}
 
 
-def _secondary_prw(args, rbg, peak):
-    """Solved boards/s of ParallelRandomWalkBoard.generate_board (the other half of BASELINE's metric)."""
+def _secondary(args, rbg, dd, peak, rank, world, sm_mhz):
+    """The other BASELINE configs, on every rank (weak scaling like the headline: per-GPU sizes fixed, keys =
+    this rank's slice of split(PRNGKey(0), total)), device-timed, max over ranks; rank 0 keeps the lines.
+      configs[0]/[2]  ParallelRandomWalkBoard.generate_board: 10x10/5 and 20x20/10 x 131 072 boards per GPU (= 1 M boards at N = 8), 32x32/16
+      configs[3]      SeedExtension 14x14/7 x 65 536 boards + rbg_validate on every board
+      configs[4]      fused generate + reset + rollout 32x32/16, 8 192 envs per GPU, 20 steps per call
+      and the headline workload through the per-step API."""
     import torch
 
+    from routing_board_generation_b200 import sharding
+
     out = []
+    sm_count = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    issue_peak = _issue_peak(sm_count, sm_mhz)
+
+    def timed(fn, reps, min_ms=40.0):
+        for _ in range(2):
+            fn()
+        _, ms = timed_samples(dd, lambda _k: fn(), 1, min_ms=min_ms, samples=3, probe_blocks=max(1, reps // 4))
+        return statistics.median(ms), ms
+
+    def issue(line, key, units_per_s):
+        """fraction of the issue roofline: warp-instructions per unit (committed ncu capture) x units/s / (SMs x 4 x f)"""
+        wi = _profile_number(key)
+        if wi:
+            line["roofline"] = {"bound": "issue", "unit": "warp-inst/s", "warp_inst_per_unit": wi, "achieved": round(wi * units_per_s / world, 1), "peak": round(issue_peak, 1),
+                                "frac": round(wi * units_per_s / world / issue_peak, 4), "peak_source": f"{sm_count} SMs x 4 SMSP x {sm_mhz:.0f} MHz x 1 warp-inst/clk", "warp_inst_source": f"profiles/traffic.json[{key}]"}
+
     for (g, n, b) in ((10, 5, 65536), (20, 10, 131072), (32, 16, 32768)):
-        keys = rbg.split(rbg.PRNGKey(0), b)
+        keys = sharding.shard_keys(rbg.PRNGKey(0), b * world, rank, world)
         board = rbg.ParallelRandomWalkBoard(g, g, n)
-        for _ in range(3):
-            board.generate_board(keys)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 10
-        e0.record()
-        for _ in range(reps):
-            board.generate_board(keys)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / reps
+        ms, all_ms = timed(lambda: board.generate_board(keys), 10)
         bytes_ = PRW_BOARD_BYTES[(g, n)] * b
-        out.append({"metric": "prw_solved_boards_per_sec", "workload": f"ParallelRandomWalkBoard.generate_board {g}x{g}/{n} B={b}", "value": round(b / (ms / 1e3), 1), "unit": "boards/s", "ms_per_batch": round(ms, 4),
-                    "output_gbs": round(bytes_ / (ms / 1e3) / 1e9, 2), "hbm_frac": round(bytes_ / (ms / 1e3) / 1e9 / peak, 5), "bound": "integer issue (threefry2x32), see DESIGN.md"})
-    # the same headline workload through the per-step API (one rbg_connector_step_random call per env step:
+        line = {"metric": "prw_solved_boards_per_sec", "workload": f"ParallelRandomWalkBoard.generate_board {g}x{g}/{n}, {b} boards per GPU ({b * world} total)", "grid": g, "agents": n, "value": round(b * world / (ms / 1e3), 1), "unit": "boards/s",
+                "n_gpus": world, "ms_per_batch": round(ms, 4), "ms_samples": [round(x, 4) for x in all_ms], "output_gbs_per_gpu": round(bytes_ / (ms / 1e3) / 1e9, 2), "hbm_frac": round(bytes_ / (ms / 1e3) / 1e9 / peak, 5),
+                "bound": "integer issue (threefry2x32), see DESIGN.md"}
+        issue(line, f"prw_kernel_{g}x{g}_{n}_warp_inst_per_board", b * world / (ms / 1e3))
+        out.append(line)
+        del keys
+    # the headline workload through the per-step API (one rbg_connector_step_random call per env step:
     # env_warp_kernel + reset kernel + side-stream cache refill), for callers that cannot use the fused rollout
     g, n, b = G, N, 65536
     env = rbg.VmapAutoResetWrapper(rbg.Connector(generator=rbg.ParallelRandomWalkGenerator(g, n), time_limit=TIME_LIMIT))
-    st, _ = env.reset(rbg.split(rbg.PRNGKey(0), b))
+    box = {"st": env.reset(sharding.shard_keys(rbg.PRNGKey(0), b * world, rank, world))[0]}
     ts1 = rbg.engine.alloc_timestep(b, g, n)
-    for _ in range(160):
-        st, _, _ = rbg.engine.connector_step(st, None, TIME_LIMIT, -0.03, 0.1, autoreset_kind="parallel_random_walk", inplace=True, random_policy=True, out=ts1, owner=env)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 200
-    e0.record()
-    for _ in range(reps):
-        st, _, _ = rbg.engine.connector_step(st, None, TIME_LIMIT, -0.03, 0.1, autoreset_kind="parallel_random_walk", inplace=True, random_policy=True, out=ts1, owner=env)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
-    out.append({"metric": "connector_env_steps_per_sec", "workload": f"per-step API (one Python call = one rbg_connector_step_random per env step) {g}x{g}/{n} B={b}", "value": round(b / (ms / 1e3), 1), "unit": "env-steps/s",
-                "ms_per_step": round(ms, 4), "output_gbs": round(STEP_BYTES * b / (ms / 1e3) / 1e9, 1), "hbm_frac": round(STEP_BYTES * b / (ms / 1e3) / 1e9 / peak, 4)})
+
+    def one_step():
+        box["st"], _, _ = rbg.engine.connector_step(box["st"], None, TIME_LIMIT, -0.03, 0.1, autoreset_kind="parallel_random_walk", inplace=True, random_policy=True, out=ts1, owner=env)
+
+    for _ in range(args.burnin):
+        one_step()
+    _, ms_l = timed_samples(dd, lambda k: [one_step() for _ in range(k)], 20, min_ms=40.0, samples=3)
+    ms = statistics.median(ms_l) / 20
+    out.append({"metric": "connector_env_steps_per_sec", "workload": f"per-step API (one Python call = one rbg_connector_step_random per env step) {g}x{g}/{n}, {b} envs per GPU", "value": round(b * world / (ms / 1e3), 1), "unit": "env-steps/s",
+                "n_gpus": world, "ms_per_step": round(ms, 5), "ms_per_step_samples": [round(x / 20, 5) for x in ms_l], "output_gbs_per_gpu": round(STEP_BYTES * b / (ms / 1e3) / 1e9, 1), "hbm_frac": round(STEP_BYTES * b / (ms / 1e3) / 1e9 / peak, 4)})
+    del ts1, box, env
     # fused generate + reset + rollout at the A2C rollout shape (BASELINE configs[4]): 32x32 / 16 agents, 20 steps
     g, n, b, T = 32, 16, 8192, 20
     env = rbg.VmapAutoResetWrapper(rbg.Connector(generator=rbg.ParallelRandomWalkGenerator(g, n), time_limit=TIME_LIMIT))
-    st, _ = env.reset(rbg.split(rbg.PRNGKey(0), b))
+    st, _ = env.reset(sharding.shard_keys(rbg.PRNGKey(0), b * world, rank, world))
     ts_big = rbg.engine.alloc_timestep(b, g, n, T)
     for _ in range(6):  # past the first episodes
-        st, _, _ = env.rollout_random(st, T, out=ts_big)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 5
-    e0.record()
-    for _ in range(reps):
-        st, _, _ = env.rollout_random(st, T, out=ts_big)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
+        env.rollout_random(st, T, out=ts_big)
+    ms, all_ms = timed(lambda: env.rollout_random(st, T, out=ts_big), 5, min_ms=30.0)
     step_bytes = 4 * n * g * g + 5 * n + 4 + 8 * n + 1 + 12 + 4 * n  # what a fused step must emit (SURVEY 8d: 65 825 B)
-    out.append({"metric": "connector_env_steps_per_sec", "workload": f"fused generate+reset+rollout {g}x{g}/{n} B={b}, {T} steps per call", "value": round(b * T / (ms / 1e3), 1), "unit": "env-steps/s",
-                "ms_per_step": round(ms / T, 4), "output_gbs": round(step_bytes * b * T / (ms / 1e3) / 1e9, 1), "hbm_frac": round(step_bytes * b * T / (ms / 1e3) / 1e9 / peak, 4)})
-    del ts_big, st
+    out.append({"metric": "connector_env_steps_per_sec", "workload": f"fused generate+reset+rollout {g}x{g}/{n}, {b} envs per GPU, {T} steps per call", "value": round(b * world * T / (ms / 1e3), 1), "unit": "env-steps/s",
+                "n_gpus": world, "ms_per_step": round(ms / T, 4), "ms_per_call_samples": [round(x, 4) for x in all_ms], "output_gbs_per_gpu": round(step_bytes * b * T / (ms / 1e3) / 1e9, 1),
+                "hbm_frac": round(step_bytes * b * T / (ms / 1e3) / 1e9 / peak, 4), "bound": "hbm"})
+    del ts_big, st, env
     torch.cuda.empty_cache()
     # SeedExtension 14x14/7 (BASELINE configs[3]): generation + on-device validity of every board
     g, n, b = 14, 7, 65536
-    keys = rbg.split(rbg.PRNGKey(0), b)
+    keys = sharding.shard_keys(rbg.PRNGKey(0), b * world, rank, world)
     board = rbg.SeedExtensionBoard(g, g, n)
-    for _ in range(2):
-        solved = board.return_solved_board(keys)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 5
-    e0.record()
-    for _ in range(reps):
-        solved = board.return_solved_board(keys)
-        flags = rbg.engine.validate(solved, n)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
-    out.append({"metric": "seedext_solved_boards_per_sec", "workload": f"SeedExtensionBoard.return_solved_board {g}x{g}/{n} B={b} + rbg_validate", "value": round(b / (ms / 1e3), 1), "unit": "boards/s",
-                "ms_per_batch": round(ms, 4), "invalid_boards": int((flags != 0).sum()), "bound": "sequential threefry chain per board (one lane per board), see DESIGN.md"})
-    return out
+    res = {}
+
+    def se():
+        res["solved"] = board.return_solved_board(keys)
+        res["flags"] = rbg.engine.validate(res["solved"], n)
+
+    ms, all_ms = timed(se, 5, min_ms=30.0)
+    line = {"metric": "seedext_solved_boards_per_sec", "workload": f"SeedExtensionBoard.return_solved_board {g}x{g}/{n}, {b} boards per GPU + rbg_validate", "value": round(b * world / (ms / 1e3), 1), "unit": "boards/s",
+            "n_gpus": world, "ms_per_batch": round(ms, 4), "ms_samples": [round(x, 4) for x in all_ms], "invalid_boards": int((res["flags"] != 0).sum()),
+            "bound": "sequential threefry chain per board (G*G*sweeps dependent split() steps), see DESIGN.md"}
+    issue(line, "seedext_pipeline_14x14_7_warp_inst_per_board", b * world / (ms / 1e3))
+    out.append(line)
+    return out if rank == 0 else []
 
 
 # ------------------------------------------------------------------ CPU arm
-def _cpu_workload(orc, B, nthreads):
-    """reset B envs with the oracle and return a stepping closure (random policy + auto-reset step)."""
+def _cpu_workload(orc, B, nthreads, burnin=0):
+    """reset B envs with the oracle, run `burnin` untimed steps (the same stationary regime as the GPU arm:
+    episode ends desynchronised, about 4 % of the envs reset per step) and return a stepping closure
+    (random policy + auto-reset step)."""
     kref = orc.split(orc.PRNGKey(0), B)
     st, _ = orc.connector_reset_batch("parallel_random_walk", kref, G, N, nthreads=nthreads)
     box = {"st": st, "ts": None}
@@ -416,6 +473,8 @@ def _cpu_workload(orc, B, nthreads):
         box["st"], box["ts"] = orc.connector_step_batch(box["st"], act, time_limit=TIME_LIMIT, autoreset_kind="parallel_random_walk", nthreads=nthreads, inplace=True, out=box["ts"])
         return box["ts"]
 
+    for _ in range(burnin):
+        step()
     return step
 
 
@@ -429,28 +488,65 @@ def _host_threads() -> int:
     return n
 
 
-def _cpu_baseline(budget_s: float = 15.0):
+def _cpu_baseline(budget_s: float = 12.0, burnin: int = 160, envs: int = ENVS_PER_GPU):
+    """The oracle port on every host core: the SAME batch and the same burn-in as the GPU arm and the
+    reference arm, for a bounded number of steps."""
     cores = _host_threads()
     from oracle import oracle as orc
 
     orc.build()
-    B = 16384
-    step = _cpu_workload(orc, B, cores)
-    for _ in range(2):
-        step()
+    step = _cpu_workload(orc, envs, cores, burnin=burnin)
     n, t0 = 0, time.perf_counter()
-    while time.perf_counter() - t0 < budget_s:
+    while time.perf_counter() - t0 < budget_s or n < 5:
         step()
         n += 1
     dt = time.perf_counter() - t0
-    return {"value": round(B * n / dt, 1), "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{n} auto-reset random-agent steps over {B} envs 10x10/5 (same workload, smaller batch), OpenMP over envs, {dt:.1f} s"}
+    return {"value": round(envs * n / dt, 1), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} auto-reset random-agent steps over {envs} envs 10x10/5 after {burnin} burn-in steps (the GPU arm's batch and regime), OpenMP over envs, {dt:.1f} s"}
+
+
+def _cpu_secondary(secondary, budget_s: float = 4.0):
+    """boards/s of the CPU port for the generator lines (all host cores, bounded samples), and the reference's own
+    NumPy BFSBoard generator (BASELINE's secondary baseline, README.md:88-93) where /root/reference is mounted
+    (the build container; it does not exist on the GPU box)."""
+    cores = _host_threads()
+    from oracle import oracle as orc
+
+    def rate(fn, n0):
+        n, t0, done = n0, time.perf_counter(), 0
+        while True:
+            fn(n)
+            done += n
+            dt = time.perf_counter() - t0
+            if dt > budget_s:
+                return done / dt, done, dt
+            n = min(n * 2, 1 << 16)
+
+    for line in secondary:
+        if line["metric"] == "prw_solved_boards_per_sec":
+            g, n = line["grid"], line["agents"]
+            v, done, dt = rate(lambda k: orc.prw_generate_batch(orc.split(orc.PRNGKey(1), k), g, n, nthreads=cores), 512)
+            line["cpu_baseline"] = {"value": round(v, 1), "unit": "boards/s", "cores": cores, "kind": "port", "sample": f"{done} boards {g}x{g}/{n} in {dt:.1f} s, OpenMP over boards"}
+        elif line["metric"] == "seedext_solved_boards_per_sec":
+            v, done, dt = rate(lambda k: orc.seedext_solved_batch(orc.split(orc.PRNGKey(1), k), 14, 7, nthreads=cores), 256)
+            line["cpu_baseline"] = {"value": round(v, 1), "unit": "boards/s", "cores": cores, "kind": "port", "sample": f"{done} boards 14x14/7 in {dt:.1f} s, OpenMP over boards"}
+    bfs = {"metric": "numpy_bfs_board_boards_per_sec", "workload": "reference NumPy BFSBoard(10, 10, 5).return_solved_board() in a Python loop, single process (README.md:88-93)", "unit": "boards/s"}
+    if os.path.isdir("/root/reference/routing_board_generation"):
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "time_bfs_board_numpy.py"), "150"], capture_output=True, text=True, timeout=120)
+            d = json.loads(r.stdout.strip().splitlines()[-1])
+            bfs.update(value=d["boards_per_sec"], cores=1, kind="reference", sample=f"{d['boards']} boards in {d['seconds']} s, measured in this run")
+        except Exception as e:  # noqa: BLE001
+            bfs.update(value=None, note=f"failed here: {e!r}")
+    else:
+        bfs.update(value=None, kind="reference", note="the reference is not mounted on this box; build-container figure: 456 boards/s on one core (profiles/r01_cpu_baselines.md, tools/time_bfs_board_numpy.py)")
+    secondary.append(bfs)
 
 
 def run_reference(args):
     """The reference's CPU implementation of the path.  The reference is pure Python on JAX and
     neither jax nor jumanji exist in this image, so this arm times the C oracle port
-    with every host thread."""
+    with every host thread, on the GPU arm's batch and after the same burn-in."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -459,21 +555,27 @@ def run_reference(args):
 
     orc.build()
     B = args.envs
-    step = _cpu_workload(orc, B, cores)
+    step = _cpu_workload(orc, B, cores, burnin=args.burnin)
     for _ in range(max(args.warmup, 1)):
         step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    dt = time.perf_counter() - t0
+    # blocks of exactly K steps until the sample is long enough to time (one block of 20 steps is 0.3 s here)
+    blocks = []
+    t_all = time.perf_counter()
+    while len(blocks) < 3 or (time.perf_counter() - t_all < args.cpu_seconds and len(blocks) < 50):
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        blocks.append(time.perf_counter() - t0)
+    dt = statistics.median(blocks)
     value = B * args.steps / dt
     world = int(os.environ.get("WORLD_SIZE", "1"))
     line = {
         "impl": "reference", "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": round(dt / args.steps * 1e3, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic (keys = split(PRNGKey(0), B), random-policy actions)",
         "config": {"workload": "connector_step_random_agent_autoreset_prw", "grid": G, "agents": N, "envs_per_gpu": B, "envs_total": B, "time_limit": TIME_LIMIT, "generator": "ParallelRandomWalkGenerator",
-                   "parallelism": f"OpenMP x{cores} host threads"},
-        "cpu_baseline": {"value": round(value, 1), "unit": UNIT, "cores": cores, "kind": "port", "sample": f"{args.steps} steps over {B} envs (rank 0 only; the CPU arm does not scale with --gpus)"},
+                   "parallelism": f"OpenMP x{cores} host threads", "burnin_steps": args.burnin},
+        "timing": {"what": f"{len(blocks)} blocks of exactly {args.steps} steps, host wall clock, median", "ms_per_block": _stats([b * 1e3 for b in blocks])},
+        "cpu_baseline": {"value": round(value, 1), "unit": UNIT, "cores": cores, "kind": "port", "sample": f"{len(blocks)} x {args.steps} steps over {B} envs after {args.burnin} burn-in steps (rank 0 only; the CPU arm does not scale with --gpus)"},
         "e2e": {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -490,6 +592,8 @@ def main():
     ap.add_argument("--burnin", type=int, default=160, help="untimed steps after reset() so that episode ends are desynchronised")
     ap.add_argument("--chunk", type=int, default=20, help="env steps per rollout call (the reference's n_steps)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--min-ms", type=float, default=60.0, help="a timed sample lasts at least this long (blocks of --steps steps back to back)")
+    ap.add_argument("--samples", type=int, default=5, help="timed samples (median reported)")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-secondary", action="store_true")
