@@ -16,11 +16,20 @@
 //   se_seed_kernel      one warp per board: key derivation, lattice seeding
 //                       (the same warp-cooperative top-N selection as the
 //                       ParallelRandomWalk start cells), uint8 board -> scratch
-//   se_extend_kernel    one LANE per board, board + sweep snapshot in that lane's
-//                       slice of shared memory (odd word stride: conflict-free
-//                       when lanes touch the same cell); the two chain blocks of a
-//                       cell are independent instruction streams (ILP 2); flips
-//                       are coordinate transforms, never data movement
+//   se_extend_kernel    one LANE per board, board in that lane's slice of shared
+//                       memory (odd word stride: conflict-free when lanes touch the
+//                       same cell).  The key chain never reads the board, so a row is
+//                       done in two phases: (i) a dense burst, every lane advances its
+//                       chain G cells (two independent blocks per cell, 32 / 32 lanes)
+//                       and parks the G cell keys in shared memory; (ii) every lane
+//                       then visits only ITS extendable cells of the row (2N of G*G
+//                       cells are), the lanes aligned on "k-th extendable cell of the
+//                       row", so the heavy head-extension path runs 3-4 times per row
+//                       with most lanes in it instead of at nearly every cell with
+//                       two.  Sweeps are processed in ROUNDS of a few sweeps: boards
+//                       that need more are compacted into dense warps for the next
+//                       round (sweep counts differ per board: 6 .. 16 at 14x14).
+//                       Flips are coordinate transforms, never data movement
 //   se_optimise_kernel  one lane per board: per wire a FIFO breadth-first search
 //                       (the reference's argmin/max queue is a FIFO in disguise),
 //                       parents as 3-bit direction codes tagged with the wire id
@@ -40,6 +49,7 @@ struct SeScratch {
   uint8_t *board;   // [B, CB]  row-major G*G codes, CB = cells rounded up to 16
   uint32_t *keys;   // [B, 4]   loop key (2), optkey of the current iteration (2)
   uint32_t *gkey;   // [B, 2]   State.key (random_seed_generator.py:34,57)
+  uint32_t *ext;    // [B, 4]   extension state between rounds: extend_wires_jax's key (2), sweeps done, unused
   int32_t *status;  // [B]      bit0 BFS ran dry / pop limit (never seen), bits 8.. sweeps
   uint32_t *snap;   // [ceil(B/32), SB2w, 32]  pre-sweep board of every lane, word-interleaved per warp
   int CB;
@@ -51,7 +61,7 @@ struct SeDims {
   uint32_t thresh;    // selection filter
   int cap;
   int S2, SB2w;       // extend: padded stride (G+4), words per padded board
-  int lane_words_ext; // extend: words per lane (the padded board), odd
+  int lane_words_ext; // extend: words per lane (the padded board + the G cell keys of a row), odd
   int S1, SB1;        // optimise: padded stride (G+2), bytes per padded board
   int lane_bytes_opt; // optimise: bytes per lane (board, parents, fifo, pins), multiple of 4 with odd word count
 };
@@ -135,91 +145,173 @@ __device__ __forceinline__ void split3(uint32_t k0, uint32_t k1, uint32_t out[6]
   tf_block(k0, k1, 2u, 5u, out[2], out[5]);
 }
 
-// The random pick of extend_wires_jax (PPU:127-144) for the lanes in `needm`, computed by the whole
-// warp.  One lane alone would run, per draw, split(k) -> split(ck) -> random_bits: five threefry
-// blocks in three dependent levels, and only 1-3 lanes of a warp need a pick at the same cell.
-// Here five worker lanes serve each needing lane (six at a time): roles 0, 1 the two blocks of
-// `k, ck = split(k)`, roles 2, 3 the two blocks of randint's `split(ck)`, role 4 the block of
-// random_bits(k2); the levels are pipelined across draws, so every pass of ONE block per lane
-// completes one draw of every needing lane (draw t comes out of pass t + 2).  The first draw that
-// lands on a valid candidate wins, exactly as in the sequential loop.
-__device__ __forceinline__ uint32_t warp_pick(uint32_t needm, bool need, uint32_t k0, uint32_t k1, uint32_t ok, uint32_t pick, int lane) {
-  const int my_rank = __popc(needm & ((1u << lane) - 1u)), total = __popc(needm);
-  const int s = lane / 5, r = lane - 5 * s;  // slot and role of this lane as a worker (lanes 30, 31 have none)
-  const uint32_t c0 = (r == 1 || r == 3) ? 1u : 0u, c1 = r == 4 ? 0u : c0 + 2u;  // (0,2) (1,3) (0,2) (1,3) (0,0)
-  const int src_a = 5 * s + (r == 4 ? 2 : 0);
-  for (int base = 0; base < total; base += 6) {
-    const int ns = total - base < 6 ? total - base : 6;
-    const bool worker = s < ns;
-    const int owner = worker ? (int)__fns(needm, 0, base + s + 1) : 0;  // the lane this slot works for
-    uint32_t x0 = __shfl_sync(FULL, k0, owner), x1 = __shfl_sync(FULL, k1, owner);
-    const uint32_t slot_ok = __shfl_sync(FULL, ok, owner);
-    bool done = !(worker && r == 4);
-    uint32_t result = 0;
-    for (int t = 0;; ++t) {
-      uint32_t o0, o1;
-      tf_block(x0, x1, c0, c1, o0, o1);
-      if (!done && t >= 2) {  // role 4: random_bits of draw t - 2
-        const uint32_t pk = 1u << (o0 & 3u);
-        if (slot_ok & pk) {
-          result = pk;
-          done = true;
-        }
-      }
-      if (!__any_sync(FULL, !done)) break;
-      // roles 0, 1 <- split(k)[0]; roles 2, 3 <- ck = split(k)[1]; role 4 <- k2 = split(ck)[1]
-      const uint32_t a0 = __shfl_sync(FULL, o0, src_a), a1 = __shfl_sync(FULL, o1, src_a);
-      const uint32_t b0 = __shfl_sync(FULL, o0, src_a + 1), b1 = __shfl_sync(FULL, o1, src_a + 1);
-      x0 = r < 2 ? a0 : a1;
-      x1 = r < 2 ? b0 : b1;
+// The random pick of extend_wires_jax (PPU:127-144): repeat `k, ck = split(k); pos = list[randint(ck, 0, 4)]`
+// until the drawn candidate is valid, starting from the cell's key, which the loop does NOT advance.  The k of
+// that loop is the cell chain itself (key = split(key)[0], PPU:156), so draw t of the cell at chain position j
+// is a function of the random_key r_{j+t} = split(key_{j+t})[1] alone:
+//     D(j + t) = random_bits(split(r_{j+t})[1]) & 3            (randint over a span of 4: the low draw)
+// and the pick is the first t whose D lands on a valid candidate.  The row burst parks r for the row's cells
+// and SE_LOOK cells beyond, so a pick needs no chain at all: the lanes of the warp evaluate, for every lane that
+// needs a pick, `per` consecutive draws at once (two dependent threefry levels for the whole warp), and a
+// ballot finds each lane's first hit.  A pick that outruns the parked keys (about 1 % of them) continues the
+// chain on its own lane.
+constexpr int SE_LOOK = 8;
+
+__device__ __forceinline__ uint32_t se_draw(uint32_t r0, uint32_t r1) {
+  uint32_t a0, a1, b0, b1;
+  tf_block(r0, r1, 0u, 2u, a0, b0);
+  tf_block(r0, r1, 1u, 3u, a1, b1);
+  return bits_scalar(b0, b1) & 3u;  // candidate index in list order up, left, down, right
+}
+
+// rb_warp: the warp's shared-memory slices; lane L's parked keys start at word L * lane_words + rb_off, two words
+// per chain position.  idx: this lane's position in its buffer, avail: parked positions from idx on.
+// (key0, key1): this lane's chain key just behind its buffer.
+__device__ __forceinline__ uint32_t warp_pick(uint32_t needm, bool need, const uint32_t *rb_warp, int lane_words, int rb_off, int idx, int avail,
+                                              uint32_t key0, uint32_t key1, uint32_t ok, uint32_t pick, int lane) {
+  const int n = __popc(needm);
+  const int per = 32 / n;                      // draws evaluated per needing lane and pass
+  const int slot = lane / per, j = lane - slot * per;
+  const bool worker = slot < n;
+  const int owner = worker ? (int)__fns(needm, 0, slot + 1) : 0;  // the lane this worker draws for
+  const uint32_t own_ok = __shfl_sync(FULL, ok, owner);
+  const int own_idx = __shfl_sync(FULL, idx, owner), own_avail = __shfl_sync(FULL, avail, owner);
+  const uint32_t *rb = rb_warp + (size_t)owner * lane_words + rb_off;
+  const int my_slot = __popc(needm & ((1u << lane) - 1u));
+  const uint32_t my_range = (per == 32 ? FULL : ((1u << per) - 1u)) << (my_slot * per);  // the lanes that draw for me
+  bool pending = need;
+  int done_draws = 0;
+  for (int t0 = 0;; t0 += per) {
+    const uint32_t pendm = __ballot_sync(FULL, pending && t0 < avail);
+    if (!pendm) break;
+    const int t = t0 + j;
+    uint32_t d = 0;
+    bool hit = false;
+    if (worker && ((pendm >> owner) & 1u) && t < own_avail) {
+      d = se_draw(rb[2 * (own_idx + t)], rb[2 * (own_idx + t) + 1]);
+      hit = ((own_ok >> d) & 1u) != 0u;
     }
-    const bool mine = need && my_rank >= base && my_rank < base + ns;
-    const uint32_t got = __shfl_sync(FULL, result, mine ? 5 * (my_rank - base) + 4 : 0);
-    if (mine) pick = got;
+    const uint32_t hits = __ballot_sync(FULL, hit) & my_range;
+    const uint32_t dd = __shfl_sync(FULL, d, hits ? __ffs((int)hits) - 1 : 0);
+    if (pending && hits) {
+      pick = 1u << dd;
+      pending = false;
+    }
+    done_draws = t0 + per;
+  }
+  if (pending) {  // outran the parked keys: the chain goes on from the key behind the buffer (draws avail, avail + 1, ...)
+    (void)done_draws;
+    uint32_t k0 = key0, k1 = key1;
+    for (;;) {
+      uint32_t n0, r0, n1, r1;
+      tf_block(k0, k1, 0u, 2u, n0, r0);
+      tf_block(k0, k1, 1u, 3u, n1, r1);
+      const uint32_t d = se_draw(r0, r1);
+      if ((ok >> d) & 1u) {
+        pick = 1u << d;
+        break;
+      }
+      k0 = n0;
+      k1 = n1;
+    }
   }
   return pick;
 }
 
-__global__ void __launch_bounds__(128) se_extend_kernel(const SeedExtParams p, const SeDims d, const SeScratch sc) {
+// One round of extend_wires_jax's sweep loop (PPU:47-195) over the boards of `list_in`.
+struct SeRound {
+  const int32_t *list_in;   // scratch slots of the boards still sweeping (NULL: 0 .. total-1, the first round)
+  const int32_t *count_in;  // device count of list_in
+  int32_t *list_out;        // boards that need more sweeps after this round (NULL: this round runs to convergence)
+  int32_t *count_out;
+  int max_sweeps;           // sweeps per board in this round (<= 0: unbounded)
+  int dense_warps;          // boards are packed 32 per warp only while that fills this many warps (see lanes_used)
+  int first;                // first round of an extension iteration: key, extkey, optkey = split(key, 3)  SE:189
+};
+
+__device__ __forceinline__ bool se_extendable(uint32_t v, bool two_sided) {
+  if (v == 0u || v == 0xFFu) return false;
+  const uint32_t wv = v - 1u, ctype = wv - 3u * ((wv * 171u) >> 9) + 1u;  // x / 3 == (x * 171) >> 9 for x < 256
+  return two_sided ? ctype != PATH : ctype == TARGET;                       // PPU:109-116
+}
+
+__global__ void __launch_bounds__(128) se_extend_kernel(const SeedExtParams p, const SeDims d, const SeScratch sc, const SeRound rd) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = m < se_total(p);
+  const long long total = rd.list_in ? (long long)(*rd.count_in) : se_total(p);
+  // A round that is left with few boards is bound by the LATENCY of a sweep (a sequential hash chain per board
+  // plus, per row, as many head-extension passes as the busiest lane of the warp needs), not by issue slots: such
+  // rounds spread their boards over more warps, `lanes_used` boards per warp, so that a warp waits for fewer boards.
+  const long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  int lanes_used = 32;
+  {
+    const long long grid_warps = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long spread = rd.dense_warps < grid_warps ? rd.dense_warps : grid_warps;  // warps the boards may be spread over
+    if ((total + 31) / 32 < spread) {
+      lanes_used = (int)((total + spread - 1) / spread);
+      if (lanes_used < 1) lanes_used = 1;
+    }
+  }
+  if (wg * lanes_used >= total) return;  // the whole warp is beyond the list
+  const long long t = wg * lanes_used + lane;
+  const bool live = lane < lanes_used && t < total;
+  const long long m = live ? (rd.list_in ? (long long)rd.list_in[t] : t) : 0;
   const int G = d.G, S = d.S2;
   uint8_t *mine = smem_raw + ((size_t)warp * 32 + lane) * d.lane_words_ext * 4;
   uint8_t *board = mine;
+  uint32_t *rb = reinterpret_cast<uint32_t *>(mine) + d.SB2w;  // [G + SE_LOOK][2] random_key of the row's cells and SE_LOOK beyond
+  const uint32_t *rb_warp = reinterpret_cast<const uint32_t *>(smem_raw) + (size_t)warp * 32 * d.lane_words_ext;
   // the pre-sweep snapshot lives in global memory (L2), word q of this lane at [q * 32 + lane] of
-  // its warp's region: written and read once per mirrored sweep, coalesced, and it halves the
-  // shared-memory footprint (twice the resident warps)
-  uint32_t *snap = sc.snap + (size_t)(m >> 5) * d.SB2w * 32 + lane;
+  // its warp's region: written and read once per mirrored sweep, coalesced
+  uint32_t *snap = sc.snap + (size_t)wg * d.SB2w * 32 + lane;
 
-  // key, extkey, optkey = split(key, 3)   SE:189
   uint32_t key0 = 0, key1 = 0;
+  long long step_num = 0;
   if (live) {
-    uint32_t f[6];
-    split3(sc.keys[4 * m], sc.keys[4 * m + 1], f);
-    sc.keys[4 * m] = f[0];
-    sc.keys[4 * m + 1] = f[1];
-    sc.keys[4 * m + 2] = f[4];
-    sc.keys[4 * m + 3] = f[5];
-    key0 = f[2];
-    key1 = f[3];
+    if (rd.first) {  // key, extkey, optkey = split(key, 3)   SE:189
+      uint32_t f[6];
+      split3(sc.keys[4 * m], sc.keys[4 * m + 1], f);
+      sc.keys[4 * m] = f[0];
+      sc.keys[4 * m + 1] = f[1];
+      sc.keys[4 * m + 2] = f[4];
+      sc.keys[4 * m + 3] = f[5];
+      key0 = f[2];
+      key1 = f[3];
+    } else {
+      key0 = sc.ext[4 * m];
+      key1 = sc.ext[4 * m + 1];
+      step_num = (long long)sc.ext[4 * m + 2];
+    }
     // padded board: 0xFF outside the grid (never EMPTY, never anybody's wire)
     uint32_t *w = reinterpret_cast<uint32_t *>(board);
     for (int q = 0; q < d.SB2w; ++q) w[q] = 0xFFFFFFFFu;
-    const uint8_t *src = sc.board + (size_t)m * sc.CB;
-    for (int r = 0; r < G; ++r)
-      for (int c = 0; c < G; ++c) board[(r + 2) * S + (c + 2)] = src[r * G + c];
+    const uint4 *src = reinterpret_cast<const uint4 *>(sc.board + (size_t)m * sc.CB);  // CB is a multiple of 16
+    int r = 0, c = 0;
+    for (int q = 0; q < (sc.CB >> 4); q += 2) {  // two 128-bit loads in flight
+      const uint4 a = src[q];
+      const uint4 b = q + 1 < (sc.CB >> 4) ? src[q + 1] : make_uint4(0, 0, 0, 0);
+      const uint32_t ws[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) {
+          if (r < G) board[(r + 2) * S + (c + 2)] = (uint8_t)(ws[k] >> (8 * bb));
+          if (++c == G) {
+            c = 0;
+            ++r;
+          }
+        }
+    }
   }
   const bool two_sided = p.two_sided != 0;
   const bool use_rand = p.randomness > 0.0f;
-  bool again = live;  // prev_layout differs from the board by construction  PPU:47
-  long long step_num = 0;
+  bool again = live;  // prev_layout differs from the board by construction  PPU:47; a board in a later round's list needs a sweep
   int sweeps = 0;
-  // The sweep is warp-synchronous: all 32 lanes walk the cells together (lanes whose board has
-  // converged idle through it), so that the random picks can be computed by the whole warp.
+  // The sweep is warp-synchronous: all 32 lanes walk the rows together (lanes whose board has converged idle
+  // through the rest of the round), so that the chain bursts run at 32 / 32 lanes and the random picks can
+  // be computed by the whole warp.
   for (;;) {
-    const bool act = again && (p.ext_steps < 0 || step_num < p.ext_steps);
+    const bool act = again && (p.ext_steps < 0 || step_num < p.ext_steps) && (rd.max_sweeps <= 0 || sweeps < rd.max_sweeps);
     if (!__any_sync(FULL, act)) break;
     bool flip = false, flop = false;
     if (act) {
@@ -239,95 +331,167 @@ __global__ void __launch_bounds__(128) se_extend_kernel(const SeedExtParams p, c
       for (int q = 0; q < d.SB2w; ++q) snap[q * 32] = a[q];
     }
     bool modified = false;
+    int mod_idx = 0;
+    uint32_t mod_v = 0;
     // walking the FLIPPED board row-major == walking the board with mirrored
     // coordinates and mirrored neighbour directions
     const int sr = flip ? -S : S, scol = flop ? -1 : 1;
     uint8_t *prow = board + ((flip ? G - 1 : 0) + 2) * S + ((flop ? G - 1 : 0) + 2);
+    uint32_t end0 = key0, end1 = key1;  // the loop key after the sweep's G*G cells (the burst runs SE_LOOK cells past them)
     for (int row = 0; row < G; ++row, prow += sr) {
-      uint8_t *pc = prow;
-      for (int col = 0; col < G; ++col, pc += scol) {
-        // key, random_key = split(key)   PPU:156 -- runs for EVERY cell
+      // ---- (i) the chain of this row: key, random_key = split(key) for EVERY cell (PPU:156), board-independent.
+      // All lanes, two independent blocks per cell.  random_key is parked for the row's G cells and SE_LOOK cells
+      // beyond (the random picks read ahead, see warp_pick); the burst of the next row continues from there.
+      const int fresh = row == 0 ? 0 : SE_LOOK;  // positions [0, fresh) are carried over from the previous row
+      if (row > 0)
+        for (int i = 0; i < 2 * SE_LOOK; ++i) rb[i] = rb[2 * G + i];
+      for (int i = fresh; i < G + SE_LOOK; ++i) {
         uint32_t n0, r0, n1, r1;
         tf_block(key0, key1, 0u, 2u, n0, r0);
         tf_block(key0, key1, 1u, 3u, n1, r1);
-        uint32_t v = 0, b3 = 0, ok = 0, pick = 0;
-        bool need = false;
+        rb[2 * i] = r0;
+        rb[2 * i + 1] = r1;
         if (act) {
-          v = pc[0];
-          const uint32_t wv = v - 1u;           // v == 0 wraps: type test below fails
-          const uint32_t w3 = (wv / 3u) * 3u;   // 3 * wire
-          const uint32_t ctype = wv - w3 + 1u;  // PATH 1, POSITION 2, TARGET 3
-          const bool extendable = v != 0u && (two_sided ? ctype != PATH : ctype == TARGET);  // PPU:109-116
-          if (extendable) {
-            b3 = w3 + 1u;
-            // candidates in list order up, left, down, right (PPU:322-369); a
-            // candidate is dropped when it touches the wire anywhere but through
-            // the current cell (PPU:86-97)
-            const uint32_t u = pc[-sr], l = pc[-scol], dn = pc[sr], r = pc[scol];
-            const bool oul = own_wire(pc[-sr - scol], b3), our = own_wire(pc[-sr + scol], b3);
-            const bool odl = own_wire(pc[sr - scol], b3), odr = own_wire(pc[sr + scol], b3);
-            ok |= (u == 0u && !own_wire(pc[-2 * sr], b3) && !oul && !our) ? 1u : 0u;
-            ok |= (l == 0u && !own_wire(pc[-2 * scol], b3) && !oul && !odl) ? 2u : 0u;
-            ok |= (dn == 0u && !own_wire(pc[2 * sr], b3) && !odl && !odr) ? 4u : 0u;
-            ok |= (r == 0u && !own_wire(pc[2 * scol], b3) && !our && !odr) ? 8u : 0u;
-            if (ok) {
-              // previous neighbour: last match among up, down, left (PPU:200-234);
-              // the priority cell mirrors it through the current cell (PPU:99-103)
-              uint32_t pri = 0;
-              if (own_wire(u, b3)) pri = 4u;   // came from above -> continue down
-              if (own_wire(dn, b3)) pri = 1u;  // from below -> up
-              if (own_wire(l, b3)) pri = 8u;   // from the left -> right
-              bool take_pri = (ok & pri) != 0u;
-              if (take_pri && use_rand) {  // PPU:157-162
-                const float uni = bits_to_uniform(bits_scalar(r0, r1));
-                take_pri = !(p.randomness > uni);
-              }
-              pick = pri;
-              need = !take_pri;
+          key0 = n0;
+          key1 = n1;
+        }
+        if (row * G + i == d.cells - 1) {
+          end0 = key0;
+          end1 = key1;
+        }
+      }
+      // ---- (ii) the extendable cells of this row, in traversal order.  One pass over the row marks them in a
+      // bit mask (no early exits: 32 lanes, G independent loads); a head that grows to the right becomes a new
+      // extendable cell further along the same row and is added to the mask, so `next cell` is a find-first-set.
+      unsigned long long emask = 0ull;
+      if (act)
+        for (int c2 = 0; c2 < G; ++c2) emask |= (unsigned long long)(se_extendable(prow[c2 * scol], two_sided) ? 1u : 0u) << c2;
+      for (;;) {
+        const bool have = emask != 0ull;
+        if (!__any_sync(FULL, have)) break;
+        const int col = have ? __ffsll((long long)emask) - 1 : 0;
+        emask &= emask - 1ull;
+        const uint32_t v = have ? prow[col * scol] : 0u;
+        uint8_t *pc = prow + col * scol;
+        uint32_t b3 = 0, ok = 0, pick = 0;
+        bool need = false;
+        if (have) {
+          const uint32_t wv = v - 1u;
+          b3 = 3u * ((wv * 171u) >> 9) + 1u;  // the wire's PATH code
+          // candidates in list order up, left, down, right (PPU:322-369); a
+          // candidate is dropped when it touches the wire anywhere but through
+          // the current cell (PPU:86-97)
+          const uint32_t u = pc[-sr], l = pc[-scol], dn = pc[sr], r = pc[scol];
+          const bool oul = own_wire(pc[-sr - scol], b3), our = own_wire(pc[-sr + scol], b3);
+          const bool odl = own_wire(pc[sr - scol], b3), odr = own_wire(pc[sr + scol], b3);
+          ok |= (u == 0u && !own_wire(pc[-2 * sr], b3) && !oul && !our) ? 1u : 0u;
+          ok |= (l == 0u && !own_wire(pc[-2 * scol], b3) && !oul && !odl) ? 2u : 0u;
+          ok |= (dn == 0u && !own_wire(pc[2 * sr], b3) && !odl && !odr) ? 4u : 0u;
+          ok |= (r == 0u && !own_wire(pc[2 * scol], b3) && !our && !odr) ? 8u : 0u;
+          if (ok) {
+            // previous neighbour: last match among up, down, left (PPU:200-234);
+            // the priority cell mirrors it through the current cell (PPU:99-103)
+            uint32_t pri = 0;
+            if (own_wire(u, b3)) pri = 4u;   // came from above -> continue down
+            if (own_wire(dn, b3)) pri = 1u;  // from below -> up
+            if (own_wire(l, b3)) pri = 8u;   // from the left -> right
+            bool take_pri = (ok & pri) != 0u;
+            if (take_pri && use_rand) {  // PPU:157-162: random_key = split(key)[1] of this cell
+              const float uni = bits_to_uniform(bits_scalar(rb[2 * col], rb[2 * col + 1]));
+              take_pri = !(p.randomness > uni);
             }
+            pick = pri;
+            need = !take_pri;
           }
         }
         // repeat `k, ck = split(k); pos = list[randint(ck, 0, 4)]` until valid, from the cell's
-        // key, which is NOT advanced by this loop (PPU:127-144): the lanes that need it are few
-        // (1-3 per cell), so the whole warp computes their draws (warp_pick)
+        // key, which is NOT advanced by this loop (PPU:127-144): the whole warp computes the draws
+        // of the lanes that need one (warp_pick)
         const uint32_t needm = __ballot_sync(FULL, need);
-        if (needm) pick = warp_pick(needm, need, key0, key1, ok, pick, lane);
+        if (needm) pick = warp_pick(needm, need, rb_warp, d.lane_words_ext, d.SB2w, col, G + SE_LOOK - col, key0, key1, ok, pick, lane);
         if (ok) {
           const int delta = pick == 1u ? -sr : (pick == 2u ? -scol : (pick == 4u ? sr : scol));
           pc[delta] = (uint8_t)v;   // the head / target moves      PPU:165-167
           pc[0] = (uint8_t)b3;      // and leaves PATH behind       PPU:168-173
           modified = true;
-        }
-        if (act) {
-          key0 = n0;
-          key1 = n1;
+          mod_idx = (int)(pc + delta - board);  // the last write of the sweep survives it
+          mod_v = v;
+          if (delta == scol) emask |= 1ull << (col + 1);  // grew along the row: visited again further on, as in the cell-by-cell walk
         }
       }
+    }
+    if (act) {
+      key0 = end0;
+      key1 = end1;
     }
     // PPU:186-189: un-flip the board (a no-op here) and loop while the FLIPPED
     // pre-sweep layout differs from the un-flipped result
     if (act) {
+      // flipped pre-sweep cell that faces cell (r, c) of the result: (flip ? G-1-r : r, flop ? G-1-c : c)
+      auto mirror_idx = [&](int idx) {
+        const int r = idx / S - 2, c = idx - (r + 2) * S - 2;
+        return ((flip ? G - 1 - r : r) + 2) * S + 2 + (flop ? G - 1 - c : c);
+      };
       if (!mirrored) {
         again = modified;
-      } else {
+      } else if (!modified) {
+        // nothing moved: the result IS the pre-sweep board, the loop goes on unless that board is its own mirror image
         bool diff = false;
-        for (int r = 0; r < G; ++r) {
+        for (int r = 0; r < G && !diff; ++r) {
           const uint8_t *a = board + (r + 2) * S + 2;
-          int o = ((flip ? G - 1 - r : r) + 2) * S + 2 + (flop ? G - 1 : 0);  // byte offset in the snapshot
-          for (int c = 0; c < G; ++c, o += scol) {
-            const uint32_t w = snap[(o >> 2) * 32];
-            diff |= (uint32_t)a[c] != ((w >> (8 * (o & 3))) & 0xffu);
+          const uint8_t *b = board + ((flip ? G - 1 - r : r) + 2) * S + 2 + (flop ? G - 1 : 0);
+          for (int c = 0; c < G; ++c) diff |= a[c] != b[c * scol];
+        }
+        again = diff;
+      } else {
+        // the cell written last holds a wire-end code, which occurs once on a board: the mirrored pre-sweep board
+        // matches there only if that very end sat on the facing cell.  One snapshot word decides nearly always.
+        const int o = mirror_idx(mod_idx);
+        bool diff = ((snap[(o >> 2) * 32] >> (8 * (o & 3))) & 0xffu) != mod_v;
+        if (!diff) {
+          for (int r = 0; r < G && !diff; ++r) {
+            const uint8_t *a = board + (r + 2) * S + 2;
+            int oo = ((flip ? G - 1 - r : r) + 2) * S + 2 + (flop ? G - 1 : 0);  // byte offset in the snapshot
+            for (int c = 0; c < G; ++c, oo += scol) {
+              const uint32_t w = snap[(oo >> 2) * 32];
+              diff |= (uint32_t)a[c] != ((w >> (8 * (oo & 3))) & 0xffu);
+            }
           }
         }
         again = diff;
       }
     }
   }
+  // ---- the board goes back to the scratch; boards that need more sweeps are compacted for the next round
+  const bool more = live && again && (p.ext_steps < 0 || step_num < p.ext_steps) && rd.list_out != nullptr;
   if (live) {
-    uint8_t *dst = sc.board + (size_t)m * sc.CB;
-    for (int r = 0; r < G; ++r)
-      for (int c = 0; c < G; ++c) dst[r * G + c] = board[(r + 2) * S + (c + 2)];
+    uint32_t *dst = reinterpret_cast<uint32_t *>(sc.board + (size_t)m * sc.CB);
+    int r = 0, c = 0;
+    for (int q = 0; q < (d.cells + 3) >> 2; ++q) {
+      uint32_t w = 0;
+#pragma unroll
+      for (int bb = 0; bb < 4; ++bb) {
+        if (r < G) w |= (uint32_t)board[(r + 2) * S + (c + 2)] << (8 * bb);
+        if (++c == G) {
+          c = 0;
+          ++r;
+        }
+      }
+      dst[q] = w;
+    }
     sc.status[m] += sweeps << 8;
+    if (more) {
+      sc.ext[4 * m] = key0;
+      sc.ext[4 * m + 1] = key1;
+      sc.ext[4 * m + 2] = (uint32_t)step_num;
+    }
+  }
+  const uint32_t morem = __ballot_sync(FULL, more);
+  if (morem) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(rd.count_out, __popc(morem));
+    base = __shfl_sync(FULL, base, 0);
+    if (more) rd.list_out[base + __popc(morem & ((1u << lane) - 1u))] = (int32_t)m;
   }
 }
 
@@ -581,7 +745,7 @@ int launch_seedext(SeedExtParams p, int64_t max_boards, cudaStream_t stream) {
   }
   d.S2 = G + 4;
   d.SB2w = (int)(round_up((size_t)d.S2 * d.S2, 4) / 4);
-  d.lane_words_ext = d.SB2w | 1;  // odd: lanes on the same cell hit 32 different banks
+  d.lane_words_ext = (d.SB2w + 2 * (G + SE_LOOK)) | 1;  // board + the parked random_keys of a row (+ look-ahead); odd: lanes on the same cell hit 32 different banks
   d.S1 = G + 2;
   d.SB1 = (int)round_up((size_t)d.S1 * d.S1, 4);
   {
@@ -595,7 +759,9 @@ int launch_seedext(SeedExtParams p, int64_t max_boards, cudaStream_t stream) {
   const size_t n = (size_t)max_boards;
   const size_t o_keys = round_up(n * sc.CB, 256), o_gkey = o_keys + round_up(n * 16, 256), o_status = o_gkey + round_up(n * 8, 256);
   const size_t o_snap = o_status + round_up(n * 4, 256);
-  const size_t total = o_snap + round_up(((n + 31) / 32) * 32 * (size_t)d.SB2w * 4, 256);
+  const size_t o_ext = o_snap + round_up(((n + 127) / 128 * 4) * 32 * (size_t)d.SB2w * 4, 256);  // one region per warp of the extend launches (up to 4 warps per CTA)
+  const size_t o_lists = o_ext + round_up(n * 16, 256);  // two ping-pong lists of scratch slots + 64 round counters
+  const size_t total = o_lists + 2 * round_up(n * 4, 256) + 256;
   uint8_t *base = nullptr;
   {  // keep the stream-ordered pool's memory cached between calls (default: released at every sync)
     static bool pool_ready = false;
@@ -616,6 +782,9 @@ int launch_seedext(SeedExtParams p, int64_t max_boards, cudaStream_t stream) {
   sc.gkey = reinterpret_cast<uint32_t *>(base + o_gkey);
   sc.status = reinterpret_cast<int32_t *>(base + o_status);
   sc.snap = reinterpret_cast<uint32_t *>(base + o_snap);
+  sc.ext = reinterpret_cast<uint32_t *>(base + o_ext);
+  int32_t *lists[2] = {reinterpret_cast<int32_t *>(base + o_lists), reinterpret_cast<int32_t *>(base + o_lists + round_up(n * 4, 256))};
+  int32_t *round_count = reinterpret_cast<int32_t *>(base + o_lists + 2 * round_up(n * 4, 256));
 
   int rc = RBG_OK;
   do {
@@ -638,13 +807,48 @@ int launch_seedext(SeedExtParams p, int64_t max_boards, cudaStream_t stream) {
     if (const char *ex = getenv("RBG_SE_OPT_WARPS")) opt_w = atoi(ex) >= 1 && atoi(ex) <= 4 ? warps_for(opt_warp, atoi(ex)) : opt_w;
     if ((rc = set_smem(reinterpret_cast<const void *>(se_extend_kernel), ext_warp * ext_w, "se_extend_kernel"))) break;
     if ((rc = set_smem(reinterpret_cast<const void *>(se_optimise_kernel), opt_warp * opt_w, "se_optimise_kernel"))) break;
+    // Rounds of the sweep loop: boards converge after different numbers of sweeps (6 .. 16 at 14x14/7), and a
+    // warp lasts as long as its slowest lane, so after every round the boards that need more sweeps are
+    // compacted into dense warps.  The launches are sized for the whole batch (the device-side count is not
+    // known here); warps beyond the list leave at once.  The last round runs whatever is left to convergence.
+    static int se_round = -1, se_rounds = -1, se_dense_warps = 1;
+    if (se_round < 0) {
+      const char *ex = getenv("RBG_SE_ROUND_SWEEPS");
+      se_round = ex ? atoi(ex) : 2;
+      if (se_round < 1) se_round = 1;
+      ex = getenv("RBG_SE_ROUNDS");
+      se_rounds = ex ? atoi(ex) : 0;  // measured: compaction rounds do not pay (the batch is bound by the slowest board's sweep latency), see DESIGN.md K3
+      if (se_rounds < 0) se_rounds = 0;
+      if (se_rounds > 30) se_rounds = 30;
+      int sms = 148;
+      int dev = 0;
+      if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      ex = getenv("RBG_SE_DENSE_WARPS");
+      se_dense_warps = ex ? atoi(ex) : sms * 8;  // about what is resident at once
+      if (se_dense_warps < 1) se_dense_warps = 1;
+    }
     for (int it = 0; it < p.iterations && rc == RBG_OK; ++it) {  // SE:180-200 while_loop over extension_iterations
-      {
+      cudaError_t me = cudaMemsetAsync(round_count, 0, 256, stream);
+      if (me != cudaSuccess) {
+        rc = set_cuda_error(me, "cudaMemsetAsync(SeedExtension round counters)");
+        break;
+      }
+      for (int r = 0; r <= se_rounds && rc == RBG_OK; ++r) {
+        SeRound rd;
+        rd.first = r == 0 ? 1 : 0;
+        rd.list_in = r == 0 ? nullptr : lists[(r - 1) & 1];
+        rd.count_in = r == 0 ? nullptr : round_count + (r - 1);
+        const bool last = r == se_rounds;
+        rd.list_out = last ? nullptr : lists[r & 1];
+        rd.count_out = last ? nullptr : round_count + r;
+        rd.max_sweeps = last ? 0 : se_round;
+        rd.dense_warps = se_dense_warps;
         const unsigned ctas = (unsigned)((max_boards + ext_w * 32 - 1) / (ext_w * 32));
         LaunchScope scope(RBG_K_SEEDEXT, stream);
-        se_extend_kernel<<<ctas, ext_w * 32, ext_warp * ext_w, stream>>>(p, d, sc);
+        se_extend_kernel<<<ctas, ext_w * 32, ext_warp * ext_w, stream>>>(p, d, sc, rd);
+        rc = check_launch("se_extend_kernel");
       }
-      if ((rc = check_launch("se_extend_kernel"))) break;
+      if (rc) break;
       {
         const unsigned ctas = (unsigned)((max_boards + opt_w * 32 - 1) / (opt_w * 32));
         LaunchScope scope(RBG_K_SEEDEXT, stream);
