@@ -407,6 +407,15 @@ def _secondary(args, rbg, dd, peak, rank, world, sm_mhz):
                 "bound": "integer issue (threefry2x32), see DESIGN.md"}
         issue(line, f"prw_kernel_{g}x{g}_{n}_warp_inst_per_board", b * world / (ms / 1e3))
         out.append(line)
+        if (g, n) == (10, 5):
+            # the consumer of solved boards in the reference's benchmark: EvaluateEmptyBoard statistics per board
+            solved = board.generate_board(keys)[2]
+            ms2, all2 = timed(lambda: rbg.engine.board_statistics(solved), 10)
+            sb = (8 * g * g + 8) * b  # int32 board in, int32 scored board out, two int32 per board
+            out.append({"metric": "board_statistics_boards_per_sec", "workload": f"EvaluateEmptyBoard statistics (scored board, count_detours, heatmap_score_diversity) {g}x{g}/{n}, {b} boards per GPU",
+                        "value": round(b * world / (ms2 / 1e3), 1), "unit": "boards/s", "n_gpus": world, "ms_per_batch": round(ms2, 4), "ms_samples": [round(x, 4) for x in all2],
+                        "output_gbs_per_gpu": round(sb / (ms2 / 1e3) / 1e9, 1), "hbm_frac": round(sb / (ms2 / 1e3) / 1e9 / peak, 4), "bound": "issue (G^3 / 32 row-column scans per lane for count_detours)"})
+            del solved
         del keys
     # the headline workload through the per-step API (one rbg_connector_step_random call per env step:
     # env_warp_kernel + reset kernel + side-stream cache refill), for callers that cannot use the fused rollout

@@ -241,6 +241,18 @@ int rbg_connector_rollout_random(const rbg_state *state, int32_t *action_out,
 int rbg_validate(const int32_t *boards, int64_t B, int G, int N, int32_t *flags,
                  void *stream);
 
+/* Board statistics of solved boards: EvaluateEmptyBoard (benchmarking/benchmarks/empty_board_evaluation.py:31-155),
+ * the deterministic part of what run_benchmark_on_generated_board collects per board.
+ *   scored[B,G,G]  score_from_neighbours (:56-88): per cell, the 3x3 window of assess_board's scores (empty -2, head /
+ *                  target 3, route 2; zero padding) weighted [[1,2,1],[2,4,2],[1,2,1]], times the number of distinct
+ *                  wire labels in the window (labels by _change_heads_to_wire_ids :90-97).  May be NULL.
+ *   detours[B]     count_detours(count_current_wire) (:99-137)
+ *   diversity[B]   heatmap_score_diversity = len(np.unique(scored_board)) (:155)
+ * Codes outside [0, 96] make detours = diversity = -1 for that board.  Not reproduced: BoardProcessor's wire lengths /
+ * bends, which come from shortest paths chosen by an unseeded random.shuffle (board_processor.py:111-162). */
+int rbg_board_statistics(const int32_t *boards, int64_t B, int G, int count_current_wire,
+                         int32_t *scored, int32_t *detours, int32_t *diversity, void *stream);
+
 /* ---- host-buffer variants: same semantics, HOST pointers, copies inside,
  * synchronous.  device < 0 = current device. ------------------------------ */
 int rbg_prw_generate_host(const uint32_t *keys, int64_t B, int G, int N,

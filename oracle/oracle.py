@@ -352,5 +352,18 @@ def validate_batch(boards, N: int, nthreads: int = 0) -> np.ndarray:
     return flags
 
 
+def board_statistics_batch(boards, count_current_wire: bool = False, nthreads: int = 0):
+    """EvaluateEmptyBoard over boards[B,G,G] -> scored[B,G,G], count_detours[B], heatmap_score_diversity[B]."""
+    boards = _i32(boards)
+    if boards.ndim == 2:
+        boards = boards[None]
+    B, G, _ = boards.shape
+    scored = np.empty((B, G, G), np.int32)
+    det = np.empty((B,), np.int32)
+    div = np.empty((B,), np.int32)
+    lib().orc_board_statistics_batch(C.c_int64(B), C.c_int(G), _p(boards, i32p), C.c_int(int(count_current_wire)), _p(scored, i32p), _p(det, i32p), _p(div, i32p), C.c_int(nthreads))
+    return scored, det, div
+
+
 def max_threads() -> int:
     return int(lib().orc_max_threads())

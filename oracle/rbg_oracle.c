@@ -1194,6 +1194,105 @@ void orc_connector_step_batch(int64_t B, int G, int N, int32_t *grid,
                               obs_step_count, nthreads);
 }
 
+/* ======================================================================== */
+/* board statistics: EvaluateEmptyBoard (benchmarking/benchmarks/                */
+/* empty_board_evaluation.py:31-155), the deterministic part; pinned by          */
+/* tests/golden/board_stats_reference.npz = that class executed unmodified        */
+/* ======================================================================== */
+
+/* assess_board (:41-54): empty -2, head (v % 3 == 2) 3, target (v % 3 == 0, v != 0) 3, route (v % 3 == 1) 2 */
+static int stat_cell_score(int32_t v) {
+  if (v == 0) return -2;
+  return v % 3 == 1 ? 2 : 3;
+}
+
+/* get_wire_num (:139-151): -1 below 2, else (label - 2) // 3 -- so PATH cells of wire w > 0 count as wire w - 1 */
+static int stat_wire_num(int32_t v) { return v < 2 ? -1 : (v - 2) / 3; }
+
+/* scored [G,G] (score_from_neighbours :56-88), *detours (count_detours :99-137),
+ * *diversity (heatmap_score_diversity :155 = number of distinct scores) */
+void orc_board_statistics(int G, const int32_t *board, int count_current_wire, int32_t *scored, int32_t *detours,
+                          int32_t *diversity) {
+  const int P = G + 2;
+  int32_t *lab = (int32_t *)calloc((size_t)P * P, sizeof(int32_t));   /* _change_heads_to_wire_ids on the padded board */
+  int32_t *ind = (int32_t *)calloc((size_t)P * P, sizeof(int32_t));   /* np.pad(individual_score, 1): zeros, not -2 */
+  int maxv = 0;
+  for (int k = 0; k < G * G; ++k)
+    if (board[k] > maxv) maxv = board[k];
+  uint8_t *present = (uint8_t *)calloc((size_t)maxv + 4, 1);          /* unique(filled_board[filled_board % 3 == 2]) */
+  for (int k = 0; k < G * G; ++k)
+    if (board[k] > 0 && board[k] % 3 == 2) present[board[k]] = 1;
+  for (int r = 0; r < G; ++r)
+    for (int c = 0; c < G; ++c) {
+      int32_t v = board[r * G + c];
+      /* for wire_id in unique ids (ascending): cells == id + 1 -> id, cells == id + 2 -> id (:90-97); the values it
+       * produces are ids (2 mod 3) and no later id looks for those, so this is a per-cell map */
+      if (v > 0 && v % 3 == 0 && present[v - 1]) v = v - 1;
+      else if (v >= 4 && v % 3 == 1 && present[v - 2]) v = v - 2;
+      lab[(r + 1) * P + c + 1] = v;
+      ind[(r + 1) * P + c + 1] = stat_cell_score(board[r * G + c]);
+    }
+  static const int filt[9] = {1, 2, 1, 2, 4, 2, 1, 2, 1};
+  for (int r = 1; r <= G; ++r)
+    for (int c = 1; c <= G; ++c) {
+      int32_t seen[9];
+      int nseen = 0, sum = 0;
+      for (int dr = -1; dr <= 1; ++dr)
+        for (int dc = -1; dc <= 1; ++dc) {
+          const int32_t l = lab[(r + dr) * P + c + dc];
+          sum += ind[(r + dr) * P + c + dc] * filt[(dr + 1) * 3 + dc + 1];
+          if (l == 0) continue;
+          int dup = 0;
+          for (int q = 0; q < nseen; ++q) dup |= seen[q] == l;
+          if (!dup) seen[nseen++] = l;
+        }
+      scored[(r - 1) * G + c - 1] = sum * nseen; /* np.sum(window * filter * diversity) */
+    }
+  int nd = 0;
+  for (int a = 0; a < G * G; ++a) {
+    int dup = 0;
+    for (int b = 0; b < a && !dup; ++b) dup = scored[b] == scored[a];
+    nd += !dup;
+  }
+  *diversity = nd;
+  /* count_detours: for every TARGET cell and every PATH cell with label >= 2, the wires (by get_wire_num, empty cells
+   * skipped, the cell's own wire excluded unless count_current_wire) that occur both above and below, plus those
+   * that occur both left and right */
+  int det = 0;
+  for (int x = 0; x < G; ++x)
+    for (int y = 0; y < G; ++y) {
+      const int32_t v = board[x * G + y];
+      if (v < 2 || v % 3 == 2) continue;
+      const int cur = stat_wire_num(v);
+      for (int pass = 0; pass < 2; ++pass) {
+        uint64_t before = 0, after = 0; /* wire nums -1 .. 62 as bits 0 .. 63 */
+        for (int t = 0; t < G; ++t) {
+          const int32_t u = pass == 0 ? board[t * G + y] : board[x * G + t];
+          const int pos = pass == 0 ? x : y;
+          if (t == pos || u == 0) continue;
+          const int w = stat_wire_num(u);
+          if (!count_current_wire && w == cur) continue;
+          if (t < pos) before |= 1ull << (w + 1);
+          else after |= 1ull << (w + 1);
+        }
+        det += __builtin_popcountll(before & after);
+      }
+    }
+  *detours = det;
+  free(lab);
+  free(ind);
+  free(present);
+}
+
+void orc_board_statistics_batch(int64_t B, int G, const int32_t *boards, int count_current_wire, int32_t *scored,
+                                int32_t *detours, int32_t *diversity, int nthreads) {
+  int nt = pick_threads(nthreads);
+  (void)nt;
+#pragma omp parallel for num_threads(nt) schedule(static)
+  for (int64_t b = 0; b < B; ++b)
+    orc_board_statistics(G, &boards[b * G * G], count_current_wire, &scored[b * G * G], &detours[b], &diversity[b]);
+}
+
 void orc_validate_batch(int64_t B, int G, int N, const int32_t *boards,
                         int32_t *flags, int nthreads) {
   int nt = pick_threads(nthreads);

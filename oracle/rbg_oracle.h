@@ -182,6 +182,12 @@ void orc_connector_step_batch_ds(int64_t B, int G, int N, int32_t *grid,
                                  float *ratio_connections,
                                  int32_t *total_path_length,
                                  int32_t *obs_step_count, int nthreads);
+/* EvaluateEmptyBoard (benchmarking/benchmarks/empty_board_evaluation.py:31-155): scored board, count_detours,
+ * heatmap_score_diversity */
+void orc_board_statistics(int G, const int32_t *board, int count_current_wire, int32_t *scored, int32_t *detours,
+                          int32_t *diversity);
+void orc_board_statistics_batch(int64_t B, int G, const int32_t *boards, int count_current_wire, int32_t *scored,
+                                int32_t *detours, int32_t *diversity, int nthreads);
 void orc_validate_batch(int64_t B, int G, int N, const int32_t *boards,
                         int32_t *flags, int nthreads);
 /* the bench's random policy (OUR convention, not a parity surface):

@@ -60,6 +60,7 @@ SYMBOLS = {
     "rbg_connector_step_random": (_int, [_SP, _SP, _vp, _i64, _int, _int, _EP, _TP, _vp, _vp]),
     "rbg_connector_rollout_random": (_int, [_SP, _vp, _i64, _i64, _int, _int, _EP, _TP, _vp, _vp]),
     "rbg_validate": (_int, [_vp, _i64, _int, _int, _vp, _vp]),
+    "rbg_board_statistics": (_int, [_vp, _i64, _int, _int, _vp, _vp, _vp, _vp]),
     "rbg_prw_generate_host": (_int, [_vp, _i64, _int, _int, _vp, _vp, _vp, _int]),
     "rbg_connector_reset_host": (_int, [_int, _vp, _i64, _int, _int, _SP, _TP, _int]),
     "rbg_connector_step_host": (_int, [_SP, _SP, _vp, _i64, _int, _int, _EP, _TP, _int]),

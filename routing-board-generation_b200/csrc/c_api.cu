@@ -999,6 +999,15 @@ int rbg_validate(const int32_t *boards, int64_t B, int G, int N, int32_t *flags,
   return launch_validate(boards, B, G, N, flags, (cudaStream_t)stream);
 }
 
+int rbg_board_statistics(const int32_t *boards, int64_t B, int G, int count_current_wire, int32_t *scored, int32_t *detours, int32_t *diversity,
+                         void *stream) {
+  int rc;
+  if ((rc = check_dims(B, G, 1, 0))) return rc;
+  if (B == 0) return RBG_OK;
+  if (!boards || !detours || !diversity) return set_error(RBG_EINVAL, "rbg_board_statistics: NULL pointer");
+  return launch_board_stats(boards, B, G, count_current_wire, scored, detours, diversity, (cudaStream_t)stream);
+}
+
 // ---------------------------------------------------------------- _host
 void *rbg_host_alloc(int64_t bytes) {
   void *p = nullptr;

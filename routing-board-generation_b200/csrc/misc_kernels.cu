@@ -290,6 +290,134 @@ __global__ void __launch_bounds__(VAL_WARPS * 32) validate_kernel(const int32_t 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Board statistics: EvaluateEmptyBoard (benchmarking/benchmarks/empty_board_evaluation.py:31-155), the
+// deterministic part -- score_from_neighbours (:56-88: 3x3 weighted window of the per-cell scores times the
+// number of distinct wire labels in the window, with _change_heads_to_wire_ids' label map :90-97),
+// count_detours (:99-137) and heatmap_score_diversity (:155, the number of distinct scores).  One warp per
+// board, the board as bytes in shared memory with a one-cell border; 4 B read and (optionally) 4 B written per
+// cell.  tests/golden/board_stats_reference.npz holds the reference class's own outputs.
+constexpr int STAT_WARPS = 4;
+constexpr int STAT_SCORE_BITS = 1024;  // scores lie in [-9 * 32, 9 * 48]; bit = score + 320
+
+__global__ void __launch_bounds__(STAT_WARPS * 32) board_stats_kernel(const int32_t *__restrict__ boards, long long B, int G, int count_current_wire,
+                                                                     int32_t *__restrict__ scored, int32_t *__restrict__ detours,
+                                                                     int32_t *__restrict__ diversity, int32_t *__restrict__ status) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int P = G + 2, PB = (P * P + 15) & ~15, cells = G * G;
+  uint8_t *raw = smem_raw + (size_t)warp * (3 * PB + STAT_SCORE_BITS / 8);  // codes, 0 on the border
+  uint8_t *lab = raw + PB;                                                  // _change_heads_to_wire_ids labels
+  int8_t *ind = reinterpret_cast<int8_t *>(lab + PB);                       // assess_board scores, 0 on the border
+  uint32_t *bits = reinterpret_cast<uint32_t *>(ind + PB);
+  for (long long b = (long long)blockIdx.x * STAT_WARPS + warp; b < B; b += (long long)gridDim.x * STAT_WARPS) {
+    const int32_t *src = boards + b * cells;
+    for (int i = lane; i < PB; i += 32) raw[i] = lab[i] = 0, ind[i] = 0;
+    if (lane < STAT_SCORE_BITS / 32) bits[lane] = 0u;
+    __syncwarp();
+    // codes must fit the label / wire-number bit sets: 0 .. 96 (32 wires); anything else is reported, not scored
+    int bad = 0;
+    uint32_t plo = 0;  // POSITION codes present: unique(filled_board[filled_board % 3 == 2])  (:92), bit w for code 3w + 2
+    for (int i = lane; i < cells; i += 32) {
+      const int v = __ldg(src + i);
+      if (v < 0 || v > 3 * RBG_MAX_N) {
+        bad = 1;
+        continue;
+      }
+      const int r = i / G, c = i - r * G;
+      raw[(r + 1) * P + c + 1] = (uint8_t)v;
+      if (v % 3 == 2) plo |= 1u << (v / 3);
+    }
+    bad = __reduce_or_sync(FULL, bad);
+    plo = __reduce_or_sync(FULL, plo);
+    if (bad) {
+      if (lane == 0) {
+        detours[b] = -1;
+        diversity[b] = -1;
+        if (status) atomicOr(status, 1);
+      }
+      __syncwarp();
+      continue;
+    }
+    __syncwarp();
+    for (int i = lane; i < cells; i += 32) {
+      const int r = i / G, c = i - r * G, idx = (r + 1) * P + c + 1;
+      int v = raw[idx];
+      ind[idx] = (int8_t)(v == 0 ? -2 : (v % 3 == 1 ? 2 : 3));  // assess_board (:41-54)
+      // for every head code id present: cells == id + 1 -> id, cells == id + 2 -> id  (:94-96)
+      if (v > 0 && v % 3 == 0 && ((plo >> ((v - 1) / 3)) & 1u)) v -= 1;
+      else if (v >= 4 && v % 3 == 1 && ((plo >> ((v - 2) / 3)) & 1u)) v -= 2;
+      lab[idx] = (uint8_t)v;
+    }
+    __syncwarp();
+    // score_from_neighbours (:56-88)
+    for (int i = lane; i < cells; i += 32) {
+      const int r = i / G, c = i - r * G, idx = (r + 1) * P + c + 1;
+      int sum = 0, nseen = 0;
+      uint32_t seen[9];
+#pragma unroll
+      for (int dr = -1; dr <= 1; ++dr)
+#pragma unroll
+        for (int dc = -1; dc <= 1; ++dc) {
+          const int q = idx + dr * P + dc;
+          sum += (int)ind[q] * ((dr == 0 ? 2 : 1) * (dc == 0 ? 2 : 1));
+          const uint32_t l = lab[q];
+          bool dup = l == 0u;
+#pragma unroll
+          for (int k = 0; k < 9; ++k) dup |= k < nseen && seen[k] == l;
+          if (!dup) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k)
+              if (k == nseen) seen[k] = l;
+            ++nseen;
+          }
+        }
+      const int sc = sum * nseen;
+      if (scored) scored[b * cells + i] = sc;
+      atomicOr(&bits[(sc + 320) >> 5], 1u << ((sc + 320) & 31));
+    }
+    // count_detours (:99-137): wire numbers by get_wire_num (:139-151), -1 .. 31 as bits 0 .. 32
+    int det = 0;
+    for (int i = lane; i < cells; i += 32) {
+      const int x = i / G, y = i - x * G;
+      const int v = raw[(x + 1) * P + y + 1];
+      if (v < 2 || v % 3 == 2) continue;
+      const int cur = (v - 2) / 3;
+      unsigned long long above = 0, below = 0, left = 0, right = 0;
+      for (int t = 0; t < G; ++t) {
+        const int u = raw[(t + 1) * P + y + 1], h = raw[(x + 1) * P + t + 1];
+        const int wu = u < 2 ? -1 : (u - 2) / 3, wh = h < 2 ? -1 : (h - 2) / 3;
+        if (t != x && u != 0 && (count_current_wire || wu != cur)) (t < x ? above : below) |= 1ull << (wu + 1);
+        if (t != y && h != 0 && (count_current_wire || wh != cur)) (t < y ? left : right) |= 1ull << (wh + 1);
+      }
+      det += __popcll(above & below) + __popcll(left & right);
+    }
+    det = __reduce_add_sync(FULL, det);
+    __syncwarp();
+    int nd = lane < STAT_SCORE_BITS / 32 ? __popc(bits[lane]) : 0;
+    nd = __reduce_add_sync(FULL, nd);
+    if (lane == 0) {
+      detours[b] = det;
+      diversity[b] = nd;
+    }
+    __syncwarp();
+  }
+}
+
+int launch_board_stats(const int32_t *boards, int64_t B, int G, int count_current_wire, int32_t *scored, int32_t *detours, int32_t *diversity,
+                       cudaStream_t stream) {
+  if (B <= 0) return RBG_OK;
+  const int P = G + 2, PB = (P * P + 15) & ~15;
+  const size_t smem = (size_t)STAT_WARPS * (3 * PB + STAT_SCORE_BITS / 8);
+  int64_t ctas = (B + STAT_WARPS - 1) / STAT_WARPS;
+  if (ctas > 148 * 32) ctas = 148 * 32;
+  {
+    LaunchScope scope(RBG_K_VALIDATE, stream);
+    board_stats_kernel<<<(unsigned)ctas, STAT_WARPS * 32, smem, stream>>>(boards, B, G, count_current_wire, scored, detours, diversity, nullptr);
+  }
+  return check_launch("board_stats_kernel");
+}
+
 int launch_validate(const int32_t *boards, int64_t B, int G, int N, int32_t *flags, cudaStream_t stream) {
   if (B <= 0) return RBG_OK;
   const int cells = G * G, cp = (cells + 15) & ~15;

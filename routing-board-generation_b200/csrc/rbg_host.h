@@ -104,6 +104,8 @@ int launch_split_keys(uint32_t k0, uint32_t k1, int64_t B, int64_t offset,
 int launch_split_each(const uint32_t *keys, int64_t B, int num, uint32_t *out, cudaStream_t stream);
 int launch_dataset_state(const uint32_t *keys, int64_t B, int G, int N, const int32_t *heads, const int32_t *targets, int64_t K,
                          const rbg_state &st, cudaStream_t stream);
+int launch_board_stats(const int32_t *boards, int64_t B, int G, int count_current_wire, int32_t *scored, int32_t *detours, int32_t *diversity,
+                       cudaStream_t stream);
 int launch_validate(const int32_t *boards, int64_t B, int G, int N,
                     int32_t *flags, cudaStream_t stream);
 

@@ -244,6 +244,23 @@ def validate(boards: torch.Tensor, N: int) -> torch.Tensor:
     return flags
 
 
+def board_statistics(boards: torch.Tensor, count_current_wire: bool = False, with_scores: bool = True):
+    """EvaluateEmptyBoard over boards[B,G,G] (or [G,G]): (scored[B,G,G] or None, count_detours[B], heatmap_score_diversity[B])."""
+    boards = as_tensor(boards, torch.int32)
+    single = boards.dim() == 2
+    if single:
+        boards = boards[None]
+    B, G, _ = boards.shape
+    dev = _device()
+    scored = torch.empty((B, G, G), dtype=torch.int32, device=dev) if with_scores else None
+    det = torch.empty((B,), dtype=torch.int32, device=dev)
+    div = torch.empty((B,), dtype=torch.int32, device=dev)
+    _lib.check(_lib.load().rbg_board_statistics(boards.data_ptr(), B, G, int(bool(count_current_wire)), scored.data_ptr() if with_scores else None, det.data_ptr(), div.data_ptr(), _stream()))
+    if single:
+        return (scored[0] if with_scores else None), det[0], div[0]
+    return scored, det, div
+
+
 # ---------------------------------------------------------------- connector
 def connector_observe(st: State, out: Optional[TimeStep] = None) -> TimeStep:
     st = _contig_state(st)

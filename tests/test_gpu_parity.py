@@ -941,6 +941,29 @@ def test_validate_matches_reference_verdicts(rbg):
     assert n == len(fx["outcome"]) >= 2000
 
 
+def test_board_statistics_match_reference(rbg, orc):
+    """rbg_board_statistics (scored board, count_detours, heatmap_score_diversity) against the outputs of the reference's
+    own EvaluateEmptyBoard class (tests/golden/board_stats_reference.npz), then against the oracle on big batches."""
+    import torch
+    from test_board_stats_reference import check_stats_against_reference, load_stats_fixture
+
+    def cuda_stats(boards, N, ccw):
+        s, d, v = rbg.engine.board_statistics(torch.from_numpy(boards).cuda(), count_current_wire=ccw)
+        return _np(s), _np(d), _np(v)
+
+    fx = load_stats_fixture()
+    assert check_stats_against_reference(fx, cuda_stats) == len(fx["G"]) + len(fx["p_G"])
+    ev = rbg.EvaluateEmptyBoard(fx["boards"][0, :5, :5].astype(np.int32))  # the class mirror, single board
+    assert np.array_equal(_np(ev.scored_board), fx["scored"][0, :5, :5]) and int(ev.count_detours()) == int(fx["detours"][0, 0])
+    assert int(ev.count_detours(True)) == int(fx["detours"][0, 1]) and int(ev.board_statistics["heatmap_score_diversity"]) == int(fx["diversity"][0])
+    for (G, N, B) in ((20, 10, 4096), (32, 16, 1024), (40, 32, 256), (3, 2, 1000)):
+        boards = orc.prw_generate_batch(orc.split(orc.PRNGKey(9), B), G, N)[2]
+        for ccw in (False, True):
+            rs, rd, rv = orc.board_statistics_batch(boards, ccw)
+            s, d, v = cuda_stats(boards, N, ccw)
+            assert np.array_equal(s, rs) and np.array_equal(d, rd) and np.array_equal(v, rv), (G, N, ccw)
+
+
 def test_validate_matches_oracle_on_corrupted_boards(rbg, orc):
     import torch
 
