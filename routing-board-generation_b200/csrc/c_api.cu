@@ -214,6 +214,8 @@ struct AutoResetCtx {
   uint64_t step = 0;
   int persist_epoch = 0;  // launches of the persistent rollout on this workspace
   int persist_groups = 0; // group size the flags were laid out for
+  cudaStream_t last_stream = nullptr;  // the stream the workspace was last used on
+  bool tail_valid = false;
   cudaStream_t side = nullptr;
   cudaEvent_t env_done = nullptr;
   cudaEvent_t refill_done[2] = {nullptr, nullptr};
@@ -240,6 +242,33 @@ static void invalidate_workspace(void *workspace, cudaStream_t stream, bool bloc
       it->second.refill_pending[i] = false;
     }
   it->second.B = 0;
+}
+
+// Per-step auto-reset: where the cache refill of step t runs.  Default: on the CALLER'S stream, as a kernel that says
+// launch_dependents at once, followed (next call) by an env kernel launched with programmatic stream serialization, so
+// the refill of step t overlaps the env kernel of step t + 1 by construction and nothing else moves (the synchronous
+// reset kernel of step t + 1 is a plain launch and waits for both).  RBG_STEP_SIDE_STREAM=1: the round-1 scheme, a
+// low-priority side stream joined two steps later, whose overlap depended on which hardware queue the side stream
+// happened to share (65.6 or 84.5 us per step).
+static bool step_side_stream() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("RBG_STEP_SIDE_STREAM");
+    v = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  return v == 1;
+}
+
+// The workspace moves to another stream (rare): its work on the old stream is awaited on the host.  Events per call
+// would do, but an event record between two launches stops the second from starting under the first's tail.
+static int workspace_follow_stream(AutoResetCtx *ctx, cudaStream_t stream) {
+  if (ctx->tail_valid && ctx->last_stream != stream) {
+    cudaStreamSynchronize(ctx->last_stream);
+    cudaGetLastError();  // (the old stream may be gone)
+  }
+  ctx->last_stream = stream;
+  ctx->tail_valid = true;
+  return RBG_OK;
 }
 
 static bool speculative_enabled() {
@@ -298,7 +327,9 @@ static int connector_step_impl(const rbg_state *in, const rbg_state *out, const 
   if (speculative) {
     std::lock_guard<std::mutex> lock(g_ar_mu);
     ctx = &g_ar[workspace];
-    if (!ctx->side) {
+    if (!step_side_stream()) {
+      if ((rc = workspace_follow_stream(ctx, stream))) return rc;
+    } else if (!ctx->side) {
       // lowest priority: the refill has a whole step of slack, env_kernel's CTAs go first
       int prio_lo = 0, prio_hi = 0;
       cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
@@ -362,13 +393,54 @@ static int connector_step_impl(const rbg_state *in, const rbg_state *out, const 
     // that are zero between steps.
     invalidate_workspace(workspace, stream);
   }
-  if ((rc = launch_env(p, stream))) return rc;
+  const bool chained = speculative && !step_side_stream() && !g_timing.load(std::memory_order_relaxed);
+  if ((rc = launch_env(p, stream, chained))) return rc;
   // VmapAutoResetWrapper._auto_reset: key, _ = split(state.key); reset(key):
   // one more leading split()[0] than a plain generator call.
+  if (chained) {
+    // one launch: the synchronous resets (rare misses), launch_dependents, then the cache refill
+    PrwParams a, q;
+    memset(&a, 0, sizeof(a));
+    a.keys = out->key;
+    a.B = B;
+    a.G = G;
+    a.N = N;
+    a.mode = kind == RBG_GEN_PRW ? PRW_MODE_STATE : PRW_MODE_UNIFORM;
+    a.extra_split = (kind == RBG_GEN_PRW ? 1 : 0) + 1;
+    a.debug = debug_flags();
+    a.st = *out;
+    a.ts = *ts;
+    a.observe = 1;
+    a.list = sync_list;
+    a.list_count = sync_count;
+    a.list_ticket = sync_count + 1;
+    memset(&q, 0, sizeof(q));
+    q.keys = p.refill_keys;
+    q.keys_compact = 1;
+    q.B = B;
+    q.G = G;
+    q.N = N;
+    q.mode = a.mode;
+    q.extra_split = a.extra_split;
+    q.debug = a.debug;
+    q.list = p.refill_list;
+    q.list_count = p.refill_count;
+    q.list_ticket = p.refill_count + 1;
+    q.to_cache = 1;
+    q.cache_tag = reinterpret_cast<unsigned long long *>(ws + wl.cache_tag);
+    q.cache_key = reinterpret_cast<uint2 *>(ws + wl.cache_key);
+    q.cache_pins = reinterpret_cast<uint32_t *>(ws + wl.cache_pins);
+    if ((rc = launch_prw_pair(a, q, B, stream))) return rc;
+    ctx->step++;
+    return RBG_OK;
+  }
   if ((rc = generator_state_impl(kind, out->key, B, G, N, out, ts, 1, sync_list, sync_count, stream, speculative ? sync_count + 1 : nullptr))) return rc;
   if (speculative) {
-    if ((e = cudaEventRecord(ctx->env_done, stream)) != cudaSuccess) return set_cuda_error(e, "cudaEventRecord");
-    if ((e = cudaStreamWaitEvent(ctx->side, ctx->env_done, 0)) != cudaSuccess) return set_cuda_error(e, "cudaStreamWaitEvent(side)");
+    const bool side = step_side_stream();
+    if (side) {
+      if ((e = cudaEventRecord(ctx->env_done, stream)) != cudaSuccess) return set_cuda_error(e, "cudaEventRecord");
+      if ((e = cudaStreamWaitEvent(ctx->side, ctx->env_done, 0)) != cudaSuccess) return set_cuda_error(e, "cudaStreamWaitEvent(side)");
+    }
     PrwParams q;
     memset(&q, 0, sizeof(q));
     q.keys = p.refill_keys;
@@ -386,9 +458,14 @@ static int connector_step_impl(const rbg_state *in, const rbg_state *out, const 
     q.cache_tag = reinterpret_cast<unsigned long long *>(ws + wl.cache_tag);
     q.cache_key = reinterpret_cast<uint2 *>(ws + wl.cache_key);
     q.cache_pins = reinterpret_cast<uint32_t *>(ws + wl.cache_pins);
-    if ((rc = launch_prw(q, B, env_int("RBG_PRW_M"), env_int("RBG_PRW_THREADS"), ctx->side))) return rc;
-    if ((e = cudaEventRecord(ctx->refill_done[par], ctx->side)) != cudaSuccess) return set_cuda_error(e, "cudaEventRecord(side)");
-    ctx->refill_pending[par] = true;
+    if (side) {
+      if ((rc = launch_prw(q, B, env_int("RBG_PRW_M"), env_int("RBG_PRW_THREADS"), ctx->side))) return rc;
+      if ((e = cudaEventRecord(ctx->refill_done[par], ctx->side)) != cudaSuccess) return set_cuda_error(e, "cudaEventRecord(side)");
+      ctx->refill_pending[par] = true;
+    } else {
+      q.trigger_dependents = 1;
+      if ((rc = launch_prw(q, B, env_int("RBG_PRW_M"), env_int("RBG_PRW_THREADS"), stream))) return rc;
+    }
     ctx->step++;
   }
   return RBG_OK;
@@ -753,6 +830,10 @@ int rbg_workspace_release(void *workspace) {
       cudaEventDestroy(c.slice_done[i]);
     }
   if (c.slice_fork) cudaEventDestroy(c.slice_fork);
+  if (c.tail_valid) {
+    cudaStreamSynchronize(c.last_stream);
+    cudaGetLastError();
+  }
   g_ar.erase(it);
   return RBG_OK;
 }
@@ -781,6 +862,7 @@ static int rollout_fused(const rbg_state *state, int32_t *action_out, int64_t T,
     std::lock_guard<std::mutex> lock(g_ar_mu);
     ctx = &g_ar[workspace];
   }
+  if ((rc = workspace_follow_stream(ctx, stream))) return rc;
   // refills launched by the step-wise path on the side stream must have landed
   for (int i = 0; i < 2; ++i)
     if (ctx->refill_pending[i]) {

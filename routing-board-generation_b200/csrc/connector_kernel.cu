@@ -1026,7 +1026,7 @@ __global__ void __launch_bounds__(256) random_actions_kernel(rbg_state st, long 
   action[t] = random_action(st.key[2 * e], st.key[2 * e + 1], (uint32_t)st.step_count[e], (uint32_t)a, mk);
 }
 
-int launch_env(EnvParams p, cudaStream_t stream) {
+int launch_env(EnvParams p, cudaStream_t stream, bool pdl) {
   const int G = p.G, N = p.N;
   p.cells = G * G;
   const bool vec = (p.cells & 3) == 0;
@@ -1047,10 +1047,19 @@ int launch_env(EnvParams p, cudaStream_t stream) {
   const size_t smem = lutB + EW_WARPS * wgrid;
   const int64_t ctas = (p.B + p.E - 1) / p.E;
   LaunchScope scope(RBG_K_ENV, stream);
-  if (vec)
-    env_warp_kernel<true><<<(unsigned)ctas, EW_WARPS * 32, smem, stream>>>(p);
-  else
-    env_warp_kernel<false><<<(unsigned)ctas, EW_WARPS * 32, smem, stream>>>(p);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)ctas);
+  cfg.blockDim = dim3(EW_WARPS * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaError_t ce = vec ? cudaLaunchKernelEx(&cfg, env_warp_kernel<true>, p) : cudaLaunchKernelEx(&cfg, env_warp_kernel<false>, p);
+  if (ce != cudaSuccess) return set_cuda_error(ce, "cudaLaunchKernelEx(env_warp_kernel)");
   return check_launch("env_warp_kernel");
 }
 
@@ -1249,6 +1258,7 @@ int launch_rollout_persist(EnvParams p, int kind, int T, int32_t *action_out, in
   pp.epoch = epoch;
   pp.ngroups = (int)((p.env_hi - p.env_lo + K - 1) / K);
   gc.group_pending = group_pending;
+  gc.seqlock = 0;  // nobody reads an entry while it is rewritten here (see gen_warp_batch)
   gc.env_lo = p.env_lo;
   gc.kshift = 0;
   while ((1 << gc.kshift) < K) ++gc.kshift;

@@ -82,7 +82,9 @@ struct GenWarpCfg {
   uint2 *cache_key;
   uint32_t *cache_pins;
   // requests in flight per env group (see rollout_persist_kernel "launch overlap"): +1 when posted, -1 once published
+  // (NULL: not counted)
   int *group_pending;
+  int seqlock;         // readers may be running (per-step path): invalidate the entry's tag before rewriting it
   long long env_lo;
   int kshift;          // log2(envs per group)
 };
@@ -252,13 +254,21 @@ __device__ inline void gen_warp_batch(const GenWarpCfg &c, const GenWarpScratch 
   // (nobody reads this entry while it is rewritten: its env consumed it before asking for the next one, and the
   // per-step path's side-stream refill is joined before a rollout launch; so no invalidation round, and one
   // release store instead of fences.  bar.warp.sync orders the other lanes' pin stores before lane 0's release.)
+  if (c.seqlock) {  // (warp-uniform) the tag is the version: invalidate, fence, write, publish
+    if (have && a == 0) *reinterpret_cast<volatile unsigned long long *>(c.cache_tag + e) = 0ull;
+    __threadfence();
+    __syncwarp();
+  }
   if (isagent) c.cache_pins[e * N + a] = ((uint32_t)start << 16) | (uint32_t)fin;
   if (have && a == 0) c.cache_key[e] = make_uint2(pk0, pk1);
+  if (c.seqlock) __threadfence();
   __syncwarp();
   if (have && a == 0) {
     st_release_u64(c.cache_tag + e, ((unsigned long long)tk1 << 32) | tk0);
-    __threadfence();  // the entry is visible before the group's count drops
-    atomicSub(c.group_pending + ((e - c.env_lo) >> c.kshift), 1);
+    if (c.group_pending) {
+      __threadfence();  // the entry is visible before the group's count drops
+      atomicSub(c.group_pending + ((e - c.env_lo) >> c.kshift), 1);
+    }
   }
 }
 

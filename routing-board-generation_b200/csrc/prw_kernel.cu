@@ -24,6 +24,7 @@
 //             coalesced stores; in auto-reset mode the Connector observation
 //             and action mask of the fresh state are written here too.
 #include "connector_device.cuh"
+#include "gen_warp.cuh"
 #include "rbg_host.h"
 #include "select.cuh"
 
@@ -84,12 +85,7 @@ __host__ __device__ inline size_t prw_carve(const PrwParams &p, int nwarps,
   return align_up(off, 16);
 }
 
-#ifdef RBG_PRW_MIN_CTAS
-__global__ void __launch_bounds__(256, RBG_PRW_MIN_CTAS) prw_kernel(const PrwParams p) {
-#else
-__global__ void __launch_bounds__(256) prw_kernel(const PrwParams p) {
-#endif
-  extern __shared__ __align__(16) uint8_t smem_raw[];
+__device__ __forceinline__ void prw_body(const PrwParams &p, uint8_t *smem_raw) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nthreads = blockDim.x, nwarps = nthreads >> 5;
   const long long total = p.list ? (long long)(*p.list_count) : p.B;
@@ -422,9 +418,77 @@ __global__ void __launch_bounds__(256) prw_kernel(const PrwParams p) {
   }
 }
 
+#ifdef RBG_PRW_MIN_CTAS
+__global__ void __launch_bounds__(256, RBG_PRW_MIN_CTAS) prw_kernel(const PrwParams p) {
+#else
+__global__ void __launch_bounds__(256) prw_kernel(const PrwParams p) {
+#endif
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  if (p.trigger_dependents) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  prw_body(p, smem_raw);
+}
+
+// The two list launches of a per-step auto-reset in one: `a` regenerates the envs whose next episode was not in
+// the cache (State + observation, needed by the next step: prw_body), then the cache entries consumed in this step
+// are refilled (needed many steps from now).  Between the two every CTA says launch_dependents, so that the next env
+// kernel (launched with programmatic stream serialization) starts once all of `a` is done, under the refill.
+// The refill is latency-bound (a few thousand boards, one walk each), so it runs on the generator-warp code of the
+// fused rollout (gen_warp.cuh: both threefry levels of a trip in one pass, shuffles instead of MATCH), a warp taking
+// 32 / W list entries at a time.
+struct RefillParams {
+  const int32_t *list;     // env ids
+  const uint32_t *keys;    // [slot, 2] State.key of the episode that has just started (the entry's tag)
+  int32_t *list_count;     // device count; cleared by the last CTA together with the ticket
+  int32_t *list_ticket;
+  int gcand_bytes, gsel_bytes, gscr_stride, tmpl_off, gscr_off;
+};
+
+__global__ void __launch_bounds__(64) prw_pair_kernel(const PrwParams a, const RefillParams rf, const GenWarpCfg gc) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  prw_body(a, smem_raw);
+  __threadfence();
+  __syncthreads();
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  uint8_t *tmpl = smem_raw + rf.tmpl_off;
+  for (int i = tid; i < gc.SBp; i += blockDim.x) {
+    const int r = i / gc.S, c = i - r * gc.S;
+    tmpl[i] = (r >= 2 && r < gc.G + 2 && c >= 2 && c < gc.G + 2) ? 0 : 0xFF;
+  }
+  __syncthreads();
+  uint8_t *gb = smem_raw + rf.gscr_off + (size_t)warp * rf.gscr_stride;
+  GenWarpScratch gs;
+  gs.cand = reinterpret_cast<uint64_t *>(gb);
+  gs.sel = reinterpret_cast<uint16_t *>(gb + rf.gcand_bytes);
+  gs.board = gb + rf.gcand_bytes + rf.gsel_bytes;
+  gs.tmpl = tmpl;
+  const int total = *rf.list_count, gpw = 32 / gc.W;
+  for (int base = (blockIdx.x * nwarps + warp) * gpw; base < total; base += gridDim.x * nwarps * gpw) {
+    const int n = total - base < gpw ? total - base : gpw;
+    int re = 0;
+    uint32_t rk0 = 0, rk1 = 0;
+    if (lane < n) {
+      re = rf.list[base + lane];
+      rk0 = rf.keys[2 * (base + lane)];
+      rk1 = rf.keys[2 * (base + lane) + 1];
+    }
+    gen_warp_batch(gc, gs, n, re, rk0, rk1, lane);
+  }
+  // the last CTA to finish recycles the list counter (every CTA has read it by then)
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(rf.list_ticket, 1) == (int)gridDim.x - 1) {
+      *rf.list_count = 0;
+      *rf.list_ticket = 0;
+      __threadfence();
+    }
+  }
+}
+
 // ---------------------------------------------------------------- host side
-int launch_prw(PrwParams p, int64_t max_boards, int force_M, int force_threads,
-               cudaStream_t stream) {
+// derived fields of PrwParams + launch shape
+static int prw_prepare(PrwParams &p, int64_t max_boards, int force_M, int force_threads, int *threads_out, size_t *smem_out, int64_t *ctas_out) {
   const int G = p.G, N = p.N;
   p.cells = G * G;
   p.S = G + 4;
@@ -464,18 +528,95 @@ int launch_prw(PrwParams p, int64_t max_boards, int force_M, int force_threads,
   p.M = M;
   const size_t smem = prw_carve(p, threads / 32, nullptr, nullptr);
   if (smem > 200 * 1024) return set_error(RBG_EINVAL, "prw_kernel: %zu bytes of shared memory per CTA", smem);
+  int64_t ctas = (max_boards + M - 1) / M;
+  if (p.list && !p.bulk_list && ctas > 148 * (p.to_cache ? 4 : 2)) ctas = 148 * (p.to_cache ? 4 : 2);  // per-step lists hold a few percent of the batch and the kernel strides over them
+  *threads_out = threads;
+  *smem_out = smem;
+  *ctas_out = ctas;
+  return RBG_OK;
+}
+
+int launch_prw(PrwParams p, int64_t max_boards, int force_M, int force_threads,
+               cudaStream_t stream) {
+  int threads = 0, rc;
+  size_t smem = 0;
+  int64_t ctas = 0;
+  if ((rc = prw_prepare(p, max_boards, force_M, force_threads, &threads, &smem, &ctas))) return rc;
+  if (ctas <= 0) return RBG_OK;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(prw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(prw_kernel)");
   }
-  int64_t ctas = (max_boards + M - 1) / M;
-  if (ctas <= 0) return RBG_OK;
-  if (p.list && !p.bulk_list && ctas > 148 * (p.to_cache ? 4 : 2)) ctas = 148 * (p.to_cache ? 4 : 2);  // per-step lists hold a few percent of the batch and the kernel strides over them
   {
     LaunchScope scope(RBG_K_PRW, stream);
     prw_kernel<<<(unsigned)ctas, threads, smem, stream>>>(p);
   }
   return check_launch("prw_kernel");
+}
+
+// per-step auto-reset: synchronous list `a` and the cache refill `b` (both short lists of the same batch) in one launch
+int launch_prw_pair(PrwParams a, PrwParams b, int64_t max_boards, cudaStream_t stream) {
+  int ta = 0, rc;
+  size_t sa = 0;
+  int64_t ca = 0;
+  if ((rc = prw_prepare(a, max_boards, 0, 64, &ta, &sa, &ca))) return rc;
+  if (ta != 64 || !a.list || !b.list || !b.to_cache || !b.keys_compact) return set_error(RBG_EINVAL, "prw_pair_kernel: a 64-thread list launch and a compact-key cache refill");
+  auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  const int G = b.G, N = b.N, kind = b.mode == PRW_MODE_UNIFORM ? RBG_GEN_UNIFORM : RBG_GEN_PRW;
+  GenWarpCfg gc;
+  memset(&gc, 0, sizeof(gc));
+  gc.kind = kind;
+  gc.G = G;
+  gc.N = N;
+  int W = 1;
+  while (W < N + 2 && W < 32) W <<= 1;
+  gc.W = W;
+  gc.S = G + 4;
+  gc.SBp = (int)up16((size_t)gc.S * gc.S);
+  gc.cells = G * G;
+  gc.nsel = kind == RBG_GEN_PRW ? N : 2 * N;
+  gc.nselp = (gc.nsel + 1) & ~1;
+  gc.cap = 4 * gc.nsel + 32;
+  {
+    const double frac = (2.0 * gc.nsel + 16.0) / (double)gc.cells;
+    gc.thresh = frac >= 1.0 ? 0xffffffffu : (uint32_t)(frac * 4294967296.0);
+  }
+  gc.divG = FastDiv::make((uint32_t)G);
+  gc.cache_tag = b.cache_tag;
+  gc.cache_key = b.cache_key;
+  gc.cache_pins = b.cache_pins;
+  gc.group_pending = nullptr;
+  gc.seqlock = 1;  // the next env kernel runs under this refill
+  RefillParams rf;
+  memset(&rf, 0, sizeof(rf));
+  rf.list = b.list;
+  rf.keys = b.keys;
+  rf.list_count = const_cast<int32_t *>(b.list_count);
+  rf.list_ticket = b.list_ticket;
+  const int gpw = 32 / W;
+  rf.gcand_bytes = (int)up16((size_t)gc.cap * 8);
+  rf.gsel_bytes = (int)up16((size_t)gpw * gc.nselp * 2);
+  rf.gscr_stride = (int)up16((size_t)rf.gcand_bytes + rf.gsel_bytes + (size_t)gpw * gc.SBp);
+  rf.tmpl_off = 0;
+  rf.gscr_off = (int)up16((size_t)gc.SBp);
+  const size_t sb = (size_t)rf.gscr_off + 2 * (size_t)rf.gscr_stride;  // the refill reuses the shared memory of `a`
+  const size_t smem = sa > sb ? sa : sb;
+  if (smem > 200 * 1024) return set_error(RBG_EINVAL, "prw_pair_kernel: %zu bytes of shared memory per CTA", smem);
+  int sms = 148, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int64_t ctas = (max_boards + 2 * gpw - 1) / (2 * gpw);
+  if (ctas > (int64_t)sms * 4) ctas = (int64_t)sms * 4;  // per-step lists hold a few percent of the batch; both halves stride
+  if (ca > ctas) ctas = ca;
+  if (ctas <= 0) return RBG_OK;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(prw_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(prw_pair_kernel)");
+  }
+  {
+    LaunchScope scope(RBG_K_PRW, stream);
+    prw_pair_kernel<<<(unsigned)ctas, 64, smem, stream>>>(a, rf, gc);
+  }
+  return check_launch("prw_pair_kernel");
 }
 
 }  // namespace rbg

@@ -45,6 +45,8 @@ struct PrwParams {
   // result goes to the env's cache entry instead of State / TimeStep
   int keys_compact, to_cache;
   int bulk_list;  // the list is large (a rollout chunk's resets): use the bulk launch shape
+  int trigger_dependents;  // griddepcontrol.launch_dependents at the start: the next kernel of the stream, if it was launched
+                           // with programmatic stream serialization, need not wait for this one (per-step cache refill)
   unsigned long long *cache_tag;  // [B]   state.key this entry succeeds (k0 | k1 << 32)
   uint2 *cache_key;               // [B]   State.key of the cached episode
   uint32_t *cache_pins;           // [B,N] start_r<<24 | start_c<<16 | target_r<<8 | target_c
@@ -56,6 +58,8 @@ struct PrwParams {
 
 int launch_prw(PrwParams p, int64_t max_boards, int force_M, int force_threads,
                cudaStream_t stream);
+// two short-list launches in one (prw_pair_kernel): `a` then launch_dependents then `b`
+int launch_prw_pair(PrwParams a, PrwParams b, int64_t max_boards, cudaStream_t stream);
 
 // ---- connector kernel (connector_kernel.cu) -----------------------------
 enum : int { ENV_MODE_STEP = 0, ENV_MODE_OBSERVE = 1 };
@@ -87,7 +91,9 @@ struct EnvParams {
   FastDiv divN, divG, divC4, divCells;
 };
 
-int launch_env(EnvParams p, cudaStream_t stream);
+// pdl: launch with programmatic stream serialization (the kernel may begin while a preceding kernel that has said
+// launch_dependents is still running; any other predecessor completes first)
+int launch_env(EnvParams p, cudaStream_t stream, bool pdl = false);
 // T random-policy auto-reset steps in one launch (kind: RBG_GEN_PRW / RBG_GEN_UNIFORM); ts fields stacked [T,B,...]
 int launch_rollout(EnvParams p, int kind, int T, int32_t *action_out, cudaStream_t stream);
 // the same as a persistent kernel whose CTAs carry their own generator warps (no refill kernel); needs the cache
