@@ -268,7 +268,8 @@ int rbg_connector_step_host(const rbg_state *in, const rbg_state *out,
 /* Env-pool style step: `state` holds DEVICE pointers and is updated in place (the State is
  * opaque env state, as it is between two `env.step` calls in the reference's loop), `action`
  * int32[B,N] comes from and every field of `ts` goes to HOST memory (pinned recommended).
- * Synchronises the device at entry and its own copy streams at exit. */
+ * `state` must have been produced on the device's default stream (or a stream that synchronises with it); the call
+ * orders itself behind that stream with an event and waits for its own copy streams at exit. */
 int rbg_connector_step_host_io(const rbg_state *state, const int32_t *action,
                                int64_t B, int G, int N,
                                const rbg_env_params *params,

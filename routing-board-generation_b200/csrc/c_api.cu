@@ -35,6 +35,26 @@ int check_launch(const char *what) {
   return RBG_OK;
 }
 
+// ---- device properties, cached per device ---------------------------------
+struct DevProps {
+  int sms = 0;
+  size_t smem_per_sm = 0;
+};
+static DevProps g_devprops[64];
+static const DevProps &dev_props() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  DevProps &d = g_devprops[dev];
+  if (d.sms == 0) {
+    int v = 0;
+    d.sms = (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) ? v : 148;
+    d.smem_per_sm = (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev) == cudaSuccess && v > 0) ? (size_t)v : (size_t)228 * 1024;
+  }
+  return d;
+}
+int device_sm_count() { return dev_props().sms; }
+size_t device_smem_per_sm() { return dev_props().smem_per_sm; }
+
 // ---- per-kernel event timing (rbg_kernel_timing / rbg_kernel_time) --------
 struct EventPair {
   cudaEvent_t a, b;
@@ -478,10 +498,9 @@ struct Scratch {
   int device = -1;
 };
 static std::mutex g_scratch_mu;
-static Scratch g_scratch;
-static cudaStream_t g_streams[3] = {nullptr, nullptr, nullptr};
-static cudaEvent_t g_stream_ev[3] = {nullptr, nullptr, nullptr};
-
+// One scratch, one set of streams and one signature PER DEVICE: a process that drives several GPUs through the
+// _host variants (one thread per device, or device switches between calls) keeps each device's workspaces alive.
+constexpr int kMaxDevices = 64;
 // Who laid the scratch out last (a step variant with auto-reset keeps its workspaces there between
 // calls): any other use, shape or base pointer means those workspaces have been overwritten.
 struct ScratchSig {
@@ -491,7 +510,20 @@ struct ScratchSig {
   void *base = nullptr;
   bool operator==(const ScratchSig &o) const { return fn == o.fn && B == o.B && G == o.G && N == o.N && kind == o.kind && base == o.base; }
 };
-static ScratchSig g_scratch_sig;
+struct HostCtx {
+  Scratch scratch;
+  cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t stream_ev[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t slice_ev[16] = {nullptr};
+  cudaEvent_t entry_ev = nullptr;
+  ScratchSig sig;
+};
+static HostCtx g_host[kMaxDevices];
+static thread_local HostCtx *g_hc = &g_host[0];  // the device of the _host call in progress (set by use_device)
+#define g_scratch (g_hc->scratch)
+#define g_streams (g_hc->streams)
+#define g_stream_ev (g_hc->stream_ev)
+#define g_scratch_sig (g_hc->sig)
 
 static int scratch_get(size_t bytes, int device, void **out) {
   if (g_scratch.ptr && (g_scratch.bytes < bytes || g_scratch.device != device)) {
@@ -1111,6 +1143,8 @@ static int use_device(int device, int *cur) {
     if (e != cudaSuccess) return set_cuda_error(e, "cudaSetDevice");
     *cur = device;
   }
+  if (*cur < 0 || *cur >= kMaxDevices) return set_error(RBG_EINVAL, "device %d out of range", *cur);
+  g_hc = &g_host[*cur];
   return RBG_OK;
 }
 
@@ -1262,9 +1296,8 @@ int rbg_connector_step_host_io(const rbg_state *state, const int32_t *action, in
   if ((rc = check_state(state, "state", G))) return rc;
   if (B == 0) return RBG_OK;
   if ((rc = use_device(device, &dev))) return rc;
-  cudaError_t e = cudaDeviceSynchronize();  // the State may have been produced on any stream of the caller
-  if (e != cudaSuccess) return set_cuda_error(e, "cudaDeviceSynchronize");
   std::lock_guard<std::mutex> lock(g_scratch_mu);
+  cudaError_t e;
   const int nsl = B >= 4096 ? 8 : 1;
   const int64_t sl = slice_size(B, nsl);
   const int64_t nslices = (B + sl - 1) / sl;
@@ -1285,8 +1318,13 @@ int rbg_connector_step_host_io(const rbg_state *state, const int32_t *action, in
   // kernels, the copies 2.4 ms); the two copy streams take the observation (96 % of the bytes)
   // of each slice as soon as its kernel is done, so the bus is busy from the first slice on.
   // The small leaves go once for the whole batch: 8 copies instead of 8 per slice.
-  static cudaEvent_t slice_ev[16] = {nullptr};
+  cudaEvent_t *slice_ev = g_hc->slice_ev;
   cudaStream_t cs = g_streams[0];
+  // The State was produced by the caller on the device's default stream (or a stream that stream synchronises
+  // with: every blocking stream does): our compute stream is ordered behind it by an event, the host does not wait.
+  if (!g_hc->entry_ev && (e = cudaEventCreateWithFlags(&g_hc->entry_ev, cudaEventDisableTiming)) != cudaSuccess) return set_cuda_error(e, "cudaEventCreate");
+  if ((e = cudaEventRecord(g_hc->entry_ev, cudaStreamLegacy)) != cudaSuccess) return set_cuda_error(e, "cudaEventRecord(entry)");
+  if ((e = cudaStreamWaitEvent(cs, g_hc->entry_ev, 0)) != cudaSuccess) return set_cuda_error(e, "cudaStreamWaitEvent(entry)");
   RBG_CPY(da, action, (size_t)B * N * 4, cudaMemcpyHostToDevice, cs);
   int si = 0;
   for (int64_t off = 0; off < B; off += sl, ++si) {

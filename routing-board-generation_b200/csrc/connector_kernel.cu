@@ -1071,7 +1071,7 @@ static size_t balance_waves(int64_t ctas, int cmax, int cmin, size_t smem_needed
   int best = cmax;
   int64_t best_cost = -1;
   for (int c = cmax; c >= cmin; --c) {
-    const int64_t rounds = (ctas + 148LL * c - 1) / (148LL * c);
+    const int64_t rounds = (ctas + (int64_t)device_sm_count() * c - 1) / ((int64_t)device_sm_count() * c);
     const int64_t cost = rounds * c;
     if (best_cost < 0 || cost < best_cost) {
       best_cost = cost;
@@ -1080,7 +1080,7 @@ static size_t balance_waves(int64_t ctas, int cmax, int cmin, size_t smem_needed
   }
   if (best == cmax) return smem_needed;
   // per-SM shared memory 228 KB, 1 KB reserved per CTA: c CTAs fit, c + 1 do not
-  const size_t pad = (size_t)(228 * 1024) / (size_t)(best + 1) + 1024;
+  const size_t pad = device_smem_per_sm() / (size_t)(best + 1) + 1024;
   return pad > smem_needed ? pad : smem_needed;
 }
 
@@ -1143,7 +1143,7 @@ int launch_rollout(EnvParams p, int kind, int T, int32_t *action_out, cudaStream
   if (smem > 200 * 1024) return set_error(RBG_EINVAL, "rollout: shared memory %zu too large", smem);
   const int64_t ctas = (p.env_hi - p.env_lo + p.E - 1) / p.E;
   {  // residency: registers allow RBG_ROLLOUT_MIN_CTAS per SM, shared memory (1 KB reserved per CTA) maybe fewer
-    int cmax = (int)((228 * 1024) / (smem + 1024));
+    int cmax = (int)(device_smem_per_sm() / (smem + 1024));
     if (cmax > RBG_ROLLOUT_MIN_CTAS) cmax = RBG_ROLLOUT_MIN_CTAS;
     static int force = -1;  // RBG_ROLLOUT_CTAS=n: n CTAs per SM instead of the wave-balanced choice (experiments)
     if (force < 0) {
@@ -1151,7 +1151,7 @@ int launch_rollout(EnvParams p, int kind, int T, int32_t *action_out, cudaStream
       force = ex ? atoi(ex) : 0;
     }
     if (force > 0) {
-      const size_t pad = (size_t)(228 * 1024) / (size_t)(force + 1) + 1024;
+      const size_t pad = device_smem_per_sm() / (size_t)(force + 1) + 1024;
       if (force < cmax && pad > smem) smem = pad;
     } else if (cmax >= 3)
       smem = balance_waves(ctas, cmax, cmax - 2, smem);
@@ -1173,16 +1173,6 @@ int launch_rollout(EnvParams p, int kind, int T, int32_t *action_out, cudaStream
     rollout_warp_kernel<0><<<(unsigned)ctas, EW_WARPS * 32, smem, stream>>>(p, rp);
   }
   return check_launch("rollout_warp_kernel");
-}
-
-static int device_sm_count() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-  }
-  return sms;
 }
 
 // The persistent rollout with in-CTA generator warps (rollout_persist_kernel).  `cache_*` of `p` must be set;

@@ -410,7 +410,7 @@ int launch_board_stats(const int32_t *boards, int64_t B, int G, int count_curren
   const int P = G + 2, PB = (P * P + 15) & ~15;
   const size_t smem = (size_t)STAT_WARPS * (3 * PB + STAT_SCORE_BITS / 8);
   int64_t ctas = (B + STAT_WARPS - 1) / STAT_WARPS;
-  if (ctas > 148 * 32) ctas = 148 * 32;
+  if (ctas > (int64_t)device_sm_count() * 32) ctas = (int64_t)device_sm_count() * 32;
   {
     LaunchScope scope(RBG_K_VALIDATE, stream);
     board_stats_kernel<<<(unsigned)ctas, STAT_WARPS * 32, smem, stream>>>(boards, B, G, count_current_wire, scored, detours, diversity, nullptr);
@@ -423,7 +423,7 @@ int launch_validate(const int32_t *boards, int64_t B, int G, int N, int32_t *fla
   const int cells = G * G, cp = (cells + 15) & ~15;
   const size_t smem = (size_t)VAL_WARPS * (2 * cp + 5 * 4 * RBG_MAX_N);
   int64_t ctas = (B + VAL_WARPS - 1) / VAL_WARPS;
-  if (ctas > 148 * 64) ctas = 148 * 64;
+  if (ctas > (int64_t)device_sm_count() * 64) ctas = (int64_t)device_sm_count() * 64;
   {
     LaunchScope scope(RBG_K_VALIDATE, stream);
     validate_kernel<<<(unsigned)ctas, VAL_WARPS * 32, smem, stream>>>(boards, B, G, N, flags);

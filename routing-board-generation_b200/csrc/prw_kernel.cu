@@ -507,7 +507,8 @@ static int prw_prepare(PrwParams &p, int64_t max_boards, int force_M, int force_
   // refill balances the divergent walk lengths), small CTAs for short lists
   int threads = 256, M = 64;
   const int gpw = 32 / p.W;
-  if (max_boards <= 148 * 64) {
+  const int64_t sms = device_sm_count();
+  if (max_boards <= sms * 64) {
     threads = 64;
     M = 2 * gpw * 2;  // one board per group + one refill
   }
@@ -529,7 +530,7 @@ static int prw_prepare(PrwParams &p, int64_t max_boards, int force_M, int force_
   const size_t smem = prw_carve(p, threads / 32, nullptr, nullptr);
   if (smem > 200 * 1024) return set_error(RBG_EINVAL, "prw_kernel: %zu bytes of shared memory per CTA", smem);
   int64_t ctas = (max_boards + M - 1) / M;
-  if (p.list && !p.bulk_list && ctas > 148 * (p.to_cache ? 4 : 2)) ctas = 148 * (p.to_cache ? 4 : 2);  // per-step lists hold a few percent of the batch and the kernel strides over them
+  if (p.list && !p.bulk_list && ctas > sms * (p.to_cache ? 4 : 2)) ctas = sms * (p.to_cache ? 4 : 2);  // per-step lists hold a few percent of the batch and the kernel strides over them
   *threads_out = threads;
   *smem_out = smem;
   *ctas_out = ctas;
@@ -602,8 +603,7 @@ int launch_prw_pair(PrwParams a, PrwParams b, int64_t max_boards, cudaStream_t s
   const size_t sb = (size_t)rf.gscr_off + 2 * (size_t)rf.gscr_stride;  // the refill reuses the shared memory of `a`
   const size_t smem = sa > sb ? sa : sb;
   if (smem > 200 * 1024) return set_error(RBG_EINVAL, "prw_pair_kernel: %zu bytes of shared memory per CTA", smem);
-  int sms = 148, dev = 0;
-  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = device_sm_count();
   int64_t ctas = (max_boards + 2 * gpw - 1) / (2 * gpw);
   if (ctas > (int64_t)sms * 4) ctas = (int64_t)sms * 4;  // per-step lists hold a few percent of the batch; both halves stride
   if (ca > ctas) ctas = ca;

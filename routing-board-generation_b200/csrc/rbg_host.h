@@ -14,6 +14,9 @@ namespace rbg {
 int set_error(int code, const char *fmt, ...);
 int set_cuda_error(cudaError_t e, const char *what);
 int check_launch(const char *what);
+// properties of the current device (cached per device): SM count, shared memory per SM in bytes
+int device_sm_count();
+size_t device_smem_per_sm();
 // Brackets one kernel launch: counts it (rbg_launch_count) and, while
 // rbg_kernel_timing is on, records a CUDA event pair on `stream` around it.
 struct LaunchScope {

@@ -820,9 +820,7 @@ int launch_seedext(SeedExtParams p, int64_t max_boards, cudaStream_t stream) {
       se_rounds = ex ? atoi(ex) : 0;  // measured: compaction rounds do not pay (the batch is bound by the slowest board's sweep latency), see DESIGN.md K3
       if (se_rounds < 0) se_rounds = 0;
       if (se_rounds > 30) se_rounds = 30;
-      int sms = 148;
-      int dev = 0;
-      if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      const int sms = device_sm_count();
       ex = getenv("RBG_SE_DENSE_WARPS");
       se_dense_warps = ex ? atoi(ex) : sms * 8;  // about what is resident at once
       if (se_dense_warps < 1) se_dense_warps = 1;
