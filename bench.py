@@ -262,17 +262,26 @@ def run_ours(args):
     steps_per_launch = n_pass / max(n_ro, 1)
     # State read once + written once per launch; per step only the emitted TimeStep and the actions
     alg = B * (2 * STATE_BYTES + steps_per_launch * (TS_BYTES + 4 * N))
-    k_ms = ms_ro / max(n_ro, 1)
-    achieved = alg / (k_ms / 1e3) / 1e9
+    # The timed region holds nothing but launches of this one kernel (one per 20-step chunk, each INCLUDING the
+    # regeneration of finished envs), chained head to tail, so its average launch duration over the region is the
+    # region's device time / launches.  The same launch timed ALONE (event pair around it, not chained: its ragged tail
+    # and the generator warps' drain are exposed) is reported next to it.
+    launches_per_block = max(1, -(-args.steps // chunk))
+    k_ms = ms_block / launches_per_block
+    achieved = alg * (args.steps / launches_per_block / steps_per_launch) / (k_ms / 1e3) / 1e9
+    alone_ms = ms_ro / max(n_ro, 1)
+    alone = alg / (alone_ms / 1e3) / 1e9
     step_alg = B * (TS_BYTES + 4 * N + 2 * STATE_BYTES / steps_per_launch)  # algorithmic bytes of one whole step
     step_gbs = step_alg / (ms_block / args.steps / 1e3) / 1e9
     roofline = {"kernel": "rollout_persist_kernel", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "traffic": _profile_number("rollout_persist_kernel"), "algorithmic_bytes_per_launch": int(alg), "steps_per_launch": steps_per_launch,
                 "avg_launch_ms": round(k_ms, 5), "peak_source": peak_src, "kernel_share_of_step": round(ms_ro / max(ms_ro + ms_prw + ms_env, 1e-9), 4),
                 "other_kernels_in_the_step": {"prw_kernel_launches": n_prw, "env_kernel_launches": n_env},
-                "note": "one launch = 20 steps over the whole batch INCLUDING the regeneration of finished envs (generator warps inside the rollout CTAs); timed alone, launches not chained",
+                "note": "one launch = 20 steps over the whole batch INCLUDING the regeneration of finished envs (generator warps inside the rollout CTAs); avg_launch_ms = device time of the timed region / launches in it (consecutive launches are chained head to tail by programmatic dependent launch)",
+                "launch_timed_alone": {"avg_launch_ms": round(alone_ms, 5), "achieved": round(alone, 1), "frac": round(alone / peak, 4),
+                                       "note": "the same launch bracketed by its own event pair in a separate pass: not chained, so the ragged end of a persistent grid and the generator warps' drain are exposed"},
                 "whole_step": {"achieved": round(step_gbs, 1), "frac": round(step_gbs / peak, 4),
-                               "note": "algorithmic bytes of a step / the timed region's ms_per_step (launches chained head to tail by programmatic dependent launch)"}}
+                               "note": "algorithmic bytes of a step / the timed region's ms_per_step; the step is that one kernel, so this equals `frac` up to the State's share"}}
 
     # ---- e2e: the env-step call with HOST buffers through the C-ABI (rbg_connector_step_host_io):
     # actions H2D from pinned memory, step, whole TimeStep D2H, every step.
