@@ -269,11 +269,18 @@ int rbg_connector_step_host(const rbg_state *in, const rbg_state *out,
  * opaque env state, as it is between two `env.step` calls in the reference's loop), `action`
  * int32[B,N] comes from and every field of `ts` goes to HOST memory (pinned recommended).
  * `state` must have been produced on the device's default stream (or a stream that synchronises with it); the call
- * orders itself behind that stream with an event and waits for its own copy streams at exit. */
+ * orders itself behind that stream with an event and waits for its own copy streams at exit.
+ * Transport: the observation (96 % of a TimeStep's bytes; codes <= 3 * RBG_MAX_N) crosses the bus as one byte per
+ * cell into a pinned staging buffer of the library and is widened to ts->obs_grid's int32 by a pool of host threads
+ * (all cores of the affinity mask / LOCAL_WORLD_SIZE, or RBG_HOST_THREADS), slice by slice while later slices are
+ * in flight; ts->obs_grid need not be pinned.  RBG_HOST_IO_WIDE=1: int32 over the bus, no host threads. */
 int rbg_connector_step_host_io(const rbg_state *state, const int32_t *action,
                                int64_t B, int G, int N,
                                const rbg_env_params *params,
                                const rbg_timestep *ts, int device);
+/* Bytes the _host_io calls moved over the bus since the last reset (counted where the copies are enqueued) and the
+ * number of host threads that widen the observation (0 with RBG_HOST_IO_WIDE=1); any pointer may be NULL. */
+int rbg_host_transfer_stats(int64_t *h2d_bytes, int64_t *d2h_bytes, int *host_threads, int reset);
 /* pinned host allocation helpers for the _host variants (optional) */
 void *rbg_host_alloc(int64_t bytes);
 void rbg_host_free(void *p);

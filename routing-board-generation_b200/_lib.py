@@ -65,6 +65,7 @@ SYMBOLS = {
     "rbg_connector_reset_host": (_int, [_int, _vp, _i64, _int, _int, _SP, _TP, _int]),
     "rbg_connector_step_host": (_int, [_SP, _SP, _vp, _i64, _int, _int, _EP, _TP, _int]),
     "rbg_connector_step_host_io": (_int, [_SP, _vp, _i64, _int, _int, _EP, _TP, _int]),
+    "rbg_host_transfer_stats": (_int, [C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_int), _int]),
     "rbg_host_alloc": (_vp, [_i64]),
     "rbg_host_free": (None, [_vp]),
     "rbg_launch_count": (_i64, [_int]),
@@ -115,3 +116,10 @@ def kernel_time(kernel) -> tuple:
     n, ms = _i64(0), C.c_double(0.0)
     check(load().rbg_kernel_time(kid, C.byref(n), C.byref(ms)))
     return int(n.value), float(ms.value)
+
+
+def host_transfer_stats(reset: bool = False) -> tuple:
+    """(H2D bytes, D2H bytes, host widening threads) of the _host_io calls since the last reset."""
+    a, b, t = _i64(0), _i64(0), _int(0)
+    check(load().rbg_host_transfer_stats(C.byref(a), C.byref(b), C.byref(t), 1 if reset else 0))
+    return int(a.value), int(b.value), int(t.value)

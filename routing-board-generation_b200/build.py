@@ -13,7 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 SO = os.path.join(LIBDIR, "librbg_b200.so")
-SOURCES = ["c_api.cu", "prw_kernel.cu", "connector_kernel.cu", "misc_kernels.cu", "seedext_kernel.cu"]
+SOURCES = ["c_api.cu", "prw_kernel.cu", "connector_kernel.cu", "misc_kernels.cu", "seedext_kernel.cu", "host_pool.cpp"]
+CXX_FLAGS = ["-O3", "-std=c++17", "-fPIC", "-pthread"]  # plain C++ sources (host threads of the transport layer): g++
 HEADERS = ["rbg_device.cuh", "connector_device.cuh", "obs_stage.cuh", "prw_warp.cuh", "gen_warp.cuh", "select.cuh", "rbg_host.h", os.path.join("..", "..", "include", "rbg_b200.h")]
 
 NVCC_FLAGS = [
@@ -49,8 +50,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
     logs = []
     procs = []
     for s in SOURCES:
-        obj = os.path.join(LIBDIR, s.replace(".cu", ".o"))
-        cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, s), "-o", obj]
+        obj = os.path.join(LIBDIR, os.path.splitext(s)[0] + ".o")
+        if s.endswith(".cpp"):
+            cmd = [os.environ.get("CXX", "g++"), *CXX_FLAGS, "-c", os.path.join(CSRC, s), "-o", obj]
+        else:
+            cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, s), "-o", obj]
         procs.append((s, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for s, obj, pr in procs:
         out, _ = pr.communicate()

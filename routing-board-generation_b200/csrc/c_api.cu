@@ -515,9 +515,22 @@ struct HostCtx {
   cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t stream_ev[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t slice_ev[16] = {nullptr};
+  cudaEvent_t copy_ev[16] = {nullptr};
   cudaEvent_t entry_ev = nullptr;
+  uint8_t *stage8 = nullptr;  // pinned host staging of the byte observation (rbg_connector_step_host_io)
+  size_t stage8_bytes = 0;
   ScratchSig sig;
 };
+// what the _host variants moved over the bus since the last reset (rbg_host_transfer_stats)
+static std::atomic<long long> g_h2d_bytes{0}, g_d2h_bytes{0};
+static bool host_io_wide() {  // RBG_HOST_IO_WIDE=1: the observation crosses the bus as int32 (round 1's transport)
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("RBG_HOST_IO_WIDE");
+    v = e && atoi(e) != 0 ? 1 : 0;
+  }
+  return v == 1;
+}
 static HostCtx g_host[kMaxDevices];
 static thread_local HostCtx *g_hc = &g_host[0];  // the device of the _host call in progress (set by use_device)
 #define g_scratch (g_hc->scratch)
@@ -1298,27 +1311,48 @@ int rbg_connector_step_host_io(const rbg_state *state, const int32_t *action, in
   if ((rc = use_device(device, &dev))) return rc;
   std::lock_guard<std::mutex> lock(g_scratch_mu);
   cudaError_t e;
-  const int nsl = B >= 4096 ? 8 : 1;
+  const bool packed = !host_io_wide();
+  static int nsl_env = -1;
+  if (nsl_env < 0) {
+    const char *ex = getenv("RBG_HOST_IO_SLICES");
+    nsl_env = ex ? atoi(ex) : 0;
+    if (nsl_env < 0 || nsl_env > 16) nsl_env = 0;
+  }
+  // 16 slices for big batches: the host starts widening after 1/16 of the copies and ends 1/16 after them (measured at
+  // 65 536 envs 10x10/5: 8 slices 1.27-1.6 ms per step, 16 slices 1.17-1.24 ms)
+  const int nsl = B >= 4096 ? (nsl_env ? nsl_env : (packed && B >= 32768 ? 16 : 8)) : 1;
   const int64_t sl = slice_size(B, nsl);
   const int64_t nslices = (B + sl - 1) / sl;
+  const size_t obs_n = (size_t)B * N * G * G;
   Carver size{nullptr};
   rbg_timestep dt;
   carve_timestep(size, B, G, N, &dt);
   size.take<int32_t>((size_t)B * N);
   const size_t ws_bytes = (size_t)rbg_step_workspace_bytes(sl, G, N);
   size.take<uint8_t>((size_t)nslices * ws_bytes);
+  if (packed) size.take<uint8_t>(obs_n);
   void *base;
   if ((rc = scratch_get(size.off + 256, dev, &base))) return rc;
   Carver c{reinterpret_cast<uint8_t *>(base)};
   carve_timestep(c, B, G, N, &dt);
   int32_t *da = c.take<int32_t>((size_t)B * N);
   uint8_t *ws = c.take<uint8_t>((size_t)nslices * ws_bytes);
+  uint8_t *obs8 = packed ? c.take<uint8_t>(obs_n) : nullptr;
   scratch_claim(ScratchSig{4, B, G, N, params->autoreset_kind, base}, ws, ws_bytes, nslices);
-  // One compute stream runs the slices' kernels back to back (the whole batch is ~0.1 ms of
-  // kernels, the copies 2.4 ms); the two copy streams take the observation (96 % of the bytes)
-  // of each slice as soon as its kernel is done, so the bus is busy from the first slice on.
-  // The small leaves go once for the whole batch: 8 copies instead of 8 per slice.
-  cudaEvent_t *slice_ev = g_hc->slice_ev;
+  if (packed && g_hc->stage8_bytes < obs_n) {
+    if (g_hc->stage8) cudaFreeHost(g_hc->stage8);
+    g_hc->stage8 = nullptr;
+    g_hc->stage8_bytes = 0;
+    if ((e = cudaHostAlloc(reinterpret_cast<void **>(&g_hc->stage8), obs_n, cudaHostAllocDefault)) != cudaSuccess) return set_cuda_error(e, "cudaHostAlloc(observation staging)");
+    g_hc->stage8_bytes = obs_n;
+  }
+  // One compute stream runs the slices' kernels back to back (the whole batch is ~0.1 ms of kernels); the two
+  // copy streams take the observation (96 % of the bytes) of each slice as soon as its kernel is done, so the
+  // bus is busy from the first slice on.  The small leaves go once for the whole batch: 8 copies instead of 8 per
+  // slice.  Packed transport (default): the observation's codes cross the bus as bytes into a pinned staging
+  // buffer and the host pool widens slice s into the caller's int32 buffer while slices s+1.. are in flight; the
+  // caller's observation buffer need not be pinned.
+  cudaEvent_t *slice_ev = g_hc->slice_ev, *copy_ev = g_hc->copy_ev;
   cudaStream_t cs = g_streams[0];
   // The State was produced by the caller on the device's default stream (or a stream that stream synchronises
   // with: every blocking stream does): our compute stream is ordered behind it by an event, the host does not wait.
@@ -1326,23 +1360,53 @@ int rbg_connector_step_host_io(const rbg_state *state, const int32_t *action, in
   if ((e = cudaEventRecord(g_hc->entry_ev, cudaStreamLegacy)) != cudaSuccess) return set_cuda_error(e, "cudaEventRecord(entry)");
   if ((e = cudaStreamWaitEvent(cs, g_hc->entry_ev, 0)) != cudaSuccess) return set_cuda_error(e, "cudaStreamWaitEvent(entry)");
   RBG_CPY(da, action, (size_t)B * N * 4, cudaMemcpyHostToDevice, cs);
+  g_h2d_bytes.fetch_add((long long)B * N * 4, std::memory_order_relaxed);
+  const size_t per_env = (size_t)N * G * G;
   int si = 0;
   for (int64_t off = 0; off < B; off += sl, ++si) {
     const int64_t n = (B - off) < sl ? (B - off) : sl;
     rbg_state dss = state_at(*state, off, G, N);
     rbg_timestep dts = timestep_at(dt, off, G, N);
     if ((rc = rbg_connector_step(&dss, &dss, da + off * N, n, G, N, params, &dts, ws + (size_t)si * ws_bytes, cs))) return rc;
+    if (packed && (rc = launch_narrow_codes(dts.obs_grid, obs8 + (size_t)off * per_env, (int64_t)((size_t)n * per_env), cs))) return rc;
     if (!slice_ev[si] && (e = cudaEventCreateWithFlags(&slice_ev[si], cudaEventDisableTiming)) != cudaSuccess) return set_cuda_error(e, "cudaEventCreate");
     if ((e = cudaEventRecord(slice_ev[si], cs)) != cudaSuccess) return set_cuda_error(e, "cudaEventRecord");
     cudaStream_t xs = g_streams[1 + (si & 1)];
     if ((e = cudaStreamWaitEvent(xs, slice_ev[si], 0)) != cudaSuccess) return set_cuda_error(e, "cudaStreamWaitEvent");
-    if ((rc = copy_timestep(ts, &dt, off, n, G, N, cudaMemcpyDeviceToHost, off, xs, 1))) return rc;
+    if (packed) {
+      RBG_CPY(g_hc->stage8 + (size_t)off * per_env, obs8 + (size_t)off * per_env, (size_t)n * per_env, cudaMemcpyDeviceToHost, xs);
+      if (!copy_ev[si] && (e = cudaEventCreateWithFlags(&copy_ev[si], cudaEventDisableTiming)) != cudaSuccess) return set_cuda_error(e, "cudaEventCreate");
+      if ((e = cudaEventRecord(copy_ev[si], xs)) != cudaSuccess) return set_cuda_error(e, "cudaEventRecord(copy)");
+    } else if ((rc = copy_timestep(ts, &dt, off, n, G, N, cudaMemcpyDeviceToHost, off, xs, 1))) {
+      return rc;
+    }
   }
   if ((rc = copy_timestep(ts, &dt, 0, B, G, N, cudaMemcpyDeviceToHost, 0, cs, 2))) return rc;
+  g_d2h_bytes.fetch_add((long long)(obs_n * (packed ? 1 : 4)) + (long long)B * (N * 5 + 4 + N * 8 + 1 + 12), std::memory_order_relaxed);
+  if (packed) {
+    si = 0;
+    for (int64_t off = 0; off < B; off += sl, ++si) {
+      const int64_t n = (B - off) < sl ? (B - off) : sl;
+      if ((e = cudaEventSynchronize(copy_ev[si])) != cudaSuccess) {
+        host_pool_wait();
+        return set_cuda_error(e, "cudaEventSynchronize(copy)");
+      }
+      host_pool_widen(g_hc->stage8 + (size_t)off * per_env, ts->obs_grid + (size_t)off * per_env, (size_t)n * per_env);
+    }
+  }
+  int rc_sync = RBG_OK;
   for (int i = 0; i < 3; ++i) {
     e = cudaStreamSynchronize(g_streams[i]);
-    if (e != cudaSuccess) return set_cuda_error(e, "cudaStreamSynchronize");
+    if (e != cudaSuccess) rc_sync = set_cuda_error(e, "cudaStreamSynchronize");
   }
+  if (packed) host_pool_wait();
+  return rc_sync;
+}
+
+int rbg_host_transfer_stats(int64_t *h2d_bytes, int64_t *d2h_bytes, int *host_threads, int reset) {
+  if (h2d_bytes) *h2d_bytes = reset ? g_h2d_bytes.exchange(0) : g_h2d_bytes.load();
+  if (d2h_bytes) *d2h_bytes = reset ? g_d2h_bytes.exchange(0) : g_d2h_bytes.load();
+  if (host_threads) *host_threads = host_io_wide() ? 0 : host_pool_threads();
   return RBG_OK;
 }
 

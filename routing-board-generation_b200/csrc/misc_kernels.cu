@@ -431,4 +431,39 @@ int launch_validate(const int32_t *boards, int64_t B, int G, int N, int32_t *fla
   return check_launch("validate_kernel");
 }
 
+// ---- host transport of the observation (rbg_connector_step_host_io) -------------------------------------
+// Codes are <= 3 * RBG_MAX_N < 256: the int32 observation crosses the bus as bytes (4x fewer) and is widened back
+// to the API's int32 by the host threads of the call (host_pool.cpp).  16 codes per thread: four 128-bit loads in
+// flight, one 128-bit store.
+__global__ void __launch_bounds__(256) narrow_codes_kernel(const int32_t *__restrict__ src, uint8_t *__restrict__ dst, long long n) {
+  const long long n16 = n >> 4;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n16; q += stride) {
+    const int4 *s = reinterpret_cast<const int4 *>(src) + 4 * q;
+    const int4 a = s[0], b = s[1], c = s[2], d = s[3];
+    uint4 o;
+    o.x = (uint32_t)a.x | ((uint32_t)a.y << 8) | ((uint32_t)a.z << 16) | ((uint32_t)a.w << 24);
+    o.y = (uint32_t)b.x | ((uint32_t)b.y << 8) | ((uint32_t)b.z << 16) | ((uint32_t)b.w << 24);
+    o.z = (uint32_t)c.x | ((uint32_t)c.y << 8) | ((uint32_t)c.z << 16) | ((uint32_t)c.w << 24);
+    o.w = (uint32_t)d.x | ((uint32_t)d.y << 8) | ((uint32_t)d.z << 16) | ((uint32_t)d.w << 24);
+    reinterpret_cast<uint4 *>(dst)[q] = o;
+  }
+  const long long t = (n16 << 4) + (long long)blockIdx.x * blockDim.x + threadIdx.x;  // the last n % 16 codes
+  if (t < n) dst[t] = (uint8_t)src[t];
+}
+
+// src and dst 16-byte aligned
+int launch_narrow_codes(const int32_t *src, uint8_t *dst, int64_t n, cudaStream_t stream) {
+  if (n <= 0) return RBG_OK;
+  int64_t ctas = ((n >> 4) + 255) / 256;
+  const int64_t cap = (int64_t)device_sm_count() * 8;
+  if (ctas > cap) ctas = cap;
+  if (ctas < 1) ctas = 1;
+  {
+    LaunchScope scope(-1, stream);
+    narrow_codes_kernel<<<(unsigned)ctas, 256, 0, stream>>>(src, dst, (long long)n);
+  }
+  return check_launch("narrow_codes_kernel");
+}
+
 }  // namespace rbg

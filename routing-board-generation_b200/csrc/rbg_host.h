@@ -117,6 +117,13 @@ int launch_board_stats(const int32_t *boards, int64_t B, int G, int count_curren
                        cudaStream_t stream);
 int launch_validate(const int32_t *boards, int64_t B, int G, int N,
                     int32_t *flags, cudaStream_t stream);
+// int32 codes (< 256) -> bytes, for the host transport of the observation
+int launch_narrow_codes(const int32_t *src, uint8_t *dst, int64_t n, cudaStream_t stream);
+
+// ---- host thread pool (host_pool.cpp): widens byte codes back to int32 in host memory ----
+int host_pool_threads();                                          // workers (created on first use)
+void host_pool_widen(const uint8_t *src, int32_t *dst, size_t n); // enqueue; split over the workers
+void host_pool_wait();                                            // until every enqueued piece is done
 
 // ---- seed extension (seedext_kernel.cu) ---------------------------------
 struct SeedExtParams {

@@ -1090,6 +1090,62 @@ def test_step_host_io_matches_oracle(rbg, orc):
         _assert_state(st, rst, f"step {step}")
 
 
+_HOST_IO_CODE = """
+import ctypes as C, sys, numpy as np
+sys.path.insert(0, {root!r})
+import routing_board_generation_b200 as rbg
+from oracle import oracle as orc
+L, lib = rbg._lib, rbg._lib.load()
+G, N, B, TL = {G}, {N}, {B}, {TL}
+kref = orc.split(orc.PRNGKey(77), B)
+keys = rbg.engine.as_tensor(kref)
+env = rbg.VmapAutoResetWrapper(rbg.Connector(generator=rbg.ParallelRandomWalkGenerator(G, N), time_limit=TL))
+st, _ = env.reset(keys)
+rst, _ = orc.connector_reset_batch("parallel_random_walk", kref, G, N)
+pad = 3  # the observation buffer starts 12 bytes into its allocation when the vector path is not needed
+ob = np.full(B * N * G * G + 8, -1, np.int32)
+o0 = pad if (G * G) % 4 else 0
+obs = ob[o0:o0 + B * N * G * G].reshape(B, N, G, G)
+h = dict(obs=obs, mask=np.empty((B, N, 5), np.uint8), sc=np.empty(B, np.int32), reward=np.empty((B, N), np.float32), discount=np.empty((B, N), np.float32),
+         step_type=np.empty(B, np.int8), nc=np.empty(B, np.int32), rc=np.empty(B, np.float32), tpl=np.empty(B, np.int32))
+a = st.agents
+s = L.rbg_state(st.grid.data_ptr(), st.step_count.data_ptr(), a.id.data_ptr(), a.start.data_ptr(), a.target.data_ptr(), a.position.data_ptr(), st.key.data_ptr())
+t = L.rbg_timestep(*(h[k].ctypes.data for k in ("obs", "mask", "sc", "reward", "discount", "step_type", "nc", "rc", "tpl")))
+params = L.rbg_env_params(TL, -0.03, 0.1, 0)
+L.host_transfer_stats(reset=True)
+for step in range(6):
+    act = orc.random_actions_batch(rst)
+    L.check(lib.rbg_connector_step_host_io(C.byref(s), act.ctypes.data, B, G, N, C.byref(params), C.byref(t), -1))
+    rst, rts = orc.connector_step_batch(rst, act, time_limit=TL, autoreset_kind="parallel_random_walk")
+    assert np.array_equal(obs, rts["obs"]) and np.array_equal(h["mask"], rts["action_mask"]), step
+    assert np.array_equal(h["reward"].view(np.uint32), rts["reward"].view(np.uint32)) and np.array_equal(h["step_type"], rts["step_type"]), step
+    assert np.array_equal(h["tpl"], rts["total_path_length"]) and np.array_equal(h["sc"], rts["obs_step_count"]) and np.array_equal(h["nc"], rts["num_connections"]), step
+assert (ob[:o0] == -1).all() and (ob[o0 + B * N * G * G:] == -1).all()  # nothing written around the buffer
+h2d, d2h, threads = L.host_transfer_stats()
+small = B * (N * 5 + 4 + N * 8 + 1 + 12)
+assert h2d == 6 * B * N * 4 and d2h == 6 * (B * N * G * G * {obs_bytes} + small), (h2d, d2h)
+assert (threads > 0) == ({obs_bytes} == 1)
+print("ok", threads)
+"""
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env_vars,G,N,B", [({}, 5, 3, 4101), ({}, 7, 2, 70), ({"RBG_HOST_THREADS": "3", "RBG_HOST_IO_SLICES": "16"}, 10, 5, 9000),
+                                            ({"RBG_HOST_IO_WIDE": "1"}, 10, 5, 4500), ({"RBG_HOST_IO_WIDE": "1"}, 5, 3, 4101)])
+def test_step_host_io_transports(env_vars, G, N, B):
+    """rbg_connector_step_host_io moves the observation as bytes and widens it on the host threads of the call
+    (default) or as int32 (RBG_HOST_IO_WIDE=1): same TimeSteps as the oracle either way, ragged last slices,
+    shapes without the vector path, unpinned and odd-aligned destination, and the byte counters say what crossed."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = _HOST_IO_CODE.format(root=root, G=G, N=N, B=B, TL=3, obs_bytes=4 if env_vars.get("RBG_HOST_IO_WIDE") else 1)
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env_vars), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().startswith("ok"), (r.stdout[-800:], r.stderr[-2000:])
+
+
 def test_step_host_io_survives_other_host_calls(rbg, orc):
     """The host-variant step keeps its auto-reset workspaces in the library's device scratch.  Another
     host-variant call in between overwrites that scratch, and a new env batch of the same shape comes
