@@ -45,13 +45,24 @@
 
 namespace rbg {
 
+// -DRBG_SE_STATS: counters of the extend kernel (tools/se_stats.py reads them through rbg_debug_se_stats)
+#ifdef RBG_SE_STATS
+__device__ unsigned long long g_se_stats[16];
+#define SE_STAT(i, v)                                                          \
+  do {                                                                         \
+    const unsigned long long v_ = (unsigned long long)(v); /* may hold a ballot */ \
+    if ((threadIdx.x & 31) == 0) atomicAdd(&g_se_stats[i], v_);                \
+  } while (0)
+#else
+#define SE_STAT(i, v)
+#endif
+
 struct SeScratch {
   uint8_t *board;   // [B, CB]  row-major G*G codes, CB = cells rounded up to 16
   uint32_t *keys;   // [B, 4]   loop key (2), optkey of the current iteration (2)
   uint32_t *gkey;   // [B, 2]   State.key (random_seed_generator.py:34,57)
-  uint32_t *ext;    // [B, 4]   extension state between rounds: extend_wires_jax's key (2), sweeps done, unused
   int32_t *status;  // [B]      bit0 BFS ran dry / pop limit (never seen), bits 8.. sweeps
-  uint32_t *snap;   // [ceil(B/32), SB2w, 32]  pre-sweep board of every lane, word-interleaved per warp
+  uint32_t *snap;   // [extend warps, SB2w, 32]  pre-sweep board of every lane, word-interleaved per warp
   int CB;
 };
 
@@ -181,9 +192,12 @@ __device__ __forceinline__ uint32_t warp_pick(uint32_t needm, bool need, const u
   const uint32_t my_range = (per == 32 ? FULL : ((1u << per) - 1u)) << (my_slot * per);  // the lanes that draw for me
   bool pending = need;
   int done_draws = 0;
+  SE_STAT(3, 1);
+  SE_STAT(5, n);
   for (int t0 = 0;; t0 += per) {
     const uint32_t pendm = __ballot_sync(FULL, pending && t0 < avail);
     if (!pendm) break;
+    SE_STAT(4, 1);
     const int t = t0 + j;
     uint32_t d = 0;
     bool hit = false;
@@ -199,6 +213,7 @@ __device__ __forceinline__ uint32_t warp_pick(uint32_t needm, bool need, const u
     }
     done_draws = t0 + per;
   }
+  SE_STAT(6, __popc(__ballot_sync(FULL, pending)));
   if (pending) {  // outran the parked keys: the chain goes on from the key behind the buffer (draws avail, avail + 1, ...)
     (void)done_draws;
     uint32_t k0 = key0, k1 = key1;
@@ -218,15 +233,14 @@ __device__ __forceinline__ uint32_t warp_pick(uint32_t needm, bool need, const u
   return pick;
 }
 
-// One round of extend_wires_jax's sweep loop (PPU:47-195) over the boards of `list_in`.
-struct SeRound {
-  const int32_t *list_in;   // scratch slots of the boards still sweeping (NULL: 0 .. total-1, the first round)
-  const int32_t *count_in;  // device count of list_in
-  int32_t *list_out;        // boards that need more sweeps after this round (NULL: this round runs to convergence)
-  int32_t *count_out;
-  int max_sweeps;           // sweeps per board in this round (<= 0: unbounded)
-  int dense_warps;          // boards are packed 32 per warp only while that fills this many warps (see lanes_used)
-  int first;                // first round of an extension iteration: key, extkey, optkey = split(key, 3)  SE:189
+// extend_wires_jax's sweep loop (PPU:47-195) as a PERSISTENT kernel: a lane takes a board from the queue, sweeps it until
+// it has converged, hands it on and takes the next one.  Every sweep is G rows whatever the board, so the lanes of a
+// warp stay aligned on rows while each is at its own sweep of its own board: the chain bursts run at 32 / 32 lanes
+// and nobody waits for the slowest board of a warp (sweeps per board at 14x14/7: mean 9.9, p99 23, max 45).
+struct SeQueue {
+  int32_t *head;       // next scratch slot to hand out (zeroed by the host before the launch)
+  int32_t *done_list;  // optional: scratch slots in completion order, -1 until published (consumed by se_optimise_kernel
+  int32_t *done_head;  //           running at the same time), and its reservation counter
 };
 
 __device__ __forceinline__ bool se_extendable(uint32_t v, bool two_sided) {
@@ -235,27 +249,17 @@ __device__ __forceinline__ bool se_extendable(uint32_t v, bool two_sided) {
   return two_sided ? ctype != PATH : ctype == TARGET;                       // PPU:109-116
 }
 
-__global__ void __launch_bounds__(128) se_extend_kernel(const SeedExtParams p, const SeDims d, const SeScratch sc, const SeRound rd) {
+__global__ void __launch_bounds__(128) se_extend_kernel(const SeedExtParams p, const SeDims d, const SeScratch sc, const SeQueue qu) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long total = rd.list_in ? (long long)(*rd.count_in) : se_total(p);
-  // A round that is left with few boards is bound by the LATENCY of a sweep (a sequential hash chain per board
-  // plus, per row, as many head-extension passes as the busiest lane of the warp needs), not by issue slots: such
-  // rounds spread their boards over more warps, `lanes_used` boards per warp, so that a warp waits for fewer boards.
+  const long long total = se_total(p);
   const long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
-  int lanes_used = 32;
-  {
-    const long long grid_warps = (long long)gridDim.x * (blockDim.x >> 5);
-    const long long spread = rd.dense_warps < grid_warps ? rd.dense_warps : grid_warps;  // warps the boards may be spread over
-    if ((total + 31) / 32 < spread) {
-      lanes_used = (int)((total + spread - 1) / spread);
-      if (lanes_used < 1) lanes_used = 1;
-    }
-  }
-  if (wg * lanes_used >= total) return;  // the whole warp is beyond the list
-  const long long t = wg * lanes_used + lane;
-  const bool live = lane < lanes_used && t < total;
-  const long long m = live ? (rd.list_in ? (long long)rd.list_in[t] : t) : 0;
+  const long long grid_warps = (long long)gridDim.x * (blockDim.x >> 5);
+  // A batch that does not fill the grid is spread over its warps, `lanes_used` boards per warp: a sweep's latency (a
+  // sequential hash chain per board plus, per row, as many head-extension passes as the busiest lane needs) falls
+  // with fewer boards per warp.
+  int lanes_used = (int)((total + grid_warps - 1) / grid_warps);
+  lanes_used = lanes_used < 1 ? 1 : (lanes_used > 32 ? 32 : lanes_used);
   const int G = d.G, S = d.S2;
   uint8_t *mine = smem_raw + ((size_t)warp * 32 + lane) * d.lane_words_ext * 4;
   uint8_t *board = mine;
@@ -267,52 +271,107 @@ __global__ void __launch_bounds__(128) se_extend_kernel(const SeedExtParams p, c
 
   uint32_t key0 = 0, key1 = 0;
   long long step_num = 0;
-  if (live) {
-    if (rd.first) {  // key, extkey, optkey = split(key, 3)   SE:189
-      uint32_t f[6];
-      split3(sc.keys[4 * m], sc.keys[4 * m + 1], f);
-      sc.keys[4 * m] = f[0];
-      sc.keys[4 * m + 1] = f[1];
-      sc.keys[4 * m + 2] = f[4];
-      sc.keys[4 * m + 3] = f[5];
-      key0 = f[2];
-      key1 = f[3];
-    } else {
-      key0 = sc.ext[4 * m];
-      key1 = sc.ext[4 * m + 1];
-      step_num = (long long)sc.ext[4 * m + 2];
-    }
-    // padded board: 0xFF outside the grid (never EMPTY, never anybody's wire)
-    uint32_t *w = reinterpret_cast<uint32_t *>(board);
-    for (int q = 0; q < d.SB2w; ++q) w[q] = 0xFFFFFFFFu;
-    const uint4 *src = reinterpret_cast<const uint4 *>(sc.board + (size_t)m * sc.CB);  // CB is a multiple of 16
-    int r = 0, c = 0;
-    for (int q = 0; q < (sc.CB >> 4); q += 2) {  // two 128-bit loads in flight
-      const uint4 a = src[q];
-      const uint4 b = q + 1 < (sc.CB >> 4) ? src[q + 1] : make_uint4(0, 0, 0, 0);
-      const uint32_t ws[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-#pragma unroll
-        for (int bb = 0; bb < 4; ++bb) {
-          if (r < G) board[(r + 2) * S + (c + 2)] = (uint8_t)(ws[k] >> (8 * bb));
-          if (++c == G) {
-            c = 0;
-            ++r;
-          }
-        }
-    }
-  }
+  long long m = -1;       // scratch slot of this lane's board, -1: none
+  bool again = false;     // the board changed in its last sweep (or has not been swept yet)
+  int sweeps = 0;
+  bool queue_open = true;  // warp-uniform: the queue may still hold boards
   const bool two_sided = p.two_sided != 0;
   const bool use_rand = p.randomness > 0.0f;
-  bool again = live;  // prev_layout differs from the board by construction  PPU:47; a board in a later round's list needs a sweep
-  int sweeps = 0;
-  // The sweep is warp-synchronous: all 32 lanes walk the rows together (lanes whose board has converged idle
-  // through the rest of the round), so that the chain bursts run at 32 / 32 lanes and the random picks can
-  // be computed by the whole warp.
+  // The sweep is warp-synchronous: all 32 lanes walk the rows together, so that the chain bursts run at 32 / 32 lanes
+  // and the random picks can be computed by the whole warp.
   for (;;) {
-    const bool act = again && (p.ext_steps < 0 || step_num < p.ext_steps) && (rd.max_sweeps <= 0 || sweeps < rd.max_sweeps);
-    if (!__any_sync(FULL, act)) break;
+    // ---- boards that have converged (or reached the step limit) go back to the scratch
+    const bool fin = m >= 0 && !(again && (p.ext_steps < 0 || step_num < p.ext_steps));
+    const uint32_t finm = __ballot_sync(FULL, fin);
+    if (finm) {
+      SE_STAT(10, 1);
+      if (fin) {
+        uint32_t *dst = reinterpret_cast<uint32_t *>(sc.board + (size_t)m * sc.CB);
+        int r = 0, c = 0;
+        for (int q = 0; q < (d.cells + 3) >> 2; ++q) {
+          uint32_t w = 0;
+#pragma unroll
+          for (int bb = 0; bb < 4; ++bb) {
+            if (r < G) w |= (uint32_t)board[(r + 2) * S + (c + 2)] << (8 * bb);
+            if (++c == G) {
+              c = 0;
+              ++r;
+            }
+          }
+          dst[q] = w;
+        }
+        sc.status[m] += sweeps << 8;
+      }
+      if (qu.done_list) {  // publish: the lane's own board stores are ordered before the release store of its list entry
+        int base = 0;
+        if (lane == 0) base = atomicAdd(qu.done_head, __popc(finm));
+        base = __shfl_sync(FULL, base, 0);
+        if (fin) {
+          __threadfence();
+          st_release_s32(qu.done_list + base + __popc(finm & ((1u << lane) - 1u)), (int)m);
+        }
+      }
+      if (fin) m = -1;
+    }
+    // ---- free lanes take the next boards of the queue
+    bool fresh = false;
+    if (queue_open) {
+      const bool want = lane < lanes_used && m < 0;
+      const uint32_t wantm = __ballot_sync(FULL, want);
+      if (wantm) {
+        long long base = 0;
+        if (lane == 0) base = (long long)atomicAdd(qu.head, __popc(wantm));
+        base = __shfl_sync(FULL, base, 0);
+        const long long t = base + __popc(wantm & ((1u << lane) - 1u));
+        if (want && t < total) {
+          m = t;
+          fresh = true;
+        }
+        if (base + __popc(wantm) >= total) queue_open = false;
+      }
+    }
+    if (__any_sync(FULL, fresh)) {
+      SE_STAT(9, 1);
+      if (fresh) {
+        // key, extkey, optkey = split(key, 3)   SE:189
+        uint32_t f[6];
+        split3(sc.keys[4 * m], sc.keys[4 * m + 1], f);
+        sc.keys[4 * m] = f[0];
+        sc.keys[4 * m + 1] = f[1];
+        sc.keys[4 * m + 2] = f[4];
+        sc.keys[4 * m + 3] = f[5];
+        key0 = f[2];
+        key1 = f[3];
+        step_num = 0;
+        sweeps = 0;
+        again = true;  // prev_layout differs from the board by construction  PPU:47
+        // padded board: 0xFF outside the grid (never EMPTY, never anybody's wire)
+        uint32_t *w = reinterpret_cast<uint32_t *>(board);
+        for (int q = 0; q < d.SB2w; ++q) w[q] = 0xFFFFFFFFu;
+        const uint4 *src = reinterpret_cast<const uint4 *>(sc.board + (size_t)m * sc.CB);  // CB is a multiple of 16
+        int r = 0, c = 0;
+        for (int q = 0; q < (sc.CB >> 4); q += 2) {  // two 128-bit loads in flight
+          const uint4 a = src[q];
+          const uint4 b = q + 1 < (sc.CB >> 4) ? src[q + 1] : make_uint4(0, 0, 0, 0);
+          const uint32_t ws[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+#pragma unroll
+            for (int bb = 0; bb < 4; ++bb) {
+              if (r < G) board[(r + 2) * S + (c + 2)] = (uint8_t)(ws[k] >> (8 * bb));
+              if (++c == G) {
+                c = 0;
+                ++r;
+              }
+            }
+        }
+      }
+    }
+    if (!__any_sync(FULL, m >= 0)) break;  // no board in the warp and none left in the queue
+    const bool act = m >= 0 && again && (p.ext_steps < 0 || step_num < p.ext_steps);
+    if (!__any_sync(FULL, act)) continue;  // only boards that do no sweep (extension_steps == 0): retired at the top
+    SE_STAT(0, 1);
+    SE_STAT(8, __popc(__ballot_sync(FULL, act)));
     bool flip = false, flop = false;
     if (act) {
       ++step_num;
@@ -342,10 +401,10 @@ __global__ void __launch_bounds__(128) se_extend_kernel(const SeedExtParams p, c
       // ---- (i) the chain of this row: key, random_key = split(key) for EVERY cell (PPU:156), board-independent.
       // All lanes, two independent blocks per cell.  random_key is parked for the row's G cells and SE_LOOK cells
       // beyond (the random picks read ahead, see warp_pick); the burst of the next row continues from there.
-      const int fresh = row == 0 ? 0 : SE_LOOK;  // positions [0, fresh) are carried over from the previous row
+      const int carried = row == 0 ? 0 : SE_LOOK;  // positions [0, carried) come from the previous row's burst
       if (row > 0)
         for (int i = 0; i < 2 * SE_LOOK; ++i) rb[i] = rb[2 * G + i];
-      for (int i = fresh; i < G + SE_LOOK; ++i) {
+      for (int i = carried; i < G + SE_LOOK; ++i) {
         uint32_t n0, r0, n1, r1;
         tf_block(key0, key1, 0u, 2u, n0, r0);
         tf_block(key0, key1, 1u, 3u, n1, r1);
@@ -368,6 +427,8 @@ __global__ void __launch_bounds__(128) se_extend_kernel(const SeedExtParams p, c
         for (int c2 = 0; c2 < G; ++c2) emask |= (unsigned long long)(se_extendable(prow[c2 * scol], two_sided) ? 1u : 0u) << c2;
       for (;;) {
         const bool have = emask != 0ull;
+        SE_STAT(1, 1);
+        SE_STAT(2, __popc(__ballot_sync(FULL, have)));
         if (!__any_sync(FULL, have)) break;
         const int col = have ? __ffsll((long long)emask) - 1 : 0;
         emask &= emask - 1ull;
@@ -409,6 +470,7 @@ __global__ void __launch_bounds__(128) se_extend_kernel(const SeedExtParams p, c
         // of the lanes that need one (warp_pick)
         const uint32_t needm = __ballot_sync(FULL, need);
         if (needm) pick = warp_pick(needm, need, rb_warp, d.lane_words_ext, d.SB2w, col, G + SE_LOOK - col, key0, key1, ok, pick, lane);
+        SE_STAT(7, __popc(__ballot_sync(FULL, ok != 0u)));
         if (ok) {
           const int delta = pick == 1u ? -sr : (pick == 2u ? -scol : (pick == 4u ? sr : scol));
           pc[delta] = (uint8_t)v;   // the head / target moves      PPU:165-167
@@ -461,37 +523,6 @@ __global__ void __launch_bounds__(128) se_extend_kernel(const SeedExtParams p, c
         again = diff;
       }
     }
-  }
-  // ---- the board goes back to the scratch; boards that need more sweeps are compacted for the next round
-  const bool more = live && again && (p.ext_steps < 0 || step_num < p.ext_steps) && rd.list_out != nullptr;
-  if (live) {
-    uint32_t *dst = reinterpret_cast<uint32_t *>(sc.board + (size_t)m * sc.CB);
-    int r = 0, c = 0;
-    for (int q = 0; q < (d.cells + 3) >> 2; ++q) {
-      uint32_t w = 0;
-#pragma unroll
-      for (int bb = 0; bb < 4; ++bb) {
-        if (r < G) w |= (uint32_t)board[(r + 2) * S + (c + 2)] << (8 * bb);
-        if (++c == G) {
-          c = 0;
-          ++r;
-        }
-      }
-      dst[q] = w;
-    }
-    sc.status[m] += sweeps << 8;
-    if (more) {
-      sc.ext[4 * m] = key0;
-      sc.ext[4 * m + 1] = key1;
-      sc.ext[4 * m + 2] = (uint32_t)step_num;
-    }
-  }
-  const uint32_t morem = __ballot_sync(FULL, more);
-  if (morem) {
-    int base = 0;
-    if (lane == 0) base = atomicAdd(rd.count_out, __popc(morem));
-    base = __shfl_sync(FULL, base, 0);
-    if (more) rd.list_out[base + __popc(morem & ((1u << lane) - 1u))] = (int32_t)m;
   }
 }
 
@@ -754,14 +785,44 @@ int launch_seedext(SeedExtParams p, int64_t max_boards, cudaStream_t stream) {
     if (((b / 4) & 1) == 0) b += 4;
     d.lane_bytes_opt = (int)b;
   }
+  // lane-per-board kernels: small CTAs (2 warps / 1 warp), so that the boards spread evenly over the SMs
+  auto warps_for = [](size_t per_warp, int w) {
+    while (w > 1 && per_warp * w > 100 * 1024) w >>= 1;
+    return w;
+  };
+  const size_t ext_warp = (size_t)32 * d.lane_words_ext * 4, opt_warp = (size_t)32 * d.lane_bytes_opt;
+  int ext_w = warps_for(ext_warp, 2), opt_w = warps_for(opt_warp, 1);
+  if (const char *ex = getenv("RBG_SE_EXT_WARPS")) ext_w = atoi(ex) >= 1 && atoi(ex) <= 4 ? warps_for(ext_warp, atoi(ex)) : ext_w;
+  if (const char *ex = getenv("RBG_SE_OPT_WARPS")) opt_w = atoi(ex) >= 1 && atoi(ex) <= 4 ? warps_for(opt_warp, atoi(ex)) : opt_w;
+  int rc = RBG_OK;
+  if ((rc = set_smem(reinterpret_cast<const void *>(se_extend_kernel), ext_warp * ext_w, "se_extend_kernel"))) return rc;
+  if ((rc = set_smem(reinterpret_cast<const void *>(se_optimise_kernel), opt_warp * opt_w, "se_optimise_kernel"))) return rc;
+  // se_extend_kernel is persistent: as many CTAs as are resident at once (RBG_SE_CTAS_PER_SM: fewer), never more than the batch needs
+  unsigned ext_ctas = 1;
+  {
+    int per_sm = 0;
+    cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, se_extend_kernel, ext_w * 32, ext_warp * ext_w);
+    if (oe != cudaSuccess) return set_cuda_error(oe, "cudaOccupancyMaxActiveBlocksPerMultiprocessor(se_extend_kernel)");
+    if (per_sm < 1) return set_error(RBG_EINVAL, "se_extend_kernel: a CTA of %d warps does not fit an SM (%zu bytes of shared memory)", ext_w, ext_warp * ext_w);
+    static int cap = -1;
+    if (cap < 0) {
+      const char *ex = getenv("RBG_SE_CTAS_PER_SM");
+      cap = ex ? atoi(ex) : 0;
+      if (cap < 0) cap = 0;
+    }
+    if (cap > 0 && per_sm > cap) per_sm = cap;
+    const long long resident = (long long)per_sm * device_sm_count();
+    const long long need = (max_boards + ext_w * 32 - 1) / (ext_w * 32);
+    ext_ctas = (unsigned)(need < resident ? need : resident);
+    if (ext_ctas < 1) ext_ctas = 1;
+  }
   SeScratch sc;
   sc.CB = (int)round_up((size_t)d.cells, 16);
   const size_t n = (size_t)max_boards;
   const size_t o_keys = round_up(n * sc.CB, 256), o_gkey = o_keys + round_up(n * 16, 256), o_status = o_gkey + round_up(n * 8, 256);
   const size_t o_snap = o_status + round_up(n * 4, 256);
-  const size_t o_ext = o_snap + round_up(((n + 127) / 128 * 4) * 32 * (size_t)d.SB2w * 4, 256);  // one region per warp of the extend launches (up to 4 warps per CTA)
-  const size_t o_lists = o_ext + round_up(n * 16, 256);  // two ping-pong lists of scratch slots + 64 round counters
-  const size_t total = o_lists + 2 * round_up(n * 4, 256) + 256;
+  const size_t o_queue = o_snap + round_up((size_t)ext_ctas * ext_w * 32 * (size_t)d.SB2w * 4, 256);  // one snapshot region per extend warp
+  const size_t total = o_queue + 256;  // queue counters: one int per extension iteration
   uint8_t *base = nullptr;
   {  // keep the stream-ordered pool's memory cached between calls (default: released at every sync)
     static bool pool_ready = false;
@@ -782,12 +843,18 @@ int launch_seedext(SeedExtParams p, int64_t max_boards, cudaStream_t stream) {
   sc.gkey = reinterpret_cast<uint32_t *>(base + o_gkey);
   sc.status = reinterpret_cast<int32_t *>(base + o_status);
   sc.snap = reinterpret_cast<uint32_t *>(base + o_snap);
-  sc.ext = reinterpret_cast<uint32_t *>(base + o_ext);
-  int32_t *lists[2] = {reinterpret_cast<int32_t *>(base + o_lists), reinterpret_cast<int32_t *>(base + o_lists + round_up(n * 4, 256))};
-  int32_t *round_count = reinterpret_cast<int32_t *>(base + o_lists + 2 * round_up(n * 4, 256));
+  int32_t *queue = reinterpret_cast<int32_t *>(base + o_queue);
+  if (p.iterations > 64) {
+    cudaFreeAsync(base, stream);
+    return set_error(RBG_EINVAL, "SeedExtension: extension_iterations=%d (max 64)", p.iterations);
+  }
 
-  int rc = RBG_OK;
   do {
+    cudaError_t me = cudaMemsetAsync(queue, 0, 256, stream);
+    if (me != cudaSuccess) {
+      rc = set_cuda_error(me, "cudaMemsetAsync(SeedExtension queue)");
+      break;
+    }
     {  // seeding: one warp per board
       const size_t smem = sizeof(uint64_t) * SE_SEED_WARPS * d.cap + sizeof(uint16_t) * SE_SEED_WARPS * ((N + 1) & ~1);
       const unsigned ctas = (unsigned)((max_boards + SE_SEED_WARPS - 1) / SE_SEED_WARPS);
@@ -795,58 +862,16 @@ int launch_seedext(SeedExtParams p, int64_t max_boards, cudaStream_t stream) {
       se_seed_kernel<<<ctas, SE_SEED_WARPS * 32, smem, stream>>>(p, d, sc);
     }
     if ((rc = check_launch("se_seed_kernel"))) break;
-    // lane-per-board kernels: small CTAs (2 warps / 1 warp), so that a batch that is a single wave
-    // spreads evenly over the SMs (65 536 boards 14x14/7: 4 + 2 warps per CTA 6.97 ms, 2 + 1 6.45 ms)
-    auto warps_for = [](size_t per_warp, int w) {
-      while (w > 1 && per_warp * w > 100 * 1024) w >>= 1;
-      return w;
-    };
-    const size_t ext_warp = (size_t)32 * d.lane_words_ext * 4, opt_warp = (size_t)32 * d.lane_bytes_opt;
-    int ext_w = warps_for(ext_warp, 2), opt_w = warps_for(opt_warp, 1);
-    if (const char *ex = getenv("RBG_SE_EXT_WARPS")) ext_w = atoi(ex) >= 1 && atoi(ex) <= 4 ? warps_for(ext_warp, atoi(ex)) : ext_w;
-    if (const char *ex = getenv("RBG_SE_OPT_WARPS")) opt_w = atoi(ex) >= 1 && atoi(ex) <= 4 ? warps_for(opt_warp, atoi(ex)) : opt_w;
-    if ((rc = set_smem(reinterpret_cast<const void *>(se_extend_kernel), ext_warp * ext_w, "se_extend_kernel"))) break;
-    if ((rc = set_smem(reinterpret_cast<const void *>(se_optimise_kernel), opt_warp * opt_w, "se_optimise_kernel"))) break;
-    // Rounds of the sweep loop: boards converge after different numbers of sweeps (6 .. 16 at 14x14/7), and a
-    // warp lasts as long as its slowest lane, so after every round the boards that need more sweeps are
-    // compacted into dense warps.  The launches are sized for the whole batch (the device-side count is not
-    // known here); warps beyond the list leave at once.  The last round runs whatever is left to convergence.
-    static int se_round = -1, se_rounds = -1, se_dense_warps = 1;
-    if (se_round < 0) {
-      const char *ex = getenv("RBG_SE_ROUND_SWEEPS");
-      se_round = ex ? atoi(ex) : 2;
-      if (se_round < 1) se_round = 1;
-      ex = getenv("RBG_SE_ROUNDS");
-      se_rounds = ex ? atoi(ex) : 0;  // measured: compaction rounds do not pay (the batch is bound by the slowest board's sweep latency), see DESIGN.md K3
-      if (se_rounds < 0) se_rounds = 0;
-      if (se_rounds > 30) se_rounds = 30;
-      const int sms = device_sm_count();
-      ex = getenv("RBG_SE_DENSE_WARPS");
-      se_dense_warps = ex ? atoi(ex) : sms * 8;  // about what is resident at once
-      if (se_dense_warps < 1) se_dense_warps = 1;
-    }
     for (int it = 0; it < p.iterations && rc == RBG_OK; ++it) {  // SE:180-200 while_loop over extension_iterations
-      cudaError_t me = cudaMemsetAsync(round_count, 0, 256, stream);
-      if (me != cudaSuccess) {
-        rc = set_cuda_error(me, "cudaMemsetAsync(SeedExtension round counters)");
-        break;
-      }
-      for (int r = 0; r <= se_rounds && rc == RBG_OK; ++r) {
-        SeRound rd;
-        rd.first = r == 0 ? 1 : 0;
-        rd.list_in = r == 0 ? nullptr : lists[(r - 1) & 1];
-        rd.count_in = r == 0 ? nullptr : round_count + (r - 1);
-        const bool last = r == se_rounds;
-        rd.list_out = last ? nullptr : lists[r & 1];
-        rd.count_out = last ? nullptr : round_count + r;
-        rd.max_sweeps = last ? 0 : se_round;
-        rd.dense_warps = se_dense_warps;
-        const unsigned ctas = (unsigned)((max_boards + ext_w * 32 - 1) / (ext_w * 32));
+      {
+        SeQueue qu;
+        qu.head = queue + it;
+        qu.done_list = nullptr;
+        qu.done_head = nullptr;
         LaunchScope scope(RBG_K_SEEDEXT, stream);
-        se_extend_kernel<<<ctas, ext_w * 32, ext_warp * ext_w, stream>>>(p, d, sc, rd);
-        rc = check_launch("se_extend_kernel");
+        se_extend_kernel<<<ext_ctas, ext_w * 32, ext_warp * ext_w, stream>>>(p, d, sc, qu);
       }
-      if (rc) break;
+      if ((rc = check_launch("se_extend_kernel"))) break;
       {
         const unsigned ctas = (unsigned)((max_boards + opt_w * 32 - 1) / (opt_w * 32));
         LaunchScope scope(RBG_K_SEEDEXT, stream);
@@ -868,3 +893,15 @@ int launch_seedext(SeedExtParams p, int64_t max_boards, cudaStream_t stream) {
 }
 
 }  // namespace rbg
+
+#ifdef RBG_SE_STATS
+extern "C" int rbg_debug_se_stats(unsigned long long *out16, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out16, rbg::g_se_stats, sizeof(unsigned long long) * 16);
+  if (reset) {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(rbg::g_se_stats, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
