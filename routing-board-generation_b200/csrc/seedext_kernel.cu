@@ -39,6 +39,8 @@
 // allocation (1 byte per cell, L2-resident for any realistic batch).
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "connector_device.cuh"
 #include "rbg_host.h"
 #include "select.cuh"
@@ -63,6 +65,7 @@ struct SeScratch {
   uint32_t *gkey;   // [B, 2]   State.key (random_seed_generator.py:34,57)
   int32_t *status;  // [B]      bit0 BFS ran dry / pop limit (never seen), bits 8.. sweeps
   uint32_t *snap;   // [extend warps, SB2w, 32]  pre-sweep board of every lane, word-interleaved per warp
+  uint2 *ring;      // [extend warps, cells + SE_LOOK + 1, 32]  random_key of every cell of the current sweep, per lane
   int CB;
 };
 
@@ -175,23 +178,22 @@ __device__ __forceinline__ uint32_t se_draw(uint32_t r0, uint32_t r1) {
   return bits_scalar(b0, b1) & 3u;  // candidate index in list order up, left, down, right
 }
 
-// rb_warp: the warp's shared-memory slices; lane L's parked keys start at word L * lane_words + rb_off, two words
-// per chain position.  idx: this lane's position in its buffer, avail: parked positions from idx on.
-// (key0, key1): this lane's chain key just behind its buffer.
-__device__ __forceinline__ uint32_t warp_pick(uint32_t needm, bool need, const uint32_t *rb_warp, int lane_words, int rb_off, int idx, int avail,
-                                              uint32_t key0, uint32_t key1, uint32_t ok, uint32_t pick, int lane) {
+// ring: this warp's parked random_keys of the sweep in global memory (L2), position j of lane L at [j * 32 + L];
+// slot ring_n holds the chain KEY behind the last parked position.  idx: this lane's position, avail: parked positions
+// from idx on.
+__device__ __forceinline__ uint32_t warp_pick(uint32_t needm, bool need, const uint2 *ring, int ring_n, int idx, uint32_t ok, uint32_t pick, int lane) {
   const int n = __popc(needm);
   const int per = 32 / n;                      // draws evaluated per needing lane and pass
   const int slot = lane / per, j = lane - slot * per;
   const bool worker = slot < n;
   const int owner = worker ? (int)__fns(needm, 0, slot + 1) : 0;  // the lane this worker draws for
   const uint32_t own_ok = __shfl_sync(FULL, ok, owner);
-  const int own_idx = __shfl_sync(FULL, idx, owner), own_avail = __shfl_sync(FULL, avail, owner);
-  const uint32_t *rb = rb_warp + (size_t)owner * lane_words + rb_off;
+  const int own_idx = __shfl_sync(FULL, idx, owner);
+  const int avail = ring_n - idx, own_avail = ring_n - own_idx;
+  const uint2 *rb = ring + owner;
   const int my_slot = __popc(needm & ((1u << lane) - 1u));
   const uint32_t my_range = (per == 32 ? FULL : ((1u << per) - 1u)) << (my_slot * per);  // the lanes that draw for me
   bool pending = need;
-  int done_draws = 0;
   SE_STAT(3, 1);
   SE_STAT(5, n);
   for (int t0 = 0;; t0 += per) {
@@ -202,7 +204,8 @@ __device__ __forceinline__ uint32_t warp_pick(uint32_t needm, bool need, const u
     uint32_t d = 0;
     bool hit = false;
     if (worker && ((pendm >> owner) & 1u) && t < own_avail) {
-      d = se_draw(rb[2 * (own_idx + t)], rb[2 * (own_idx + t) + 1]);
+      const uint2 r = __ldcg(rb + (size_t)(own_idx + t) * 32);
+      d = se_draw(r.x, r.y);
       hit = ((own_ok >> d) & 1u) != 0u;
     }
     const uint32_t hits = __ballot_sync(FULL, hit) & my_range;
@@ -211,12 +214,11 @@ __device__ __forceinline__ uint32_t warp_pick(uint32_t needm, bool need, const u
       pick = 1u << dd;
       pending = false;
     }
-    done_draws = t0 + per;
   }
   SE_STAT(6, __popc(__ballot_sync(FULL, pending)));
-  if (pending) {  // outran the parked keys: the chain goes on from the key behind the buffer (draws avail, avail + 1, ...)
-    (void)done_draws;
-    uint32_t k0 = key0, k1 = key1;
+  if (pending) {  // outran the parked keys: the chain goes on from the key behind them (draws avail, avail + 1, ...)
+    const uint2 kk = __ldcg(ring + (size_t)ring_n * 32 + lane);
+    uint32_t k0 = kk.x, k1 = kk.y;
     for (;;) {
       uint32_t n0, r0, n1, r1;
       tf_block(k0, k1, 0u, 2u, n0, r0);
@@ -249,7 +251,10 @@ __device__ __forceinline__ bool se_extendable(uint32_t v, bool two_sided) {
   return two_sided ? ctype != PATH : ctype == TARGET;                       // PPU:109-116
 }
 
+// WIDE: G > 32, a row's mask of wire ends takes two words
+template <bool WIDE>
 __global__ void __launch_bounds__(128) se_extend_kernel(const SeedExtParams p, const SeDims d, const SeScratch sc, const SeQueue qu) {
+  typedef typename std::conditional<WIDE, unsigned long long, uint32_t>::type mask_t;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long total = se_total(p);
@@ -263,8 +268,12 @@ __global__ void __launch_bounds__(128) se_extend_kernel(const SeedExtParams p, c
   const int G = d.G, S = d.S2;
   uint8_t *mine = smem_raw + ((size_t)warp * 32 + lane) * d.lane_words_ext * 4;
   uint8_t *board = mine;
-  uint32_t *rb = reinterpret_cast<uint32_t *>(mine) + d.SB2w;  // [G + SE_LOOK][2] random_key of the row's cells and SE_LOOK beyond
-  const uint32_t *rb_warp = reinterpret_cast<const uint32_t *>(smem_raw) + (size_t)warp * 32 * d.lane_words_ext;
+  // rm[r]: bit c set = cell (r, c) holds an extendable wire end; for G > 32 the bits 32.. of row r are in rm[G + r]
+  uint32_t *rm = reinterpret_cast<uint32_t *>(mine) + d.SB2w;
+  constexpr bool wide = WIDE;
+  // the sweep's random_keys, parked in global memory (L2) by the chain phase: position j of lane L at ring[j * 32 + L]
+  const int ring_n = d.cells + SE_LOOK;
+  uint2 *ring = sc.ring + (size_t)wg * (ring_n + 1) * 32;
   // the pre-sweep snapshot lives in global memory (L2), word q of this lane at [q * 32 + lane] of
   // its warp's region: written and read once per mirrored sweep, coalesced
   uint32_t *snap = sc.snap + (size_t)wg * d.SB2w * 32 + lane;
@@ -365,6 +374,14 @@ __global__ void __launch_bounds__(128) se_extend_kernel(const SeedExtParams p, c
               }
             }
         }
+        // the extendable cells (wire ends) of every row
+        for (int r2 = 0; r2 < G; ++r2) {
+          unsigned long long mk = 0ull;
+          const uint8_t *rowp = board + (r2 + 2) * S + 2;
+          for (int c2 = 0; c2 < G; ++c2) mk |= (unsigned long long)(se_extendable(rowp[c2], two_sided) ? 1u : 0u) << c2;
+          rm[r2] = (uint32_t)mk;
+          if (wide) rm[G + r2] = (uint32_t)(mk >> 32);
+        }
       }
     }
     if (!__any_sync(FULL, m >= 0)) break;  // no board in the warp and none left in the queue
@@ -395,91 +412,115 @@ __global__ void __launch_bounds__(128) se_extend_kernel(const SeedExtParams p, c
     // walking the FLIPPED board row-major == walking the board with mirrored
     // coordinates and mirrored neighbour directions
     const int sr = flip ? -S : S, scol = flop ? -1 : 1;
-    uint8_t *prow = board + ((flip ? G - 1 : 0) + 2) * S + ((flop ? G - 1 : 0) + 2);
-    uint32_t end0 = key0, end1 = key1;  // the loop key after the sweep's G*G cells (the burst runs SE_LOOK cells past them)
-    for (int row = 0; row < G; ++row, prow += sr) {
-      // ---- (i) the chain of this row: key, random_key = split(key) for EVERY cell (PPU:156), board-independent.
-      // All lanes, two independent blocks per cell.  random_key is parked for the row's G cells and SE_LOOK cells
-      // beyond (the random picks read ahead, see warp_pick); the burst of the next row continues from there.
-      const int carried = row == 0 ? 0 : SE_LOOK;  // positions [0, carried) come from the previous row's burst
-      if (row > 0)
-        for (int i = 0; i < 2 * SE_LOOK; ++i) rb[i] = rb[2 * G + i];
-      for (int i = carried; i < G + SE_LOOK; ++i) {
+    // ---- (i) the chain of the sweep: key, random_key = split(key) for EVERY cell (PPU:156) never reads the board.
+    // All lanes, two independent blocks per cell, nothing else in the loop; random_key is parked for the sweep's
+    // cells and SE_LOOK cells beyond (the random picks read ahead, see warp_pick), then the key behind them.
+    uint32_t end0 = key0, end1 = key1;  // the loop key after the sweep's G*G cells
+    {
+      uint32_t c0 = key0, c1 = key1;
+      uint2 *rp = ring + lane;
+      for (int i = 0; i < ring_n; ++i, rp += 32) {
         uint32_t n0, r0, n1, r1;
-        tf_block(key0, key1, 0u, 2u, n0, r0);
-        tf_block(key0, key1, 1u, 3u, n1, r1);
-        rb[2 * i] = r0;
-        rb[2 * i + 1] = r1;
-        if (act) {
-          key0 = n0;
-          key1 = n1;
-        }
-        if (row * G + i == d.cells - 1) {
-          end0 = key0;
-          end1 = key1;
+        tf_block(c0, c1, 0u, 2u, n0, r0);
+        tf_block(c0, c1, 1u, 3u, n1, r1);
+        __stcg(rp, make_uint2(r0, r1));
+        c0 = n0;
+        c1 = n1;
+        if (i == d.cells - 1) {
+          end0 = c0;
+          end1 = c1;
         }
       }
-      // ---- (ii) the extendable cells of this row, in traversal order.  One pass over the row marks them in a
-      // bit mask (no early exits: 32 lanes, G independent loads); a head that grows to the right becomes a new
-      // extendable cell further along the same row and is added to the mask, so `next cell` is a find-first-set.
-      unsigned long long emask = 0ull;
-      if (act)
-        for (int c2 = 0; c2 < G; ++c2) emask |= (unsigned long long)(se_extendable(prow[c2 * scol], two_sided) ? 1u : 0u) << c2;
-      for (;;) {
-        const bool have = emask != 0ull;
-        SE_STAT(1, 1);
-        SE_STAT(2, __popc(__ballot_sync(FULL, have)));
-        if (!__any_sync(FULL, have)) break;
-        const int col = have ? __ffsll((long long)emask) - 1 : 0;
-        emask &= emask - 1ull;
-        const uint32_t v = have ? prow[col * scol] : 0u;
-        uint8_t *pc = prow + col * scol;
-        uint32_t b3 = 0, ok = 0, pick = 0;
-        bool need = false;
-        if (have) {
-          const uint32_t wv = v - 1u;
-          b3 = 3u * ((wv * 171u) >> 9) + 1u;  // the wire's PATH code
-          // candidates in list order up, left, down, right (PPU:322-369); a
-          // candidate is dropped when it touches the wire anywhere but through
-          // the current cell (PPU:86-97)
-          const uint32_t u = pc[-sr], l = pc[-scol], dn = pc[sr], r = pc[scol];
-          const bool oul = own_wire(pc[-sr - scol], b3), our = own_wire(pc[-sr + scol], b3);
-          const bool odl = own_wire(pc[sr - scol], b3), odr = own_wire(pc[sr + scol], b3);
-          ok |= (u == 0u && !own_wire(pc[-2 * sr], b3) && !oul && !our) ? 1u : 0u;
-          ok |= (l == 0u && !own_wire(pc[-2 * scol], b3) && !oul && !odl) ? 2u : 0u;
-          ok |= (dn == 0u && !own_wire(pc[2 * sr], b3) && !odl && !odr) ? 4u : 0u;
-          ok |= (r == 0u && !own_wire(pc[2 * scol], b3) && !our && !odr) ? 8u : 0u;
-          if (ok) {
-            // previous neighbour: last match among up, down, left (PPU:200-234);
-            // the priority cell mirrors it through the current cell (PPU:99-103)
-            uint32_t pri = 0;
-            if (own_wire(u, b3)) pri = 4u;   // came from above -> continue down
-            if (own_wire(dn, b3)) pri = 1u;  // from below -> up
-            if (own_wire(l, b3)) pri = 8u;   // from the left -> right
-            bool take_pri = (ok & pri) != 0u;
-            if (take_pri && use_rand) {  // PPU:157-162: random_key = split(key)[1] of this cell
-              const float uni = bits_to_uniform(bits_scalar(rb[2 * col], rb[2 * col + 1]));
-              take_pri = !(p.randomness > uni);
-            }
-            pick = pri;
-            need = !take_pri;
-          }
-        }
-        // repeat `k, ck = split(k); pos = list[randint(ck, 0, 4)]` until valid, from the cell's
-        // key, which is NOT advanced by this loop (PPU:127-144): the whole warp computes the draws
-        // of the lanes that need one (warp_pick)
-        const uint32_t needm = __ballot_sync(FULL, need);
-        if (needm) pick = warp_pick(needm, need, rb_warp, d.lane_words_ext, d.SB2w, col, G + SE_LOOK - col, key0, key1, ok, pick, lane);
-        SE_STAT(7, __popc(__ballot_sync(FULL, ok != 0u)));
+      __stcg(rp, make_uint2(c0, c1));
+    }
+    __syncwarp();  // the lanes read each other's parked keys
+    // ---- (ii) the extendable cells of the sweep in traversal order, the lanes aligned on "k-th visit of the sweep".
+    // The wire ends are the only extendable cells; rm holds them per row.  A row's mask is read when the walk
+    // reaches the row (an end that moved down into it is there, one that moved up is behind the walk), an end that
+    // grows along the row is added to the mask in hand and visited again, exactly as in the cell-by-cell walk.
+    auto trav_mask = [&](int rowt) -> mask_t {
+      const int r = flip ? G - 1 - rowt : rowt;
+      if (wide) {
+        const unsigned long long mk = (unsigned long long)rm[r] | ((unsigned long long)rm[G + r] << 32);
+        return (mask_t)(flop ? (__brevll(mk) >> (64 - G)) : mk);
+      }
+      const uint32_t mk = rm[r];
+      return (mask_t)(flop ? (__brev(mk) >> (32 - G)) : mk);
+    };
+    int rowt = 0;
+    mask_t emask = act ? trav_mask(0) : (mask_t)0;
+    for (;;) {
+      while (act && emask == 0 && rowt < G - 1) emask = trav_mask(++rowt);
+      const bool have = emask != 0;
+      SE_STAT(1, 1);
+      SE_STAT(2, __popc(__ballot_sync(FULL, have)));
+      if (!__any_sync(FULL, have)) break;
+      const int colt = have ? (wide ? __ffsll((long long)emask) : __ffs((int)emask)) - 1 : 0;
+      emask &= emask - 1;
+      const int r_act = flip ? G - 1 - rowt : rowt, c_act = flop ? G - 1 - colt : colt;
+      uint8_t *pc = board + (r_act + 2) * S + (c_act + 2);
+      const uint32_t v = have ? pc[0] : 0u;
+      const int pos = rowt * G + colt;  // chain position of this cell
+      uint32_t b3 = 0, ok = 0, pick = 0;
+      bool need = false;
+      if (have) {
+        const uint32_t wv = v - 1u;
+        b3 = 3u * ((wv * 171u) >> 9) + 1u;  // the wire's PATH code
+        // candidates in list order up, left, down, right (PPU:322-369); a
+        // candidate is dropped when it touches the wire anywhere but through
+        // the current cell (PPU:86-97)
+        const uint32_t u = pc[-sr], l = pc[-scol], dn = pc[sr], r = pc[scol];
+        const bool oul = own_wire(pc[-sr - scol], b3), our = own_wire(pc[-sr + scol], b3);
+        const bool odl = own_wire(pc[sr - scol], b3), odr = own_wire(pc[sr + scol], b3);
+        ok |= (u == 0u && !own_wire(pc[-2 * sr], b3) && !oul && !our) ? 1u : 0u;
+        ok |= (l == 0u && !own_wire(pc[-2 * scol], b3) && !oul && !odl) ? 2u : 0u;
+        ok |= (dn == 0u && !own_wire(pc[2 * sr], b3) && !odl && !odr) ? 4u : 0u;
+        ok |= (r == 0u && !own_wire(pc[2 * scol], b3) && !our && !odr) ? 8u : 0u;
         if (ok) {
-          const int delta = pick == 1u ? -sr : (pick == 2u ? -scol : (pick == 4u ? sr : scol));
-          pc[delta] = (uint8_t)v;   // the head / target moves      PPU:165-167
-          pc[0] = (uint8_t)b3;      // and leaves PATH behind       PPU:168-173
-          modified = true;
-          mod_idx = (int)(pc + delta - board);  // the last write of the sweep survives it
-          mod_v = v;
-          if (delta == scol) emask |= 1ull << (col + 1);  // grew along the row: visited again further on, as in the cell-by-cell walk
+          // previous neighbour: last match among up, down, left (PPU:200-234);
+          // the priority cell mirrors it through the current cell (PPU:99-103)
+          uint32_t pri = 0;
+          if (own_wire(u, b3)) pri = 4u;   // came from above -> continue down
+          if (own_wire(dn, b3)) pri = 1u;  // from below -> up
+          if (own_wire(l, b3)) pri = 8u;   // from the left -> right
+          bool take_pri = (ok & pri) != 0u;
+          if (take_pri && use_rand) {  // PPU:157-162: random_key = split(key)[1] of this cell
+            const uint2 rk = __ldcg(ring + (size_t)pos * 32 + lane);
+            const float uni = bits_to_uniform(bits_scalar(rk.x, rk.y));
+            take_pri = !(p.randomness > uni);
+          }
+          pick = pri;
+          need = !take_pri;
         }
+      }
+      // repeat `k, ck = split(k); pos = list[randint(ck, 0, 4)]` until valid, from the cell's
+      // key, which is NOT advanced by this loop (PPU:127-144): the whole warp computes the draws
+      // of the lanes that need one (warp_pick)
+      const uint32_t needm = __ballot_sync(FULL, need);
+      if (needm) pick = warp_pick(needm, need, ring, ring_n, pos, ok, pick, lane);
+      SE_STAT(7, __popc(__ballot_sync(FULL, ok != 0u)));
+      if (ok) {
+        const int delta = pick == 1u ? -sr : (pick == 2u ? -scol : (pick == 4u ? sr : scol));
+        pc[delta] = (uint8_t)v;   // the head / target moves      PPU:165-167
+        pc[0] = (uint8_t)b3;      // and leaves PATH behind       PPU:168-173
+        modified = true;
+        mod_idx = (int)(pc + delta - board);  // the last write of the sweep survives it
+        mod_v = v;
+        // the end's bit moves with it
+        const int dr = pick == 1u ? -1 : (pick == 4u ? 1 : 0), dc = pick == 2u ? -1 : (pick == 8u ? 1 : 0);  // in walk coordinates
+        const int r_new = flip ? r_act - dr : r_act + dr, c_new = flop ? c_act - dc : c_act + dc;
+        {
+          uint32_t *w0 = rm + (wide && c_act >= 32 ? G : 0) + r_act;
+          *w0 &= ~(1u << (c_act & 31));
+          uint32_t *w1 = rm + (wide && c_new >= 32 ? G : 0) + r_new;
+          *w1 |= 1u << (c_new & 31);
+        }
+        if (pick == 8u) emask |= (mask_t)1 << (colt + 1);  // grew along the row: visited again further on, as in the cell-by-cell walk
+      } else if (have) {
+        // No candidate left.  Cells are only ever filled during the extension (EMPTY -> end -> PATH) and a wire's
+        // cells only grow, so a candidate that is taken or touches the own wire stays so: this end will never move
+        // again and need not be visited any more.
+        rm[(wide && c_act >= 32 ? G : 0) + r_act] &= ~(1u << (c_act & 31));
       }
     }
     if (act) {
@@ -776,7 +817,7 @@ int launch_seedext(SeedExtParams p, int64_t max_boards, cudaStream_t stream) {
   }
   d.S2 = G + 4;
   d.SB2w = (int)(round_up((size_t)d.S2 * d.S2, 4) / 4);
-  d.lane_words_ext = (d.SB2w + 2 * (G + SE_LOOK)) | 1;  // board + the parked random_keys of a row (+ look-ahead); odd: lanes on the same cell hit 32 different banks
+  d.lane_words_ext = (d.SB2w + (G > 32 ? 2 : 1) * G) | 1;  // board + one mask of wire ends per row; odd: lanes on the same cell hit 32 different banks
   d.S1 = G + 2;
   d.SB1 = (int)round_up((size_t)d.S1 * d.S1, 4);
   {
@@ -795,13 +836,16 @@ int launch_seedext(SeedExtParams p, int64_t max_boards, cudaStream_t stream) {
   if (const char *ex = getenv("RBG_SE_EXT_WARPS")) ext_w = atoi(ex) >= 1 && atoi(ex) <= 4 ? warps_for(ext_warp, atoi(ex)) : ext_w;
   if (const char *ex = getenv("RBG_SE_OPT_WARPS")) opt_w = atoi(ex) >= 1 && atoi(ex) <= 4 ? warps_for(opt_warp, atoi(ex)) : opt_w;
   int rc = RBG_OK;
-  if ((rc = set_smem(reinterpret_cast<const void *>(se_extend_kernel), ext_warp * ext_w, "se_extend_kernel"))) return rc;
+  const bool wide = G > 32;
+  const void *ext_fn = wide ? reinterpret_cast<const void *>(se_extend_kernel<true>) : reinterpret_cast<const void *>(se_extend_kernel<false>);
+  if ((rc = set_smem(ext_fn, ext_warp * ext_w, "se_extend_kernel"))) return rc;
   if ((rc = set_smem(reinterpret_cast<const void *>(se_optimise_kernel), opt_warp * opt_w, "se_optimise_kernel"))) return rc;
   // se_extend_kernel is persistent: as many CTAs as are resident at once (RBG_SE_CTAS_PER_SM: fewer), never more than the batch needs
   unsigned ext_ctas = 1;
   {
     int per_sm = 0;
-    cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, se_extend_kernel, ext_w * 32, ext_warp * ext_w);
+    cudaError_t oe = wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, se_extend_kernel<true>, ext_w * 32, ext_warp * ext_w)
+                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, se_extend_kernel<false>, ext_w * 32, ext_warp * ext_w);
     if (oe != cudaSuccess) return set_cuda_error(oe, "cudaOccupancyMaxActiveBlocksPerMultiprocessor(se_extend_kernel)");
     if (per_sm < 1) return set_error(RBG_EINVAL, "se_extend_kernel: a CTA of %d warps does not fit an SM (%zu bytes of shared memory)", ext_w, ext_warp * ext_w);
     static int cap = -1;
@@ -821,7 +865,8 @@ int launch_seedext(SeedExtParams p, int64_t max_boards, cudaStream_t stream) {
   const size_t n = (size_t)max_boards;
   const size_t o_keys = round_up(n * sc.CB, 256), o_gkey = o_keys + round_up(n * 16, 256), o_status = o_gkey + round_up(n * 8, 256);
   const size_t o_snap = o_status + round_up(n * 4, 256);
-  const size_t o_queue = o_snap + round_up((size_t)ext_ctas * ext_w * 32 * (size_t)d.SB2w * 4, 256);  // one snapshot region per extend warp
+  const size_t o_ring = o_snap + round_up((size_t)ext_ctas * ext_w * 32 * (size_t)d.SB2w * 4, 256);  // one snapshot region per extend warp
+  const size_t o_queue = o_ring + round_up((size_t)ext_ctas * ext_w * 32 * (size_t)(d.cells + SE_LOOK + 1) * 8, 256);  // and one ring of parked keys
   const size_t total = o_queue + 256;  // queue counters: one int per extension iteration
   uint8_t *base = nullptr;
   {  // keep the stream-ordered pool's memory cached between calls (default: released at every sync)
@@ -843,6 +888,7 @@ int launch_seedext(SeedExtParams p, int64_t max_boards, cudaStream_t stream) {
   sc.gkey = reinterpret_cast<uint32_t *>(base + o_gkey);
   sc.status = reinterpret_cast<int32_t *>(base + o_status);
   sc.snap = reinterpret_cast<uint32_t *>(base + o_snap);
+  sc.ring = reinterpret_cast<uint2 *>(base + o_ring);
   int32_t *queue = reinterpret_cast<int32_t *>(base + o_queue);
   if (p.iterations > 64) {
     cudaFreeAsync(base, stream);
@@ -869,7 +915,10 @@ int launch_seedext(SeedExtParams p, int64_t max_boards, cudaStream_t stream) {
         qu.done_list = nullptr;
         qu.done_head = nullptr;
         LaunchScope scope(RBG_K_SEEDEXT, stream);
-        se_extend_kernel<<<ext_ctas, ext_w * 32, ext_warp * ext_w, stream>>>(p, d, sc, qu);
+        if (wide)
+          se_extend_kernel<true><<<ext_ctas, ext_w * 32, ext_warp * ext_w, stream>>>(p, d, sc, qu);
+        else
+          se_extend_kernel<false><<<ext_ctas, ext_w * 32, ext_warp * ext_w, stream>>>(p, d, sc, qu);
       }
       if ((rc = check_launch("se_extend_kernel"))) break;
       {
