@@ -75,6 +75,7 @@ struct SeDims {
   uint32_t thresh;    // selection filter
   int cap;
   int S2, SB2w;       // extend: padded stride (G+4), words per padded board
+  int refill_min;     // extend: a warp takes new boards when that many of its lanes are free
   int lane_words_ext; // extend: words per lane (the padded board + the G cell keys of a row), odd
   int S1, SB1;        // optimise: padded stride (G+2), bytes per padded board
   int lane_bytes_opt; // optimise: bytes per lane (board, parents, fifo, pins), multiple of 4 with odd word count
@@ -178,10 +179,9 @@ __device__ __forceinline__ uint32_t se_draw(uint32_t r0, uint32_t r1) {
   return bits_scalar(b0, b1) & 3u;  // candidate index in list order up, left, down, right
 }
 
-// ring: this warp's parked random_keys of the sweep in global memory (L2), position j of lane L at [j * 32 + L];
-// slot ring_n holds the chain KEY behind the last parked position.  idx: this lane's position, avail: parked positions
-// from idx on.
-__device__ __forceinline__ uint32_t warp_pick(uint32_t needm, bool need, const uint2 *ring, int ring_n, int idx, uint32_t ok, uint32_t pick, int lane) {
+// ring + col: this lane's column of the sweep's parked random_keys in global memory (L2), position j at [j * 32];
+// position ring_n holds the chain KEY behind the last parked position.  idx: this lane's position.
+__device__ __forceinline__ uint32_t warp_pick(uint32_t needm, bool need, const uint2 *ring, uint32_t col, int ring_n, int idx, uint32_t ok, uint32_t pick, int lane) {
   const int n = __popc(needm);
   const int per = 32 / n;                      // draws evaluated per needing lane and pass
   const int slot = lane / per, j = lane - slot * per;
@@ -190,7 +190,7 @@ __device__ __forceinline__ uint32_t warp_pick(uint32_t needm, bool need, const u
   const uint32_t own_ok = __shfl_sync(FULL, ok, owner);
   const int own_idx = __shfl_sync(FULL, idx, owner);
   const int avail = ring_n - idx, own_avail = ring_n - own_idx;
-  const uint2 *rb = ring + owner;
+  const uint2 *rb = ring + __shfl_sync(FULL, col, owner);
   const int my_slot = __popc(needm & ((1u << lane) - 1u));
   const uint32_t my_range = (per == 32 ? FULL : ((1u << per) - 1u)) << (my_slot * per);  // the lanes that draw for me
   bool pending = need;
@@ -217,7 +217,7 @@ __device__ __forceinline__ uint32_t warp_pick(uint32_t needm, bool need, const u
   }
   SE_STAT(6, __popc(__ballot_sync(FULL, pending)));
   if (pending) {  // outran the parked keys: the chain goes on from the key behind them (draws avail, avail + 1, ...)
-    const uint2 kk = __ldcg(ring + (size_t)ring_n * 32 + lane);
+    const uint2 kk = __ldcg(ring + col + (size_t)ring_n * 32);
     uint32_t k0 = kk.x, k1 = kk.y;
     for (;;) {
       uint32_t n0, r0, n1, r1;
@@ -236,9 +236,12 @@ __device__ __forceinline__ uint32_t warp_pick(uint32_t needm, bool need, const u
 }
 
 // extend_wires_jax's sweep loop (PPU:47-195) as a PERSISTENT kernel: a lane takes a board from the queue, sweeps it until
-// it has converged, hands it on and takes the next one.  Every sweep is G rows whatever the board, so the lanes of a
-// warp stay aligned on rows while each is at its own sweep of its own board: the chain bursts run at 32 / 32 lanes
-// and nobody waits for the slowest board of a warp (sweeps per board at 14x14/7: mean 9.9, p99 23, max 45).
+// it has converged, hands it on and takes the next one (sweeps per board at 14x14/7: mean 9.9, p99 23, max 45).  A sweep
+// has two phases for the whole CTA.  (i) The key chain of the sweep (`key, random_key = split(key)` per cell, 57 % of the
+// kernel's instructions) never reads the board, so it is not tied to the lane that owns the board: the boards of the CTA
+// that still sweep hand their keys to a dense prefix of the CTA's threads, ceil(active / 32) warps run the chain at
+// 32 / 32 lanes and park the random_keys in a ring in global memory (L2); warps beyond the prefix skip the phase.
+// (ii) Every lane walks the wire ends of its own board (in its slice of shared memory) in traversal order.
 struct SeQueue {
   int32_t *head;       // next scratch slot to hand out (zeroed by the host before the launch)
   int32_t *done_list;  // optional: scratch slots in completion order, -1 until published (consumed by se_optimise_kernel
@@ -253,7 +256,7 @@ __device__ __forceinline__ bool se_extendable(uint32_t v, bool two_sided) {
 
 // WIDE: G > 32, a row's mask of wire ends takes two words
 template <bool WIDE>
-__global__ void __launch_bounds__(128) se_extend_kernel(const SeedExtParams p, const SeDims d, const SeScratch sc, const SeQueue qu) {
+__global__ void __launch_bounds__(256) se_extend_kernel(const SeedExtParams p, const SeDims d, const SeScratch sc, const SeQueue qu) {
   typedef typename std::conditional<WIDE, unsigned long long, uint32_t>::type mask_t;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -266,14 +269,18 @@ __global__ void __launch_bounds__(128) se_extend_kernel(const SeedExtParams p, c
   int lanes_used = (int)((total + grid_warps - 1) / grid_warps);
   lanes_used = lanes_used < 1 ? 1 : (lanes_used > 32 ? 32 : lanes_used);
   const int G = d.G, S = d.S2;
-  uint8_t *mine = smem_raw + ((size_t)warp * 32 + lane) * d.lane_words_ext * 4;
+  // shared memory: [cnt: 8 ints][kx: one key per thread][per-lane slices]
+  const int nwarps = blockDim.x >> 5;
+  int *cnt = reinterpret_cast<int *>(smem_raw);
+  uint2 *kx = reinterpret_cast<uint2 *>(smem_raw + 32);
+  uint8_t *mine = smem_raw + 32 + (size_t)blockDim.x * 8 + ((size_t)warp * 32 + lane) * d.lane_words_ext * 4;
   uint8_t *board = mine;
   // rm[r]: bit c set = cell (r, c) holds an extendable wire end; for G > 32 the bits 32.. of row r are in rm[G + r]
   uint32_t *rm = reinterpret_cast<uint32_t *>(mine) + d.SB2w;
   constexpr bool wide = WIDE;
   // the sweep's random_keys, parked in global memory (L2) by the chain phase: position j of lane L at ring[j * 32 + L]
   const int ring_n = d.cells + SE_LOOK;
-  uint2 *ring = sc.ring + (size_t)wg * (ring_n + 1) * 32;
+  uint2 *ring = sc.ring + (size_t)blockIdx.x * nwarps * (ring_n + 1) * 32;  // the CTA's rings, one per chain warp
   // the pre-sweep snapshot lives in global memory (L2), word q of this lane at [q * 32 + lane] of
   // its warp's region: written and read once per mirrored sweep, coalesced
   uint32_t *snap = sc.snap + (size_t)wg * d.SB2w * 32 + lane;
@@ -325,8 +332,12 @@ __global__ void __launch_bounds__(128) se_extend_kernel(const SeedExtParams p, c
     // ---- free lanes take the next boards of the queue
     bool fresh = false;
     if (queue_open) {
+      // Boards are taken in batches (d.refill_min free lanes at least): boards of one age sweep together, and a
+      // board's first sweeps are the long ones (its ends run across the empty grid: ~50 visits against ~10 later), so a
+      // warp pays for them once per batch instead of in every sweep; idle lanes cost nothing in the chain phase.
       const bool want = lane < lanes_used && m < 0;
-      const uint32_t wantm = __ballot_sync(FULL, want);
+      uint32_t wantm = __ballot_sync(FULL, want);
+      if (__popc(wantm) < (lanes_used < d.refill_min ? lanes_used : d.refill_min)) wantm = 0u;
       if (wantm) {
         long long base = 0;
         if (lane == 0) base = (long long)atomicAdd(qu.head, __popc(wantm));
@@ -384,9 +395,8 @@ __global__ void __launch_bounds__(128) se_extend_kernel(const SeedExtParams p, c
         }
       }
     }
-    if (!__any_sync(FULL, m >= 0)) break;  // no board in the warp and none left in the queue
-    const bool act = m >= 0 && again && (p.ext_steps < 0 || step_num < p.ext_steps);
-    if (!__any_sync(FULL, act)) continue;  // only boards that do no sweep (extension_steps == 0): retired at the top
+    if (!__syncthreads_or(m >= 0)) break;  // no board in the CTA and none left in the queue
+    const bool act = m >= 0 && again && (p.ext_steps < 0 || step_num < p.ext_steps);  // false only with extension_steps == 0
     SE_STAT(0, 1);
     SE_STAT(8, __popc(__ballot_sync(FULL, act)));
     bool flip = false, flop = false;
@@ -413,12 +423,24 @@ __global__ void __launch_bounds__(128) se_extend_kernel(const SeedExtParams p, c
     // coordinates and mirrored neighbour directions
     const int sr = flip ? -S : S, scol = flop ? -1 : 1;
     // ---- (i) the chain of the sweep: key, random_key = split(key) for EVERY cell (PPU:156) never reads the board.
-    // All lanes, two independent blocks per cell, nothing else in the loop; random_key is parked for the sweep's
-    // cells and SE_LOOK cells beyond (the random picks read ahead, see warp_pick), then the key behind them.
-    uint32_t end0 = key0, end1 = key1;  // the loop key after the sweep's G*G cells
-    {
-      uint32_t c0 = key0, c1 = key1;
-      uint2 *rp = ring + lane;
+    // The sweeping boards of the CTA are ranked; thread t of the CTA runs the chain of the board of rank t: two
+    // independent blocks per cell, nothing else in the loop.  random_key is parked for the sweep's cells and SE_LOOK
+    // cells beyond (the random picks read ahead, see warp_pick), then the key behind them.
+    const uint32_t actm = __ballot_sync(FULL, act);
+    if (lane == 0) cnt[warp] = __popc(actm);
+    __syncthreads();
+    int rank = __popc(actm & ((1u << lane) - 1u)), nact = 0;
+    for (int w2 = 0; w2 < nwarps; ++w2) {
+      const int c2 = cnt[w2];
+      rank += w2 < warp ? c2 : 0;
+      nact += c2;
+    }
+    if (act) kx[rank] = make_uint2(key0, key1);
+    __syncthreads();
+    if (warp * 32 < nact) {  // a chain warp (lanes beyond nact run along on a stale key: harmless)
+      const uint2 k = kx[threadIdx.x];
+      uint32_t c0 = k.x, c1 = k.y, e0 = c0, e1 = c1;
+      uint2 *rp = ring + (size_t)warp * (ring_n + 1) * 32 + lane;
       for (int i = 0; i < ring_n; ++i, rp += 32) {
         uint32_t n0, r0, n1, r1;
         tf_block(c0, c1, 0u, 2u, n0, r0);
@@ -427,13 +449,21 @@ __global__ void __launch_bounds__(128) se_extend_kernel(const SeedExtParams p, c
         c0 = n0;
         c1 = n1;
         if (i == d.cells - 1) {
-          end0 = c0;
-          end1 = c1;
+          e0 = c0;
+          e1 = c1;
         }
       }
       __stcg(rp, make_uint2(c0, c1));
+      kx[threadIdx.x] = make_uint2(e0, e1);  // the loop key after the sweep's G*G cells
     }
-    __syncwarp();  // the lanes read each other's parked keys
+    __syncthreads();  // parked keys (global) and end keys (shared) are visible to the whole CTA
+    uint32_t end0 = key0, end1 = key1;
+    if (act) {
+      const uint2 e = kx[rank];
+      end0 = e.x;
+      end1 = e.y;
+    }
+    const uint32_t col = (uint32_t)(((rank >> 5) * (ring_n + 1)) * 32 + (rank & 31));  // this board's column of the ring
     // ---- (ii) the extendable cells of the sweep in traversal order, the lanes aligned on "k-th visit of the sweep".
     // The wire ends are the only extendable cells; rm holds them per row.  A row's mask is read when the walk
     // reaches the row (an end that moved down into it is there, one that moved up is behind the walk), an end that
@@ -485,7 +515,7 @@ __global__ void __launch_bounds__(128) se_extend_kernel(const SeedExtParams p, c
           if (own_wire(l, b3)) pri = 8u;   // from the left -> right
           bool take_pri = (ok & pri) != 0u;
           if (take_pri && use_rand) {  // PPU:157-162: random_key = split(key)[1] of this cell
-            const uint2 rk = __ldcg(ring + (size_t)pos * 32 + lane);
+            const uint2 rk = __ldcg(ring + col + (size_t)pos * 32);
             const float uni = bits_to_uniform(bits_scalar(rk.x, rk.y));
             take_pri = !(p.randomness > uni);
           }
@@ -497,7 +527,7 @@ __global__ void __launch_bounds__(128) se_extend_kernel(const SeedExtParams p, c
       // key, which is NOT advanced by this loop (PPU:127-144): the whole warp computes the draws
       // of the lanes that need one (warp_pick)
       const uint32_t needm = __ballot_sync(FULL, need);
-      if (needm) pick = warp_pick(needm, need, ring, ring_n, pos, ok, pick, lane);
+      if (needm) pick = warp_pick(needm, need, ring, col, ring_n, pos, ok, pick, lane);
       SE_STAT(7, __popc(__ballot_sync(FULL, ok != 0u)));
       if (ok) {
         const int delta = pick == 1u ? -sr : (pick == 2u ? -scol : (pick == 4u ? sr : scol));
@@ -828,26 +858,36 @@ int launch_seedext(SeedExtParams p, int64_t max_boards, cudaStream_t stream) {
   }
   // lane-per-board kernels: small CTAs (2 warps / 1 warp), so that the boards spread evenly over the SMs
   auto warps_for = [](size_t per_warp, int w) {
-    while (w > 1 && per_warp * w > 100 * 1024) w >>= 1;
+    while (w > 1 && per_warp * w > 100 * 1024) --w;
     return w;
   };
-  const size_t ext_warp = (size_t)32 * d.lane_words_ext * 4, opt_warp = (size_t)32 * d.lane_bytes_opt;
-  int ext_w = warps_for(ext_warp, 2), opt_w = warps_for(opt_warp, 1);
-  if (const char *ex = getenv("RBG_SE_EXT_WARPS")) ext_w = atoi(ex) >= 1 && atoi(ex) <= 4 ? warps_for(ext_warp, atoi(ex)) : ext_w;
+  const size_t ext_warp = (size_t)32 * d.lane_words_ext * 4 + 32 * 8, opt_warp = (size_t)32 * d.lane_bytes_opt;  // extend: + one exchanged key per thread
+  int ext_w = warps_for(ext_warp, 4), opt_w = warps_for(opt_warp, 1);
+  if (const char *ex = getenv("RBG_SE_EXT_WARPS")) ext_w = atoi(ex) >= 1 && atoi(ex) <= 8 ? warps_for(ext_warp, atoi(ex)) : ext_w;
   if (const char *ex = getenv("RBG_SE_OPT_WARPS")) opt_w = atoi(ex) >= 1 && atoi(ex) <= 4 ? warps_for(opt_warp, atoi(ex)) : opt_w;
   int rc = RBG_OK;
   const bool wide = G > 32;
   const void *ext_fn = wide ? reinterpret_cast<const void *>(se_extend_kernel<true>) : reinterpret_cast<const void *>(se_extend_kernel<false>);
-  if ((rc = set_smem(ext_fn, ext_warp * ext_w, "se_extend_kernel"))) return rc;
+  if ((rc = set_smem(ext_fn, ext_warp * ext_w + 32, "se_extend_kernel"))) return rc;
   if ((rc = set_smem(reinterpret_cast<const void *>(se_optimise_kernel), opt_warp * opt_w, "se_optimise_kernel"))) return rc;
+  {
+    static int rmin = -1;
+    if (rmin < 0) {
+      const char *ex = getenv("RBG_SE_REFILL_MIN");
+      rmin = ex ? atoi(ex) : 1;
+      if (rmin < 1) rmin = 1;
+      if (rmin > 32) rmin = 32;
+    }
+    d.refill_min = rmin;
+  }
   // se_extend_kernel is persistent: as many CTAs as are resident at once (RBG_SE_CTAS_PER_SM: fewer), never more than the batch needs
   unsigned ext_ctas = 1;
   {
     int per_sm = 0;
-    cudaError_t oe = wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, se_extend_kernel<true>, ext_w * 32, ext_warp * ext_w)
-                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, se_extend_kernel<false>, ext_w * 32, ext_warp * ext_w);
+    cudaError_t oe = wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, se_extend_kernel<true>, ext_w * 32, ext_warp * ext_w + 32)
+                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, se_extend_kernel<false>, ext_w * 32, ext_warp * ext_w + 32);
     if (oe != cudaSuccess) return set_cuda_error(oe, "cudaOccupancyMaxActiveBlocksPerMultiprocessor(se_extend_kernel)");
-    if (per_sm < 1) return set_error(RBG_EINVAL, "se_extend_kernel: a CTA of %d warps does not fit an SM (%zu bytes of shared memory)", ext_w, ext_warp * ext_w);
+    if (per_sm < 1) return set_error(RBG_EINVAL, "se_extend_kernel: a CTA of %d warps does not fit an SM (%zu bytes of shared memory)", ext_w, ext_warp * ext_w + 32);
     static int cap = -1;
     if (cap < 0) {
       const char *ex = getenv("RBG_SE_CTAS_PER_SM");
@@ -916,9 +956,9 @@ int launch_seedext(SeedExtParams p, int64_t max_boards, cudaStream_t stream) {
         qu.done_head = nullptr;
         LaunchScope scope(RBG_K_SEEDEXT, stream);
         if (wide)
-          se_extend_kernel<true><<<ext_ctas, ext_w * 32, ext_warp * ext_w, stream>>>(p, d, sc, qu);
+          se_extend_kernel<true><<<ext_ctas, ext_w * 32, ext_warp * ext_w + 32, stream>>>(p, d, sc, qu);
         else
-          se_extend_kernel<false><<<ext_ctas, ext_w * 32, ext_warp * ext_w, stream>>>(p, d, sc, qu);
+          se_extend_kernel<false><<<ext_ctas, ext_w * 32, ext_warp * ext_w + 32, stream>>>(p, d, sc, qu);
       }
       if ((rc = check_launch("se_extend_kernel"))) break;
       {
