@@ -44,6 +44,7 @@ STATE_BYTES = 4 * CELLS + 4 + 28 * N + 8            # 552
 TS_BYTES = 4 * N * CELLS + 5 * N + 4 + 8 * N + 1 + 12  # obs + mask + step_count + reward/discount + step_type + extras = 2082
 STEP_BYTES = STATE_BYTES + 4 * N + STATE_BYTES + TS_BYTES  # 3206 B per env-step
 PRW_BOARD_BYTES = {(10, 5): 488, (20, 10): 1768, (32, 16): 4360}
+SE_MEAN_SWEEPS_14_7 = 9.86  # extend_wires_jax sweeps per 14x14/7 board, mean over split(PRNGKey(0), 262144) (oracle; tools/se_stats.py)
 METRIC = "connector_env_steps_per_sec"
 UNIT = "env-steps/s"
 
@@ -466,22 +467,33 @@ def _secondary(args, rbg, dd, peak, rank, world, sm_mhz):
                 "hbm_frac": round(step_bytes * b * T / (ms / 1e3) / 1e9 / peak, 4), "bound": "hbm"})
     del ts_big, st, env
     torch.cuda.empty_cache()
-    # SeedExtension 14x14/7 (BASELINE configs[3]): generation + on-device validity of every board
-    g, n, b = 14, 7, 65536
-    keys = sharding.shard_keys(rbg.PRNGKey(0), b * world, rank, world)
+    # SeedExtension 14x14/7 (BASELINE configs[3]): generation + on-device validity of every board, at the batch round 1
+    # used (one wave of the extend kernel: bound by the slowest board's 45 sweeps) and at dataset-generation scale (the
+    # reference builds its offline dataset of number_of_boards = 100 000 boards, agent_training/configs/env/connector.yaml:15)
+    g, n = 14, 7
     board = rbg.SeedExtensionBoard(g, g, n)
-    res = {}
+    # floor of the pipeline: the key chain alone (key, random_key = split(key) per cell and sweep, SE_LOOK = 8 cells past the
+    # sweep) at the ALU-pipe rate of the chain microbenchmark (tools/micro/tf_chain_bench.cu: 196 cycles per chain step and
+    # warp with the SM sub-partition's ALU pipe saturated), 32 boards per warp, mean sweeps per board from the oracle
+    chain_floor = sm_count * 4 * sm_mhz * 1e6 / (SE_MEAN_SWEEPS_14_7 * (g * g + 8) * 196.0 / 32.0)
+    for b in (65536, 262144):
+        keys = sharding.shard_keys(rbg.PRNGKey(0), b * world, rank, world)
+        res = {}
 
-    def se():
-        res["solved"] = board.return_solved_board(keys)
-        res["flags"] = rbg.engine.validate(res["solved"], n)
+        def se():
+            res["solved"] = board.return_solved_board(keys)
+            res["flags"] = rbg.engine.validate(res["solved"], n)
 
-    ms, all_ms = timed(se, 5, min_ms=30.0)
-    line = {"metric": "seedext_solved_boards_per_sec", "workload": f"SeedExtensionBoard.return_solved_board {g}x{g}/{n}, {b} boards per GPU + rbg_validate", "value": round(b * world / (ms / 1e3), 1), "unit": "boards/s",
-            "n_gpus": world, "ms_per_batch": round(ms, 4), "ms_samples": [round(x, 4) for x in all_ms], "invalid_boards": int((res["flags"] != 0).sum()),
-            "bound": "sequential threefry chain per board (G*G*sweeps dependent split() steps), see DESIGN.md"}
-    issue(line, "seedext_pipeline_14x14_7_warp_inst_per_board", b * world / (ms / 1e3))
-    out.append(line)
+        ms, all_ms = timed(se, 5, min_ms=30.0)
+        rate = b * world / (ms / 1e3)
+        line = {"metric": "seedext_solved_boards_per_sec", "workload": f"SeedExtensionBoard.return_solved_board {g}x{g}/{n}, {b} boards per GPU + rbg_validate", "boards_per_gpu": b, "value": round(rate, 1), "unit": "boards/s",
+                "n_gpus": world, "ms_per_batch": round(ms, 4), "ms_samples": [round(x, 4) for x in all_ms], "invalid_boards": int((res["flags"] != 0).sum()),
+                "bound": "sequential threefry chain per board (G*G*sweeps dependent split() steps) on the ALU pipe, see DESIGN.md K3",
+                "chain_floor": {"boards_per_s_per_gpu": round(chain_floor, 1), "frac": round(rate / world / chain_floor, 4),
+                                "note": "what the GPU would do if the pipeline were nothing but the key chain at the measured ALU-pipe rate: 196 cycles per chain step and warp, 32 boards per warp, 9.86 sweeps per board"}}
+        issue(line, f"seedext_pipeline_14x14_7_b{b}_warp_inst_per_board", rate)
+        out.append(line)
+        del keys, res
     return out if rank == 0 else []
 
 
@@ -549,14 +561,17 @@ def _cpu_secondary(secondary, budget_s: float = 4.0):
                 return done / dt, done, dt
             n = min(n * 2, 1 << 16)
 
+    se_cpu = None
     for line in secondary:
         if line["metric"] == "prw_solved_boards_per_sec":
             g, n = line["grid"], line["agents"]
             v, done, dt = rate(lambda k: orc.prw_generate_batch(orc.split(orc.PRNGKey(1), k), g, n, nthreads=cores), 512)
             line["cpu_baseline"] = {"value": round(v, 1), "unit": "boards/s", "cores": cores, "kind": "port", "sample": f"{done} boards {g}x{g}/{n} in {dt:.1f} s, OpenMP over boards"}
         elif line["metric"] == "seedext_solved_boards_per_sec":
-            v, done, dt = rate(lambda k: orc.seedext_solved_batch(orc.split(orc.PRNGKey(1), k), 14, 7, nthreads=cores), 256)
-            line["cpu_baseline"] = {"value": round(v, 1), "unit": "boards/s", "cores": cores, "kind": "port", "sample": f"{done} boards 14x14/7 in {dt:.1f} s, OpenMP over boards"}
+            if se_cpu is None:
+                v, done, dt = rate(lambda k: orc.seedext_solved_batch(orc.split(orc.PRNGKey(1), k), 14, 7, nthreads=cores), 256)
+                se_cpu = {"value": round(v, 1), "unit": "boards/s", "cores": cores, "kind": "port", "sample": f"{done} boards 14x14/7 in {dt:.1f} s, OpenMP over boards"}
+            line["cpu_baseline"] = se_cpu
     bfs = {"metric": "numpy_bfs_board_boards_per_sec", "workload": "reference NumPy BFSBoard(10, 10, 5).return_solved_board() in a Python loop, single process (README.md:88-93)", "unit": "boards/s"}
     if os.path.isdir("/root/reference/routing_board_generation"):
         try:

@@ -63,6 +63,8 @@ static std::atomic<int> g_timing{0};
 static std::mutex g_timing_mu;
 static std::vector<EventPair> g_events[RBG_K_COUNT];
 
+bool kernel_timing_on() { return g_timing.load(std::memory_order_relaxed) != 0; }
+
 LaunchScope::LaunchScope(int kernel_id, cudaStream_t s) : id(kernel_id), stream(s), rec(nullptr) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (!g_timing.load(std::memory_order_relaxed) || id < 0 || id >= RBG_K_COUNT) return;

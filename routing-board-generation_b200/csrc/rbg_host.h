@@ -19,6 +19,7 @@ int device_sm_count();
 size_t device_smem_per_sm();
 // Brackets one kernel launch: counts it (rbg_launch_count) and, while
 // rbg_kernel_timing is on, records a CUDA event pair on `stream` around it.
+bool kernel_timing_on();  // rbg_kernel_timing(1) is in effect
 struct LaunchScope {
   int id;
   cudaStream_t stream;

@@ -16,23 +16,23 @@
 //   se_seed_kernel      one warp per board: key derivation, lattice seeding
 //                       (the same warp-cooperative top-N selection as the
 //                       ParallelRandomWalk start cells), uint8 board -> scratch
-//   se_extend_kernel    one LANE per board, board in that lane's slice of shared
-//                       memory (odd word stride: conflict-free when lanes touch the
-//                       same cell).  The key chain never reads the board, so a row is
-//                       done in two phases: (i) a dense burst, every lane advances its
-//                       chain G cells (two independent blocks per cell, 32 / 32 lanes)
-//                       and parks the G cell keys in shared memory; (ii) every lane
-//                       then visits only ITS extendable cells of the row (2N of G*G
-//                       cells are), the lanes aligned on "k-th extendable cell of the
-//                       row", so the heavy head-extension path runs 3-4 times per row
-//                       with most lanes in it instead of at nearly every cell with
-//                       two.  Sweeps are processed in ROUNDS of a few sweeps: boards
-//                       that need more are compacted into dense warps for the next
-//                       round (sweep counts differ per board: 6 .. 16 at 14x14).
+//   se_extend_kernel    persistent; one LANE per board, board in that lane's slice of shared
+//                       memory (odd word stride: conflict-free when lanes touch the same cell);
+//                       lanes take boards from a queue and hand them on when they have converged
+//                       (6 .. 45 sweeps).  A sweep has two phases for the whole CTA: (i) the key
+//                       chain of the sweep never reads the board, so the boards of the CTA that
+//                       still sweep hand their keys to a dense prefix of the CTA's threads, which
+//                       run the chain (two independent blocks per cell, nothing else in the loop)
+//                       and park the G*G random_keys in a ring in global memory (L2); (ii) every
+//                       lane walks the wire ends of its board in traversal order (per-row bit
+//                       masks; an end that can no longer move is dropped for good), the lanes
+//                       aligned on "k-th visit of the sweep" so that the random picks are computed
+//                       by the whole warp from the parked keys.
 //                       Flips are coordinate transforms, never data movement
 //   se_optimise_kernel  one lane per board: per wire a FIFO breadth-first search
 //                       (the reference's argmin/max queue is a FIFO in disguise),
-//                       parents as 3-bit direction codes tagged with the wire id
+//                       parents as 3-bit direction codes tagged with the wire id; runs on a second
+//                       stream WHILE the extend kernel does, on the boards that kernel has finished
 //   se_finish_kernel    one warp per board: uint8 -> int32 with 128-bit stores,
 //                       starts/ends extraction, State / observation / action mask
 // Boards travel between the kernels as uint8 in a stream-ordered scratch
@@ -78,6 +78,7 @@ struct SeDims {
   int refill_min;     // extend: a warp takes new boards when that many of its lanes are free
   int lane_words_ext; // extend: words per lane (the padded board + the G cell keys of a row), odd
   int S1, SB1;        // optimise: padded stride (G+2), bytes per padded board
+  int fifo_bytes;     // optimise: bytes of a lane's FIFO (entries of 1 or 2 bytes), even
   int lane_bytes_opt; // optimise: bytes per lane (board, parents, fifo, pins), multiple of 4 with odd word count
 };
 
@@ -186,7 +187,12 @@ __device__ __forceinline__ uint32_t warp_pick(uint32_t needm, bool need, const u
   const int per = 32 / n;                      // draws evaluated per needing lane and pass
   const int slot = lane / per, j = lane - slot * per;
   const bool worker = slot < n;
-  const int owner = worker ? (int)__fns(needm, 0, slot + 1) : 0;  // the lane this worker draws for
+  int owner = 0;  // the lane this worker draws for: the slot-th set bit of needm (few bits are set; __fns is a long software sequence)
+  {
+    uint32_t mk = needm;
+    for (int k = 0; k < slot && mk; ++k) mk &= mk - 1u;
+    owner = worker ? __ffs((int)mk) - 1 : 0;
+  }
   const uint32_t own_ok = __shfl_sync(FULL, ok, owner);
   const int own_idx = __shfl_sync(FULL, idx, owner);
   const int avail = ring_n - idx, own_avail = ring_n - own_idx;
@@ -246,6 +252,7 @@ struct SeQueue {
   int32_t *head;       // next scratch slot to hand out (zeroed by the host before the launch)
   int32_t *done_list;  // optional: scratch slots in completion order, -1 until published (consumed by se_optimise_kernel
   int32_t *done_head;  //           running at the same time), and its reservation counter
+  int32_t *resident;   // optional: counts the CTAs of this launch that have started
 };
 
 __device__ __forceinline__ bool se_extendable(uint32_t v, bool two_sided) {
@@ -260,6 +267,7 @@ __global__ void __launch_bounds__(256) se_extend_kernel(const SeedExtParams p, c
   typedef typename std::conditional<WIDE, unsigned long long, uint32_t>::type mask_t;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0 && qu.resident) atomicAdd(qu.resident, 1);
   const long long total = se_total(p);
   const long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   const long long grid_warps = (long long)gridDim.x * (blockDim.x >> 5);
@@ -598,18 +606,53 @@ __global__ void __launch_bounds__(256) se_extend_kernel(const SeedExtParams p, c
 }
 
 // ------------------------------------------------------- optimise_wire (BFS)
-__global__ void __launch_bounds__(128) se_optimise_kernel(const SeedExtParams p, const SeDims d, const SeScratch sc) {
+// FIFO_T: uint8_t when a padded board has at most 256 cells (G <= 14), which takes a lane's footprint from 940 to
+// 740 bytes at 14x14 and two more warps onto an SM; the kernel is latency-bound, so warps per SM are what it runs on
+// done_list != NULL: the kernel runs WHILE se_extend_kernel does; a warp takes 32 consecutive entries of the list of
+// finished boards, waits until they are published (acquire loads, pairs with the extend kernel's release stores),
+// optimises them and takes the next 32.  Lanes never synchronise with each other.
+// ext_resident != NULL (the launch that runs beside the extend kernel): a warp takes work only once all ext_ctas CTAs
+// of the extend kernel have started, and leaves if that does not happen within a millisecond.  CTAs of this kernel
+// that spin on the list while CTAs of the extend kernel wait for their shared memory would never get an entry; a
+// second launch of this kernel behind the extend kernel takes whatever the first one has left.
+template <typename FIFO_T>
+__global__ void __launch_bounds__(128)
+    se_optimise_kernel(const SeedExtParams p, const SeDims d, const SeScratch sc, const int32_t *done_list, int32_t *take_head, const int32_t *ext_resident, int ext_ctas) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= se_total(p)) return;
+  if (ext_resident) {
+    int seen = 0;
+    for (int tries = 0; tries < 1000; ++tries) {
+      if (lane == 0) seen = ld_acquire_s32(ext_resident);
+      seen = __shfl_sync(FULL, seen, 0);
+      if (seen >= ext_ctas) break;
+      __nanosleep(1000);
+    }
+    if (seen < ext_ctas) return;
+  }
+  const long long total = se_total(p);
   const int G = d.G, S = d.S1, cells = d.cells;
   uint8_t *mine = smem_raw + ((size_t)warp * 32 + lane) * d.lane_bytes_opt;
   uint8_t *board = mine;                                      // [(G+2)^2] 0xFF border
   uint8_t *par = mine + d.SB1;                                // parents: (wire << 3) | (dir + 1)
-  uint16_t *fifo = reinterpret_cast<uint16_t *>(mine + 2 * d.SB1);  // [cells + 2]
-  uint16_t *pins = fifo + ((cells + 3) & ~1);                 // [2N] first POSITION / TARGET per wire
-
+  FIFO_T *fifo = reinterpret_cast<FIFO_T *>(mine + 2 * d.SB1);  // [cells + 2]
+  uint16_t *pins = reinterpret_cast<uint16_t *>(mine + 2 * d.SB1 + d.fifo_bytes);  // [2N] first POSITION / TARGET per wire
+  for (bool first_trip = true;; first_trip = false) {
+  long long m;
+  if (done_list) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(take_head, 32);
+    base = __shfl_sync(FULL, base, 0);
+    if (base >= total) return;
+    if (base + lane >= total) continue;  // (the next trip ends this lane: the head is beyond the list)
+    int v;
+    while ((v = ld_acquire_s32(done_list + base + lane)) < 0) __nanosleep(200);
+    m = v;
+  } else {
+    if (!first_trip) return;
+    m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= total) return;
+  }
   for (int q = 0; q < (d.SB1 >> 2); ++q) {
     reinterpret_cast<uint32_t *>(board)[q] = 0xFFFFFFFFu;
     reinterpret_cast<uint32_t *>(par)[q] = 0u;
@@ -670,7 +713,7 @@ __global__ void __launch_bounds__(128) se_optimise_kernel(const SeedExtParams p,
     board[end] = (uint8_t)path_num;
     const uint32_t tag = (uint32_t)w << 3;
     int head = 0, tail = 0, pops = 0;
-    fifo[tail++] = (uint16_t)start;
+    fifo[tail++] = (FIFO_T)start;
     auto seen = [&](int q) { const uint32_t b = par[q]; return (b & 7u) != 0u && (b & ~7u) == tag; };
     bool dry = false;
     while (pops < cells && !seen(end)) {  // GU:560-566
@@ -686,7 +729,7 @@ __global__ void __launch_bounds__(128) se_optimise_kernel(const SeedExtParams p,
         const uint32_t bv = board[q];
         if ((bv == path_num || bv == 0u) && !seen(q)) {  // GU:118-160
           par[q] = (uint8_t)(tag | (uint32_t)(j + 1));
-          fifo[tail++] = (uint16_t)q;
+          fifo[tail++] = (FIFO_T)q;
         }
       }
     }
@@ -716,6 +759,7 @@ __global__ void __launch_bounds__(128) se_optimise_kernel(const SeedExtParams p,
   for (int r = 0; r < G; ++r)
     for (int c = 0; c < G; ++c) gb[r * G + c] = board[(r + 1) * S + (c + 1)];
   if (bad) sc.status[m] |= 1;
+  }
 }
 
 // ------------------------------------------------------------------ outputs
@@ -828,6 +872,26 @@ static int set_smem(const void *fn, size_t bytes, const char *name) {
   return RBG_OK;
 }
 
+// second stream + fork / join events of the overlapped optimise kernel, one set per device
+struct SeOverlap {
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+static SeOverlap *se_overlap() {
+  static SeOverlap per_dev[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  SeOverlap &o = per_dev[dev];
+  if (!o.side) {
+    if (cudaStreamCreateWithFlags(&o.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&o.fork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&o.join, cudaEventDisableTiming) != cudaSuccess) {
+      o.side = nullptr;
+      return nullptr;
+    }
+  }
+  return &o;
+}
+
 int launch_seedext(SeedExtParams p, int64_t max_boards, cudaStream_t stream) {
   const int G = p.G, N = p.N;
   SeDims d;
@@ -851,7 +915,9 @@ int launch_seedext(SeedExtParams p, int64_t max_boards, cudaStream_t stream) {
   d.S1 = G + 2;
   d.SB1 = (int)round_up((size_t)d.S1 * d.S1, 4);
   {
-    size_t b = 2 * (size_t)d.SB1 + 2 * (size_t)((d.cells + 3) & ~1) + 2 * (size_t)(2 * N);
+    const bool byte_fifo = d.S1 * d.S1 <= 256;
+    d.fifo_bytes = (int)((byte_fifo ? 1 : 2) * (size_t)((d.cells + 3) & ~1));
+    size_t b = 2 * (size_t)d.SB1 + (size_t)d.fifo_bytes + 2 * (size_t)(2 * N);
     b = round_up(b, 4);
     if (((b / 4) & 1) == 0) b += 4;
     d.lane_bytes_opt = (int)b;
@@ -863,13 +929,29 @@ int launch_seedext(SeedExtParams p, int64_t max_boards, cudaStream_t stream) {
   };
   const size_t ext_warp = (size_t)32 * d.lane_words_ext * 4 + 32 * 8, opt_warp = (size_t)32 * d.lane_bytes_opt;  // extend: + one exchanged key per thread
   int ext_w = warps_for(ext_warp, 4), opt_w = warps_for(opt_warp, 1);
-  if (const char *ex = getenv("RBG_SE_EXT_WARPS")) ext_w = atoi(ex) >= 1 && atoi(ex) <= 8 ? warps_for(ext_warp, atoi(ex)) : ext_w;
+  // A batch that is a single wave of the extend kernel ends in a long tail of half-empty CTAs: 3-warp CTAs leave
+  // shared memory for the optimise kernel to move in beside them (14x14/7, 65 536 boards: 4.17 -> 3.84 ms; bigger
+  // batches are faster with 4-warp CTAs: 262 144 boards 12.7 against 13.0 ms)
+  bool one_wave = false;
+  if (ext_w == 4 && ext_warp * 4 + 1024 <= device_smem_per_sm() / 4) {
+    one_wave = max_boards <= (int64_t)device_sm_count() * 4 * 128;
+    if (one_wave) ext_w = 3;
+  }
+  if (const char *ex = getenv("RBG_SE_EXT_WARPS")) {
+    if (atoi(ex) >= 1 && atoi(ex) <= 8) {
+      ext_w = warps_for(ext_warp, atoi(ex));
+      one_wave = false;
+    }
+  }
   if (const char *ex = getenv("RBG_SE_OPT_WARPS")) opt_w = atoi(ex) >= 1 && atoi(ex) <= 4 ? warps_for(opt_warp, atoi(ex)) : opt_w;
   int rc = RBG_OK;
   const bool wide = G > 32;
   const void *ext_fn = wide ? reinterpret_cast<const void *>(se_extend_kernel<true>) : reinterpret_cast<const void *>(se_extend_kernel<false>);
   if ((rc = set_smem(ext_fn, ext_warp * ext_w + 32, "se_extend_kernel"))) return rc;
-  if ((rc = set_smem(reinterpret_cast<const void *>(se_optimise_kernel), opt_warp * opt_w, "se_optimise_kernel"))) return rc;
+  const bool byte_fifo = d.S1 * d.S1 <= 256;
+  if ((rc = set_smem(byte_fifo ? reinterpret_cast<const void *>(se_optimise_kernel<uint8_t>) : reinterpret_cast<const void *>(se_optimise_kernel<uint16_t>), opt_warp * opt_w,
+                     "se_optimise_kernel")))
+    return rc;
   {
     static int rmin = -1;
     if (rmin < 0) {
@@ -894,11 +976,26 @@ int launch_seedext(SeedExtParams p, int64_t max_boards, cudaStream_t stream) {
       cap = ex ? atoi(ex) : 0;
       if (cap < 0) cap = 0;
     }
+    if (one_wave && per_sm > 4) per_sm = 4;
     if (cap > 0 && per_sm > cap) per_sm = cap;
     const long long resident = (long long)per_sm * device_sm_count();
     const long long need = (max_boards + ext_w * 32 - 1) / (ext_w * 32);
     ext_ctas = (unsigned)(need < resident ? need : resident);
     if (ext_ctas < 1) ext_ctas = 1;
+  }
+  static int overlap_env = -1;
+  if (overlap_env < 0) {
+    const char *ex = getenv("RBG_SE_OVERLAP");
+    overlap_env = ex ? (atoi(ex) != 0 ? 1 : 0) : 1;
+  }
+  const bool overlap = overlap_env == 1 && !kernel_timing_on();  // per-kernel timing wants one kernel at a time
+  unsigned opt_resident = 1;
+  {
+    int per_sm = 0;
+    cudaError_t oe = byte_fifo ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, se_optimise_kernel<uint8_t>, opt_w * 32, opt_warp * opt_w)
+                               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, se_optimise_kernel<uint16_t>, opt_w * 32, opt_warp * opt_w);
+    if (oe != cudaSuccess) return set_cuda_error(oe, "cudaOccupancyMaxActiveBlocksPerMultiprocessor(se_optimise_kernel)");
+    opt_resident = (unsigned)((per_sm < 1 ? 1 : per_sm) * device_sm_count());
   }
   SeScratch sc;
   sc.CB = (int)round_up((size_t)d.cells, 16);
@@ -906,8 +1003,9 @@ int launch_seedext(SeedExtParams p, int64_t max_boards, cudaStream_t stream) {
   const size_t o_keys = round_up(n * sc.CB, 256), o_gkey = o_keys + round_up(n * 16, 256), o_status = o_gkey + round_up(n * 8, 256);
   const size_t o_snap = o_status + round_up(n * 4, 256);
   const size_t o_ring = o_snap + round_up((size_t)ext_ctas * ext_w * 32 * (size_t)d.SB2w * 4, 256);  // one snapshot region per extend warp
-  const size_t o_queue = o_ring + round_up((size_t)ext_ctas * ext_w * 32 * (size_t)(d.cells + SE_LOOK + 1) * 8, 256);  // and one ring of parked keys
-  const size_t total = o_queue + 256;  // queue counters: one int per extension iteration
+  const size_t o_done = o_ring + round_up((size_t)ext_ctas * ext_w * 32 * (size_t)(d.cells + SE_LOOK + 1) * 8, 256);  // and one ring of parked keys
+  const size_t o_queue = o_done + round_up(n * 4, 256);  // list of finished boards (overlapped optimise)
+  const size_t total = o_queue + 1024;  // queue counters: three ints per extension iteration
   uint8_t *base = nullptr;
   {  // keep the stream-ordered pool's memory cached between calls (default: released at every sync)
     static bool pool_ready = false;
@@ -929,14 +1027,15 @@ int launch_seedext(SeedExtParams p, int64_t max_boards, cudaStream_t stream) {
   sc.status = reinterpret_cast<int32_t *>(base + o_status);
   sc.snap = reinterpret_cast<uint32_t *>(base + o_snap);
   sc.ring = reinterpret_cast<uint2 *>(base + o_ring);
-  int32_t *queue = reinterpret_cast<int32_t *>(base + o_queue);
+  int32_t *queue = reinterpret_cast<int32_t *>(base + o_queue);  // [0, 64) queue heads, [64, 128) done-list heads, [128, 192) take heads
+  int32_t *done_list = reinterpret_cast<int32_t *>(base + o_done);
   if (p.iterations > 64) {
     cudaFreeAsync(base, stream);
     return set_error(RBG_EINVAL, "SeedExtension: extension_iterations=%d (max 64)", p.iterations);
   }
 
   do {
-    cudaError_t me = cudaMemsetAsync(queue, 0, 256, stream);
+    cudaError_t me = cudaMemsetAsync(queue, 0, 1024, stream);
     if (me != cudaSuccess) {
       rc = set_cuda_error(me, "cudaMemsetAsync(SeedExtension queue)");
       break;
@@ -949,11 +1048,26 @@ int launch_seedext(SeedExtParams p, int64_t max_boards, cudaStream_t stream) {
     }
     if ((rc = check_launch("se_seed_kernel"))) break;
     for (int it = 0; it < p.iterations && rc == RBG_OK; ++it) {  // SE:180-200 while_loop over extension_iterations
+      // The optimise kernel runs WHILE the extend kernel does (on a second stream), on the boards the extend kernel
+      // has finished: extension ends in a long tail (a board needs 6 .. 45 sweeps and every sweep is a sequential hash
+      // chain), during which most SMs would idle, and the optimise kernel is latency-bound at a few warps per SM.
+      // Neither kernel waits for the other to become resident: the extend kernel's CTAs take boards from a queue, so
+      // it completes with whatever share of the SMs it gets, and the optimise warps only wait for list entries.
+      SeOverlap *ov = overlap ? se_overlap() : nullptr;
+      SeQueue qu;
+      qu.head = queue + it;
+      qu.done_list = ov ? done_list : nullptr;
+      qu.done_head = ov ? queue + 64 + it : nullptr;
+      qu.resident = ov ? queue + 192 + it : nullptr;
+      cudaError_t ce2 = cudaSuccess;
+      if (ov) {
+        if ((ce2 = cudaMemsetAsync(done_list, 0xFF, n * 4, stream)) != cudaSuccess || (ce2 = cudaEventRecord(ov->fork, stream)) != cudaSuccess ||
+            (ce2 = cudaStreamWaitEvent(ov->side, ov->fork, 0)) != cudaSuccess) {
+          rc = set_cuda_error(ce2, "SeedExtension: fork to the optimise stream");
+          break;
+        }
+      }
       {
-        SeQueue qu;
-        qu.head = queue + it;
-        qu.done_list = nullptr;
-        qu.done_head = nullptr;
         LaunchScope scope(RBG_K_SEEDEXT, stream);
         if (wide)
           se_extend_kernel<true><<<ext_ctas, ext_w * 32, ext_warp * ext_w + 32, stream>>>(p, d, sc, qu);
@@ -961,12 +1075,32 @@ int launch_seedext(SeedExtParams p, int64_t max_boards, cudaStream_t stream) {
           se_extend_kernel<false><<<ext_ctas, ext_w * 32, ext_warp * ext_w + 32, stream>>>(p, d, sc, qu);
       }
       if ((rc = check_launch("se_extend_kernel"))) break;
-      {
-        const unsigned ctas = (unsigned)((max_boards + opt_w * 32 - 1) / (opt_w * 32));
-        LaunchScope scope(RBG_K_SEEDEXT, stream);
-        se_optimise_kernel<<<ctas, opt_w * 32, opt_warp * opt_w, stream>>>(p, d, sc);
+      if (ov) {  // beside the extend kernel: as many CTAs as the device holds; they move in as the extend CTAs leave
+        unsigned ctas = (unsigned)((max_boards + opt_w * 32 - 1) / (opt_w * 32));
+        if (ctas > opt_resident) ctas = opt_resident;
+        LaunchScope scope(RBG_K_SEEDEXT, ov->side);
+        if (byte_fifo)
+          se_optimise_kernel<uint8_t><<<ctas, opt_w * 32, opt_warp * opt_w, ov->side>>>(p, d, sc, done_list, queue + 128 + it, qu.resident, (int)ext_ctas);
+        else
+          se_optimise_kernel<uint16_t><<<ctas, opt_w * 32, opt_warp * opt_w, ov->side>>>(p, d, sc, done_list, queue + 128 + it, qu.resident, (int)ext_ctas);
+        if ((rc = check_launch("se_optimise_kernel"))) break;
       }
-      rc = check_launch("se_optimise_kernel");
+      {  // behind the extend kernel: everything (no overlap), or what the first launch has not taken
+        unsigned ctas = (unsigned)((max_boards + opt_w * 32 - 1) / (opt_w * 32));
+        if (ov && ctas > opt_resident) ctas = opt_resident;
+        LaunchScope scope(RBG_K_SEEDEXT, stream);
+        if (byte_fifo)
+          se_optimise_kernel<uint8_t><<<ctas, opt_w * 32, opt_warp * opt_w, stream>>>(p, d, sc, ov ? done_list : nullptr, queue + 128 + it, nullptr, 0);
+        else
+          se_optimise_kernel<uint16_t><<<ctas, opt_w * 32, opt_warp * opt_w, stream>>>(p, d, sc, ov ? done_list : nullptr, queue + 128 + it, nullptr, 0);
+      }
+      if ((rc = check_launch("se_optimise_kernel"))) break;
+      if (ov) {
+        if ((ce2 = cudaEventRecord(ov->join, ov->side)) != cudaSuccess || (ce2 = cudaStreamWaitEvent(stream, ov->join, 0)) != cudaSuccess) {
+          rc = set_cuda_error(ce2, "SeedExtension: join of the optimise stream");
+          break;
+        }
+      }
     }
     if (rc) break;
     {
