@@ -9,6 +9,7 @@
 #include <sched.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <unistd.h>
 
 #include <atomic>
 #include <condition_variable>
@@ -167,7 +168,15 @@ class Pool {
 };
 
 Pool &pool() {
-  static Pool *p = new Pool();  // leaked on purpose, see the constructor
+  // leaked on purpose (see the constructor); a forked child has the pointer but none of the threads: it gets its own
+  static Pool *p = nullptr;
+  static pid_t owner = 0;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!p || owner != getpid()) {
+    p = new Pool();
+    owner = getpid();
+  }
   return *p;
 }
 

@@ -247,6 +247,41 @@ def test_seedext_options_match_oracle(rbg, orc, kw):
     assert np.array_equal(_np(solved), ref)
 
 
+_SE_SWITCH_CODE = """
+import sys, numpy as np
+sys.path.insert(0, {root!r})
+import routing_board_generation_b200 as rbg
+from oracle import oracle as orc
+for (G, N, B, kw) in {cases!r}:
+    kref = orc.split(orc.PRNGKey(5), B)
+    keys = rbg.engine.as_tensor(kref)
+    okw = dict(randomness=kw.get("randomness", 0.0), two_sided=kw.get("two_sided", True), iterations=kw.get("extension_iterations", 1), ext_steps=int(kw.get("extension_steps", -1)))
+    ref, _ = orc.seedext_solved_batch(kref, G, N, **okw)
+    for rep in range(2):  # the second call reuses the cached scratch pool and the second stream
+        got = rbg.SeedExtensionBoard(G, G, N).return_solved_board(keys, **kw).cpu().numpy()
+        assert np.array_equal(got, ref), (G, N, B, kw, rep, int((got != ref).any(axis=(1, 2)).sum()))
+print("ok")
+"""
+
+
+@pytest.mark.parametrize("env_vars", [{"RBG_SE_CTAS_PER_SM": "1"}, {"RBG_SE_OVERLAP": "0"}, {"RBG_SE_CTAS_PER_SM": "1", "RBG_SE_EXT_WARPS": "8", "RBG_SE_REFILL_MIN": "16"},
+                                      {"RBG_SE_EXT_WARPS": "1", "RBG_SE_CTAS_PER_SM": "2"}])
+def test_seedext_queue_and_overlap_switches(env_vars):
+    """The extend kernel is persistent (lanes take boards from a queue: RBG_SE_CTAS_PER_SM=1 makes a 40 000-board batch
+    several times what is resident, so every lane is refilled), its chain phase is shared by the CTA (1, 3, 4, 8 warps
+    per CTA), and the optimise kernel runs beside it on the list of finished boards (RBG_SE_OVERLAP=0: behind it).  All
+    of it must leave the boards bit-identical to the oracle's, with the options that change the sweep loop as well."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cases = [(10, 5, 40000, {}), (14, 7, 9000, {}), (10, 5, 3000, dict(randomness=0.4, extension_iterations=2)), (9, 4, 2500, dict(two_sided=False, extension_steps=4)), (34, 12, 200, {})]
+    code = _SE_SWITCH_CODE.format(root=root, cases=cases)
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env_vars), capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and r.stdout.strip().startswith("ok"), (r.stdout[-800:], r.stderr[-2000:])
+
+
 def test_seedext_single_key_and_ragged(rbg, orc):
     k = rbg.PRNGKey(0)
     solved = rbg.SeedExtensionBoard(10, 10, 5).return_solved_board(k)
