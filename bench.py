@@ -347,7 +347,7 @@ def _e2e_host(args, rbg, lib, state, B, world, rank, dev):
     def step():
         L.check(lib.rbg_connector_step_host_io(C.byref(s), act.data_ptr(), B, G, N, C.byref(params), C.byref(t), -1))
 
-    for _ in range(3):
+    for _ in range(12):  # the library tries four host-thread counts on its first eight calls of a batch shape and keeps the fastest
         step()
     torch.cuda.synchronize()
     if world > 1:

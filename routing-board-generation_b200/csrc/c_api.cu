@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <chrono>
 #include <mutex>
 #include <unordered_map>
 #include <vector>
@@ -521,6 +522,11 @@ struct HostCtx {
   cudaEvent_t entry_ev = nullptr;
   uint8_t *stage8 = nullptr;  // pinned host staging of the byte observation (rbg_connector_step_host_io)
   size_t stage8_bytes = 0;
+  // thread-count tuning of the packed transport: the first calls of a batch shape try 1/4, 1/2, 3/4 and all of the
+  // pool's workers (two calls each, the second one timed) and the fastest count stays
+  int64_t tune_B = -1;
+  int tune_call = 0, tune_best = 0;
+  double tune_best_s = 0.0;
   ScratchSig sig;
 };
 // what the _host variants moved over the bus since the last reset (rbg_host_transfer_stats)
@@ -1314,6 +1320,27 @@ int rbg_connector_step_host_io(const rbg_state *state, const int32_t *action, in
   std::lock_guard<std::mutex> lock(g_scratch_mu);
   cudaError_t e;
   const bool packed = !host_io_wide();
+  const auto t_call0 = std::chrono::steady_clock::now();
+  int tune_slot = -1;  // which candidate this call measures (odd calls of the tuning phase)
+  if (packed && !host_pool_fixed() && host_pool_max_threads() >= 4) {
+    const int64_t key = B * 4096 + (int64_t)G * 64 + N;
+    if (g_hc->tune_B != key) {
+      g_hc->tune_B = key;
+      g_hc->tune_call = 0;
+      g_hc->tune_best = 0;
+      g_hc->tune_best_s = 0.0;
+    }
+    if (g_hc->tune_call < 8) {
+      const int cand = g_hc->tune_call / 2;  // 0..3 -> 1/4, 1/2, 3/4, 1 of the workers
+      int n = host_pool_max_threads() * (cand + 1) / 4;
+      host_pool_set_threads(n < 1 ? 1 : n);
+      if (g_hc->tune_call & 1) tune_slot = cand;
+      g_hc->tune_call++;
+    } else if (g_hc->tune_call == 8) {
+      host_pool_set_threads(g_hc->tune_best ? g_hc->tune_best : (host_pool_max_threads() + 1) / 2);
+      g_hc->tune_call++;
+    }
+  }
   static int nsl_env = -1;
   if (nsl_env < 0) {
     const char *ex = getenv("RBG_HOST_IO_SLICES");
@@ -1402,6 +1429,13 @@ int rbg_connector_step_host_io(const rbg_state *state, const int32_t *action, in
     if (e != cudaSuccess) rc_sync = set_cuda_error(e, "cudaStreamSynchronize");
   }
   if (packed) host_pool_wait();
+  if (tune_slot >= 0 && rc_sync == RBG_OK) {
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_call0).count();
+    if (g_hc->tune_best == 0 || dt < g_hc->tune_best_s) {
+      g_hc->tune_best = host_pool_threads();
+      g_hc->tune_best_s = dt;
+    }
+  }
   return rc_sync;
 }
 

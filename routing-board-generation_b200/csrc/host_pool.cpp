@@ -101,27 +101,38 @@ class Pool {
       const int w = atoi(e);
       if (w > 1) n = n / w;
     }
-    // half of them: the conversion is bound by host memory bandwidth long before that (measured on a 16-vCPU box:
-    // 8 threads 1.60 ms per 65 536-env step, 16 threads 2.3 ms), the caller's thread polls the copy events, and
-    // the other hardware thread of a core adds nothing to a stream of stores
-    if (n >= 4) n /= 2;
+    // The conversion is bound by host memory bandwidth long before all cores stream stores (measured on a 16-vCPU
+    // box: 8 threads 1.2-1.6 ms per 65 536-env step, 16 threads 2.3 ms; the caller's thread polls the copy events,
+    // and the other hardware thread of a core adds nothing to a stream of stores): half of them to start with, the
+    // caller (rbg_connector_step_host_io) tries the other counts on its first calls and keeps the fastest.
+    fixed_ = false;
     if (const char *e = getenv("RBG_HOST_THREADS")) {
       const int v = atoi(e);
-      if (v >= 1) n = v;
+      if (v >= 1) {
+        n = v;
+        fixed_ = true;
+      }
     }
     if (n < 1) n = 1;
     if (n > 64) n = 64;
     for (int i = 0; i < n; ++i) {
-      std::thread t([this] { run(); });
+      std::thread t([this, i] { run(i); });
       t.detach();  // the pool lives as long as the process (never destroyed: workers may be parked at exit)
     }
     threads_ = n;
+    active_ = fixed_ || n < 4 ? n : n / 2;
   }
-  int threads() const { return threads_; }
+  int threads() const { return active_; }
+  int max_threads() const { return threads_; }
+  bool fixed() const { return fixed_; }
+  void set_active(int a) {
+    std::lock_guard<std::mutex> lock(mu_);
+    active_ = a < 1 ? 1 : (a > threads_ ? threads_ : a);
+  }
   void submit(const uint8_t *src, int32_t *dst, size_t n) {
     if (n == 0) return;
     // pieces of whole 64-byte destination lines, a few per worker so that a slow core does not hold the slice back
-    size_t per = (n + (size_t)threads_ * 2 - 1) / ((size_t)threads_ * 2);
+    size_t per = (n + (size_t)active_ * 2 - 1) / ((size_t)active_ * 2);
     per = (per + 63) & ~(size_t)63;
     if (per < 16384) per = 16384;
     {
@@ -140,14 +151,15 @@ class Pool {
   }
 
  private:
-  void run() {
+  void run(int idx) {
     for (;;) {
       Piece p;
       {
         // a step hands over a slice every ~70 us: poll for a short while before parking on the condition variable
-        for (int spin = 0; spin < 4000 && avail_.load(std::memory_order_acquire) == 0; ++spin) cpu_relax();
+        if (idx < active_)
+          for (int spin = 0; spin < 4000 && avail_.load(std::memory_order_acquire) == 0; ++spin) cpu_relax();
         std::unique_lock<std::mutex> lock(mu_);
-        cv_.wait(lock, [this] { return !q_.empty(); });
+        cv_.wait(lock, [this, idx] { return !q_.empty() && idx < active_; });
         p = q_.front();
         q_.pop_front();
         avail_.fetch_sub(1, std::memory_order_relaxed);
@@ -164,7 +176,8 @@ class Pool {
   std::deque<Piece> q_;
   size_t pending_ = 0;
   std::atomic<long> avail_{0};
-  int threads_ = 0;
+  int threads_ = 0, active_ = 0;
+  bool fixed_ = false;
 };
 
 Pool &pool() {
@@ -183,6 +196,9 @@ Pool &pool() {
 }  // namespace
 
 int host_pool_threads() { return pool().threads(); }
+int host_pool_max_threads() { return pool().max_threads(); }
+bool host_pool_fixed() { return pool().fixed(); }
+void host_pool_set_threads(int n) { pool().set_active(n); }
 void host_pool_widen(const uint8_t *src, int32_t *dst, size_t n) { pool().submit(src, dst, n); }
 void host_pool_wait() { pool().wait(); }
 

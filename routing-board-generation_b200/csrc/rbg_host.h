@@ -122,7 +122,10 @@ int launch_validate(const int32_t *boards, int64_t B, int G, int N,
 int launch_narrow_codes(const int32_t *src, uint8_t *dst, int64_t n, cudaStream_t stream);
 
 // ---- host thread pool (host_pool.cpp): widens byte codes back to int32 in host memory ----
-int host_pool_threads();                                          // workers (created on first use)
+int host_pool_threads();                                          // workers in use (the pool is created on first use)
+int host_pool_max_threads();                                      // workers that exist
+bool host_pool_fixed();                                           // RBG_HOST_THREADS is set: no tuning
+void host_pool_set_threads(int n);                                // workers that take pieces from now on
 void host_pool_widen(const uint8_t *src, int32_t *dst, size_t n); // enqueue; split over the workers
 void host_pool_wait();                                            // until every enqueued piece is done
 

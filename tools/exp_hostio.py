@@ -19,7 +19,7 @@ s = L.rbg_state(st.grid.data_ptr(), st.step_count.data_ptr(), a.id.data_ptr(), a
 t = L.rbg_timestep(*(h[k].data_ptr() for k in ("obs", "mask", "sc", "reward", "discount", "step_type", "nc", "rc", "tpl")))
 params = L.rbg_env_params(50, -0.03, 0.1, 0)
 step = lambda: L.check(lib.rbg_connector_step_host_io(C.byref(s), act.data_ptr(), B, G, N, C.byref(params), C.byref(t), -1))
-for _ in range(5): step()
+for _ in range(12): step()
 best = 1e9
 for rep in range(3):
     t0 = time.perf_counter()
@@ -27,7 +27,7 @@ for rep in range(3):
     best = min(best, (time.perf_counter() - t0) / 20)
 print("%%.3f ms/step  %%.1f M env-steps/s  threads %%d" %% (best * 1e3, B / best / 1e6, L.host_transfer_stats()[2]))
 ''' % root
-settings = [{"RBG_HOST_THREADS": str(n), "RBG_HOST_IO_SLICES": str(sl), "RBG_HOST_NT": nt} for nt in ("1", "0") for sl in (8, 16) for n in (6, 8, 10)] + [{}]
+settings = [{}, {}, {"RBG_HOST_THREADS": "8"}, {"RBG_HOST_THREADS": "4"}, {"RBG_HOST_THREADS": "12"}]
 for env in settings:
     r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
     print(env, r.stdout.strip() or r.stderr[-600:], flush=True)
