@@ -246,7 +246,12 @@ __global__ void __launch_bounds__(VAL_WARPS * 32) validate_kernel(const int32_t 
     // lane w just walks the one that starts at its head; otherwise flood from every first head at once.
     bool connected = false;
     if (!__any_sync(FULL, struct_bad)) {
-      if (eligible) {
+      // A wire with exactly one head and one target whose cells all obey the neighbour rule has exactly two cells of
+      // degree one, its head and its target: the chain that starts at one ends at the other (whatever cycles of PATH
+      // cells may lie beside it), so there is nothing to walk.  Only duplicated heads / targets need the walk.
+      const bool single = eligible && s.heads[lane] == 1 && s.targets[lane] == 1;
+      connected = single;
+      if (eligible && !single) {
         int cur = s.hpos[lane], prev = -1;
         const int goal = s.tpos[lane];
         for (int step = 0; step < cells && cur != goal; ++step) {
