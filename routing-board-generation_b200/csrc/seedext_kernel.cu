@@ -39,6 +39,7 @@
 // allocation (1 byte per cell, L2-resident for any realistic batch).
 #include <stdlib.h>
 
+#include <mutex>
 #include <type_traits>
 
 #include "connector_device.cuh"
@@ -876,6 +877,7 @@ static int set_smem(const void *fn, size_t bytes, const char *name) {
 struct SeOverlap {
   cudaStream_t side = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
+  std::mutex mu;  // a record + wait pair on the shared events is made under it (callers on several host threads)
 };
 static SeOverlap *se_overlap() {
   static SeOverlap per_dev[64];
@@ -1060,6 +1062,8 @@ int launch_seedext(SeedExtParams p, int64_t max_boards, cudaStream_t stream) {
       qu.done_head = ov ? queue + 64 + it : nullptr;
       qu.resident = ov ? queue + 192 + it : nullptr;
       cudaError_t ce2 = cudaSuccess;
+      std::unique_lock<std::mutex> ovlock;
+      if (ov) ovlock = std::unique_lock<std::mutex>(ov->mu);  // held for the iteration: the side stream's work is enqueued in one piece
       if (ov) {
         if ((ce2 = cudaMemsetAsync(done_list, 0xFF, n * 4, stream)) != cudaSuccess || (ce2 = cudaEventRecord(ov->fork, stream)) != cudaSuccess ||
             (ce2 = cudaStreamWaitEvent(ov->side, ov->fork, 0)) != cudaSuccess) {
