@@ -5,8 +5,9 @@ code = r'''
 import sys, torch
 sys.path.insert(0, %r)
 import routing_board_generation_b200 as rbg
-G, N = 14, 7
-for B in (65536, 262144):
+import os
+G, N = int(os.environ.get('SE_G', '14')), int(os.environ.get('SE_N', '7'))
+for B in [int(x) for x in os.environ.get('SE_B', '65536,262144').split(',')]:
     keys = rbg.split(rbg.PRNGKey(0), B)
     board = rbg.SeedExtensionBoard(G, G, N)
     for _ in range(2):
