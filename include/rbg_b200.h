@@ -37,6 +37,7 @@
  *   PRWG routing_board_generation/rl_training/online_generators/parallel_random_walk_generator.py
  *   UG   routing_board_generation/rl_training/online_generators/uniform_generator.py
  *   RSG  routing_board_generation/rl_training/online_generators/random_seed_generator.py
+ *   SRW  .../jax_implementation/board_generation/sequential_random_walk.py
  *   ST   routing_board_generation/rl_training/setup_train.py
  *   JUM  jumanji==0.2.2 jumanji/environments/routing/connector/ (UPSTREAM, requirements.txt:5)
  */
@@ -66,6 +67,8 @@ extern "C" {
 #define RBG_GEN_SEEDEXT 2 /* SeedExtensionGenerator       RSG:28-57  */
 #define RBG_GEN_DATASET 3 /* BoardDatasetGeneratorJAX     rl_training/offline_generation/dataset_generator_jax.py:112-141
                              (needs rbg_env_params.dataset_* / the *_dataset entry points) */
+#define RBG_GEN_SEQRW 4   /* SequentialRandomWalkGenerator rl_training/online_generators/sequential_random_walk_generator.py:19-62
+                             (G >= 3; auto-reset through the reset-list path, like RBG_GEN_SEEDEXT) */
 
 /* jumanji Connector `State` pytree (JUM types.py; field order as printed in
  * package_evaluation/profiling_generators.ipynb cell 4), struct-of-arrays with
@@ -160,6 +163,22 @@ int rbg_seedext_starts_ends(const uint32_t *keys, int64_t B, int G, int N,
                             float randomness, int two_sided, int iterations,
                             int64_t extension_steps, int32_t *starts,
                             int32_t *ends, void *stream);
+
+/* SequentialRandomWalkBoard(G,G,N).generate(key)   SRW:324-392 (SRW = .../jax_implementation/board_generation/
+ * sequential_random_walk.py): wires placed one after the other, each a self-avoiding walk from a random empty cell;
+ * up to 2G attempts from the same key with a shrinking maximum walk length; a zero board when every attempt fails.
+ * board: int32[B,G,G], or with as_float32 != 0 float32[B,G,G] (the reference returns the codes in jnp.zeros'
+ * default dtype).  stats (may be NULL): int32[B,2] = (attempt that succeeded, 0 = none; steps of that attempt).
+ * The reference draws every cell with jax.random.choice(p in {0,1}, replace=False) = a float32 Gumbel top-k; the
+ * result is reproduced exactly for any strictly monotone float32 log.  The class is not
+ * instantiable in the reference as shipped (abstract methods, abstract_board.py:47-53); this is its method bodies.
+ * 3 <= G. */
+int rbg_seqrw_generate(const uint32_t *keys, int64_t B, int G, int N, void *board, int as_float32, int32_t *stats,
+                       void *stream);
+/* SequentialRandomWalkBoard.generate_starts_ends   SRW:394-431 -> starts[B,2,N], ends[B,2,N]
+ * (first POSITION / TARGET cell of every wire; (0,0) on a zero board) */
+int rbg_seqrw_starts_ends(const uint32_t *keys, int64_t B, int G, int N, int32_t *starts, int32_t *ends,
+                          void *stream);
 
 /* The observation half of Connector.reset on an existing State (the recipe
  * at demos/board_generator_demo.py:83-96): action mask, per-agent
@@ -304,7 +323,8 @@ int64_t rbg_launch_count(int reset);
 #define RBG_K_VALIDATE 4   /* validate_kernel */
 #define RBG_K_SEEDEXT 5    /* seedext_kernel */
 #define RBG_K_ROLLOUT 6    /* rollout_warp_kernel: T fused steps */
-#define RBG_K_COUNT 7
+#define RBG_K_SEQRW 7      /* seqrw_walk_kernel + its finish kernel */
+#define RBG_K_COUNT 8
 int rbg_kernel_timing(int enable);
 int rbg_kernel_time(int kernel, int64_t *launches, double *total_ms);
 

@@ -19,8 +19,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "librbg_oracle.so")
 
-GEN_PRW, GEN_UNIFORM, GEN_SEEDEXT, GEN_DATASET = 0, 1, 2, 3
-GEN_KINDS = {"parallel_random_walk": GEN_PRW, "uniform": GEN_UNIFORM, "seed_extension": GEN_SEEDEXT, "dataset": GEN_DATASET}
+GEN_PRW, GEN_UNIFORM, GEN_SEEDEXT, GEN_DATASET, GEN_SEQRW = 0, 1, 2, 3, 4
+GEN_KINDS = {"parallel_random_walk": GEN_PRW, "uniform": GEN_UNIFORM, "seed_extension": GEN_SEEDEXT, "dataset": GEN_DATASET, "sequential_random_walk": GEN_SEQRW}
 
 u32p = C.POINTER(C.c_uint32)
 i32p = C.POINTER(C.c_int32)
@@ -242,6 +242,33 @@ def optimise_wire(key, board, wire: int):
     pops = C.c_int32()
     rc = lib().orc_optimise_wire(_p(key, u32p), C.c_int(board.shape[0]), _p(board, i32p), C.c_int(wire), C.byref(pops))
     return board, pops.value, rc
+
+
+# ----------------------------------------------------- SequentialRandomWalk
+def seqrw_generate_batch(keys, G: int, N: int, nthreads: int = 0):
+    """SequentialRandomWalkBoard.generate over keys[B,2] -> boards[B,G,G] int32, stats[B,2] (attempt, steps)."""
+    keys = _u32(keys).reshape(-1, 2)
+    B = keys.shape[0]
+    boards = np.empty((B, G, G), np.int32)
+    stats = np.empty((B, 2), np.int32)
+    rc = lib().orc_seqrw_generate_batch(_p(keys, u32p), C.c_int64(B), C.c_int(G), C.c_int(N), _p(boards, i32p), _p(stats, i32p), C.c_int(nthreads))
+    if rc:
+        raise ValueError(f"orc_seqrw_generate_batch rc={rc}")
+    return boards, stats
+
+
+def seqrw_generate(key, G: int, N: int) -> np.ndarray:
+    return seqrw_generate_batch(_u32(key).reshape(1, 2), G, N, nthreads=1)[0][0]
+
+
+def seqrw_starts_ends(key, G: int, N: int):
+    key = _u32(key)
+    s = np.empty((2, N), np.int32)
+    e = np.empty((2, N), np.int32)
+    rc = lib().orc_seqrw_starts_ends(_p(key, u32p), C.c_int(G), C.c_int(N), _p(s, i32p), _p(e, i32p))
+    if rc:
+        raise ValueError(f"orc_seqrw_starts_ends rc={rc}")
+    return s, e
 
 
 # ------------------------------------------------------- generator -> State

@@ -754,6 +754,150 @@ int orc_seedext_starts_ends(const uint32_t key[2], int G, int N, float randomnes
 }
 
 /* ======================================================================== */
+/* SequentialRandomWalkBoard  (SRW = routing_board_generation/board_generation_methods/
+ *   jax_implementation/board_generation/sequential_random_walk.py)              */
+/* ======================================================================== */
+/* jax.random.choice(key, a, shape=(), replace=False, p) with p in {0,1}^n, as SRW:57-63 and :211-217
+ * call it: jax 0.4.8 evaluates g = -gumbel(key, (n,)) - log(p) and takes argsort(g)[0] (stable).  log(1) = 0 and
+ * log(0) = -inf, so an entry with p = 0 gets g = +inf and an entry with p = 1 gets
+ * g = log(-log(u)), u = uniform(key, (n,), minval=tiny, maxval=1) = max(tiny, m * 2^-23) with m the top 23 bits of
+ * the entry's random word.  That map is decreasing in m, so the pick is the candidate with the LARGEST m, the
+ * lowest index among equal m (stable sort).  The only assumption is that float32 log is strictly monotone over
+ * the 2^23 values u takes and over their negated logs, so that two different m never tie: NumPy's is (checked
+ * exhaustively by tests/tools/make_seqrw_fixtures.py, which also checks this integer rule against the float
+ * formula on every draw of every fixture); XLA's cannot be run here.  Returns the index (0 when no entry has
+ * p = 1: argsort of all +inf). */
+static int choice_gumbel01(const uint32_t key[2], int n, const uint8_t *p) {
+  uint32_t *bits = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(n + 1));
+  orc_random_bits(key, n, bits);
+  int best = -1;
+  uint32_t bm = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!p[i]) continue;
+    uint32_t m = bits[i] >> 9;
+    if (best < 0 || m > bm) best = i, bm = m;
+  }
+  free(bits);
+  return best < 0 ? 0 : best;
+}
+
+/* SRW:85-113 adjacent_cells: [up, down, left, right] as flat indices, -1 when off the board */
+static void seqrw_adjacent(int G, int cell, int out[4]) {
+  int r = cell / G, c = cell % G;
+  out[0] = r > 0 ? cell - G : -1;
+  out[1] = r < G - 1 ? cell + G : -1;
+  out[2] = c > 0 ? cell - 1 : -1;
+  out[3] = c < G - 1 ? cell + 1 : -1;
+}
+
+/* SRW:115-140 available_cells: an adjacent cell is available when it is free (:142-156) and touches at most one
+ * cell of the wire (:158-191; the cell the wire stands on is that one) */
+static int seqrw_available(int G, const int32_t *board, int cell, int w, int out[4]) {
+  int adj[4], any = 0;
+  seqrw_adjacent(G, cell, adj);
+  for (int k = 0; k < 4; ++k) {
+    out[k] = -1;
+    if (adj[k] < 0 || board[adj[k]] != 0) continue;
+    int nb[4], touching = 0;
+    seqrw_adjacent(G, adj[k], nb);
+    for (int j = 0; j < 4; ++j)
+      if (nb[j] >= 0 && board[nb[j]] >= 3 * w + 1 && board[nb[j]] <= 3 * w + 3) touching++;
+    if (touching > 1) continue;
+    out[k] = adj[k];
+    any = 1;
+  }
+  return any;
+}
+
+/* SRW:290-322 add_agents with :34-83 pick_start, :193-228 one_step, :230-288 walk_randomly */
+static int seqrw_add_agents(const uint32_t key_in[2], int G, int N, int max_length, int32_t *board, int32_t *steps_out) {
+  const int cells = G * G;
+  uint32_t key[2] = {key_in[0], key_in[1]};
+  uint8_t *p = (uint8_t *)malloc((size_t)(cells > G + 1 ? cells : G + 1));
+  int success = 1, steps = 0;
+  memset(board, 0, sizeof(int32_t) * (size_t)cells);
+  for (int w = 0; w < N; ++w) {
+    uint32_t ks[4], ps[4];
+    orc_split(key, 2, ks);     /* :307 key, subkey = split(key); that `key` is dropped (:306 reads the tuple's) */
+    orc_split(&ks[2], 2, ps);  /* :51  key, subkey = split(key) inside pick_start(subkey) */
+    key[0] = ps[0];
+    key[1] = ps[1];            /* the tuple's key from here on */
+    int can_start = 0;
+    for (int i = 0; i < cells; ++i) can_start |= (p[i] = (uint8_t)(board[i] == 0));
+    if (!can_start) {          /* :315 lambda x: (x, False) */
+      success = 0;
+      continue;
+    }
+    const int start = choice_gumbel01(&ps[2], cells, p); /* :57-63; divmod(flat, rows) :66 */
+    board[start] = 3 * w + POSITION;                       /* :71 */
+    int cur = start, moved = 0;
+    for (int t = 0; t < max_length; ++t) {                 /* :280 fori_loop(0, max_length) */
+      int avail[4];
+      if (!seqrw_available(G, board, cur, w, avail)) break; /* can_step False: the board no longer changes */
+      moved = 1;
+      uint32_t ss[4];
+      orc_split(key, 2, ss);                               /* :204 */
+      key[0] = ss[0];
+      key[1] = ss[1];
+      /* :138-140 available_cells is padded with -1 to rows + 1 entries; choice draws one word per entry */
+      memset(p, 0, (size_t)(G + 1));
+      for (int k = 0; k < 4; ++k) p[k] = (uint8_t)(avail[k] >= 0);
+      const int nxt = avail[choice_gumbel01(&ss[2], G + 1, p)]; /* :211-217 */
+      board[nxt] = 3 * w + TARGET;                          /* :221 */
+      board[cur] = 3 * w + PATH;                            /* :223-227 */
+      cur = nxt;
+      steps++;
+    }
+    board[start] = 3 * w + POSITION;                        /* :286 */
+    success &= moved;                                       /* :319 */
+  }
+  free(p);
+  if (steps_out) *steps_out = steps;
+  return success;
+}
+
+/* SRW:324-392 generate: attempts with max_length = rows + cols - i, i = 1 .. rows + cols, ALL from the same key,
+ * until one places every wire and moves it at least once; a zero board otherwise.  The reference returns the
+ * codes as float32 (jnp.zeros default dtype, :350); they are given as int32 here.
+ * stats (may be NULL): [0] = i of the attempt that succeeded (0 = none), [1] = its steps. */
+int orc_seqrw_generate(const uint32_t key[2], int G, int N, int32_t *board, int32_t *stats) {
+  if (G < 3 || G > ORC_MAX_G || N < 1 || N > ORC_MAX_N) return -1; /* :138-140 jnp.full(rows - 3) needs rows >= 3 */
+  const int L0 = 2 * G;
+  int success = 0, steps = 0, i;
+  for (i = 1; i <= L0 && !success; ++i) success = seqrw_add_agents(key, G, N, L0 - i, board, &steps);
+  if (!success) memset(board, 0, sizeof(int32_t) * (size_t)(G * G)); /* :389-391 */
+  if (stats) {
+    stats[0] = success ? i - 1 : 0;
+    stats[1] = success ? steps : 0;
+  }
+  return 0;
+}
+
+/* SRW:394-431 generate_starts_ends: first POSITION / TARGET cell of every wire in row-major order, (0,0) when
+ * absent (argwhere(size=2) fill value): starts[2,N], ends[2,N] */
+int orc_seqrw_starts_ends(const uint32_t key[2], int G, int N, int32_t *starts, int32_t *ends) {
+  int32_t *board = (int32_t *)malloc(sizeof(int32_t) * (size_t)(G * G));
+  int rc = orc_seqrw_generate(key, G, N, board, NULL);
+  if (rc) {
+    free(board);
+    return rc;
+  }
+  for (int w = 0; w < N; ++w) {
+    int s = 0, e = 0, fs = 0, fe = 0;
+    for (int k = 0; k < G * G; ++k) {
+      if (!fs && board[k] == 3 * w + POSITION) s = k, fs = 1;
+      if (!fe && board[k] == 3 * w + TARGET) e = k, fe = 1;
+    }
+    starts[w] = s / G;
+    starts[N + w] = s % G;
+    ends[w] = e / G;
+    ends[N + w] = e % G;
+  }
+  free(board);
+  return 0;
+}
+
+/* ======================================================================== */
 /* Generator.__call__(key) -> State  (PRWG:46-77, UG:70-109, RSG:28-57)      */
 /* ======================================================================== */
 int orc_state(int kind, const uint32_t key_in[2], int G, int N, int32_t *grid,
@@ -781,6 +925,11 @@ int orc_state(int kind, const uint32_t key_in[2], int G, int N, int32_t *grid,
     free(perm);
   } else if (kind == ORC_GEN_SEEDEXT) {
     rc = orc_seedext_starts_ends(&ks[0], G, N, 0.0f, 1, 1, -1, a, b);
+  } else if (kind == ORC_GEN_SEQRW) {
+    /* rl_training/online_generators/sequential_random_walk_generator.py:36-62: key, pos_key = split(key);
+     * generate_starts_ends(key); a failed generation leaves every pin at (0,0) and the scatters below
+     * keep the last one */
+    rc = orc_seqrw_starts_ends(&ks[0], G, N, a, b);
   } else {
     return -3;
   }
@@ -1108,6 +1257,18 @@ int orc_state_batch(int kind, const uint32_t *keys, int64_t B, int G, int N,
     int rc = orc_state(kind, &keys[2 * b], G, N, &grid[b * G * G], &step_count[b],
                        &agent_id[b * N], &start[b * 2 * N], &target[b * 2 * N],
                        &position[b * 2 * N], &key_out[2 * b]);
+    if (rc) rc_all = rc;
+  }
+  return rc_all;
+}
+
+int orc_seqrw_generate_batch(const uint32_t *keys, int64_t B, int G, int N, int32_t *boards, int32_t *stats, int nthreads) {
+  int rc_all = 0;
+  int nt = pick_threads(nthreads);
+  (void)nt;
+#pragma omp parallel for num_threads(nt) schedule(dynamic, 16)
+  for (int64_t b = 0; b < B; ++b) {
+    int rc = orc_seqrw_generate(&keys[2 * b], G, N, &boards[b * G * G], stats ? &stats[2 * b] : NULL);
     if (rc) rc_all = rc;
   }
   return rc_all;

@@ -47,6 +47,7 @@ extern "C" {
 #define ORC_GEN_PRW 0
 #define ORC_GEN_UNIFORM 1
 #define ORC_GEN_SEEDEXT 2
+#define ORC_GEN_SEQRW 4 /* 3 = dataset (orc_dataset_state) */
 
 /* ---- jax.random (0.4.8) primitives ------------------------------------- */
 void orc_threefry2x32(uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1,
@@ -98,6 +99,16 @@ void orc_extend_wires(int G, int32_t *board, const uint32_t key[2],
                       int32_t *sweeps_out);
 int orc_optimise_wire(const uint32_t key[2], int G, int32_t *board, int wire,
                       int32_t *pops_out);
+
+/* ---- SequentialRandomWalkBoard (SRW = .../jax_implementation/board_generation/sequential_random_walk.py;
+ *      pinned by tests/golden/seqrw_reference.json: the reference's own class run on the NumPy stand-in) ---- */
+/* generate SRW:324-392: board[G,G] (the reference returns the same codes as float32); stats may be NULL:
+ * [0] = attempt that succeeded (1 .. 2G, 0 = none: zero board), [1] = steps of that attempt */
+int orc_seqrw_generate(const uint32_t key[2], int G, int N, int32_t *board, int32_t *stats);
+/* generate_starts_ends SRW:394-431 -> starts[2,N], ends[2,N] */
+int orc_seqrw_starts_ends(const uint32_t key[2], int G, int N, int32_t *starts, int32_t *ends);
+int orc_seqrw_generate_batch(const uint32_t *keys, int64_t B, int G, int N, int32_t *boards,
+                             int32_t *stats /* [B,2] or NULL */, int nthreads);
 
 /* ---- Generator __call__(key) -> State ---------------------------------- */
 /* State fields (one env): grid[G,G], step_count, agent_id[N], start[N,2],

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("RBG_B200_LIB") or os.path.join(_HERE, "lib", "librbg_b200.so")  # override: A/B builds of the same CUDA library
 
-GEN_PRW, GEN_UNIFORM, GEN_SEEDEXT, GEN_DATASET = 0, 1, 2, 3
+GEN_PRW, GEN_UNIFORM, GEN_SEEDEXT, GEN_DATASET, GEN_SEQRW = 0, 1, 2, 3, 4
 MAX_G, MAX_N = 40, 32
 
 
@@ -51,6 +51,8 @@ SYMBOLS = {
     "rbg_split_each": (_int, [_vp, _i64, _int, _vp, _vp]),
     "rbg_seedext_solved": (_int, [_vp, _i64, _int, _int, _f, _int, _int, _i64, _vp, _vp]),
     "rbg_seedext_starts_ends": (_int, [_vp, _i64, _int, _int, _f, _int, _int, _i64, _vp, _vp, _vp]),
+    "rbg_seqrw_generate": (_int, [_vp, _i64, _int, _int, _vp, _int, _vp, _vp]),
+    "rbg_seqrw_starts_ends": (_int, [_vp, _i64, _int, _int, _vp, _vp, _vp]),
     "rbg_connector_observe": (_int, [_SP, _i64, _int, _int, _TP, _vp]),
     "rbg_connector_reset": (_int, [_int, _vp, _i64, _int, _int, _SP, _TP, _vp]),
     "rbg_step_workspace_bytes": (_i64, [_i64, _int, _int]),
@@ -103,7 +105,7 @@ def launch_count(reset: bool = False) -> int:
     return int(load().rbg_launch_count(1 if reset else 0))
 
 
-KERNELS = {"prw": 0, "env": 1, "random_actions": 2, "split": 3, "validate": 4, "seedext": 5, "rollout": 6}
+KERNELS = {"prw": 0, "env": 1, "random_actions": 2, "split": 3, "validate": 4, "seedext": 5, "rollout": 6, "seqrw": 7}
 
 
 def kernel_timing(enable: bool) -> None:

@@ -25,7 +25,7 @@ from . import engine
 from .online_generators import Generator, UniformRandomGenerator
 from .types import LAST, Agent, Observation, State, TimeStep
 
-_KERNEL_KINDS = ("uniform", "parallel_random_walk", "seed_extension")
+_KERNEL_KINDS = ("uniform", "parallel_random_walk", "seed_extension", "sequential_random_walk")
 
 
 @dataclass

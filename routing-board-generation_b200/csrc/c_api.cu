@@ -190,6 +190,24 @@ static int generator_state_impl(int kind, const uint32_t *keys, int64_t B, int G
     p.list_count = list_count;
     return launch_seedext(p, B, stream);
   }
+  if (kind == RBG_GEN_SEQRW) {
+    SeqRwParams p;
+    memset(&p, 0, sizeof(p));
+    p.keys = keys;
+    p.B = B;
+    p.G = G;
+    p.N = N;
+    p.extra_split = 1 + extra_split;  // sequential_random_walk_generator.py:42 key, pos_key = split(key)
+    p.mode = 2;
+    p.st = *out;
+    if (ts) {
+      p.ts = *ts;
+      p.observe = 1;
+    }
+    p.list = list;
+    p.list_count = list_count;
+    return launch_seqrw(p, B, stream);
+  }
   return set_error(RBG_EINVAL, "unknown generator kind %d", kind);
 }
 
@@ -316,7 +334,7 @@ static int connector_step_impl(const rbg_state *in, const rbg_state *out, const 
   const bool autoreset = params->autoreset_kind >= 0;
   const bool dataset = params->autoreset_kind == RBG_GEN_DATASET;
   if (autoreset && !dataset && !workspace) return set_error(RBG_EINVAL, "auto-reset needs a workspace (rbg_step_workspace_bytes)");
-  if (autoreset && params->autoreset_kind > RBG_GEN_DATASET)
+  if (autoreset && params->autoreset_kind > RBG_GEN_SEQRW)
     return set_error(RBG_EINVAL, "unknown autoreset generator kind %d", params->autoreset_kind);
   if (dataset && (rc = check_dataset(params))) return rc;
   if (B == 0) return RBG_OK;
@@ -818,6 +836,42 @@ int rbg_seedext_starts_ends(const uint32_t *keys, int64_t B, int G, int N, float
   return launch_seedext(p, B, (cudaStream_t)stream);
 }
 
+int rbg_seqrw_generate(const uint32_t *keys, int64_t B, int G, int N, void *board, int as_float32, int32_t *stats, void *stream) {
+  int rc;
+  if ((rc = check_dims(B, G, N, 0))) return rc;
+  if (!keys || !board) return set_error(RBG_EINVAL, "rbg_seqrw_generate: NULL argument");
+  if (!aligned16(board)) return set_error(RBG_EALIGN, "board not 16-byte aligned");
+  if (B == 0) return RBG_OK;
+  SeqRwParams p;
+  memset(&p, 0, sizeof(p));
+  p.keys = keys;
+  p.B = B;
+  p.G = G;
+  p.N = N;
+  p.mode = 0;
+  p.float_board = as_float32 ? 1 : 0;
+  p.board = reinterpret_cast<int32_t *>(board);
+  p.stats = stats;
+  return launch_seqrw(p, B, (cudaStream_t)stream);
+}
+
+int rbg_seqrw_starts_ends(const uint32_t *keys, int64_t B, int G, int N, int32_t *starts, int32_t *ends, void *stream) {
+  int rc;
+  if ((rc = check_dims(B, G, N, 0))) return rc;
+  if (!keys || !starts || !ends) return set_error(RBG_EINVAL, "rbg_seqrw_starts_ends: NULL argument");
+  if (B == 0) return RBG_OK;
+  SeqRwParams p;
+  memset(&p, 0, sizeof(p));
+  p.keys = keys;
+  p.B = B;
+  p.G = G;
+  p.N = N;
+  p.mode = 1;
+  p.starts = starts;
+  p.ends = ends;
+  return launch_seqrw(p, B, (cudaStream_t)stream);
+}
+
 int rbg_connector_observe(const rbg_state *state, int64_t B, int G, int N, const rbg_timestep *ts, void *stream) {
   int rc;
   if ((rc = check_dims(B, G, N, 1))) return rc;
@@ -1082,7 +1136,7 @@ int rbg_connector_rollout_random(const rbg_state *state, int32_t *action_out, in
   const int kind = params->autoreset_kind;
   static int fused = -1;
   if (fused < 0) fused = env_int("RBG_NO_FUSED_ROLLOUT") ? 0 : 1;
-  if (kind > RBG_GEN_DATASET) return set_error(RBG_EINVAL, "unknown autoreset generator kind %d", kind);
+  if (kind > RBG_GEN_SEQRW) return set_error(RBG_EINVAL, "unknown autoreset generator kind %d", kind);
   if (kind < 0) return set_error(RBG_EINVAL, "rollout needs an auto-reset generator kind (params->autoreset_kind >= 0)");
   if (kind == RBG_GEN_DATASET && (rc = check_dataset(params))) return rc;
   if (fused && kind == RBG_GEN_DATASET) {
@@ -1110,7 +1164,7 @@ int rbg_connector_rollout_random(const rbg_state *state, int32_t *action_out, in
     if (!aligned16(workspace)) return set_error(RBG_EALIGN, "workspace not 16-byte aligned");
     return rollout_fused(state, action_out, T, B, G, N, params, ts, workspace, (cudaStream_t)stream);
   }
-  for (int64_t t = 0; t < T; ++t) {  // step-wise: SeedExtension resets, or the fused kernel switched off
+  for (int64_t t = 0; t < T; ++t) {  // step-wise: SeedExtension / SequentialRandomWalk resets, or the fused kernel switched off
     const rbg_timestep tt = timestep_at(*ts, t * B, G, N);
     rc = connector_step_impl(state, state, nullptr, action_out ? action_out + t * B * N : nullptr, 1, B, G, N, params, &tt, workspace,
                              (cudaStream_t)stream);

@@ -145,7 +145,31 @@ struct SeedExtParams {
   int observe;
   const int32_t *list;
   const int32_t *list_count;
+  int solved_f32;  // mode 0: the codes as float32 (SequentialRandomWalkBoard.generate returns jnp.zeros' default dtype)
 };
 int launch_seedext(SeedExtParams p, int64_t max_boards, cudaStream_t stream);
+// se_finish_kernel on its own: boards[max_boards, CB] bytes (row-major G*G codes, CB = cells rounded up to 16) and
+// gkey[max_boards, 2] (State.key) -> the outputs of p.mode (0 board, 1 first POSITION / TARGET cell per wire, 2 State
+// (+ observation)); slot m of the scratch is board p.list[m] when p.list is set
+int launch_board_finish(const SeedExtParams &p, const uint8_t *boards, const uint32_t *gkey, int CB, int64_t max_boards, int kernel_id,
+                        cudaStream_t stream);
+
+// ---- sequential random walk (seqrw_kernel.cu) ----------------------------
+struct SeqRwParams {
+  const uint32_t *keys;
+  long long B;
+  int G, N;
+  int extra_split;
+  int mode;         // 0 board, 1 starts/ends, 2 State
+  int float_board;  // mode 0: float32 codes
+  int32_t *board, *starts, *ends;
+  int32_t *stats;  // optional [B,2]: attempt that succeeded (0 = none), its steps
+  rbg_state st;
+  rbg_timestep ts;
+  int observe;
+  const int32_t *list;
+  const int32_t *list_count;
+};
+int launch_seqrw(SeqRwParams p, int64_t max_boards, cudaStream_t stream);
 
 }  // namespace rbg

@@ -788,7 +788,17 @@ __global__ void __launch_bounds__(SE_FIN_WARPS * 32) se_finish_kernel(const Seed
 
   if (p.mode == 0) {  // return_solved_board: int32[G,G]
     int32_t *out = p.solved + e * cells;
-    if ((cells & 3) == 0) {
+    if (p.solved_f32) {  // SequentialRandomWalkBoard.generate: the same codes as float32
+      float *fo = reinterpret_cast<float *>(out);
+      if ((cells & 3) == 0) {
+        for (int q = lane; q < (cells >> 2); q += 32) {
+          const int4 v = bytes_to_int4(reinterpret_cast<const uint32_t *>(grid)[q]);
+          reinterpret_cast<float4 *>(fo)[q] = make_float4((float)v.x, (float)v.y, (float)v.z, (float)v.w);
+        }
+      } else {
+        for (int i = lane; i < cells; i += 32) fo[i] = (float)grid[i];
+      }
+    } else if ((cells & 3) == 0) {
       int4 *o = reinterpret_cast<int4 *>(out);
       for (int q = lane; q < (cells >> 2); q += 32) o[q] = bytes_to_int4(reinterpret_cast<const uint32_t *>(grid)[q]);
     } else {
@@ -828,10 +838,21 @@ __global__ void __launch_bounds__(SE_FIN_WARPS * 32) se_finish_kernel(const Seed
     return;
   }
   // SeedExtensionGenerator.__call__ RSG:34-57: pins-only grid (heads, then targets), Agent pytree
-  if (lane < N) pinsg[sr * G + scol] = (uint8_t)(3 * lane + POSITION);
-  __syncwarp();
-  if (lane < N) pinsg[tr * G + tc] = (uint8_t)(3 * lane + TARGET);
-  __syncwarp();
+  // `grid.at[starts].set(...)`, `grid.at[targets].set(...)`: when several wires share a cell (a failed
+  // SequentialRandomWalk generation leaves every pin at (0,0)) the last one stays (sequential scatter)
+  {
+    const unsigned act = __ballot_sync(FULL, lane < N);
+    if (lane < N) {
+      const unsigned peers = __match_any_sync(act, sr * G + scol);
+      if ((31 - __clz(peers)) == lane) pinsg[sr * G + scol] = (uint8_t)(3 * lane + POSITION);
+    }
+    __syncwarp();
+    if (lane < N) {
+      const unsigned peers = __match_any_sync(act, tr * G + tc);
+      if ((31 - __clz(peers)) == lane) pinsg[tr * G + tc] = (uint8_t)(3 * lane + TARGET);
+    }
+    __syncwarp();
+  }
   int32_t *gout = p.st.grid + e * cells;
   if ((cells & 3) == 0) {
     int4 *o = reinterpret_cast<int4 *>(gout);
@@ -1117,6 +1138,27 @@ int launch_seedext(SeedExtParams p, int64_t max_boards, cudaStream_t stream) {
   } while (0);
   cudaFreeAsync(base, stream);
   return rc;
+}
+
+int launch_board_finish(const SeedExtParams &p, const uint8_t *boards, const uint32_t *gkey, int CB, int64_t max_boards, int kernel_id,
+                        cudaStream_t stream) {
+  SeDims d;
+  memset(&d, 0, sizeof(d));
+  d.G = p.G;
+  d.N = p.N;
+  d.cells = p.G * p.G;
+  SeScratch sc;
+  memset(&sc, 0, sizeof(sc));
+  sc.board = const_cast<uint8_t *>(boards);
+  sc.gkey = const_cast<uint32_t *>(gkey);
+  sc.CB = CB;
+  const size_t smem = (size_t)SE_FIN_WARPS * (2 * sc.CB + 8 * RBG_MAX_N);
+  const unsigned ctas = (unsigned)((max_boards + SE_FIN_WARPS - 1) / SE_FIN_WARPS);
+  {
+    LaunchScope scope(kernel_id, stream);
+    se_finish_kernel<<<ctas < 1 ? 1 : ctas, SE_FIN_WARPS * 32, smem, stream>>>(p, d, sc, FastDiv::make((uint32_t)p.G));
+  }
+  return check_launch("se_finish_kernel");
 }
 
 }  // namespace rbg

@@ -16,10 +16,10 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import GEN_DATASET, GEN_PRW, GEN_SEEDEXT, GEN_UNIFORM, rbg_env_params, rbg_state, rbg_timestep
+from ._lib import GEN_DATASET, GEN_PRW, GEN_SEEDEXT, GEN_SEQRW, GEN_UNIFORM, rbg_env_params, rbg_state, rbg_timestep
 from .types import Agent, Observation, State, TimeStep
 
-GENERATOR_KINDS = {"parallel_random_walk": GEN_PRW, "uniform": GEN_UNIFORM, "seed_extension": GEN_SEEDEXT, "dataset": GEN_DATASET}
+GENERATOR_KINDS = {"parallel_random_walk": GEN_PRW, "uniform": GEN_UNIFORM, "seed_extension": GEN_SEEDEXT, "dataset": GEN_DATASET, "sequential_random_walk": GEN_SEQRW}
 
 
 _cuda_checked = False
@@ -231,6 +231,26 @@ def seedext_starts_ends(keys: torch.Tensor, G: int, N: int, randomness: float = 
     ends = torch.empty((B, 2, N), dtype=torch.int32, device=dev)
     steps = -1 if extension_steps >= 2**62 else int(extension_steps)
     _lib.check(_lib.load().rbg_seedext_starts_ends(keys.data_ptr(), B, G, N, float(randomness), int(bool(two_sided)), int(iterations), steps, starts.data_ptr(), ends.data_ptr(), _stream()))
+    return starts, ends
+
+
+def seqrw_generate(keys: torch.Tensor, G: int, N: int, as_float32: bool = True, with_stats: bool = False):
+    """SequentialRandomWalkBoard.generate over keys[B,2] -> board[B,G,G] (float32 codes like the reference, or int32);
+    with_stats adds int32[B,2] = (attempt that succeeded, 0 = none: zero board; steps of that attempt)."""
+    B = keys.shape[0]
+    dev = _device()
+    board = torch.empty((B, G, G), dtype=torch.float32 if as_float32 else torch.int32, device=dev)
+    stats = torch.empty((B, 2), dtype=torch.int32, device=dev) if with_stats else None
+    _lib.check(_lib.load().rbg_seqrw_generate(keys.data_ptr(), B, G, N, board.data_ptr(), int(bool(as_float32)), stats.data_ptr() if with_stats else None, _stream()))
+    return (board, stats) if with_stats else board
+
+
+def seqrw_starts_ends(keys: torch.Tensor, G: int, N: int):
+    B = keys.shape[0]
+    dev = _device()
+    starts = torch.empty((B, 2, N), dtype=torch.int32, device=dev)
+    ends = torch.empty((B, 2, N), dtype=torch.int32, device=dev)
+    _lib.check(_lib.load().rbg_seqrw_starts_ends(keys.data_ptr(), B, G, N, starts.data_ptr(), ends.data_ptr(), _stream()))
     return starts, ends
 
 

@@ -4,6 +4,7 @@ Mirrors routing_board_generation/rl_training/online_generators/
   uniform_generator.py:26-109                 Generator, UniformRandomGenerator
   parallel_random_walk_generator.py:28-77     ParallelRandomWalkGenerator
   random_seed_generator.py:15-57              SeedExtensionGenerator
+  sequential_random_walk_generator.py:19-62   SequentialRandomWalkGenerator
 so that `Connector(generator=...)` (rl_training/setup_train.py:112-161) takes them unchanged.
 """
 from __future__ import annotations
@@ -11,7 +12,7 @@ from __future__ import annotations
 import abc
 
 from . import engine
-from .board_generation import ParallelRandomWalkBoard, SeedExtensionBoard
+from .board_generation import ParallelRandomWalkBoard, SeedExtensionBoard, SequentialRandomWalkBoard
 from .types import State
 
 
@@ -68,3 +69,15 @@ class SeedExtensionGenerator(_KernelGenerator):
     def __init__(self, grid_size: int, num_agents: int) -> None:
         super().__init__(grid_size, num_agents)
         self.board_generator = SeedExtensionBoard(grid_size, grid_size, num_agents)
+
+
+class SequentialRandomWalkGenerator(_KernelGenerator):
+    """Boards from the sequential random walk (sequential_random_walk_generator.py:19-62; `online_seq_rw`,
+    rl_training/setup_train.py:137-141).  A generation whose every attempt fails leaves all pins at (0, 0), as the
+    reference's argwhere(size=2) fill value does."""
+
+    kind = "sequential_random_walk"
+
+    def __init__(self, grid_size: int, num_agents: int) -> None:
+        super().__init__(grid_size, num_agents)
+        self.board_generator = SequentialRandomWalkBoard(grid_size, grid_size, num_agents)

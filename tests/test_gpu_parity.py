@@ -382,10 +382,13 @@ def _rollout(rbg, orc, kind, G, N, B, steps, autoreset, time_limit=50, seed=3):
     import torch
 
     keys, kref = _keys(rbg, orc, seed, B)
-    gen = {"parallel_random_walk": rbg.ParallelRandomWalkGenerator, "uniform": rbg.UniformRandomGenerator, "seed_extension": rbg.SeedExtensionGenerator}[kind](G, N)
+    gen = {"parallel_random_walk": rbg.ParallelRandomWalkGenerator, "uniform": rbg.UniformRandomGenerator, "seed_extension": rbg.SeedExtensionGenerator,
+           "sequential_random_walk": rbg.SequentialRandomWalkGenerator}[kind](G, N)
     env = rbg.Connector(generator=gen, time_limit=time_limit)
     st, ts = env.reset(keys)
     rst, rts = orc.connector_reset_batch(kind, kref, G, N)
+    _assert_state(st, rst, "after reset")
+    _assert_timestep(ts, rts, "after reset")
     rng = np.random.default_rng(seed)
     n_last = 0
     for t in range(steps):
@@ -1265,3 +1268,112 @@ def test_errors_are_reported_not_swallowed(rbg):
         rbg.ParallelRandomWalkBoard(4, 5, 2)
     with pytest.raises(ValueError):
         rbg.ParallelRandomWalkBoard(5, 5, 2).generate_board(torch.zeros(3, dtype=torch.int32, device="cuda"))
+
+
+# ------------------------------------------------------ SequentialRandomWalk
+def _seqrw_fixtures():
+    import json
+    import os
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "seqrw_reference.json")) as f:
+        return json.load(f)
+
+
+def test_seqrw_reference_fixtures_on_gpu(rbg):
+    """The CUDA path against the reference's own SequentialRandomWalkBoard / SequentialRandomWalkGenerator run on the
+    jax shim (tests/golden/seqrw_reference.json, made by tests/tools/make_seqrw_fixtures.py): boards that succeed at once,
+    boards that need several attempts, boards on which every attempt fails."""
+    import torch
+
+    fx = _seqrw_fixtures()
+    assert fx["numpy_log_strictly_monotone_on_all_uniforms"] and fx["gumbel_draws_checked"] > 5000
+    seen = set()
+    for cfg in fx["generate"]:
+        board = rbg.SequentialRandomWalkBoard(cfg["G"], cfg["G"], cfg["N"])
+        key = torch.tensor(cfg["key"], dtype=torch.int64)
+        out = board.generate(key)
+        assert out.dtype == torch.float32 and out.shape == (cfg["G"], cfg["G"])  # the reference's dtype (jnp.zeros default)
+        assert _np(out).astype(np.int64).tolist() == cfg["board"], cfg["key"]
+        b2, stats = board.generate_with_stats(key)
+        assert b2.dtype == torch.int32 and _np(b2).tolist() == cfg["board"] and int(stats[0]) == cfg["attempt"]
+        seen.add(0 if cfg["attempt"] == 0 else 1 if cfg["attempt"] == 1 else 2)
+    assert seen == {0, 1, 2}
+    for cfg in fx["starts_ends"]:
+        (sr, sc), (er, ec) = rbg.SequentialRandomWalkBoard(cfg["G"], cfg["G"], cfg["N"]).generate_starts_ends(torch.tensor(cfg["key"], dtype=torch.int64))
+        assert [_np(sr).tolist(), _np(sc).tolist()] == cfg["starts"] and [_np(er).tolist(), _np(ec).tolist()] == cfg["ends"], cfg["key"]
+    for cfg in fx["generator_states"]:
+        st = rbg.SequentialRandomWalkGenerator(cfg["G"], cfg["N"])(torch.tensor(cfg["key_in"], dtype=torch.int64))
+        assert _np(st.key).tolist() == cfg["key"] and _np(st.grid).tolist() == cfg["grid"] and int(st.step_count) == cfg["step_count"]
+        assert _np(st.agents.id).tolist() == cfg["agent_id"] and _np(st.agents.start).tolist() == cfg["start"]
+        assert _np(st.agents.target).tolist() == cfg["target"] and _np(st.agents.position).tolist() == cfg["position"]
+
+
+@pytest.mark.parametrize("G,N,B", [(3, 1, 257), (3, 4, 2048), (4, 6, 2048), (5, 3, 2048), (6, 12, 1024), (7, 4, 2048), (10, 5, 4096), (10, 20, 512), (14, 7, 2048), (17, 9, 512),
+                                   (20, 10, 1024), (32, 16, 256), (40, 32, 64)])
+def test_seqrw_generate_matches_oracle(rbg, orc, G, N, B):
+    keys, kref = _keys(rbg, orc, 11, B)
+    board = rbg.SequentialRandomWalkBoard(G, G, N)
+    got, stats = board.generate_with_stats(keys)
+    ref, rstats = orc.seqrw_generate_batch(kref, G, N)
+    assert np.array_equal(_np(stats), rstats), "attempt / step counts differ"
+    assert np.array_equal(_np(got), ref)
+    assert np.array_equal(_np(board.generate(keys)), ref.astype(np.float32))
+    (sr, sc), (er, ec) = board.generate_starts_ends(keys)
+    for b in range(0, B, max(1, B // 64)):
+        rs, re_ = orc.seqrw_starts_ends(kref[b], G, N)
+        assert np.array_equal(np.stack([_np(sr)[b], _np(sc)[b]]), rs) and np.array_equal(np.stack([_np(er)[b], _np(ec)[b]]), re_)
+    # a generated board is sound by the reference's validity rules; a failed one is all zeros
+    ok = rstats[:, 0] > 0
+    flags = _np(rbg.engine.validate(got, N))
+    assert ((flags[ok] & (1 | 8 | 32 | 64 | 128)) == 0).all()
+    assert (ref[~ok] == 0).all()
+
+
+@pytest.mark.parametrize("G,N", [(3, 4), (5, 3), (10, 5), (14, 7)])
+def test_seqrw_generator_state_matches_oracle(rbg, orc, G, N):
+    keys, kref = _keys(rbg, orc, 5, 777)
+    _assert_state(rbg.SequentialRandomWalkGenerator(G, N)(keys), orc.state_batch("sequential_random_walk", kref, G, N))
+
+
+def test_seqrw_single_key_ragged_and_errors(rbg, orc):
+    k = rbg.PRNGKey(42)
+    out = rbg.SequentialRandomWalkBoard(6, 6, 3).generate(k, as_float32=False)
+    assert out.shape == (6, 6) and np.array_equal(_np(out), orc.seqrw_generate(orc.PRNGKey(42), 6, 3))
+    for B in (1, 3, 15, 16, 17, 129):
+        keys, kref = _keys(rbg, orc, 9, B)
+        assert np.array_equal(_np(rbg.SequentialRandomWalkBoard(8, 8, 4).generate(keys, as_float32=False)), orc.seqrw_generate_batch(kref, 8, 4)[0])
+    with pytest.raises(ValueError):
+        rbg.SequentialRandomWalkBoard(2, 2, 1)
+    with pytest.raises(ValueError):
+        rbg.SequentialRandomWalkBoard(5, 6, 2)
+    import torch
+
+    lib = rbg._lib.load()
+    keys = rbg.split(rbg.PRNGKey(0), 4)
+    out = torch.empty((4, 2, 2), dtype=torch.int32, device="cuda")
+    assert lib.rbg_seqrw_generate(keys.data_ptr(), 4, 2, 1, out.data_ptr(), 0, None, None) == -1  # rows < 3
+
+
+def test_seqrw_connector_autoreset_matches_oracle(rbg, orc):
+    """Connector(generator=SequentialRandomWalkGenerator) as `online_seq_rw` builds it (setup_train.py:137-141,158): reset, steps,
+    auto-resets through the reset-list path; crowded boards include failed generations (every pin at (0, 0))."""
+    n_last = _rollout(rbg, orc, "sequential_random_walk", 10, 5, B=512, steps=40, autoreset=True, time_limit=15)
+    assert n_last > 512
+    _rollout(rbg, orc, "sequential_random_walk", 3, 4, B=300, steps=9, autoreset=True, time_limit=2, seed=23)
+    _rollout(rbg, orc, "sequential_random_walk", 6, 3, B=300, steps=12, autoreset=False, time_limit=8, seed=24)
+
+
+def test_seqrw_rollout_random_matches_oracle(rbg, orc):
+    G, N, B, T, TL = 8, 4, 600, 14, 5
+    keys, kref = _keys(rbg, orc, 31, B)
+    env = rbg.VmapAutoResetWrapper(rbg.Connector(generator=rbg.SequentialRandomWalkGenerator(G, N), time_limit=TL))
+    st, _ = env.reset(keys)
+    rst, _ = orc.connector_reset_batch("sequential_random_walk", kref, G, N)
+    st, ts, act = env.rollout_random(st, T)
+    for t in range(T):
+        a = orc.random_actions_batch(rst)
+        assert np.array_equal(_np(act[t]), a), t
+        rst, rts = orc.connector_step_batch(rst, a, time_limit=TL, autoreset_kind="sequential_random_walk")
+        assert np.array_equal(_np(ts.observation.grid[t]), rts["obs"]) and np.array_equal(_np(ts.step_type[t]), rts["step_type"]), t
+        assert np.array_equal(_np(ts.reward[t]).view(np.uint32), rts["reward"].view(np.uint32)), t
+    _assert_state(st, rst, "after the rollout")

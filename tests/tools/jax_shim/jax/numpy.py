@@ -59,6 +59,10 @@ def concatenate(arrays, axis=0):
     return _w(_np.concatenate([_np.asarray(a) for a in arrays], axis=axis))
 
 
+def hstack(arrays):
+    return _w(_np.hstack([_np.atleast_1d(_np.asarray(a)) for a in arrays]))
+
+
 def divmod(a, b):  # noqa: A001
     q, r = _np.divmod(_np.asarray(a), _np.asarray(b))
     return _w(q), _w(r)

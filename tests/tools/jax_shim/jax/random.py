@@ -77,6 +77,16 @@ def uniform(key, shape=(), dtype=_np.float32, minval=0.0, maxval=1.0):
     return asarr(_np.maximum(lo, f).reshape(_shape(shape)), _np.float32)
 
 
+GUMBEL_TRACE = []  # (23-bit mantissas, candidate mask, pick) of every choice(p, replace=False): see make_seqrw_fixtures.py
+
+
+def gumbel(key, shape=(), dtype=_np.float32):
+    """-log(-log(uniform(key, shape, minval=tiny, maxval=1))) in float32 (jax/_src/random.py v0.4.8 `_gumbel`)."""
+    u = _np.asarray(uniform(key, shape, minval=_np.finfo(_np.float32).tiny, maxval=1.0))
+    with _np.errstate(divide="ignore"):
+        return asarr((-_np.log(-_np.log(u))).astype(_np.float32), _np.float32)
+
+
 def randint(key, shape, minval, maxval, dtype=_np.int32):
     shape = _shape(shape)
     k1, k2 = _np.asarray(split(key))
@@ -142,11 +152,18 @@ def choice(key, a, shape=(), replace=True, p=None, axis=0):
     else:
         p_arr = _np.asarray(p).astype(_np.float32)
         assert p_arr.shape == (n_inputs,)
-        assert replace, "choice(p=..., replace=False) is not used by the reference"
-        p_cuml = _np.cumsum(p_arr, dtype=_np.float32)
-        r = p_cuml[-1] * (_np.float32(1.0) - _np.asarray(uniform(key, shape)))
-        ind = _np.searchsorted(p_cuml, r.astype(_np.float32), side="left")
-        ind = _np.clip(ind, 0, n_inputs - 1)
+        if replace:
+            p_cuml = _np.cumsum(p_arr, dtype=_np.float32)
+            r = p_cuml[-1] * (_np.float32(1.0) - _np.asarray(uniform(key, shape)))
+            ind = _np.searchsorted(p_cuml, r.astype(_np.float32), side="left")
+            ind = _np.clip(ind, 0, n_inputs - 1)
+        else:
+            # Gumbel top-k (jax/_src/random.py v0.4.8): g = -gumbel(key, (n,)) - log(p); ind = argsort(g)[:n_draws].
+            # SequentialRandomWalkBoard (sequential_random_walk.py:57-63, 211-217) draws every cell this way.
+            with _np.errstate(divide="ignore"):
+                g = -_np.asarray(gumbel(key, (n_inputs,))) - _np.log(p_arr)
+            ind = _np.argsort(g, kind="stable")[:n_draws]
+            GUMBEL_TRACE.append((_np.asarray(_random_bits(key, (n_inputs,))) >> _U32(9), p_arr > 0, int(ind[0])))
         result = _np.take(a, ind, axis=axis)
     full_shape = shape if a.ndim == 0 else a.shape[:axis] + tuple(shape) + a.shape[axis + 1:]
     return asarr(_np.asarray(result).reshape(full_shape))
