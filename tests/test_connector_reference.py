@@ -22,7 +22,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 STATE_F = ("grid", "step_count", "start", "target", "position", "key")
 TS_F = ("obs", "action_mask", "obs_step_count", "reward", "discount", "step_type", "num_connections", "ratio_connections", "total_path_length")
 GEN_KIND = {"parallel_random_walk": "parallel_random_walk", "uniform": "uniform", "seed_extension": "seed_extension",
-            "offline_parallel_rw": "dataset", "offline_seed_extension": "dataset"}
+            "offline_parallel_rw": "dataset", "offline_seed_extension": "dataset", "sequential_random_walk": "sequential_random_walk"}
 
 
 def load_connector_fixture():
@@ -111,7 +111,7 @@ def run_episodes(z, m, env):
 def test_fixture_covers_the_transition_surface():
     z, meta = load_connector_fixture()
     kinds = {m["generator"] for m in meta if "generator" in m}
-    assert {"parallel_random_walk", "uniform", "seed_extension", "offline_parallel_rw", "offline_seed_extension"} <= kinds
+    assert {"parallel_random_walk", "uniform", "seed_extension", "offline_parallel_rw", "offline_seed_extension", "sequential_random_walk"} <= kinds
     st = np.concatenate([z[f"{m['tag']}/t_step_type"].reshape(-1) for m in meta])
     assert (st == 0).sum() > 50 and (st == 1).sum() > 1000 and (st == 2).sum() > 150
     rew = np.concatenate([z[f"{m['tag']}/t_reward"].reshape(-1) for m in meta if not m.get("aggregate")])

@@ -735,7 +735,8 @@ class _CudaFixtureEnv:
             gen.heads = rbg.engine.as_tensor(z[f"{m['tag']}/dataset_heads"])
             gen.targets = rbg.engine.as_tensor(z[f"{m['tag']}/dataset_targets"])
         else:
-            gen = {"parallel_random_walk": rbg.ParallelRandomWalkGenerator, "uniform": rbg.UniformRandomGenerator, "seed_extension": rbg.SeedExtensionGenerator}[g](G, N)
+            gen = {"parallel_random_walk": rbg.ParallelRandomWalkGenerator, "uniform": rbg.UniformRandomGenerator, "seed_extension": rbg.SeedExtensionGenerator,
+                   "sequential_random_walk": rbg.SequentialRandomWalkGenerator}[g](G, N)
         self.env = rbg.Connector(generator=gen, time_limit=m["time_limit"])
         self.vec = rbg.VmapAutoResetWrapper(rbg.MultiToSingleWrapper(self.env) if m.get("aggregate") else self.env)
 

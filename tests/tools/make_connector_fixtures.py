@@ -98,6 +98,13 @@ def make_generator(name, G, N):
         return UniformRandomGenerator(G, N)
     if name == "seed_extension":
         return SeedExtensionGenerator(G, N)
+    if name == "sequential_random_walk":  # setup_train.py:137-141 online_seq_rw
+        from routing_board_generation.board_generation_methods.jax_implementation.board_generation.sequential_random_walk import SequentialRandomWalkBoard
+        from routing_board_generation.rl_training.online_generators.sequential_random_walk_generator import SequentialRandomWalkGenerator
+
+        # not instantiable as shipped (abstract methods of the NumPy AbstractBoard): lift the check, see make_seqrw_fixtures.py
+        SequentialRandomWalkBoard.__abstractmethods__ = frozenset()
+        return SequentialRandomWalkGenerator(G, N)
     if name.startswith("offline_"):  # setup_train.py:119-131
         return BoardDatasetGeneratorJAX(grid_size=G, num_agents=N, board_name=name, number_of_boards=7)
     raise ValueError(name)
@@ -220,10 +227,29 @@ def main():
     meta.append(episode_scenario(out, "episodes_uniform", "uniform", 10, 5, 4, 50, 209))
     meta.append(episode_scenario(out, "episodes_prw", "parallel_random_walk", 8, 4, 4, 20, 210))
     meta.append(demo_recipe_scenario(out, "demo_recipe", 211, 6))
+    meta.append(vmapped_scenario(out, "seq6", "sequential_random_walk", 6, 3, 6, 14, 6, 214, False))
+    meta.append(vmapped_scenario(out, "seq4agg", "sequential_random_walk", 4, 5, 6, 8, 3, 215, True))
+    out["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    np.savez_compressed(OUT, **out)
+    print("wrote", OUT, os.path.getsize(OUT), "bytes")
+
+
+def append_seqrw():
+    """`python tests/tools/make_connector_fixtures.py append_seqrw`: adds the SequentialRandomWalkGenerator scenarios to the
+    existing file (the other scenarios are kept as they are)."""
+    import json
+
+    z = np.load(OUT)
+    out = {k: z[k] for k in z.files}
+    meta = [m for m in json.loads(bytes(z["meta"]).decode()) if m.get("generator") != "sequential_random_walk"]
+    for k in [k for k in out if k.split("/")[0] in ("seq6", "seq4agg")]:
+        del out[k]
+    meta.append(vmapped_scenario(out, "seq6", "sequential_random_walk", 6, 3, 6, 14, 6, 214, False))
+    meta.append(vmapped_scenario(out, "seq4agg", "sequential_random_walk", 4, 5, 6, 8, 3, 215, True))  # crowded: retries and failed generations
     out["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
 
 
 if __name__ == "__main__":
-    main()
+    append_seqrw() if sys.argv[1:] == ["append_seqrw"] else main()
