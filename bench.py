@@ -494,6 +494,16 @@ def _secondary(args, rbg, dd, peak, rank, world, sm_mhz):
         issue(line, f"seedext_pipeline_14x14_7_b{b}_warp_inst_per_board", rate)
         out.append(line)
         del keys, res
+    # SequentialRandomWalkBoard.generate (the reference quotes 685 us for ONE 10x10/5 board and its vmap fails)
+    g, n, b = 10, 5, 65536
+    keys = sharding.shard_keys(rbg.PRNGKey(0), b * world, rank, world)
+    sboard = rbg.SequentialRandomWalkBoard(g, g, n)
+    ms, all_ms = timed(lambda: sboard.generate(keys), 5, min_ms=30.0)
+    line = {"metric": "seqrw_boards_per_sec", "workload": f"SequentialRandomWalkBoard.generate {g}x{g}/{n}, {b} boards per GPU", "grid": g, "agents": n, "value": round(b * world / (ms / 1e3), 1), "unit": "boards/s",
+            "n_gpus": world, "ms_per_batch": round(ms, 4), "ms_samples": [round(x, 4) for x in all_ms], "bound": "integer issue (threefry2x32), see DESIGN.md K5"}
+    issue(line, f"seqrw_kernel_{g}x{g}_{n}_warp_inst_per_board", b * world / (ms / 1e3))
+    out.append(line)
+    del keys
     return out if rank == 0 else []
 
 
@@ -566,6 +576,10 @@ def _cpu_secondary(secondary, budget_s: float = 4.0):
         if line["metric"] == "prw_solved_boards_per_sec":
             g, n = line["grid"], line["agents"]
             v, done, dt = rate(lambda k: orc.prw_generate_batch(orc.split(orc.PRNGKey(1), k), g, n, nthreads=cores), 512)
+            line["cpu_baseline"] = {"value": round(v, 1), "unit": "boards/s", "cores": cores, "kind": "port", "sample": f"{done} boards {g}x{g}/{n} in {dt:.1f} s, OpenMP over boards"}
+        elif line["metric"] == "seqrw_boards_per_sec":
+            g, n = line["grid"], line["agents"]
+            v, done, dt = rate(lambda k: orc.seqrw_generate_batch(orc.split(orc.PRNGKey(1), k), g, n, nthreads=cores), 512)
             line["cpu_baseline"] = {"value": round(v, 1), "unit": "boards/s", "cores": cores, "kind": "port", "sample": f"{done} boards {g}x{g}/{n} in {dt:.1f} s, OpenMP over boards"}
         elif line["metric"] == "seedext_solved_boards_per_sec":
             if se_cpu is None:

@@ -148,6 +148,7 @@ struct SeedExtParams {
   int solved_f32;  // mode 0: the codes as float32 (SequentialRandomWalkBoard.generate returns jnp.zeros' default dtype)
 };
 int launch_seedext(SeedExtParams p, int64_t max_boards, cudaStream_t stream);
+void keep_pool_cached();  // cudaMallocAsync's default pool keeps its memory across synchronisations (scratch of the generators)
 // se_finish_kernel on its own: boards[max_boards, CB] bytes (row-major G*G codes, CB = cells rounded up to 16) and
 // gkey[max_boards, 2] (State.key) -> the outputs of p.mode (0 board, 1 first POSITION / TARGET cell per wire, 2 State
 // (+ observation)); slot m of the scratch is board p.list[m] when p.list is set

@@ -915,6 +915,19 @@ static SeOverlap *se_overlap() {
   return &o;
 }
 
+// keep the stream-ordered pool's memory cached between calls (default: released at every sync); once per device
+void keep_pool_cached() {
+  static bool ready[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || ready[dev]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  ready[dev] = true;
+}
+
 int launch_seedext(SeedExtParams p, int64_t max_boards, cudaStream_t stream) {
   const int G = p.G, N = p.N;
   SeDims d;
@@ -1030,18 +1043,7 @@ int launch_seedext(SeedExtParams p, int64_t max_boards, cudaStream_t stream) {
   const size_t o_queue = o_done + round_up(n * 4, 256);  // list of finished boards (overlapped optimise)
   const size_t total = o_queue + 1024;  // queue counters: three ints per extension iteration
   uint8_t *base = nullptr;
-  {  // keep the stream-ordered pool's memory cached between calls (default: released at every sync)
-    static bool pool_ready = false;
-    if (!pool_ready) {
-      int dev = 0;
-      cudaMemPool_t pool;
-      if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        uint64_t thr = ~0ull;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-      }
-      pool_ready = true;
-    }
-  }
+  keep_pool_cached();
   cudaError_t ce = cudaMallocAsync(reinterpret_cast<void **>(&base), total, stream);
   if (ce != cudaSuccess) return set_cuda_error(ce, "cudaMallocAsync(SeedExtension scratch)");
   sc.board = base;

@@ -30,6 +30,11 @@
 //   WALK         lanes 2..5: the step's 4 words under s and the availability of their direction;
 //                lanes 0,1: split(c') for the NEXT step in the same pass (the chain does not depend on the
 //                board); ballot, pick, move                              (:193-228, :230-288)
+// The body is written so that all 32 lanes execute the same instructions whatever phase their board is in (operands
+// are selected, board reads are unconditional on a safe cell); only the once-per-wire events (start cell found, walk
+// over) and the once-per-board events (new board, failed attempt, output) branch, behind warp votes.  The first
+// version branched on the phase and spent 70 % of its instructions in bookkeeping executed one group at a time
+// (profiles/r02g_seqrw_full.csv: 13.6 k warp-instructions per 10x10/5 board).
 // A failed attempt is abandoned at once (its board can only be discarded, :355-366).  Groups take boards from a
 // global queue.  The finished board goes to a byte scratch and through se_finish_kernel's outputs (board /
 // first POSITION and TARGET cell per wire / State + observation), which SeedExtension shares.
@@ -52,258 +57,245 @@ __global__ void __launch_bounds__(SQ_THREADS) seqrw_walk_kernel(const SeqRwParam
   const int G = p.G, N = p.N, S = G + 4, cells = G * G;
   const int SB = (S * S + 15) & ~15;
   uint8_t *board = smem_raw + (size_t)(tid / SQ_W) * SB;
+  uint8_t *tmpl = smem_raw + (size_t)SQ_GROUPS * SB;  // the empty board: 0xFF border, 0 interior
+  for (int i = tid; i < SB; i += SQ_THREADS) {
+    const int r = i / S, c = i - r * S;
+    tmpl[i] = (r >= 2 && r < G + 2 && c >= 2 && c < G + 2) ? 0 : 0xFF;
+  }
+  __syncthreads();
   const long long total = p.list ? (long long)(*p.list_count) : p.B;
   const int n1 = cells, h1 = (cells + 1) >> 1;  // pick_start: random_bits(d, (G*G,)), odd sizes padded with a zero counter
   const int n2 = G + 1, h2 = (n2 + 1) >> 1;     // one_step:   random_bits(s, (G+1,))
   const int P = (h1 + SQ_W - 1) / SQ_W;
+  const int safe = 2 * S + 2;  // an interior cell: what the unconditional board reads fall back to
+
+  // per-lane constants of the walk pass: lanes 2..5 draw word k = l - 2 of random_bits(s, (G+1,)) (o0 of block k, or o1 of
+  // block k - h2) and test direction k of [up, down, left, right]
+  const bool draw_lane = (unsigned)(l - 2) < 4u;
+  const int kdir = (l - 2) & 3;
+  const bool k_low = kdir < h2;
+  const uint32_t wx0 = (uint32_t)(k_low ? kdir : kdir - h2);
+  const uint32_t wx1 = ((int)wx0 + h2 < n2) ? wx0 + (uint32_t)h2 : 0u;
+  const int dirk = kdir == 0 ? -S : kdir == 1 ? S : kdir == 2 ? -1 : 1;
+  const uint32_t sx0 = (uint32_t)(l & 1), sx1 = sx0 + 2u;  // split(): blocks (0,2), (1,3)
 
   int phase = SQ_IDLE;
   long long m = -1, e = -1;
-  uint32_t K0 = 0, K1 = 0;        // the board's key (every attempt starts from it)
-  uint32_t key0 = 0, key1 = 0;    // the tuple's key between wires
-  uint32_t c0 = 0, c1 = 0;        // chain key of the walk (committed)
-  uint32_t cn0 = 0, cn1 = 0;      // split(c)[0], ready for when the step is taken
-  uint32_t s0 = 0, s1 = 0;        // SPLIT_START: subkey b; WALK: the step's draw key
-  uint32_t d0 = 0, d1 = 0;        // pick_start's draw key
-  int w = 0, L = 0, t = 0, filled = 0, cur = 0, startc = 0, j = 0, steps = 0, attempt = 0;
-  uint32_t bestm = 0;
-  int besti = -1;
+  uint32_t K0 = 0, K1 = 0;    // the board's key (every attempt starts from it)
+  uint32_t h0 = 0, h1k = 0;   // the key the next pass hashes: the wire's key, its subkey, the draw key of the start, the chain key
+  uint32_t c0 = 0, c1 = 0;    // chain key of the walk (committed) = the tuple's key between wires
+  uint32_t s0 = 0, s1 = 0;    // the step's draw key
+  int w = 0, L = 0, t = 0, filled = 0, cur = safe, startc = safe, j = 0, steps = 0, attempt = 0;
+  unsigned long long best = 0;  // PICK: (mantissa << 32) | (0xffff - cell) of the lane's best empty cell, 0 = none
 
   for (;;) {
     __syncwarp();
     if (__all_sync(FULL, phase == SQ_DONE)) break;
-    bool fresh = false;  // (re)start an attempt: empty board, wire 0
-    if (phase == SQ_IDLE) {
-      int nm = 0;
-      if (l == 0) nm = atomicAdd(queue, 1);
-      nm = __shfl_sync(gmask, nm, gbase);
-      if ((long long)nm >= total) {
-        phase = SQ_DONE;
-      } else {
-        m = nm;
-        e = p.list ? (long long)p.list[m] : m;
-        uint32_t k0 = p.keys[2 * e], k1 = p.keys[2 * e + 1], a0, a1, b0, b1;
-        for (int sp = 0; sp < p.extra_split; ++sp) {  // generator / auto-reset: key = split(key)[0]
-          split2(k0, k1, a0, a1, b0, b1);
-          k0 = a0;
-          k1 = a1;
+    if (__any_sync(FULL, phase == SQ_IDLE)) {
+      bool fresh = false;
+      if (phase == SQ_IDLE) {
+        int nm = 0;
+        if (l == 0) nm = atomicAdd(queue, 1);
+        nm = __shfl_sync(gmask, nm, gbase);
+        if ((long long)nm >= total) {
+          phase = SQ_DONE;
+        } else {
+          m = nm;
+          e = p.list ? (long long)p.list[m] : m;
+          uint32_t k0 = p.keys[2 * e], k1 = p.keys[2 * e + 1], a0, a1, b0, b1;
+          for (int sp = 0; sp < p.extra_split; ++sp) {  // generator / auto-reset: key = split(key)[0]
+            split2(k0, k1, a0, a1, b0, b1);
+            k0 = a0;
+            k1 = a1;
+          }
+          K0 = k0;
+          K1 = k1;
+          if (l == 0) {
+            out_gkey[2 * m] = k0;
+            out_gkey[2 * m + 1] = k1;
+          }
+          L = 2 * G - 1;  // SRW:352 max_length_int - i, i = 1
+          attempt = 1;
+          fresh = true;
         }
-        K0 = k0;
-        K1 = k1;
-        if (l == 0) {
-          out_gkey[2 * m] = k0;
-          out_gkey[2 * m + 1] = k1;
-        }
-        L = 2 * G - 1;  // SRW:352 max_length_int - i, i = 1
-        attempt = 1;
-        fresh = true;
       }
-    }
-    if (fresh) {
-      for (int r = 0; r < S; ++r) {
-        const bool rin = r >= 2 && r < G + 2;
-        for (int c = l; c < S; c += SQ_W) board[r * S + c] = (rin && c >= 2 && c < G + 2) ? 0 : 0xFF;
+      if (fresh) {
+        for (int q = l; q < (SB >> 2); q += SQ_W) reinterpret_cast<uint32_t *>(board)[q] = reinterpret_cast<const uint32_t *>(tmpl)[q];
+        w = 0;
+        filled = 0;
+        steps = 0;
+        h0 = K0;
+        h1k = K1;
+        cur = startc = safe;
+        phase = SQ_SPLIT_WIRE;
       }
-      w = 0;
-      filled = 0;
-      steps = 0;
-      key0 = K0;
-      key1 = K1;
-      phase = SQ_SPLIT_WIRE;
-      __syncwarp(gmask);
+      __syncwarp();
     }
 
-    // ---- one threefry block per lane
-    uint32_t hk0 = key0, hk1 = key1, x0 = (uint32_t)(l & 1), x1 = (uint32_t)(l & 1) + 2u;  // split(): blocks (0,2), (1,3)
-    if (phase == SQ_SPLIT_START) {
-      hk0 = s0;
-      hk1 = s1;
-    } else if (phase == SQ_PICK) {
-      const int i = j * SQ_W + l;
-      hk0 = d0;
-      hk1 = d1;
-      x0 = (uint32_t)i;
-      x1 = (i + h1 < n1) ? (uint32_t)(i + h1) : 0u;
-    } else if (phase == SQ_SPLIT_WALK) {
-      hk0 = c0;
-      hk1 = c1;
-    } else if (phase == SQ_WALK) {
-      if (l >= 2 && l < 6) {
-        const int k = l - 2, blk = k < h2 ? k : k - h2;  // word k of random_bits(s, (G+1,)): o0 of block k, or o1 of block k - h2
-        hk0 = s0;
-        hk1 = s1;
-        x0 = (uint32_t)blk;
-        x1 = (blk + h2 < n2) ? (uint32_t)(blk + h2) : 0u;
-      } else {
-        hk0 = cn0;
-        hk1 = cn1;
-      }
-    }
-    __syncwarp();
+    // ---- one threefry block per lane (everything from here to the rare events below is executed by all 32 lanes together:
+    // the phases differ in operands, not in instructions)
+    const bool ph_sw = phase == SQ_SPLIT_WIRE, ph_ss = phase == SQ_SPLIT_START, ph_pk = phase == SQ_PICK, ph_swk = phase == SQ_SPLIT_WALK,
+               ph_wk = phase == SQ_WALK;
+    const int ip = j * SQ_W + l;
+    const bool wdraw = ph_wk && draw_lane;
+    const uint32_t hk0 = wdraw ? s0 : h0, hk1 = wdraw ? s1 : h1k;
+    const uint32_t x0 = ph_pk ? (uint32_t)ip : wdraw ? wx0 : sx0;
+    const uint32_t x1 = ph_pk ? ((ip + h1 < n1) ? (uint32_t)(ip + h1) : 0u) : wdraw ? wx1 : sx1;
     uint32_t o0, o1;
     tf_block(hk0, hk1, x0, x1, o0, o1);
     const uint32_t a0 = __shfl_sync(FULL, o0, gbase), a1 = __shfl_sync(FULL, o0, gbase + 1);
     const uint32_t b0 = __shfl_sync(FULL, o1, gbase), b1 = __shfl_sync(FULL, o1, gbase + 1);
 
-    // ---- what the pass meant for this board
-    bool failed = false, finished = false;
-    if (phase == SQ_SPLIT_WIRE) {
-      s0 = b0;  // SRW:307 subkey; the other half is dropped (:306 takes the key from the tuple)
-      s1 = b1;
-      phase = SQ_SPLIT_START;
-    } else if (phase == SQ_SPLIT_START) {
-      c0 = a0;  // SRW:51 key (the tuple's key from here on), subkey
-      c1 = a1;
-      d0 = b0;
-      d1 = b1;
-      if (filled == cells) {  // SRW:53 can_start False: the attempt cannot succeed
-        failed = true;
-      } else {
-        phase = SQ_PICK;
-        j = 0;
-        bestm = 0;
-        besti = -1;
+    // ---- WALK: SRW:115-140 available_cells of the cell the wire stands on, one direction per draw lane
+    const int cand = cur + dirk;
+    const uint32_t wbase = 3u * w + 1u;
+    const uint32_t vc = board[cand];
+    const int touching = (int)own_wire(board[cand - S], wbase) + (int)own_wire(board[cand + S], wbase) + (int)own_wire(board[cand - 1], wbase) +
+                         (int)own_wire(board[cand + 1], wbase);
+    // :142-156 is_cell_free (the border is never free), :158-191 touches the wire through at most one cell
+    const bool av = wdraw && t < L && vc == 0u && touching <= 1;
+    const unsigned bal = (__ballot_sync(FULL, av) >> (gbase + 2)) & 0xFu;
+    const uint32_t mant = (k_low ? o0 : o1) >> 9;
+    // :211-217 choice over the padded list: largest mantissa among the available entries, lowest index on ties
+    int pick = -1;
+    uint32_t pm = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t mk = __shfl_sync(FULL, mant, gbase + 2 + k);
+      const bool take = ((bal >> k) & 1u) && (pick < 0 || mk > pm);
+      pick = take ? k : pick;
+      pm = take ? mk : pm;
+    }
+    const bool step = ph_wk && bal != 0u;
+    const bool wover = ph_wk && bal == 0u;  // :241 can_step False (or max_length steps done): the walk is over
+    const int nxt = cur + (pick == 0 ? -S : pick == 1 ? S : pick == 2 ? -1 : 1);
+    if (step && l == 0) {
+      board[nxt] = (uint8_t)(3 * w + TARGET);  // :221
+      board[cur] = (uint8_t)(3 * w + PATH);    // :223-227
+    }
+
+    // ---- PICK: the lane's two cells of this pass (words ip and ip + h1 of random_bits(d, (G*G,)))
+    {
+      const int i1 = ip < cells ? ip : cells - 1, i2 = ip + h1 < cells ? ip + h1 : cells - 1;
+      uint32_t q, r;
+      divG.divmod((uint32_t)i1, q, r);
+      const bool f1 = ph_pk && ip < h1 && board[(q + 2) * S + r + 2] == 0;
+      divG.divmod((uint32_t)i2, q, r);
+      const bool f2 = ph_pk && ip < h1 && ip + h1 < n1 && board[(q + 2) * S + r + 2] == 0;
+      const unsigned long long c1k = ((unsigned long long)(o0 >> 9) << 32) | (unsigned)(0xffff - i1);
+      const unsigned long long c2k = ((unsigned long long)(o1 >> 9) << 32) | (unsigned)(0xffff - i2);
+      best = (f1 && c1k > best) ? c1k : best;
+      best = (f2 && c2k > best) ? c2k : best;
+    }
+    const bool pick_end = ph_pk && (j + 1 == P);
+    j += ph_pk ? 1 : 0;
+
+    // ---- key / phase bookkeeping of the common transitions (selects)
+    //   SPLIT_WIRE  -> SPLIT_START: hash the subkey b next                        (SRW:307; the other half is dropped, :306)
+    //   SPLIT_START -> PICK:        chain key c = a, hash the draw key d = b next (:51)
+    //   SPLIT_WALK  -> WALK:        next chain key a is hashed next, s = b draws the first step (:204)
+    //   WALK, step taken:           c <- the key hashed by lanes 0,1 a pass ago; a, b as above for the next step
+    const bool can_start = filled < cells;  // SRW:53
+    {
+      const bool to_b = ph_sw || ph_ss, to_a = ph_swk || step;
+      const uint32_t oh0 = h0, oh1 = h1k;
+      h0 = to_b ? b0 : to_a ? a0 : h0;
+      h1k = to_b ? b1 : to_a ? a1 : h1k;
+      c0 = ph_ss ? a0 : step ? oh0 : c0;
+      c1 = ph_ss ? a1 : step ? oh1 : c1;
+      s0 = to_a ? b0 : s0;
+      s1 = to_a ? b1 : s1;
+      cur = step ? nxt : cur;
+      t += step ? 1 : 0;
+      filled += step ? 1 : 0;
+      steps += step ? 1 : 0;
+      j = ph_ss ? 0 : j;
+      best = ph_ss ? 0ull : best;
+      phase = ph_sw ? SQ_SPLIT_START : ph_ss ? SQ_PICK : ph_swk ? SQ_WALK : phase;
+    }
+
+    // ---- once per wire: the start cell, the end of the walk
+    bool failed = ph_ss && !can_start, finished = false;  // can_start False: the attempt cannot succeed
+    if (__any_sync(FULL, pick_end)) {
+#pragma unroll
+      for (int off = SQ_W / 2; off > 0; off >>= 1) {
+        const unsigned long long ob = __shfl_xor_sync(FULL, best, off);
+        best = ob > best ? ob : best;
       }
-    } else if (phase == SQ_PICK) {
-      const int i = j * SQ_W + l;
-      if (i < h1) {
+      if (pick_end) {
         uint32_t q, r;
-        divG.divmod((uint32_t)i, q, r);
-        if (board[(q + 2) * S + r + 2] == 0) {
-          const uint32_t mm = o0 >> 9;
-          if (besti < 0 || mm > bestm || (mm == bestm && i < besti)) bestm = mm, besti = i;
-        }
-        const int i2 = i + h1;
-        if (i2 < n1) {
-          divG.divmod((uint32_t)i2, q, r);
-          if (board[(q + 2) * S + r + 2] == 0) {
-            const uint32_t mm = o1 >> 9;
-            if (besti < 0 || mm > bestm || (mm == bestm && i2 < besti)) bestm = mm, besti = i2;
-          }
-        }
-      }
-      if (++j == P) {
-        for (int off = SQ_W / 2; off > 0; off >>= 1) {
-          const uint32_t om = __shfl_xor_sync(gmask, bestm, off);
-          const int oi = __shfl_xor_sync(gmask, besti, off);
-          if (oi >= 0 && (besti < 0 || om > bestm || (om == bestm && oi < besti))) bestm = om, besti = oi;
-        }
-        uint32_t q, r;
-        divG.divmod((uint32_t)besti, q, r);  // SRW:66 divmod(flat, rows)
+        divG.divmod(0xffffu - (uint32_t)(best & 0xffffull), q, r);  // SRW:66 divmod(flat, rows)
         startc = (int)((q + 2) * S + r + 2);
         cur = startc;
         if (l == 0) board[startc] = (uint8_t)(3 * w + POSITION);  // SRW:71
         filled++;
         t = 0;
+        h0 = c0;  // SPLIT_WALK hashes the chain key
+        h1k = c1;
         phase = SQ_SPLIT_WALK;
-        __syncwarp(gmask);
       }
-    } else if (phase == SQ_SPLIT_WALK) {
-      cn0 = a0;  // SRW:204 of the first step
-      cn1 = a1;
-      s0 = b0;
-      s1 = b1;
-      phase = SQ_WALK;
-    } else if (phase == SQ_WALK) {
-      // SRW:115-140 available_cells of the cell the wire stands on: [up, down, left, right]
-      bool av = false;
-      uint32_t mant = 0;
-      if (l >= 2 && l < 6 && t < L) {
-        const int k = l - 2;
-        const int cand = cur + (k == 0 ? -S : k == 1 ? S : k == 2 ? -1 : 1);
-        if (board[cand] == 0) {  // :142-156 is_cell_free (the border is never free)
-          const uint32_t base = 3u * w + 1u;  // :158-191 touches the wire through at most one cell
-          const int touching = (int)own_wire(board[cand - S], base) + (int)own_wire(board[cand + S], base) + (int)own_wire(board[cand - 1], base) +
-                               (int)own_wire(board[cand + 1], base);
-          av = touching <= 1;
-        }
-        mant = (k < h2 ? o0 : o1) >> 9;
-      }
-      const unsigned bal = (__ballot_sync(gmask, av) >> (gbase + 2)) & 0xFu;
-      if (bal == 0) {  // :241 can_step False (or max_length steps done): the walk is over
-        if (t == 0) {
-          failed = true;  // :319 the wire did not move
-        } else {
-          if (l == 0) board[startc] = (uint8_t)(3 * w + POSITION);  // :286
-          key0 = c0;
-          key1 = c1;
-          ++w;
-          if (w == N)
-            finished = true;
-          else
-            phase = SQ_SPLIT_WIRE;
-          __syncwarp(gmask);
-        }
+    }
+    if (wover) {
+      if (t == 0) {
+        failed = true;  // :319 the wire did not move
       } else {
-        // :211-217 choice over the padded list: largest mantissa among the available entries, lowest index on ties
-        int pick = -1;
-        uint32_t pm = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint32_t mk = __shfl_sync(gmask, mant, gbase + 2 + k);
-          if (((bal >> k) & 1u) && (pick < 0 || mk > pm)) pick = k, pm = mk;
-        }
-        const int nxt = cur + (pick == 0 ? -S : pick == 1 ? S : pick == 2 ? -1 : 1);
-        if (l == 0) {
-          board[nxt] = (uint8_t)(3 * w + TARGET);  // :221
-          board[cur] = (uint8_t)(3 * w + PATH);    // :223-227
-        }
-        cur = nxt;
-        ++t;
-        ++filled;
-        ++steps;
-        c0 = cn0;  // the step is taken: its split is the one computed a pass ago; this pass computed the next one
-        c1 = cn1;
-        cn0 = a0;
-        cn1 = a1;
-        s0 = b0;
-        s1 = b1;
-        __syncwarp(gmask);
+        if (l == 0) board[startc] = (uint8_t)(3 * w + POSITION);  // :286
+        ++w;
+        h0 = c0;  // the tuple's key: the next wire splits it
+        h1k = c1;
+        cur = startc = safe;
+        if (w == N)
+          finished = true;
+        else
+          phase = SQ_SPLIT_WIRE;
       }
     }
 
-    if (failed) {  // SRW:342-366: the next attempt walks one step less, from the same key
-      --L;
-      ++attempt;
-      if (L <= 0) {  // an attempt with max_length 0 cannot move: SRW:389-391 zero board
-        attempt = 0;
-        steps = 0;
-        finished = true;
-      } else {
-        for (int r = 2; r < G + 2; ++r)
-          for (int c = 2 + l; c < G + 2; c += SQ_W) board[r * S + c] = 0;
-        w = 0;
-        filled = 0;
-        steps = 0;
-        key0 = K0;
-        key1 = K1;
-        phase = SQ_SPLIT_WIRE;
-        __syncwarp(gmask);
+    // ---- rare: a failed attempt, a finished board
+    if (__any_sync(FULL, failed || finished)) {
+      if (failed) {  // SRW:342-366: the next attempt walks one step less, from the same key
+        --L;
+        ++attempt;
+        if (L <= 0) {  // an attempt with max_length 0 cannot move: SRW:389-391 zero board
+          attempt = 0;
+          steps = 0;
+          finished = true;
+        } else {
+          __syncwarp(gmask);
+          for (int q = l; q < (SB >> 2); q += SQ_W) reinterpret_cast<uint32_t *>(board)[q] = reinterpret_cast<const uint32_t *>(tmpl)[q];
+          w = 0;
+          filled = 0;
+          steps = 0;
+          h0 = K0;
+          h1k = K1;
+          cur = startc = safe;
+          phase = SQ_SPLIT_WIRE;
+        }
       }
-    }
-    if (finished) {
-      uint32_t *ob = reinterpret_cast<uint32_t *>(out_board + (size_t)m * CB);
-      for (int qd = l; qd < (CB >> 2); qd += SQ_W) {
-        uint32_t word = 0;
-        if (attempt != 0) {
+      if (finished) {
+        __syncwarp(gmask);
+        uint32_t *ob = reinterpret_cast<uint32_t *>(out_board + (size_t)m * CB);
+        for (int qd = l; qd < (CB >> 2); qd += SQ_W) {
+          uint32_t word = 0;
+          if (attempt != 0) {
 #pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            const int i = 4 * qd + b;
-            if (i < cells) {
-              uint32_t q, r;
-              divG.divmod((uint32_t)i, q, r);
-              word |= (uint32_t)board[(q + 2) * S + r + 2] << (8 * b);
+            for (int b = 0; b < 4; ++b) {
+              const int i = 4 * qd + b;
+              if (i < cells) {
+                uint32_t q, r;
+                divG.divmod((uint32_t)i, q, r);
+                word |= (uint32_t)board[(q + 2) * S + r + 2] << (8 * b);
+              }
             }
           }
+          ob[qd] = word;
         }
-        ob[qd] = word;
+        if (l == 0 && p.stats) {
+          p.stats[2 * e] = attempt;
+          p.stats[2 * e + 1] = steps;
+        }
+        phase = SQ_IDLE;
       }
-      if (l == 0 && p.stats) {
-        p.stats[2 * e] = attempt;
-        p.stats[2 * e + 1] = steps;
-      }
-      phase = SQ_IDLE;
-      __syncwarp(gmask);
     }
   }
 }
@@ -312,10 +304,11 @@ int launch_seqrw(SeqRwParams p, int64_t max_boards, cudaStream_t stream) {
   const int G = p.G, N = p.N;
   if (G < 3) return set_error(RBG_EINVAL, "SequentialRandomWalk: rows=%d (available_cells pads with jnp.full(rows - 3, -1): rows >= 3)", G);
   const int S = G + 4, SB = (S * S + 15) & ~15, CB = (G * G + 15) & ~15;
-  const size_t smem = (size_t)SQ_GROUPS * SB;
+  const size_t smem = (size_t)(SQ_GROUPS + 1) * SB;
   const size_t n = (size_t)max_boards;
   const size_t o_gkey = (n * CB + 255) & ~(size_t)255, o_queue = o_gkey + ((n * 8 + 255) & ~(size_t)255), total = o_queue + 256;
   uint8_t *base = nullptr;
+  keep_pool_cached();
   cudaError_t ce = cudaMallocAsync(reinterpret_cast<void **>(&base), total, stream);
   if (ce != cudaSuccess) return set_cuda_error(ce, "cudaMallocAsync(SequentialRandomWalk scratch)");
   uint32_t *gkey = reinterpret_cast<uint32_t *>(base + o_gkey);

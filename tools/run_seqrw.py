@@ -18,7 +18,7 @@ for G, N, B in shapes:
         out, stats = board.generate_with_stats(keys)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    R = 5
+    R = 20
     e0.record()
     for _ in range(R):
         out = board.generate(keys)
