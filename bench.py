@@ -347,7 +347,7 @@ def _e2e_host(args, rbg, lib, state, B, world, rank, dev):
     def step():
         L.check(lib.rbg_connector_step_host_io(C.byref(s), act.data_ptr(), B, G, N, C.byref(params), C.byref(t), -1))
 
-    for _ in range(12):  # the library tries four host-thread counts on its first eight calls of a batch shape and keeps the fastest
+    for _ in range(24):  # the library tries four host-thread counts on its first sixteen calls of a batch shape and keeps the fastest
         step()
     torch.cuda.synchronize()
     if world > 1:
@@ -377,6 +377,27 @@ def _e2e_host(args, rbg, lib, state, B, world, rank, dev):
     delivered = d2h * k / dt / 1e9
     moved = d2h_moved / dt / 1e9
     packed = host_threads > 0
+    # context: the host half of the packed transport alone (byte codes already in pinned host memory -> the int32 observation
+    # buffer, same thread count, every rank at once): what this host's memory system allows the call to deliver
+    ceiling = None
+    if packed:
+        src8 = torch.empty((B, N, G, G), dtype=torch.uint8).pin_memory()
+        src8.random_(0, 16)
+        n_obs = src8.numel()
+        for _ in range(2):
+            L.check(lib.rbg_host_widen(src8.data_ptr(), hts["obs"].data_ptr(), n_obs))
+        if world > 1:
+            dist.barrier()
+        w0 = time.perf_counter()
+        for _ in range(5):
+            L.check(lib.rbg_host_widen(src8.data_ptr(), hts["obs"].data_ptr(), n_obs))
+        wt = torch.tensor([(time.perf_counter() - w0) / 5], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(wt, op=dist.ReduceOp.MAX)
+        wdt = float(wt.item())
+        ceiling = {"env_steps_per_s": round(B * world / wdt, 1), "int32_gbs_per_rank": round(n_obs * 4 / wdt / 1e9, 1), "frac": round((B * world * k / dt) / (B * world / wdt), 4),
+                   "note": "rbg_host_widen of one step's observation alone on every rank at once (bytes resident in pinned host memory, no GPU work, no bus): the rate at which this host's cores and memory system can write the API's int32 observation; `frac` = e2e value / this"}
+        del src8
     return {"value": round(B * world * k / dt, 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d_moved // k), "d2h_bytes_per_step": int(d2h_moved // k), "steps": k,
             "api": "rbg_connector_step_host_io (pinned host actions in, full TimeStep out to host memory, State device-resident, auto-reset on)",
             "transport": (f"observation codes cross the bus as uint8 and are widened to the API's int32 by {host_threads} host threads inside the call (slices pipelined)"
@@ -385,7 +406,7 @@ def _e2e_host(args, rbg, lib, state, B, world, rank, dev):
             "timer": "host wall clock around synchronous calls, max over ranks",
             "bytes_counted": "by the library where it enqueues the copies (rbg_host_transfer_stats)",
             "d2h_gbs": round(moved, 1), "delivered_gbs": round(delivered, 1), "pinned_d2h_copy_gbs": round(bus, 1),
-            "delivered_vs_plain_int32_copy": round(delivered / bus, 3)}
+            "delivered_vs_plain_int32_copy": round(delivered / bus, 3), "host_widen_ceiling": ceiling}
 
 
 def _secondary(args, rbg, dd, peak, rank, world, sm_mhz):

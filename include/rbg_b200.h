@@ -297,6 +297,10 @@ int rbg_connector_step_host_io(const rbg_state *state, const int32_t *action,
                                int64_t B, int G, int N,
                                const rbg_env_params *params,
                                const rbg_timestep *ts, int device);
+/* The host half of that transport on its own: n byte codes in HOST memory -> int32 in HOST memory on the library's
+ * thread pool (synchronous).  For consumers that keep observations as bytes and widen on demand, and for bench.py:
+ * its rate is the ceiling of what rbg_connector_step_host_io can deliver on a host (no GPU work, no bus). */
+int rbg_host_widen(const uint8_t *src, int32_t *dst, int64_t n);
 /* Bytes the _host_io calls moved over the bus since the last reset (counted where the copies are enqueued) and the
  * number of host threads that widen the observation (0 with RBG_HOST_IO_WIDE=1); any pointer may be NULL. */
 int rbg_host_transfer_stats(int64_t *h2d_bytes, int64_t *d2h_bytes, int *host_threads, int reset);

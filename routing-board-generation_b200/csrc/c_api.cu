@@ -541,7 +541,7 @@ struct HostCtx {
   uint8_t *stage8 = nullptr;  // pinned host staging of the byte observation (rbg_connector_step_host_io)
   size_t stage8_bytes = 0;
   // thread-count tuning of the packed transport: the first calls of a batch shape try 1/4, 1/2, 3/4 and all of the
-  // pool's workers (two calls each, the second one timed) and the fastest count stays
+  // pool's workers (four calls each, the last three timed; more threads must win by 3 %) and the fastest count stays
   int64_t tune_B = -1;
   int tune_call = 0, tune_best = 0;
   double tune_best_s = 0.0;
@@ -1384,13 +1384,13 @@ int rbg_connector_step_host_io(const rbg_state *state, const int32_t *action, in
       g_hc->tune_best = 0;
       g_hc->tune_best_s = 0.0;
     }
-    if (g_hc->tune_call < 8) {
-      const int cand = g_hc->tune_call / 2;  // 0..3 -> 1/4, 1/2, 3/4, 1 of the workers
+    if (g_hc->tune_call < 16) {
+      const int cand = g_hc->tune_call / 4;  // 0..3 -> 1/4, 1/2, 3/4, 1 of the workers; four calls each, the last three timed
       int n = host_pool_max_threads() * (cand + 1) / 4;
       host_pool_set_threads(n < 1 ? 1 : n);
-      if (g_hc->tune_call & 1) tune_slot = cand;
+      if (g_hc->tune_call & 3) tune_slot = cand;
       g_hc->tune_call++;
-    } else if (g_hc->tune_call == 8) {
+    } else if (g_hc->tune_call == 16) {
       host_pool_set_threads(g_hc->tune_best ? g_hc->tune_best : (host_pool_max_threads() + 1) / 2);
       g_hc->tune_call++;
     }
@@ -1485,12 +1485,23 @@ int rbg_connector_step_host_io(const rbg_state *state, const int32_t *action, in
   if (packed) host_pool_wait();
   if (tune_slot >= 0 && rc_sync == RBG_OK) {
     const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_call0).count();
-    if (g_hc->tune_best == 0 || dt < g_hc->tune_best_s) {
-      g_hc->tune_best = host_pool_threads();
+    // the fastest call decides; a larger thread count must beat a smaller one by 3 % to replace it (one sample more or
+    // less of noise must not hand the memory system to twice the threads)
+    const int nthr = host_pool_threads();
+    if (g_hc->tune_best == 0 || (nthr == g_hc->tune_best ? dt < g_hc->tune_best_s : dt < 0.97 * g_hc->tune_best_s)) {
+      g_hc->tune_best = nthr;
       g_hc->tune_best_s = dt;
     }
   }
   return rc_sync;
+}
+
+int rbg_host_widen(const uint8_t *src, int32_t *dst, int64_t n) {
+  if (n < 0 || (n > 0 && (!src || !dst))) return set_error(RBG_EINVAL, "rbg_host_widen: n=%lld, src=%p, dst=%p", (long long)n, (const void *)src, (void *)dst);
+  if (n == 0) return RBG_OK;
+  host_pool_widen(src, dst, (size_t)n);
+  host_pool_wait();
+  return RBG_OK;
 }
 
 int rbg_host_transfer_stats(int64_t *h2d_bytes, int64_t *d2h_bytes, int *host_threads, int reset) {

@@ -123,3 +123,24 @@ def test_bench_product_arm_refuses_to_run_without_a_gpu():
         pytest.skip("a CUDA device is present")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=300)
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_host_widen_matches_numpy():
+    """rbg_host_widen (the host half of the byte transport of rbg_connector_step_host_io): bytes -> int32 on the
+    library's thread pool; needs no GPU.  Ragged sizes and unaligned ends."""
+    import ctypes as C
+
+    import numpy as np
+
+    import routing_board_generation_b200 as pkg
+
+    lib = pkg._lib.load()
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 31, 32, 33, 1000, 65536 * 5 + 7, 1 << 22):
+        src = rng.integers(0, 97, size=n + 3, dtype=np.uint8)
+        dst = np.full(n + 8, -1, np.int32)
+        for off in (0, 1, 3):  # misaligned source
+            assert lib.rbg_host_widen(C.c_void_p(src.ctypes.data + off), C.c_void_p(dst.ctypes.data), n - off if n >= off else 0) == 0
+            m = n - off if n >= off else 0
+            assert np.array_equal(dst[:m], src[off:off + m].astype(np.int32)) and (dst[m:m + 8 - 0][-1] == -1)
+    assert lib.rbg_host_widen(None, None, 5) == -1
