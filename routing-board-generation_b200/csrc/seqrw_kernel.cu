@@ -35,7 +35,9 @@
 // over) and the once-per-board events (new board, failed attempt, output) branch, behind warp votes.  The first
 // version branched on the phase and spent 70 % of its instructions in bookkeeping executed one group at a time
 // (profiles/r02g_seqrw_full.csv: 13.6 k warp-instructions per 10x10/5 board).
-// A failed attempt is abandoned at once (its board can only be discarded, :355-366).  Groups take boards from a
+// A failed attempt is abandoned at once (its board can only be discarded, :355-366), and the attempts that would repeat
+// it exactly are skipped: all attempts start from the same key, so an attempt differs from the previous one only from
+// the first wire whose walk the smaller max_length truncates.  Groups take boards from a
 // global queue.  The finished board goes to a byte scratch and through se_finish_kernel's outputs (board /
 // first POSITION and TARGET cell per wire / State + observation), which SeedExtension shares.
 #include "connector_device.cuh"
@@ -86,6 +88,7 @@ __global__ void __launch_bounds__(SQ_THREADS) seqrw_walk_kernel(const SeqRwParam
   uint32_t c0 = 0, c1 = 0;    // chain key of the walk (committed) = the tuple's key between wires
   uint32_t s0 = 0, s1 = 0;    // the step's draw key
   int w = 0, L = 0, t = 0, filled = 0, cur = safe, startc = safe, j = 0, steps = 0, attempt = 0;
+  int max_t = 0;  // longest walk among the wires placed so far in this attempt
   unsigned long long best = 0;  // PICK: (mantissa << 32) | (0xffff - cell) of the lane's best empty cell, 0 = none
 
   for (;;) {
@@ -124,6 +127,7 @@ __global__ void __launch_bounds__(SQ_THREADS) seqrw_walk_kernel(const SeqRwParam
         w = 0;
         filled = 0;
         steps = 0;
+        max_t = 0;
         h0 = K0;
         h1k = K1;
         cur = startc = safe;
@@ -240,6 +244,7 @@ __global__ void __launch_bounds__(SQ_THREADS) seqrw_walk_kernel(const SeqRwParam
         failed = true;  // :319 the wire did not move
       } else {
         if (l == 0) board[startc] = (uint8_t)(3 * w + POSITION);  // :286
+        max_t = t > max_t ? t : max_t;
         ++w;
         h0 = c0;  // the tuple's key: the next wire splits it
         h1k = c1;
@@ -253,9 +258,14 @@ __global__ void __launch_bounds__(SQ_THREADS) seqrw_walk_kernel(const SeqRwParam
 
     // ---- rare: a failed attempt, a finished board
     if (__any_sync(FULL, failed || finished)) {
-      if (failed) {  // SRW:342-366: the next attempt walks one step less, from the same key
-        --L;
-        ++attempt;
+      if (failed) {
+        // SRW:342-366: the next attempt walks one step less, from the SAME key.  Every attempt whose max_length is still
+        // >= the longest walk of the wires placed before the failing one repeats this attempt exactly (same keys, same
+        // board, same steps: max_length only ever truncates a walk) and fails at the same wire, so those attempts are
+        // skipped: the next one that can differ has max_length = (longest walk so far) - 1.  No wire placed: nothing
+        // can change, every attempt fails.
+        L = max_t - 1;
+        attempt = 2 * G - L;  // max_length = rows + cols - i
         if (L <= 0) {  // an attempt with max_length 0 cannot move: SRW:389-391 zero board
           attempt = 0;
           steps = 0;
@@ -266,6 +276,7 @@ __global__ void __launch_bounds__(SQ_THREADS) seqrw_walk_kernel(const SeqRwParam
           w = 0;
           filled = 0;
           steps = 0;
+          max_t = 0;
           h0 = K0;
           h1k = K1;
           cur = startc = safe;
