@@ -558,6 +558,14 @@ static bool host_io_wide() {  // RBG_HOST_IO_WIDE=1: the observation crosses the
   return v == 1;
 }
 static HostCtx g_host[kMaxDevices];
+static bool host_io_blocking_sync() {  // RBG_HOST_BLOCKING_SYNC=1: the calling thread sleeps on the copy events instead of spinning
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("RBG_HOST_BLOCKING_SYNC");
+    v = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  return v == 1;
+}
 static thread_local HostCtx *g_hc = &g_host[0];  // the device of the _host call in progress (set by use_device)
 #define g_scratch (g_hc->scratch)
 #define g_streams (g_hc->streams)
@@ -1384,13 +1392,17 @@ int rbg_connector_step_host_io(const rbg_state *state, const int32_t *action, in
       g_hc->tune_best = 0;
       g_hc->tune_best_s = 0.0;
     }
-    if (g_hc->tune_call < 16) {
-      const int cand = g_hc->tune_call / 4;  // 0..3 -> 1/4, 1/2, 3/4, 1 of the workers; four calls each, the last three timed
+    // candidates: 1/4, 1/2, 3/4 of the workers, and all of them only when the pool is small (several ranks share the host):
+    // with one rank per host the calling thread, which polls the copy events, needs a core of its own (16 of 16: 25-44 M
+    // env-steps/s against 61-66 M for 8 on 16-core boxes)
+    const int ncand = host_pool_max_threads() >= 8 ? 3 : 4;
+    if (g_hc->tune_call < 4 * ncand) {
+      const int cand = g_hc->tune_call / 4;  // four calls each, the last three timed
       int n = host_pool_max_threads() * (cand + 1) / 4;
       host_pool_set_threads(n < 1 ? 1 : n);
       if (g_hc->tune_call & 3) tune_slot = cand;
       g_hc->tune_call++;
-    } else if (g_hc->tune_call == 16) {
+    } else if (g_hc->tune_call == 4 * ncand) {
       host_pool_set_threads(g_hc->tune_best ? g_hc->tune_best : (host_pool_max_threads() + 1) / 2);
       g_hc->tune_call++;
     }
@@ -1458,7 +1470,8 @@ int rbg_connector_step_host_io(const rbg_state *state, const int32_t *action, in
     if ((e = cudaStreamWaitEvent(xs, slice_ev[si], 0)) != cudaSuccess) return set_cuda_error(e, "cudaStreamWaitEvent");
     if (packed) {
       RBG_CPY(g_hc->stage8 + (size_t)off * per_env, obs8 + (size_t)off * per_env, (size_t)n * per_env, cudaMemcpyDeviceToHost, xs);
-      if (!copy_ev[si] && (e = cudaEventCreateWithFlags(&copy_ev[si], cudaEventDisableTiming)) != cudaSuccess) return set_cuda_error(e, "cudaEventCreate");
+      if (!copy_ev[si] && (e = cudaEventCreateWithFlags(&copy_ev[si], cudaEventDisableTiming | (host_io_blocking_sync() ? cudaEventBlockingSync : 0))) != cudaSuccess)
+        return set_cuda_error(e, "cudaEventCreate");
       if ((e = cudaEventRecord(copy_ev[si], xs)) != cudaSuccess) return set_cuda_error(e, "cudaEventRecord(copy)");
     } else if ((rc = copy_timestep(ts, &dt, off, n, G, N, cudaMemcpyDeviceToHost, off, xs, 1))) {
       return rc;

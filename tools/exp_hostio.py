@@ -19,7 +19,7 @@ s = L.rbg_state(st.grid.data_ptr(), st.step_count.data_ptr(), a.id.data_ptr(), a
 t = L.rbg_timestep(*(h[k].data_ptr() for k in ("obs", "mask", "sc", "reward", "discount", "step_type", "nc", "rc", "tpl")))
 params = L.rbg_env_params(50, -0.03, 0.1, 0)
 step = lambda: L.check(lib.rbg_connector_step_host_io(C.byref(s), act.data_ptr(), B, G, N, C.byref(params), C.byref(t), -1))
-for _ in range(12): step()
+for _ in range(24): step()
 best = 1e9
 for rep in range(3):
     t0 = time.perf_counter()
@@ -27,7 +27,11 @@ for rep in range(3):
     best = min(best, (time.perf_counter() - t0) / 20)
 print("%%.3f ms/step  %%.1f M env-steps/s  threads %%d" %% (best * 1e3, B / best / 1e6, L.host_transfer_stats()[2]))
 ''' % root
-settings = [{}, {}, {"RBG_HOST_THREADS": "8"}, {"RBG_HOST_THREADS": "4"}, {"RBG_HOST_THREADS": "12"}]
+settings = [{}, {"RBG_HOST_THREADS": "8"}, {"RBG_HOST_THREADS": "10"}, {"RBG_HOST_THREADS": "12"}, {"RBG_HOST_THREADS": "16"},
+            {"RBG_HOST_BLOCKING_SYNC": "1"}, {"RBG_HOST_BLOCKING_SYNC": "1", "RBG_HOST_THREADS": "8"}, {"RBG_HOST_BLOCKING_SYNC": "1", "RBG_HOST_THREADS": "12"},
+            {"RBG_HOST_BLOCKING_SYNC": "1", "RBG_HOST_THREADS": "16"}]
+if len(sys.argv) > 1:
+    settings = [dict(kv.split("=") for kv in a.split(",") if kv) for a in sys.argv[1:]]
 for env in settings:
     r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
     print(env, r.stdout.strip() or r.stderr[-600:], flush=True)
