@@ -545,6 +545,10 @@ struct HostCtx {
   int64_t tune_B = -1;
   int tune_call = 0, tune_best = 0;
   double tune_best_s = 0.0;
+  // mixed transport: how many of the step's slices cross the bus as int32 straight into the caller's (pinned) buffer
+  // instead of as bytes for the host threads to widen; moved by one slice per call towards the balance of bus and host
+  int wide_slices = 0;
+  int64_t wide_B = -1;
   ScratchSig sig;
 };
 // what the _host variants moved over the bus since the last reset (rbg_host_transfer_stats)
@@ -558,6 +562,27 @@ static bool host_io_wide() {  // RBG_HOST_IO_WIDE=1: the observation crosses the
   return v == 1;
 }
 static HostCtx g_host[kMaxDevices];
+// RBG_HOST_IO_SPLIT=k: k of a step's slices cross the bus as int32 straight into the caller's (pinned) buffer instead of as
+// bytes for the host threads; RBG_HOST_IO_SPLIT=auto: adaptive (one slice per call towards whichever of bus and host
+// finished last).  Default: none.  Measured (profiles/r02g_hostio_split.log): on the boxes of this pool the bus (38 MB of
+// bytes per step land after 0.87 ms) and 8 widening threads (1.0 ms) are already balanced, so moving slices to the bus gains
+// nothing (1 / 3 of 16 slices at the end of the step: 44.5 / 42.2 against 43.5 M env-steps/s on the same box) and a wide
+// slice at the START of the step costs 0.7 ms.
+static int host_io_split_env() {  // -2 off, -1 auto, >= 0 fixed
+  static int v = -3;
+  if (v == -3) {
+    const char *e = getenv("RBG_HOST_IO_SPLIT");
+    v = !e ? -2 : (strcmp(e, "auto") == 0 ? -1 : atoi(e));
+    if (v < -2) v = -2;
+  }
+  return v;
+}
+static bool host_io_fixed_split() { return host_io_split_env() >= 0; }
+static int host_io_split_init(int nslices) {
+  const int v = host_io_split_env();
+  if (v >= 0) return v > nslices ? nslices : v;
+  return v == -1 ? nslices / 8 : 0;
+}
 static bool host_io_blocking_sync() {  // RBG_HOST_BLOCKING_SYNC=1: the calling thread sleeps on the copy events instead of spinning
   static int v = -1;
   if (v < 0) {
@@ -1384,6 +1409,7 @@ int rbg_connector_step_host_io(const rbg_state *state, const int32_t *action, in
   const bool packed = !host_io_wide();
   const auto t_call0 = std::chrono::steady_clock::now();
   int tune_slot = -1;  // which candidate this call measures (odd calls of the tuning phase)
+  bool in_tuning = false;  // the thread count is being tried out: the bus / host split stays put meanwhile
   if (packed && !host_pool_fixed() && host_pool_max_threads() >= 4) {
     const int64_t key = B * 4096 + (int64_t)G * 64 + N;
     if (g_hc->tune_B != key) {
@@ -1392,13 +1418,16 @@ int rbg_connector_step_host_io(const rbg_state *state, const int32_t *action, in
       g_hc->tune_best = 0;
       g_hc->tune_best_s = 0.0;
     }
-    // candidates: 1/4, 1/2, 3/4 of the workers, and all of them only when the pool is small (several ranks share the host):
-    // with one rank per host the calling thread, which polls the copy events, needs a core of its own (16 of 16: 25-44 M
-    // env-steps/s against 61-66 M for 8 on 16-core boxes)
-    const int ncand = host_pool_max_threads() >= 8 ? 3 : 4;
+    // candidates: a big pool (one rank per host) tries 1/4, 3/8 and 1/2 of the cores: beyond half of them the calling thread
+    // (which polls the copy events), the driver's threads and whatever else the process runs collide with the workers and
+    // the step becomes bimodal (16-core boxes: 8 threads 61-66 M env-steps/s; 12 threads 35-58 M; 16 threads 25-44 M).  A
+    // small pool (several ranks share the host) tries 1/4, 1/2, 3/4 and all of its few workers.
+    const bool big = host_pool_max_threads() >= 8;
+    const int ncand = big ? 3 : 4;
     if (g_hc->tune_call < 4 * ncand) {
+      in_tuning = true;
       const int cand = g_hc->tune_call / 4;  // four calls each, the last three timed
-      int n = host_pool_max_threads() * (cand + 1) / 4;
+      int n = big ? host_pool_max_threads() * (cand + 2) / 8 : host_pool_max_threads() * (cand + 1) / 4;
       host_pool_set_threads(n < 1 ? 1 : n);
       if (g_hc->tune_call & 3) tune_slot = cand;
       g_hc->tune_call++;
@@ -1457,18 +1486,43 @@ int rbg_connector_step_host_io(const rbg_state *state, const int32_t *action, in
   RBG_CPY(da, action, (size_t)B * N * 4, cudaMemcpyHostToDevice, cs);
   g_h2d_bytes.fetch_add((long long)B * N * 4, std::memory_order_relaxed);
   const size_t per_env = (size_t)N * G * G;
+  // Mixed transport (off by default, see host_io_split_env): `nwide` of the step's slices go over the bus as int32, the
+  // rest as bytes.
+  bool mix = false;
+  if (packed && nslices > 1 && host_io_split_env() == -1) {
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, ts->obs_grid) == cudaSuccess && pa.type == cudaMemoryTypeHost) mix = true;
+    (void)cudaGetLastError();
+  }
+  const int64_t mix_key = B * 4096 + (int64_t)G * 64 + N;
+  if (g_hc->wide_B != mix_key) {
+    g_hc->wide_B = mix_key;
+    g_hc->wide_slices = host_io_split_init((int)nslices);
+  }
+  const int nwide = !packed ? (int)nslices : (mix || host_io_fixed_split()) ? (g_hc->wide_slices > (int)nslices ? (int)nslices : g_hc->wide_slices) : 0;
+  // evenly spread, the first slice first and never the last one (its widening is the host's tail either way)
+  static const int split_pos = env_int("RBG_HOST_IO_SPLIT_POS");  // experiment: 1 = evenly spread from the first slice on, 2 = the first ones
+  auto slice_is_wide = [&](int i) {
+    if (!packed) return true;
+    if (split_pos == 1) return ((int64_t)i * nwide) % nslices < nwide;
+    if (split_pos == 2) return i < nwide;
+    return i >= (int)nslices - nwide;  // the last ones: the host threads get their bytes first
+  };
+  size_t packed_cells = 0, wide_cells = 0;
   int si = 0;
   for (int64_t off = 0; off < B; off += sl, ++si) {
     const int64_t n = (B - off) < sl ? (B - off) : sl;
+    const bool wide = slice_is_wide(si);
     rbg_state dss = state_at(*state, off, G, N);
     rbg_timestep dts = timestep_at(dt, off, G, N);
     if ((rc = rbg_connector_step(&dss, &dss, da + off * N, n, G, N, params, &dts, ws + (size_t)si * ws_bytes, cs))) return rc;
-    if (packed && (rc = launch_narrow_codes(dts.obs_grid, obs8 + (size_t)off * per_env, (int64_t)((size_t)n * per_env), cs))) return rc;
+    if (!wide && (rc = launch_narrow_codes(dts.obs_grid, obs8 + (size_t)off * per_env, (int64_t)((size_t)n * per_env), cs))) return rc;
     if (!slice_ev[si] && (e = cudaEventCreateWithFlags(&slice_ev[si], cudaEventDisableTiming)) != cudaSuccess) return set_cuda_error(e, "cudaEventCreate");
     if ((e = cudaEventRecord(slice_ev[si], cs)) != cudaSuccess) return set_cuda_error(e, "cudaEventRecord");
     cudaStream_t xs = g_streams[1 + (si & 1)];
     if ((e = cudaStreamWaitEvent(xs, slice_ev[si], 0)) != cudaSuccess) return set_cuda_error(e, "cudaStreamWaitEvent");
-    if (packed) {
+    (wide ? wide_cells : packed_cells) += (size_t)n * per_env;
+    if (!wide) {
       RBG_CPY(g_hc->stage8 + (size_t)off * per_env, obs8 + (size_t)off * per_env, (size_t)n * per_env, cudaMemcpyDeviceToHost, xs);
       if (!copy_ev[si] && (e = cudaEventCreateWithFlags(&copy_ev[si], cudaEventDisableTiming | (host_io_blocking_sync() ? cudaEventBlockingSync : 0))) != cudaSuccess)
         return set_cuda_error(e, "cudaEventCreate");
@@ -1478,11 +1532,13 @@ int rbg_connector_step_host_io(const rbg_state *state, const int32_t *action, in
     }
   }
   if ((rc = copy_timestep(ts, &dt, 0, B, G, N, cudaMemcpyDeviceToHost, 0, cs, 2))) return rc;
-  g_d2h_bytes.fetch_add((long long)(obs_n * (packed ? 1 : 4)) + (long long)B * (N * 5 + 4 + N * 8 + 1 + 12), std::memory_order_relaxed);
+  const auto t_issued = std::chrono::steady_clock::now();
+  g_d2h_bytes.fetch_add((long long)(packed_cells + 4 * wide_cells) + (long long)B * (N * 5 + 4 + N * 8 + 1 + 12), std::memory_order_relaxed);
   if (packed) {
     si = 0;
     for (int64_t off = 0; off < B; off += sl, ++si) {
       const int64_t n = (B - off) < sl ? (B - off) : sl;
+      if (slice_is_wide(si)) continue;
       if ((e = cudaEventSynchronize(copy_ev[si])) != cudaSuccess) {
         host_pool_wait();
         return set_cuda_error(e, "cudaEventSynchronize(copy)");
@@ -1495,7 +1551,41 @@ int rbg_connector_step_host_io(const rbg_state *state, const int32_t *action, in
     e = cudaStreamSynchronize(g_streams[i]);
     if (e != cudaSuccess) rc_sync = set_cuda_error(e, "cudaStreamSynchronize");
   }
+  const auto t_bus_done = std::chrono::steady_clock::now();
   if (packed) host_pool_wait();
+  {  // RBG_HOST_IO_TRACE=1: where a call's time goes (issue of the launches and copies / until the last copy landed / until
+     // the last slice is widened), averaged over 32 calls, on stderr
+    static const int trace = env_int("RBG_HOST_IO_TRACE");
+    if (trace) {
+      static double acc[3] = {0, 0, 0};
+      static int ncalls = 0;
+      const auto t_now = std::chrono::steady_clock::now();
+      acc[0] += std::chrono::duration<double>(t_issued - t_call0).count();
+      acc[1] += std::chrono::duration<double>(t_bus_done - t_call0).count();
+      acc[2] += std::chrono::duration<double>(t_now - t_call0).count();
+      if (++ncalls == 32) {
+        fprintf(stderr, "[rbg host_io] threads %d wide slices %d/%d: issued %.3f ms, copies landed %.3f ms, widened %.3f ms\n", host_pool_threads(), nwide, (int)nslices,
+                acc[0] / 32 * 1e3, acc[1] / 32 * 1e3, acc[2] / 32 * 1e3);
+        acc[0] = acc[1] = acc[2] = 0;
+        ncalls = 0;
+      }
+    }
+  }
+  if (mix && rc_sync == RBG_OK) {
+    // who finished last?  The host threads still busy well after the last copy landed: the host is the bound, one more
+    // slice goes over the bus as int32.  The pool idle when the copies ended (their last slice is widened within a
+    // twentieth of the call): the bus is the bound, one slice fewer.
+    const auto t_end = std::chrono::steady_clock::now();
+    const double total = std::chrono::duration<double>(t_end - t_call0).count();
+    const double host_tail = std::chrono::duration<double>(t_end - t_bus_done).count();
+    // (the widening of the last byte slice always trails the copies by about 1 / nslices of the call: the dead band)
+    if (!in_tuning) {
+      if (host_tail > 1.6 / (double)nslices * total && g_hc->wide_slices < (int)nslices - 1)
+        g_hc->wide_slices++;
+      else if (host_tail < 0.6 / (double)nslices * total && g_hc->wide_slices > 0)
+        g_hc->wide_slices--;
+    }
+  }
   if (tune_slot >= 0 && rc_sync == RBG_OK) {
     const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_call0).count();
     // the fastest call decides; a larger thread count must beat a smaller one by 3 % to replace it (one sample more or

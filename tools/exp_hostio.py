@@ -19,13 +19,16 @@ s = L.rbg_state(st.grid.data_ptr(), st.step_count.data_ptr(), a.id.data_ptr(), a
 t = L.rbg_timestep(*(h[k].data_ptr() for k in ("obs", "mask", "sc", "reward", "discount", "step_type", "nc", "rc", "tpl")))
 params = L.rbg_env_params(50, -0.03, 0.1, 0)
 step = lambda: L.check(lib.rbg_connector_step_host_io(C.byref(s), act.data_ptr(), B, G, N, C.byref(params), C.byref(t), -1))
-for _ in range(24): step()
+for _ in range(32): step()
 best = 1e9
 for rep in range(3):
     t0 = time.perf_counter()
     for _ in range(20): step()
     best = min(best, (time.perf_counter() - t0) / 20)
-print("%%.3f ms/step  %%.1f M env-steps/s  threads %%d" %% (best * 1e3, B / best / 1e6, L.host_transfer_stats()[2]))
+L.host_transfer_stats(reset=True)
+for _ in range(10): step()
+st_ = L.host_transfer_stats()
+print("%%.3f ms/step  %%.1f M env-steps/s  threads %%d  d2h MB/step %%.1f" %% (best * 1e3, B / best / 1e6, st_[2], st_[1] / 10 / 1e6))
 ''' % root
 settings = [{}, {"RBG_HOST_THREADS": "8"}, {"RBG_HOST_THREADS": "10"}, {"RBG_HOST_THREADS": "12"}, {"RBG_HOST_THREADS": "16"},
             {"RBG_HOST_BLOCKING_SYNC": "1"}, {"RBG_HOST_BLOCKING_SYNC": "1", "RBG_HOST_THREADS": "8"}, {"RBG_HOST_BLOCKING_SYNC": "1", "RBG_HOST_THREADS": "12"},
@@ -35,3 +38,5 @@ if len(sys.argv) > 1:
 for env in settings:
     r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
     print(env, r.stdout.strip() or r.stderr[-600:], flush=True)
+    if 'RBG_HOST_IO_TRACE' in env:
+        print('   ' + '\n   '.join([l for l in r.stderr.splitlines() if 'host_io' in l][-3:]), flush=True)
