@@ -326,6 +326,7 @@ static int connector_step_impl(const rbg_state *in, const rbg_state *out, const 
                                const rbg_timestep *ts, void *workspace, cudaStream_t stream) {
   int rc;
   if ((rc = check_dims(B, G, N, 1))) return rc;
+  if (B == 0) return RBG_OK;  // an empty batch has no buffers to check
   if ((rc = check_state(in, "state_in", G))) return rc;
   if ((rc = check_state(out, "state_out", G))) return rc;
   if ((rc = check_timestep(ts, G))) return rc;
@@ -808,9 +809,9 @@ int rbg_prw_generate(const uint32_t *keys, int64_t B, int G, int N, int32_t *hea
 int rbg_generator_state(int kind, const uint32_t *keys, int64_t B, int G, int N, const rbg_state *out, void *stream) {
   int rc;
   if ((rc = check_dims(B, G, N, kind == RBG_GEN_UNIFORM ? 2 : 1))) return rc;
+  if (B == 0) return RBG_OK;  // an empty batch has no buffers to check
   if (!keys) return set_error(RBG_EINVAL, "keys is NULL");
   if ((rc = check_state(out, "state", G))) return rc;
-  if (B == 0) return RBG_OK;
   return generator_state_impl(kind, keys, B, G, N, out, nullptr, 0, nullptr, nullptr, (cudaStream_t)stream);
 }
 
@@ -829,9 +830,9 @@ int rbg_seedext_solved(const uint32_t *keys, int64_t B, int G, int N, float rand
                        int iterations, int64_t extension_steps, int32_t *solved, void *stream) {
   int rc;
   if ((rc = check_dims(B, G, N, 1))) return rc;
+  if (B == 0) return RBG_OK;  // an empty batch has no buffers to check
   if (!keys || !solved) return set_error(RBG_EINVAL, "rbg_seedext_solved: NULL pointer");
   if (!aligned16(solved)) return set_error(RBG_EALIGN, "rbg_seedext_solved: solved not 16-byte aligned");
-  if (B == 0) return RBG_OK;
   SeedExtParams p;
   memset(&p, 0, sizeof(p));
   p.keys = keys;
@@ -851,8 +852,8 @@ int rbg_seedext_starts_ends(const uint32_t *keys, int64_t B, int G, int N, float
                             int iterations, int64_t extension_steps, int32_t *starts, int32_t *ends, void *stream) {
   int rc;
   if ((rc = check_dims(B, G, N, 1))) return rc;
+  if (B == 0) return RBG_OK;  // an empty batch has no buffers to check
   if (!keys || !starts || !ends) return set_error(RBG_EINVAL, "rbg_seedext_starts_ends: NULL pointer");
-  if (B == 0) return RBG_OK;
   SeedExtParams p;
   memset(&p, 0, sizeof(p));
   p.keys = keys;
@@ -872,9 +873,10 @@ int rbg_seedext_starts_ends(const uint32_t *keys, int64_t B, int G, int N, float
 int rbg_seqrw_generate(const uint32_t *keys, int64_t B, int G, int N, void *board, int as_float32, int32_t *stats, void *stream) {
   int rc;
   if ((rc = check_dims(B, G, N, 0))) return rc;
+  if (B == 0) return RBG_OK;
+  if (G < 3) return set_error(RBG_EINVAL, "SequentialRandomWalk: rows=%d (available_cells pads with jnp.full(rows - 3, -1): rows >= 3)", G);
   if (!keys || !board) return set_error(RBG_EINVAL, "rbg_seqrw_generate: NULL argument");
   if (!aligned16(board)) return set_error(RBG_EALIGN, "board not 16-byte aligned");
-  if (B == 0) return RBG_OK;
   SeqRwParams p;
   memset(&p, 0, sizeof(p));
   p.keys = keys;
@@ -891,8 +893,8 @@ int rbg_seqrw_generate(const uint32_t *keys, int64_t B, int G, int N, void *boar
 int rbg_seqrw_starts_ends(const uint32_t *keys, int64_t B, int G, int N, int32_t *starts, int32_t *ends, void *stream) {
   int rc;
   if ((rc = check_dims(B, G, N, 0))) return rc;
-  if (!keys || !starts || !ends) return set_error(RBG_EINVAL, "rbg_seqrw_starts_ends: NULL argument");
   if (B == 0) return RBG_OK;
+  if (!keys || !starts || !ends) return set_error(RBG_EINVAL, "rbg_seqrw_starts_ends: NULL argument");
   SeqRwParams p;
   memset(&p, 0, sizeof(p));
   p.keys = keys;
@@ -908,9 +910,9 @@ int rbg_seqrw_starts_ends(const uint32_t *keys, int64_t B, int G, int N, int32_t
 int rbg_connector_observe(const rbg_state *state, int64_t B, int G, int N, const rbg_timestep *ts, void *stream) {
   int rc;
   if ((rc = check_dims(B, G, N, 1))) return rc;
+  if (B == 0) return RBG_OK;  // an empty batch has no buffers to check
   if ((rc = check_state(state, "state", G))) return rc;
   if ((rc = check_timestep(ts, G))) return rc;
-  if (B == 0) return RBG_OK;
   EnvParams p;
   memset(&p, 0, sizeof(p));
   p.in = *state;
@@ -1160,6 +1162,7 @@ int rbg_connector_rollout_random(const rbg_state *state, int32_t *action_out, in
   int rc;
   if (T < 0) return set_error(RBG_EINVAL, "rollout length T=%lld", (long long)T);
   if ((rc = check_dims(B, G, N, 1))) return rc;
+  if (B == 0 || T == 0) return RBG_OK;  // an empty batch has no buffers to check
   if ((rc = check_state(state, "state", G))) return rc;
   if ((rc = check_timestep(ts, G))) return rc;
   if (!params) return set_error(RBG_EINVAL, "params is NULL");
@@ -1209,6 +1212,7 @@ int rbg_connector_rollout_random(const rbg_state *state, int32_t *action_out, in
 int rbg_random_actions(const rbg_state *state, int64_t B, int G, int N, int32_t *action, void *stream) {
   int rc;
   if ((rc = check_dims(B, G, N, 1))) return rc;
+  if (B == 0) return RBG_OK;  // an empty batch has no buffers to check
   if ((rc = check_state(state, "state", G))) return rc;
   if (!action) return set_error(RBG_EINVAL, "action is NULL");
   return launch_random_actions(*state, B, G, N, action, (cudaStream_t)stream);
@@ -1217,6 +1221,7 @@ int rbg_random_actions(const rbg_state *state, int64_t B, int G, int N, int32_t 
 int rbg_validate(const int32_t *boards, int64_t B, int G, int N, int32_t *flags, void *stream) {
   int rc;
   if ((rc = check_dims(B, G, N, 0))) return rc;
+  if (B == 0) return RBG_OK;  // an empty batch has no buffers to check
   if (!boards || !flags) return set_error(RBG_EINVAL, "rbg_validate: NULL pointer");
   return launch_validate(boards, B, G, N, flags, (cudaStream_t)stream);
 }
@@ -1269,8 +1274,8 @@ int rbg_prw_generate_host(const uint32_t *keys, int64_t B, int G, int N, int32_t
                           int32_t *solved, int device) {
   int rc, dev;
   if ((rc = check_dims(B, G, N, 1))) return rc;
+  if (B == 0) return RBG_OK;  // an empty batch has no buffers to check
   if (!keys || !heads || !targets || !solved) return set_error(RBG_EINVAL, "rbg_prw_generate_host: NULL pointer");
-  if (B == 0) return RBG_OK;
   if ((rc = use_device(device, &dev))) return rc;
   std::lock_guard<std::mutex> lock(g_scratch_mu);
   Carver size{nullptr};
@@ -1310,8 +1315,8 @@ int rbg_connector_reset_host(int kind, const uint32_t *keys, int64_t B, int G, i
                              const rbg_timestep *ts, int device) {
   int rc, dev;
   if ((rc = check_dims(B, G, N, kind == RBG_GEN_UNIFORM ? 2 : 1))) return rc;
+  if (B == 0) return RBG_OK;  // an empty batch has no buffers to check
   if (!keys || !state || !ts) return set_error(RBG_EINVAL, "rbg_connector_reset_host: NULL pointer");
-  if (B == 0) return RBG_OK;
   if ((rc = use_device(device, &dev))) return rc;
   std::lock_guard<std::mutex> lock(g_scratch_mu);
   Carver size{nullptr};
@@ -1351,8 +1356,8 @@ int rbg_connector_step_host(const rbg_state *in, const rbg_state *out, const int
                             int N, const rbg_env_params *params, const rbg_timestep *ts, int device) {
   int rc, dev;
   if ((rc = check_dims(B, G, N, 1))) return rc;
+  if (B == 0) return RBG_OK;  // an empty batch has no buffers to check
   if (!in || !out || !action || !params || !ts) return set_error(RBG_EINVAL, "rbg_connector_step_host: NULL pointer");
-  if (B == 0) return RBG_OK;
   if ((rc = use_device(device, &dev))) return rc;
   std::lock_guard<std::mutex> lock(g_scratch_mu);
   const int nsl = B >= 4096 ? 8 : 1;
@@ -1400,9 +1405,9 @@ int rbg_connector_step_host_io(const rbg_state *state, const int32_t *action, in
                                const rbg_env_params *params, const rbg_timestep *ts, int device) {
   int rc, dev;
   if ((rc = check_dims(B, G, N, 1))) return rc;
+  if (B == 0) return RBG_OK;  // an empty batch has no buffers to check
   if (!action || !params || !ts) return set_error(RBG_EINVAL, "rbg_connector_step_host_io: NULL pointer");
   if ((rc = check_state(state, "state", G))) return rc;
-  if (B == 0) return RBG_OK;
   if ((rc = use_device(device, &dev))) return rc;
   std::lock_guard<std::mutex> lock(g_scratch_mu);
   cudaError_t e;

@@ -191,6 +191,24 @@ def test_prw_empty_batch(rbg):
     assert h.shape == (0, 2, 5) and s.shape == (0, 10, 10)
 
 
+def test_empty_batches_everywhere(rbg):
+    """B = 0 through every batched entry point of the mirror: an empty batch has no buffers (torch gives NULL data pointers)."""
+    import torch
+
+    keys = torch.empty((0, 2), dtype=torch.uint32, device="cuda")
+    for gen in (rbg.ParallelRandomWalkGenerator(10, 5), rbg.UniformRandomGenerator(10, 5), rbg.SeedExtensionGenerator(10, 5), rbg.SequentialRandomWalkGenerator(10, 5)):
+        assert gen(keys).grid.shape == (0, 10, 10)
+        env = rbg.VmapAutoResetWrapper(rbg.Connector(generator=gen, time_limit=5))
+        st, ts = env.reset(keys)
+        assert ts.observation.grid.shape == (0, 5, 10, 10)
+        st, ts = env.step(st, torch.empty((0, 5), dtype=torch.int32, device="cuda"))
+        assert ts.reward.shape == (0, 5)
+        st, ts, act = env.rollout_random(st, 3)
+        assert ts.observation.grid.shape == (3, 0, 5, 10, 10) and act.shape == (3, 0, 5)
+    assert rbg.SeedExtensionBoard(10, 10, 5).return_solved_board(keys).shape == (0, 10, 10)
+    assert rbg.engine.validate(torch.empty((0, 10, 10), dtype=torch.int32, device="cuda"), 5).shape == (0,)
+
+
 @pytest.mark.parametrize("G,N,B", [(20, 10, 131072), (32, 16, 16384)])
 def test_prw_full_size_invariants(rbg, G, N, B):
     """BASELINE config 3 per-GPU slice (131 072 boards 20x20/10): every board passes the validity
@@ -1343,6 +1361,11 @@ def test_seqrw_single_key_ragged_and_errors(rbg, orc):
     for B in (1, 3, 15, 16, 17, 129):
         keys, kref = _keys(rbg, orc, 9, B)
         assert np.array_equal(_np(rbg.SequentialRandomWalkBoard(8, 8, 4).generate(keys, as_float32=False)), orc.seqrw_generate_batch(kref, 8, 4)[0])
+    import torch
+
+    empty = torch.empty((0, 2), dtype=torch.uint32, device="cuda")
+    assert rbg.SequentialRandomWalkBoard(8, 8, 4).generate(empty).shape == (0, 8, 8)
+    assert rbg.SequentialRandomWalkGenerator(8, 4)(empty).grid.shape == (0, 8, 8)
     with pytest.raises(ValueError):
         rbg.SequentialRandomWalkBoard(2, 2, 1)
     with pytest.raises(ValueError):
@@ -1378,3 +1401,26 @@ def test_seqrw_rollout_random_matches_oracle(rbg, orc):
         assert np.array_equal(_np(ts.observation.grid[t]), rts["obs"]) and np.array_equal(_np(ts.step_type[t]), rts["step_type"]), t
         assert np.array_equal(_np(ts.reward[t]).view(np.uint32), rts["reward"].view(np.uint32)), t
     _assert_state(st, rst, "after the rollout")
+
+
+@pytest.mark.parametrize("G,N,B", [(10, 5, 65536), (20, 10, 16384)])
+def test_seqrw_full_size_invariants(rbg, G, N, B):
+    """Size-independent properties at full batch size, on the device: a successful board holds one head and one target per
+    wire, exactly steps + N filled cells (a step fills one cell, a wire starts on one), passes the reference's validity rules;
+    a failed one is all zeros.  Idempotence: the same keys give the same boards."""
+    import torch
+
+    keys = rbg.split(rbg.PRNGKey(0), B)
+    gen = rbg.SequentialRandomWalkBoard(G, G, N)
+    board, stats = gen.generate_with_stats(keys)
+    ok = stats[:, 0] > 0
+    assert int(ok.sum()) > 0.99 * B
+    assert int((board != 0).sum(dim=(1, 2))[~ok].sum()) == 0
+    assert torch.equal((board != 0).sum(dim=(1, 2))[ok], (stats[:, 1] + N)[ok].to(torch.int64))
+    for w in range(N):
+        assert torch.equal(((board == 3 * w + 2).sum(dim=(1, 2)) == 1), ok) and torch.equal(((board == 3 * w + 3).sum(dim=(1, 2)) == 1), ok)
+    flags = rbg.engine.validate(board, N)
+    assert int((flags[ok] & (1 | 8 | 32 | 64 | 128)).abs().max()) == 0
+    assert int(stats[:, 0].max()) < 2 * G and int(stats[:, 0].min()) >= 0
+    again = gen.generate(keys, as_float32=False)
+    assert torch.equal(again, board)
