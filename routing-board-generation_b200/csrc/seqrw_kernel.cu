@@ -45,21 +45,29 @@
 
 namespace rbg {
 
-constexpr int SQ_W = 8;
 constexpr int SQ_THREADS = 128;
-constexpr int SQ_GROUPS = SQ_THREADS / SQ_W;
+// lanes per board: 8 (4 boards per warp) or 6 (5 boards per warp, lanes 30 and 31 idle: the walk pass uses exactly 2 split
+// lanes + 4 draw lanes, the start-cell scan takes ceil(G*G/2 / 6) passes instead of ceil(G*G/2 / 8))
+template <int SQ_W>
+struct SqShape {
+  static constexpr int GPW = 32 / SQ_W;                      // groups per warp
+  static constexpr int GROUPS = (SQ_THREADS / 32) * GPW;     // boards in flight per CTA
+};
 
 enum : int { SQ_SPLIT_WIRE = 0, SQ_SPLIT_START = 1, SQ_PICK = 2, SQ_SPLIT_WALK = 3, SQ_WALK = 4, SQ_IDLE = 5, SQ_DONE = 6 };
 
+template <int SQ_W>
 __global__ void __launch_bounds__(SQ_THREADS) seqrw_walk_kernel(const SeqRwParams p, uint8_t *__restrict__ out_board, uint32_t *__restrict__ out_gkey,
                                                                 const int CB, int *__restrict__ queue, const FastDiv divG) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  const int tid = threadIdx.x, lane = tid & 31, l = lane & (SQ_W - 1), gbase = lane & ~(SQ_W - 1);
-  const unsigned gmask = 0xFFu << gbase;
+  constexpr int GPW = SqShape<SQ_W>::GPW, SQ_GROUPS = SqShape<SQ_W>::GROUPS;
+  const int tid = threadIdx.x, lane = tid & 31, l = lane % SQ_W, gbase = lane - l;
+  const bool spare = lane >= GPW * SQ_W;  // SQ_W = 6: lanes 30, 31 own no board (they run along, DONE from the start)
+  const unsigned gmask = spare ? (FULL << (GPW * SQ_W)) : (((1u << SQ_W) - 1u) << gbase);
   const int G = p.G, N = p.N, S = G + 4, cells = G * G;
   const int SB = (S * S + 15) & ~15;
-  uint8_t *board = smem_raw + (size_t)(tid / SQ_W) * SB;
   uint8_t *tmpl = smem_raw + (size_t)SQ_GROUPS * SB;  // the empty board: 0xFF border, 0 interior
+  uint8_t *board = spare ? tmpl : smem_raw + (size_t)((tid >> 5) * GPW + lane / SQ_W) * SB;
   for (int i = tid; i < SB; i += SQ_THREADS) {
     const int r = i / S, c = i - r * S;
     tmpl[i] = (r >= 2 && r < G + 2 && c >= 2 && c < G + 2) ? 0 : 0xFF;
@@ -81,7 +89,7 @@ __global__ void __launch_bounds__(SQ_THREADS) seqrw_walk_kernel(const SeqRwParam
   const int dirk = kdir == 0 ? -S : kdir == 1 ? S : kdir == 2 ? -1 : 1;
   const uint32_t sx0 = (uint32_t)(l & 1), sx1 = sx0 + 2u;  // split(): blocks (0,2), (1,3)
 
-  int phase = SQ_IDLE;
+  int phase = spare ? SQ_DONE : SQ_IDLE;
   long long m = -1, e = -1;
   uint32_t K0 = 0, K1 = 0;    // the board's key (every attempt starts from it)
   uint32_t h0 = 0, h1k = 0;   // the key the next pass hashes: the wire's key, its subkey, the draw key of the start, the chain key
@@ -221,10 +229,21 @@ __global__ void __launch_bounds__(SQ_THREADS) seqrw_walk_kernel(const SeqRwParam
     // ---- once per wire: the start cell, the end of the walk
     bool failed = ph_ss && !can_start, finished = false;  // can_start False: the attempt cannot succeed
     if (__any_sync(FULL, pick_end)) {
+      if (SQ_W == 8) {
 #pragma unroll
-      for (int off = SQ_W / 2; off > 0; off >>= 1) {
-        const unsigned long long ob = __shfl_xor_sync(FULL, best, off);
-        best = ob > best ? ob : best;
+        for (int off = SQ_W / 2; off > 0; off >>= 1) {
+          const unsigned long long ob = __shfl_xor_sync(FULL, best, off);
+          best = ob > best ? ob : best;
+        }
+      } else {  // not a power of two: every lane looks at the other lanes of its group in turn
+        const unsigned long long mine = best;
+#pragma unroll
+        for (int k = 1; k < SQ_W; ++k) {
+          int src = l + k;
+          src = gbase + (src >= SQ_W ? src - SQ_W : src);
+          const unsigned long long ob = __shfl_sync(FULL, mine, src & 31);
+          best = ob > best ? ob : best;
+        }
       }
       if (pick_end) {
         uint32_t q, r;
@@ -311,10 +330,24 @@ __global__ void __launch_bounds__(SQ_THREADS) seqrw_walk_kernel(const SeqRwParam
   }
 }
 
+static int env_w() {  // RBG_SEQRW_W=6 | 8: lanes per board
+  const char *e = getenv("RBG_SEQRW_W");
+  const int v = e ? atoi(e) : 0;
+  return v == 6 || v == 8 ? v : 0;
+}
+
 int launch_seqrw(SeqRwParams p, int64_t max_boards, cudaStream_t stream) {
   const int G = p.G, N = p.N;
   if (G < 3) return set_error(RBG_EINVAL, "SequentialRandomWalk: rows=%d (available_cells pads with jnp.full(rows - 3, -1): rows >= 3)", G);
   const int S = G + 4, SB = (S * S + 15) & ~15, CB = (G * G + 15) & ~15;
+  static int w_env = -1;
+  if (w_env < 0) w_env = env_w();
+  // 6 lanes per board where the walk dominates (5 boards per warp, every lane of a walk pass busy), 8 where the start-cell
+  // scan does (G*G/2 blocks per wire): 10x10/5 74.9 against 66.7 M boards/s, 14x14/7 36.5 / 35.0, 20x20/10 15.8 / 15.7,
+  // 32x32/16 2.48 / 2.82
+  const int W = w_env ? w_env : (G <= 16 ? 6 : 8);
+  const int SQ_GROUPS = W == 6 ? SqShape<6>::GROUPS : SqShape<8>::GROUPS;
+  const void *fn = W == 6 ? reinterpret_cast<const void *>(seqrw_walk_kernel<6>) : reinterpret_cast<const void *>(seqrw_walk_kernel<8>);
   const size_t smem = (size_t)(SQ_GROUPS + 1) * SB;
   const size_t n = (size_t)max_boards;
   const size_t o_gkey = (n * CB + 255) & ~(size_t)255, o_queue = o_gkey + ((n * 8 + 255) & ~(size_t)255), total = o_queue + 256;
@@ -330,12 +363,13 @@ int launch_seqrw(SeqRwParams p, int64_t max_boards, cudaStream_t stream) {
       rc = set_cuda_error(ce, "cudaMemsetAsync(SequentialRandomWalk queue)");
       break;
     }
-    if (smem > 48 * 1024 && (ce = cudaFuncSetAttribute(seqrw_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) {
+    if (smem > 48 * 1024 && (ce = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) {
       rc = set_cuda_error(ce, "seqrw_walk_kernel shared memory");
       break;
     }
     int per_sm = 0;
-    if ((ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, seqrw_walk_kernel, SQ_THREADS, smem)) != cudaSuccess) {
+    if ((ce = (W == 6 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, seqrw_walk_kernel<6>, SQ_THREADS, smem)
+                      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, seqrw_walk_kernel<8>, SQ_THREADS, smem))) != cudaSuccess) {
       rc = set_cuda_error(ce, "cudaOccupancyMaxActiveBlocksPerMultiprocessor(seqrw_walk_kernel)");
       break;
     }
@@ -344,7 +378,10 @@ int launch_seqrw(SeqRwParams p, int64_t max_boards, cudaStream_t stream) {
     const unsigned ctas = (unsigned)(need < resident ? (need < 1 ? 1 : need) : resident);
     {
       LaunchScope scope(RBG_K_SEQRW, stream);
-      seqrw_walk_kernel<<<ctas, SQ_THREADS, smem, stream>>>(p, base, gkey, CB, queue, FastDiv::make((uint32_t)G));
+      if (W == 6)
+        seqrw_walk_kernel<6><<<ctas, SQ_THREADS, smem, stream>>>(p, base, gkey, CB, queue, FastDiv::make((uint32_t)G));
+      else
+        seqrw_walk_kernel<8><<<ctas, SQ_THREADS, smem, stream>>>(p, base, gkey, CB, queue, FastDiv::make((uint32_t)G));
     }
     if ((rc = check_launch("seqrw_walk_kernel"))) break;
     SeedExtParams f;

@@ -1424,3 +1424,29 @@ def test_seqrw_full_size_invariants(rbg, G, N, B):
     assert int(stats[:, 0].max()) < 2 * G and int(stats[:, 0].min()) >= 0
     again = gen.generate(keys, as_float32=False)
     assert torch.equal(again, board)
+
+
+@pytest.mark.parametrize("lanes", ["6", "8"])
+def test_seqrw_lanes_per_board_switch(lanes):
+    """seqrw_walk_kernel comes with 6 or 8 lanes per board (6 by default up to 16x16, 8 beyond): RBG_SEQRW_W forces either one
+    on every shape, incl. crowded boards (retries, failed generations) and a board larger than the default range of each."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r)\n"
+        "import routing_board_generation_b200 as rbg\n"
+        "from oracle import oracle as orc\n"
+        "for G, N, B in ((3, 4, 600), (4, 6, 600), (7, 4, 1500), (10, 5, 3000), (10, 20, 300), (17, 9, 300), (20, 10, 400), (33, 8, 60)):\n"
+        "    k = rbg.split(rbg.PRNGKey(13), B); kr = orc.split(orc.PRNGKey(13), B)\n"
+        "    b, s = rbg.SequentialRandomWalkBoard(G, G, N).generate_with_stats(k)\n"
+        "    rb, rs = orc.seqrw_generate_batch(kr, G, N)\n"
+        "    assert np.array_equal(b.cpu().numpy(), rb) and np.array_equal(s.cpu().numpy(), rs), (G, N)\n"
+        "    st = rbg.SequentialRandomWalkGenerator(G, N)(k)\n"
+        "    assert np.array_equal(st.grid.cpu().numpy(), orc.state_batch('sequential_random_walk', kr, G, N)['grid']), (G, N)\n"
+        "print('ok')\n"
+    ) % root
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, RBG_SEQRW_W=lanes), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().startswith("ok"), (r.stdout[-500:], r.stderr[-2000:])
