@@ -808,7 +808,8 @@ int rbg_prw_generate(const uint32_t *keys, int64_t B, int G, int N, int32_t *hea
 
 int rbg_generator_state(int kind, const uint32_t *keys, int64_t B, int G, int N, const rbg_state *out, void *stream) {
   int rc;
-  if ((rc = check_dims(B, G, N, kind == RBG_GEN_UNIFORM ? 2 : 1))) return rc;
+  // (the sequential random walk has no choice(replace=False) over the agents: more agents than cells is a failed generation)
+  if ((rc = check_dims(B, G, N, kind == RBG_GEN_UNIFORM ? 2 : kind == RBG_GEN_SEQRW ? 0 : 1))) return rc;
   if (B == 0) return RBG_OK;  // an empty batch has no buffers to check
   if (!keys) return set_error(RBG_EINVAL, "keys is NULL");
   if ((rc = check_state(out, "state", G))) return rc;

@@ -1363,6 +1363,10 @@ def test_seqrw_single_key_ragged_and_errors(rbg, orc):
         assert np.array_equal(_np(rbg.SequentialRandomWalkBoard(8, 8, 4).generate(keys, as_float32=False)), orc.seqrw_generate_batch(kref, 8, 4)[0])
     import torch
 
+    # more agents than cells: every attempt fails (zero board, every pin at (0, 0)), as the reference's loop would end
+    keys, kref = _keys(rbg, orc, 9, 40)
+    assert not _np(rbg.SequentialRandomWalkBoard(3, 3, 12).generate(keys)).any() and not orc.seqrw_generate_batch(kref, 3, 12)[0].any()
+    _assert_state(rbg.SequentialRandomWalkGenerator(3, 12)(keys), orc.state_batch("sequential_random_walk", kref, 3, 12))
     empty = torch.empty((0, 2), dtype=torch.uint32, device="cuda")
     assert rbg.SequentialRandomWalkBoard(8, 8, 4).generate(empty).shape == (0, 8, 8)
     assert rbg.SequentialRandomWalkGenerator(8, 4)(empty).grid.shape == (0, 8, 8)
