@@ -35,9 +35,10 @@
 // over) and the once-per-board events (new board, failed attempt, output) branch, behind warp votes.  The first
 // version branched on the phase and spent 70 % of its instructions in bookkeeping executed one group at a time
 // (profiles/r02g_seqrw_full.csv: 13.6 k warp-instructions per 10x10/5 board).
-// A failed attempt is abandoned at once (its board can only be discarded, :355-366), and the attempts that would repeat
-// it exactly are skipped: all attempts start from the same key, so an attempt differs from the previous one only from
-// the first wire whose walk the smaller max_length truncates.  Groups take boards from a
+// A failed attempt is abandoned at once (its board can only be discarded, :355-366), the attempts that would repeat it
+// exactly are skipped, and the next one resumes where it first differs: all attempts start from the same key, so an
+// attempt differs from the previous one only from the first wire whose walk the smaller max_length truncates; the wires
+// before it stay on the board and that wire restarts its walk from the same start cell.  Groups take boards from a
 // global queue.  The finished board goes to a byte scratch and through se_finish_kernel's outputs (board /
 // first POSITION and TARGET cell per wire / State + observation), which SeedExtension shares.
 #include "connector_device.cuh"
@@ -67,7 +68,10 @@ __global__ void __launch_bounds__(SQ_THREADS) seqrw_walk_kernel(const SeqRwParam
   const int G = p.G, N = p.N, S = G + 4, cells = G * G;
   const int SB = (S * S + 15) & ~15;
   uint8_t *tmpl = smem_raw + (size_t)SQ_GROUPS * SB;  // the empty board: 0xFF border, 0 interior
-  uint8_t *board = spare ? tmpl : smem_raw + (size_t)((tid >> 5) * GPW + lane / SQ_W) * SB;
+  const int grp = spare ? 0 : (tid >> 5) * GPW + lane / SQ_W;
+  uint8_t *board = spare ? tmpl : smem_raw + (size_t)grp * SB;
+  // per placed wire of the current attempt: chain key at the start of its walk (2 words), start cell, steps walked
+  uint32_t *winfo = reinterpret_cast<uint32_t *>(smem_raw + (size_t)(SQ_GROUPS + 1) * SB) + (size_t)grp * 4 * RBG_MAX_N;
   for (int i = tid; i < SB; i += SQ_THREADS) {
     const int r = i / S, c = i - r * S;
     tmpl[i] = (r >= 2 && r < G + 2 && c >= 2 && c < G + 2) ? 0 : 0xFF;
@@ -250,7 +254,12 @@ __global__ void __launch_bounds__(SQ_THREADS) seqrw_walk_kernel(const SeqRwParam
         divG.divmod(0xffffu - (uint32_t)(best & 0xffffull), q, r);  // SRW:66 divmod(flat, rows)
         startc = (int)((q + 2) * S + r + 2);
         cur = startc;
-        if (l == 0) board[startc] = (uint8_t)(3 * w + POSITION);  // SRW:71
+        if (l == 0) {
+          board[startc] = (uint8_t)(3 * w + POSITION);  // SRW:71
+          winfo[4 * w] = c0;
+          winfo[4 * w + 1] = c1;
+          winfo[4 * w + 2] = (uint32_t)startc;
+        }
         filled++;
         t = 0;
         h0 = c0;  // SPLIT_WALK hashes the chain key
@@ -262,7 +271,10 @@ __global__ void __launch_bounds__(SQ_THREADS) seqrw_walk_kernel(const SeqRwParam
       if (t == 0) {
         failed = true;  // :319 the wire did not move
       } else {
-        if (l == 0) board[startc] = (uint8_t)(3 * w + POSITION);  // :286
+        if (l == 0) {
+          board[startc] = (uint8_t)(3 * w + POSITION);  // :286
+          winfo[4 * w + 3] = (uint32_t)t;
+        }
         max_t = t > max_t ? t : max_t;
         ++w;
         h0 = c0;  // the tuple's key: the next wire splits it
@@ -290,16 +302,42 @@ __global__ void __launch_bounds__(SQ_THREADS) seqrw_walk_kernel(const SeqRwParam
           steps = 0;
           finished = true;
         } else {
+          // The attempt with max_length = L replays this one up to the first wire that walked max_t = L + 1 steps (the
+          // wires before it are shorter: untouched by the smaller limit) and walks that wire from the same start cell
+          // with the same keys, one step less.  So nothing before that wire is recomputed: the later wires are taken off
+          // the board, the wire restarts its walk (its start cell needs no new scan) and the attempt goes on from there.
           __syncwarp(gmask);
-          for (int q = l; q < (SB >> 2); q += SQ_W) reinterpret_cast<uint32_t *>(board)[q] = reinterpret_cast<const uint32_t *>(tmpl)[q];
-          w = 0;
-          filled = 0;
-          steps = 0;
-          max_t = 0;
-          h0 = K0;
-          h1k = K1;
-          cur = startc = safe;
-          phase = SQ_SPLIT_WIRE;
+          int wm = 0, psum = 0, pmax = 0;
+          for (int i = 0; i < w; ++i) {  // w wires were placed before the failing one
+            const int ti = (int)winfo[4 * i + 3];
+            if (ti == max_t) {
+              wm = i;
+              break;
+            }
+            psum += ti;
+            pmax = ti > pmax ? ti : pmax;
+          }
+          const uint32_t keep_below = 3u * wm + 1u;  // codes of the wires before wm: 1 .. 3 wm
+          for (int r = 2; r < G + 2; ++r)
+            for (int c = 2 + l; c < G + 2; c += SQ_W) {
+              const uint32_t v = board[r * S + c];
+              if (v >= keep_below) board[r * S + c] = 0;
+            }
+          w = wm;
+          c0 = winfo[4 * wm];
+          c1 = winfo[4 * wm + 1];
+          startc = (int)winfo[4 * wm + 2];
+          cur = startc;
+          __syncwarp(gmask);
+          if (l == 0) board[startc] = (uint8_t)(3 * wm + POSITION);
+          filled = psum + wm + 1;  // a wire holds its steps + its start cell
+          steps = psum;
+          max_t = pmax;
+          t = 0;
+          h0 = c0;  // SPLIT_WALK hashes the chain key
+          h1k = c1;
+          phase = SQ_SPLIT_WALK;
+          __syncwarp(gmask);
         }
       }
       if (finished) {
@@ -348,7 +386,7 @@ int launch_seqrw(SeqRwParams p, int64_t max_boards, cudaStream_t stream) {
   const int W = w_env ? w_env : (G <= 16 ? 6 : 8);
   const int SQ_GROUPS = W == 6 ? SqShape<6>::GROUPS : SqShape<8>::GROUPS;
   const void *fn = W == 6 ? reinterpret_cast<const void *>(seqrw_walk_kernel<6>) : reinterpret_cast<const void *>(seqrw_walk_kernel<8>);
-  const size_t smem = (size_t)(SQ_GROUPS + 1) * SB;
+  const size_t smem = (size_t)(SQ_GROUPS + 1) * SB + (size_t)SQ_GROUPS * 4 * RBG_MAX_N * sizeof(uint32_t);
   const size_t n = (size_t)max_boards;
   const size_t o_gkey = (n * CB + 255) & ~(size_t)255, o_queue = o_gkey + ((n * 8 + 255) & ~(size_t)255), total = o_queue + 256;
   uint8_t *base = nullptr;
