@@ -13,7 +13,8 @@ import test_gpu_parity as T
 
 ops = int(sys.argv[1]) if len(sys.argv) > 1 else 300
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
-GENS = {"parallel_random_walk": rbg.ParallelRandomWalkGenerator, "uniform": rbg.UniformRandomGenerator, "seed_extension": rbg.SeedExtensionGenerator}
+GENS = {"parallel_random_walk": rbg.ParallelRandomWalkGenerator, "uniform": rbg.UniformRandomGenerator, "seed_extension": rbg.SeedExtensionGenerator,
+        "sequential_random_walk": rbg.SequentialRandomWalkGenerator}
 SHAPES = [(10, 5, 700), (10, 5, 4500), (8, 4, 300), (6, 3, 1000)]
 live = []
 made = 0
@@ -21,7 +22,7 @@ made = 0
 
 def make():
     global made
-    kind = list(GENS)[int(rng.integers(0, 3))]
+    kind = list(GENS)[int(rng.integers(0, len(GENS)))]
     G, N, B = SHAPES[int(rng.integers(0, len(SHAPES)))]
     tl = int(rng.integers(1, 6))
     env = rbg.VmapAutoResetWrapper(rbg.Connector(generator=GENS[kind](G, N), time_limit=tl))
