@@ -667,7 +667,6 @@ __global__ void __launch_bounds__(EW_WARPS * 32, RBG_ROLLOUT_MIN_CTAS) rollout_w
 //    however many small launches are in flight at once they never share a counter.
 constexpr int kPersistSets = 16;
 constexpr int kPersistSetInts = 4;
-constexpr int GEN_WARPS_MAX = 4;
 #ifndef RBG_PERSIST_MIN_CTAS
 #define RBG_PERSIST_MIN_CTAS 4
 #endif

@@ -100,7 +100,7 @@ struct GenWarpScratch {
 // and publish them.  All 32 lanes must call.
 __device__ inline void gen_warp_batch(const GenWarpCfg &c, const GenWarpScratch &s, int n, int req_env, uint32_t req_k0,
                                       uint32_t req_k1, int lane) {
-  const int G = c.G, N = c.N, W = c.W, S = c.S, SBp = c.SBp;
+  const int N = c.N, W = c.W, S = c.S, SBp = c.SBp;
   const bool uniform_mode = c.kind != RBG_GEN_PRW;
   // ---- keys: two lanes per request walk the split() chain (as prw_kernel phase A0)
   uint32_t sub0, sub1, ks0, ks1, nk0, nk1;

@@ -64,7 +64,8 @@ __global__ void __launch_bounds__(SQ_THREADS) seqrw_walk_kernel(const SeqRwParam
   constexpr int GPW = SqShape<SQ_W>::GPW, SQ_GROUPS = SqShape<SQ_W>::GROUPS;
   const int tid = threadIdx.x, lane = tid & 31, l = lane % SQ_W, gbase = lane - l;
   const bool spare = lane >= GPW * SQ_W;  // SQ_W = 6: lanes 30, 31 own no board (they run along, DONE from the start)
-  const unsigned gmask = spare ? (FULL << (GPW * SQ_W)) : (((1u << SQ_W) - 1u) << gbase);
+  constexpr unsigned spare_mask = GPW * SQ_W < 32 ? (FULL << ((GPW * SQ_W) & 31)) : 0u;
+  const unsigned gmask = spare ? spare_mask : (((1u << SQ_W) - 1u) << gbase);
   const int G = p.G, N = p.N, S = G + 4, cells = G * G;
   const int SB = (S * S + 15) & ~15;
   uint8_t *tmpl = smem_raw + (size_t)SQ_GROUPS * SB;  // the empty board: 0xFF border, 0 interior
