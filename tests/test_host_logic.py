@@ -50,6 +50,15 @@ def test_plugin_surface_names():
     assert (gen.board_generator.rows, gen.board_generator.cols, gen.board_generator.num_agents) == (10, 10, 5)
     assert isinstance(pkg.SeedExtensionGenerator(10, 5).board_generator, pkg.SeedExtensionBoard)
     assert isinstance(pkg.UniformRandomGenerator(10, 5), pkg.Generator)
+    # sequential_random_walk_generator.py:19-31: same constructor, board_generator = SequentialRandomWalkBoard(size, size, n)
+    sq = pkg.SequentialRandomWalkGenerator(grid_size=8, num_agents=3)
+    assert isinstance(sq, pkg.Generator) and isinstance(sq.board_generator, pkg.SequentialRandomWalkBoard) and sq.kind == "sequential_random_walk"
+    assert pkg.SequentialRandomWalkBoard(6, 6)._num_agents == 3  # sequential_random_walk.py:26 default num_agents=3
+    for name in ("return_blank_board", "generate", "generate_starts_ends"):
+        assert callable(getattr(sq.board_generator, name))
+    with pytest.raises(ValueError):
+        pkg.SequentialRandomWalkBoard(2, 2, 1)  # available_cells needs rows >= 3 (sequential_random_walk.py:138-140)
+    assert pkg.Connector(generator=sq)._kind == "sequential_random_walk"  # reset / auto-reset inside the kernels, not the generic path
     # interface/board_generator_interface.py:45-46,55,64
     assert pkg.BoardGenerator.get_board_generator(pkg.BoardName("offline_parallel_rw")) is pkg.ParallelRandomWalkBoard
     assert pkg.BoardGenerator.get_board_generator(pkg.BoardName.JAX_SEED_EXTENSION) is pkg.SeedExtensionBoard
