@@ -288,16 +288,29 @@ def run_ours(args):
     # actions H2D from pinned memory, step, whole TimeStep D2H, every step.
     e2e = None
     cpu_baseline = None
+    # the legs below are additions to the headline numbers above: an error in one of them (it would hit every rank alike) is
+    # reported in its place instead of costing the run its line
     if not args.skip_e2e:
-        e2e = _e2e_host(args, rbg, lib, state, B, world, rank, dev)
+        try:
+            e2e = _e2e_host(args, rbg, lib, state, B, world, rank, dev)
+        except Exception as e:  # noqa: BLE001
+            e2e = {"value": None, "unit": UNIT, "error": repr(e)}
     del ts, act
     torch.cuda.empty_cache()
     sm_mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
-    secondary = [] if args.skip_secondary else _secondary(args, rbg, dd, peak, rank, world, sm_mhz)
+    secondary = []
+    if not args.skip_secondary:
+        try:
+            secondary = _secondary(args, rbg, dd, peak, rank, world, sm_mhz)
+        except Exception as e:  # noqa: BLE001
+            secondary = [{"error": repr(e)}]
     if rank == 0 and world == 1 and not args.skip_cpu:
-        cpu_baseline = _cpu_baseline(budget_s=args.cpu_seconds, burnin=args.burnin, envs=B)
-        if not args.skip_secondary:
-            _cpu_secondary(secondary, budget_s=max(2.0, args.cpu_seconds / 3))
+        try:
+            cpu_baseline = _cpu_baseline(budget_s=args.cpu_seconds, burnin=args.burnin, envs=B)
+            if not args.skip_secondary:
+                _cpu_secondary(secondary, budget_s=max(2.0, args.cpu_seconds / 3))
+        except Exception as e:  # noqa: BLE001
+            cpu_baseline = cpu_baseline or {"value": None, "error": repr(e)}
 
     if rank == 0:
         line = {
@@ -602,15 +615,15 @@ def _cpu_secondary(secondary, budget_s: float = 4.0):
 
     se_cpu = None
     for line in secondary:
-        if line["metric"] == "prw_solved_boards_per_sec":
+        if line.get("metric") == "prw_solved_boards_per_sec":
             g, n = line["grid"], line["agents"]
             v, done, dt = rate(lambda k: orc.prw_generate_batch(orc.split(orc.PRNGKey(1), k), g, n, nthreads=cores), 512)
             line["cpu_baseline"] = {"value": round(v, 1), "unit": "boards/s", "cores": cores, "kind": "port", "sample": f"{done} boards {g}x{g}/{n} in {dt:.1f} s, OpenMP over boards"}
-        elif line["metric"] == "seqrw_boards_per_sec":
+        elif line.get("metric") == "seqrw_boards_per_sec":
             g, n = line["grid"], line["agents"]
             v, done, dt = rate(lambda k: orc.seqrw_generate_batch(orc.split(orc.PRNGKey(1), k), g, n, nthreads=cores), 512)
             line["cpu_baseline"] = {"value": round(v, 1), "unit": "boards/s", "cores": cores, "kind": "port", "sample": f"{done} boards {g}x{g}/{n} in {dt:.1f} s, OpenMP over boards"}
-        elif line["metric"] == "seedext_solved_boards_per_sec":
+        elif line.get("metric") == "seedext_solved_boards_per_sec":
             if se_cpu is None:
                 v, done, dt = rate(lambda k: orc.seedext_solved_batch(orc.split(orc.PRNGKey(1), k), 14, 7, nthreads=cores), 256)
                 se_cpu = {"value": round(v, 1), "unit": "boards/s", "cores": cores, "kind": "port", "sample": f"{done} boards 14x14/7 in {dt:.1f} s, OpenMP over boards"}
