@@ -404,23 +404,25 @@ def _e2e_host(args, rbg, lib, state, B, world, rank, dev):
         src8 = torch.empty((B, N, G, G), dtype=torch.uint8).pin_memory()
         src8.random_(0, 16)
         n_obs = src8.numel()
+        widen = lib.rbg_host_widen4 if d2h_moved // k < n_obs else lib.rbg_host_widen  # the transport the step used
         for _ in range(2):
-            L.check(lib.rbg_host_widen(src8.data_ptr(), hts["obs"].data_ptr(), n_obs))
+            L.check(widen(src8.data_ptr(), hts["obs"].data_ptr(), n_obs))
         if world > 1:
             dist.barrier()
         w0 = time.perf_counter()
         for _ in range(5):
-            L.check(lib.rbg_host_widen(src8.data_ptr(), hts["obs"].data_ptr(), n_obs))
+            L.check(widen(src8.data_ptr(), hts["obs"].data_ptr(), n_obs))
         wt = torch.tensor([(time.perf_counter() - w0) / 5], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(wt, op=dist.ReduceOp.MAX)
         wdt = float(wt.item())
         ceiling = {"env_steps_per_s": round(B * world / wdt, 1), "int32_gbs_per_rank": round(n_obs * 4 / wdt / 1e9, 1), "frac": round((B * world * k / dt) / (B * world / wdt), 4),
-                   "note": "rbg_host_widen of one step's observation alone on every rank at once (bytes resident in pinned host memory, no GPU work, no bus): the rate at which this host's cores and memory system can write the API's int32 observation; `frac` = e2e value / this"}
+                   "note": "rbg_host_widen / rbg_host_widen4 of one step's observation alone on every rank at once (codes resident in pinned host memory, no GPU work, no bus): the rate at which this host's cores and memory system can write the API's int32 observation; `frac` = e2e value / this"}
         del src8
     return {"value": round(B * world * k / dt, 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d_moved // k), "d2h_bytes_per_step": int(d2h_moved // k), "steps": k,
             "api": "rbg_connector_step_host_io (pinned host actions in, full TimeStep out to host memory, State device-resident, auto-reset on)",
-            "transport": (f"observation codes cross the bus as uint8 and are widened to the API's int32 by {host_threads} host threads inside the call (slices pipelined)"
+            "transport": ((f"observation codes (<= 3 N = {3 * N}) cross the bus as {'nibbles, two cells per byte,' if d2h_moved // k < B * N * G * G else 'uint8'} and are widened to the API's int32 "
+                           f"by {host_threads} host threads inside the call (slices pipelined)")
                           if packed else "int32 observation over the bus (RBG_HOST_IO_WIDE=1)"),
             "host_threads": host_threads, "timestep_bytes_delivered_per_step": int(d2h),
             "timer": "host wall clock around synchronous calls, max over ranks; median of five groups of `steps` steps",

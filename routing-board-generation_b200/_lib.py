@@ -68,6 +68,7 @@ SYMBOLS = {
     "rbg_connector_step_host": (_int, [_SP, _SP, _vp, _i64, _int, _int, _EP, _TP, _int]),
     "rbg_connector_step_host_io": (_int, [_SP, _vp, _i64, _int, _int, _EP, _TP, _int]),
     "rbg_host_widen": (_int, [_vp, _vp, _i64]),
+    "rbg_host_widen4": (_int, [_vp, _vp, _i64]),
     "rbg_host_transfer_stats": (_int, [C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_int), _int]),
     "rbg_host_alloc": (_vp, [_i64]),
     "rbg_host_free": (None, [_vp]),

@@ -1492,6 +1492,12 @@ int rbg_connector_step_host_io(const rbg_state *state, const int32_t *action, in
   RBG_CPY(da, action, (size_t)B * N * 4, cudaMemcpyHostToDevice, cs);
   g_h2d_bytes.fetch_add((long long)B * N * 4, std::memory_order_relaxed);
   const size_t per_env = (size_t)N * G * G;
+  // Observation codes are <= 3 N: with at most 5 agents they fit a nibble, two cells per byte over the bus (a slice is a
+  // multiple of 64 envs, so every slice starts on a whole, 16-byte aligned byte when an env has an even number of cells).
+  // RBG_HOST_IO_BITS=8 keeps a byte per cell.
+  static const int bits_env = env_int("RBG_HOST_IO_BITS");
+  const int obits = (packed && 3 * N <= 15 && (per_env & 1u) == 0 && bits_env != 8) ? 4 : 8;
+  const int oshift = obits == 4 ? 1 : 0;
   // Mixed transport (off by default, see host_io_split_env): `nwide` of the step's slices go over the bus as int32, the
   // rest as bytes.
   bool mix = false;
@@ -1522,14 +1528,14 @@ int rbg_connector_step_host_io(const rbg_state *state, const int32_t *action, in
     rbg_state dss = state_at(*state, off, G, N);
     rbg_timestep dts = timestep_at(dt, off, G, N);
     if ((rc = rbg_connector_step(&dss, &dss, da + off * N, n, G, N, params, &dts, ws + (size_t)si * ws_bytes, cs))) return rc;
-    if (!wide && (rc = launch_narrow_codes(dts.obs_grid, obs8 + (size_t)off * per_env, (int64_t)((size_t)n * per_env), cs))) return rc;
+    if (!wide && (rc = launch_narrow_codes(dts.obs_grid, obs8 + (((size_t)off * per_env) >> oshift), (int64_t)((size_t)n * per_env), cs, obits))) return rc;
     if (!slice_ev[si] && (e = cudaEventCreateWithFlags(&slice_ev[si], cudaEventDisableTiming)) != cudaSuccess) return set_cuda_error(e, "cudaEventCreate");
     if ((e = cudaEventRecord(slice_ev[si], cs)) != cudaSuccess) return set_cuda_error(e, "cudaEventRecord");
     cudaStream_t xs = g_streams[1 + (si & 1)];
     if ((e = cudaStreamWaitEvent(xs, slice_ev[si], 0)) != cudaSuccess) return set_cuda_error(e, "cudaStreamWaitEvent");
     (wide ? wide_cells : packed_cells) += (size_t)n * per_env;
     if (!wide) {
-      RBG_CPY(g_hc->stage8 + (size_t)off * per_env, obs8 + (size_t)off * per_env, (size_t)n * per_env, cudaMemcpyDeviceToHost, xs);
+      RBG_CPY(g_hc->stage8 + (((size_t)off * per_env) >> oshift), obs8 + (((size_t)off * per_env) >> oshift), ((size_t)n * per_env) >> oshift, cudaMemcpyDeviceToHost, xs);
       if (!copy_ev[si] && (e = cudaEventCreateWithFlags(&copy_ev[si], cudaEventDisableTiming | (host_io_blocking_sync() ? cudaEventBlockingSync : 0))) != cudaSuccess)
         return set_cuda_error(e, "cudaEventCreate");
       if ((e = cudaEventRecord(copy_ev[si], xs)) != cudaSuccess) return set_cuda_error(e, "cudaEventRecord(copy)");
@@ -1539,7 +1545,7 @@ int rbg_connector_step_host_io(const rbg_state *state, const int32_t *action, in
   }
   if ((rc = copy_timestep(ts, &dt, 0, B, G, N, cudaMemcpyDeviceToHost, 0, cs, 2))) return rc;
   const auto t_issued = std::chrono::steady_clock::now();
-  g_d2h_bytes.fetch_add((long long)(packed_cells + 4 * wide_cells) + (long long)B * (N * 5 + 4 + N * 8 + 1 + 12), std::memory_order_relaxed);
+  g_d2h_bytes.fetch_add((long long)((packed_cells >> oshift) + 4 * wide_cells) + (long long)B * (N * 5 + 4 + N * 8 + 1 + 12), std::memory_order_relaxed);
   if (packed) {
     si = 0;
     for (int64_t off = 0; off < B; off += sl, ++si) {
@@ -1549,7 +1555,10 @@ int rbg_connector_step_host_io(const rbg_state *state, const int32_t *action, in
         host_pool_wait();
         return set_cuda_error(e, "cudaEventSynchronize(copy)");
       }
-      host_pool_widen(g_hc->stage8 + (size_t)off * per_env, ts->obs_grid + (size_t)off * per_env, (size_t)n * per_env);
+      if (obits == 4)
+        host_pool_widen4(g_hc->stage8 + (((size_t)off * per_env) >> 1), ts->obs_grid + (size_t)off * per_env, (size_t)n * per_env);
+      else
+        host_pool_widen(g_hc->stage8 + (size_t)off * per_env, ts->obs_grid + (size_t)off * per_env, (size_t)n * per_env);
     }
   }
   int rc_sync = RBG_OK;
@@ -1609,6 +1618,14 @@ int rbg_host_widen(const uint8_t *src, int32_t *dst, int64_t n) {
   if (n < 0 || (n > 0 && (!src || !dst))) return set_error(RBG_EINVAL, "rbg_host_widen: n=%lld, src=%p, dst=%p", (long long)n, (const void *)src, (void *)dst);
   if (n == 0) return RBG_OK;
   host_pool_widen(src, dst, (size_t)n);
+  host_pool_wait();
+  return RBG_OK;
+}
+
+int rbg_host_widen4(const uint8_t *src, int32_t *dst, int64_t n) {
+  if (n < 0 || (n & 1) || (n > 0 && (!src || !dst))) return set_error(RBG_EINVAL, "rbg_host_widen4: n=%lld (even), src=%p, dst=%p", (long long)n, (const void *)src, (void *)dst);
+  if (n == 0) return RBG_OK;
+  host_pool_widen4(src, dst, (size_t)n);
   host_pool_wait();
   return RBG_OK;
 }

@@ -30,7 +30,12 @@ struct Piece {
   const uint8_t *src;
   int32_t *dst;
   size_t n;
+  int bits;  // 8: a code per byte; 4: two codes per byte, low nibble first
 };
+
+void widen4_scalar(const uint8_t *src, int32_t *dst, size_t n) {
+  for (size_t i = 0; i < n; ++i) dst[i] = (src[i >> 1] >> (4 * (i & 1))) & 15;
+}
 
 void widen_scalar(const uint8_t *src, int32_t *dst, size_t n) {
   for (size_t i = 0; i < n; ++i) dst[i] = src[i];
@@ -67,6 +72,55 @@ __attribute__((target("avx2"))) void widen_avx2_cached(const uint8_t *src, int32
   for (; i < n; ++i) dst[i] = src[i];
 }
 #endif
+
+#if defined(__x86_64__)
+// 16 source bytes -> 32 int32 per iteration; NT: the destination is 32-byte aligned after an EVEN number of scalar outputs
+// (the caller checks), so that the vector loop starts on a whole source byte
+template <bool NT>
+__attribute__((target("avx2"))) void widen4_avx2(const uint8_t *src, int32_t *dst, size_t n) {
+  size_t i = 0;
+  if (NT)
+    while (i < n && (reinterpret_cast<uintptr_t>(dst + i) & 31u)) {
+      dst[i] = (src[i >> 1] >> (4 * (i & 1))) & 15;
+      ++i;
+    }
+  const __m128i m = _mm_set1_epi8(15);
+  for (; i + 32 <= n; i += 32) {
+    const __m128i x = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + (i >> 1)));
+    const __m128i lo = _mm_and_si128(x, m), hi = _mm_and_si128(_mm_srli_epi16(x, 4), m);
+    const __m128i a = _mm_unpacklo_epi8(lo, hi), b = _mm_unpackhi_epi8(lo, hi);
+    const __m256i o0 = _mm256_cvtepu8_epi32(a), o1 = _mm256_cvtepu8_epi32(_mm_srli_si128(a, 8));
+    const __m256i o2 = _mm256_cvtepu8_epi32(b), o3 = _mm256_cvtepu8_epi32(_mm_srli_si128(b, 8));
+    if (NT) {
+      _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i), o0);
+      _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 8), o1);
+      _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 16), o2);
+      _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 24), o3);
+    } else {
+      _mm256_storeu_si256(reinterpret_cast<__m256i *>(dst + i), o0);
+      _mm256_storeu_si256(reinterpret_cast<__m256i *>(dst + i + 8), o1);
+      _mm256_storeu_si256(reinterpret_cast<__m256i *>(dst + i + 16), o2);
+      _mm256_storeu_si256(reinterpret_cast<__m256i *>(dst + i + 24), o3);
+    }
+  }
+  for (; i < n; ++i) dst[i] = (src[i >> 1] >> (4 * (i & 1))) & 15;
+  if (NT) _mm_sfence();
+}
+#endif
+
+void widen4(const uint8_t *src, int32_t *dst, size_t n) {
+#if defined(__x86_64__)
+  static const bool avx2 = __builtin_cpu_supports("avx2");
+  static const bool nt = !(getenv("RBG_HOST_NT") && atoi(getenv("RBG_HOST_NT")) == 0);
+  if (avx2) {
+    // outputs to the next 32-byte boundary of dst: odd (a destination at an odd int32 offset) would leave the vector loop
+    // in the middle of a source byte: plain unaligned stores then
+    const size_t head = ((32u - (reinterpret_cast<uintptr_t>(dst) & 31u)) & 31u) >> 2;
+    return (nt && (head & 1u) == 0) ? widen4_avx2<true>(src, dst, n) : widen4_avx2<false>(src, dst, n);
+  }
+#endif
+  widen4_scalar(src, dst, n);
+}
 
 void widen(const uint8_t *src, int32_t *dst, size_t n) {
 #if defined(__x86_64__)
@@ -133,7 +187,7 @@ class Pool {
     park_.notify_all();
     cv_.notify_all();
   }
-  void submit(const uint8_t *src, int32_t *dst, size_t n) {
+  void submit(const uint8_t *src, int32_t *dst, size_t n, int bits = 8) {
     if (n == 0) return;
     // pieces of whole 64-byte destination lines, a few per worker so that a slow core does not hold the slice back
     size_t per = (n + (size_t)active_ * 2 - 1) / ((size_t)active_ * 2);
@@ -142,7 +196,7 @@ class Pool {
     {
       std::lock_guard<std::mutex> lock(mu_);
       for (size_t off = 0; off < n; off += per) {
-        q_.push_back(Piece{src + off, dst + off, n - off < per ? n - off : per});
+        q_.push_back(Piece{src + (bits == 4 ? off >> 1 : off), dst + off, n - off < per ? n - off : per, bits});  // per is a multiple of 64
         ++pending_;
         avail_.fetch_add(1, std::memory_order_release);
       }
@@ -175,7 +229,10 @@ class Pool {
         q_.pop_front();
         avail_.fetch_sub(1, std::memory_order_relaxed);
       }
-      widen(p.src, p.dst, p.n);
+      if (p.bits == 4)
+        widen4(p.src, p.dst, p.n);
+      else
+        widen(p.src, p.dst, p.n);
       {
         std::lock_guard<std::mutex> lock(mu_);
         if (--pending_ == 0) done_.notify_all();
@@ -212,6 +269,7 @@ int host_pool_max_threads() { return pool().max_threads(); }
 bool host_pool_fixed() { return pool().fixed(); }
 void host_pool_set_threads(int n) { pool().set_active(n); }
 void host_pool_widen(const uint8_t *src, int32_t *dst, size_t n) { pool().submit(src, dst, n); }
+void host_pool_widen4(const uint8_t *src, int32_t *dst, size_t n) { pool().submit(src, dst, n, 4); }
 void host_pool_wait() { pool().wait(); }
 
 }  // namespace rbg

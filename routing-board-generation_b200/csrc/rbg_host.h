@@ -119,7 +119,7 @@ int launch_board_stats(const int32_t *boards, int64_t B, int G, int count_curren
 int launch_validate(const int32_t *boards, int64_t B, int G, int N,
                     int32_t *flags, cudaStream_t stream);
 // int32 codes (< 256) -> bytes, for the host transport of the observation
-int launch_narrow_codes(const int32_t *src, uint8_t *dst, int64_t n, cudaStream_t stream);
+int launch_narrow_codes(const int32_t *src, uint8_t *dst, int64_t n, cudaStream_t stream, int bits = 8);  // bits = 4: two codes < 16 per byte
 
 // ---- host thread pool (host_pool.cpp): widens byte codes back to int32 in host memory ----
 int host_pool_threads();                                          // workers in use (the pool is created on first use)
@@ -127,6 +127,7 @@ int host_pool_max_threads();                                      // workers tha
 bool host_pool_fixed();                                           // RBG_HOST_THREADS is set: no tuning
 void host_pool_set_threads(int n);                                // workers that take pieces from now on
 void host_pool_widen(const uint8_t *src, int32_t *dst, size_t n); // enqueue; split over the workers
+void host_pool_widen4(const uint8_t *src, int32_t *dst, size_t n); // the same for two codes per byte (low nibble first), n even
 void host_pool_wait();                                            // until every enqueued piece is done
 
 // ---- seed extension (seedext_kernel.cu) ---------------------------------

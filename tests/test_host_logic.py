@@ -153,3 +153,24 @@ def test_host_widen_matches_numpy():
             m = n - off if n >= off else 0
             assert np.array_equal(dst[:m], src[off:off + m].astype(np.int32)) and (dst[m:m + 8 - 0][-1] == -1)
     assert lib.rbg_host_widen(None, None, 5) == -1
+
+
+def test_host_widen4_matches_numpy():
+    """rbg_host_widen4: two codes < 16 per byte (low nibble first) -> int32, on the library's thread pool; needs no GPU.
+    Destinations at even and odd int32 offsets (the latter cannot use aligned streaming stores), ragged sizes."""
+    import ctypes as C
+
+    import numpy as np
+
+    import routing_board_generation_b200 as pkg
+
+    lib = pkg._lib.load()
+    rng = np.random.default_rng(1)
+    for n in (0, 2, 30, 32, 34, 1000, 65536 * 5 + 6, 1 << 22):
+        codes = rng.integers(0, 16, size=n, dtype=np.uint8)
+        packed = (codes[0::2] | (codes[1::2] << 4)).astype(np.uint8) if n else np.zeros(0, np.uint8)
+        for doff in (0, 1, 2, 5):
+            dst = np.full(n + 16, -1, np.int32)
+            assert lib.rbg_host_widen4(C.c_void_p(packed.ctypes.data), C.c_void_p(dst.ctypes.data + 4 * doff), n) == 0
+            assert np.array_equal(dst[doff:doff + n], codes.astype(np.int32)) and (dst[:doff] == -1).all() and (dst[doff + n:] == -1).all(), (n, doff)
+    assert lib.rbg_host_widen4(None, None, 4) == -1 and lib.rbg_host_widen4(C.c_void_p(1), C.c_void_p(4), 3) == -1  # odd n
